@@ -1,0 +1,603 @@
+"""TEST INFRASTRUCTURE — CPU restatement of the reference's hot path.
+
+This module is the *checker*: only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s `cpu_baseline` / `--impl reference` legs may import it.  It is
+never on the product path (the product fails loudly without its CUDA library).
+
+It restates, in vectorised numpy plus a small C helper for exact FMA chains
+(oracle/fmachain.c), what robin-karlsson0/pc-accumulation-lib computes on the
+path  project -> mask -> gather -> class filter -> pose transform -> accumulate
+-> BEV preprocess -> per-cell reductions -> finalise.  Each function cites the
+reference file:line it follows (paths relative to /root/reference).
+
+Pinning: the reference ships no tests or golden vectors ("parity unpinned" at
+the source).  This restatement is therefore pinned against
+outputs of the reference itself, run in the build container under the stub
+recipe of oracle/ref_loader.py: `tests/golden/*.npz` (made by
+tests/golden/make_golden.py) and oracle/validate_against_reference.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, 'liboracle_fma.so')
+        src = os.path.join(_HERE, 'fmachain.c')
+        if (not os.path.exists(so)
+                or os.path.getmtime(so) < os.path.getmtime(src)):
+            subprocess.check_call(['make', '-C', _HERE, '-s'])
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---------------------------------------------------------------------------
+#  Exact small-matrix transforms (FMA chains)
+# ---------------------------------------------------------------------------
+def affine(M: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    """rows 0..2 of  M @ [pts 1]^T  as (N,3) f64, FMA chain over k=0..3.
+    Equals np.matmul for N >= 2 on FMA-capable x86 hosts (checked in tests)."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    assert M.shape in ((3, 4), (4, 4))
+    n = pts.shape[0]
+    out = np.empty((n, 3), dtype=np.float64)
+    if n == 0:
+        return out
+    if pts.dtype == np.float32:
+        p = np.ascontiguousarray(pts[:, :3])
+        _lib().orc_affine_f32(_ptr(M), ctypes.c_int(4), _ptr(p),
+                              ctypes.c_int64(n), ctypes.c_int64(3), _ptr(out))
+    else:
+        p = np.ascontiguousarray(pts[:, :3], dtype=np.float64)
+        _lib().orc_affine_f64(_ptr(M), ctypes.c_int(4), _ptr(p),
+                              ctypes.c_int64(n), ctypes.c_int64(3), _ptr(out))
+    return out
+
+
+def rot33(R: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    n = pts.shape[0]
+    out = np.empty((n, 3), dtype=np.float64)
+    if n == 0:
+        return out
+    p = np.ascontiguousarray(pts[:, :3], dtype=np.float64)
+    _lib().orc_rot33_f64(_ptr(R), _ptr(p), ctypes.c_int64(n),
+                         ctypes.c_int64(3), _ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------
+#  a1-a4: projection, mask, gather, class filter
+# ---------------------------------------------------------------------------
+def velo2frame(pc_xyz: np.ndarray, P_velo_frame: np.ndarray) -> np.ndarray:
+    """sem_pc_accum.py:347-365 — (N,3) -> (N,3) f64 homogeneous image coords."""
+    return affine(np.asarray(P_velo_frame, dtype=np.float64), pc_xyz)
+
+
+def project(pc_velo: np.ndarray, P_velo_frame, img_h: int, img_w: int,
+            max_depth=np.inf):
+    """sem_pc_accum.py:382-396 — returns (u, v, mask) for ALL N points.
+    u, v are int64 (np.round = half-to-even, then astype(int))."""
+    frame = velo2frame(pc_velo[:, :3], P_velo_frame)
+    depth = frame[:, 2].copy()
+    depth[depth == 0] = -1e-6
+    with np.errstate(invalid='ignore', over='ignore'):
+        u = np.round(frame[:, 0] / np.abs(depth)).astype(int)
+        v = np.round(frame[:, 1] / np.abs(depth)).astype(int)
+    mask = (u >= 0) & (u < img_w) & (v >= 0) & (v < img_h)
+    mask = mask & (depth > 0) & (depth < max_depth)
+    return u, v, mask
+
+
+def velo2img(pc_velo, P_velo_frame, img_h, img_w, max_depth=np.inf):
+    """sem_pc_accum.py:367-402 — (M,6) f64 [x,y,z,i,u,v] of in-image points,
+    original order."""
+    u, v, mask = project(pc_velo, P_velo_frame, img_h, img_w, max_depth)
+    out = np.concatenate([pc_velo, u[:, None], v[:, None]], axis=1)
+    return out[mask]
+
+
+def gen_semantic_pc(pc_velo, semantic_map, P_velo_frame):
+    """sem_pc_accum.py:323-345 — (M,4+K) [x,y,z,i,feat_1..K]."""
+    img_h, img_w, _ = semantic_map.shape
+    pc_img = velo2img(pc_velo, P_velo_frame, img_h, img_w)
+    u = pc_img[:, -2].astype(int)
+    v = pc_img[:, -1].astype(int)
+    return np.concatenate([pc_img[:, :4], semantic_map[v, u, :]], axis=1)
+
+
+def filter_semseg_pc(pc, filters):
+    """sem_pc_accum.py:317-321."""
+    keep = np.ones(pc.shape[0], dtype=bool)
+    for f in filters:
+        keep &= pc[:, -1] != f
+    return pc[keep]
+
+
+def kitti_obs2sem(pc, rgb, class_map, P_velo_frame, filters, sem_gt=None):
+    """kitti360_sem_pc_accum.py:129-156 without ICP — (M',10) f64 record
+    [x,y,z,i,r,g,b,sem,inst=0,dyn=0]."""
+    if sem_gt is None:
+        pc_rgb = gen_semantic_pc(pc, np.asarray(rgb), P_velo_frame)
+        pc_sem = gen_semantic_pc(pc, class_map[..., None], P_velo_frame)
+        rec = np.concatenate([pc_rgb, pc_sem[:, -1:]], axis=1)
+    else:
+        n = sem_gt.shape[0]
+        rec = np.concatenate([pc, np.zeros((n, 3)), sem_gt[:, -1:]], axis=1)
+    rec = filter_semseg_pc(rec, filters)
+    z = np.zeros((rec.shape[0], 2))
+    return np.concatenate([rec, z], axis=1)
+
+
+# ---------------------------------------------------------------------------
+#  a9-a11: nuScenes nearest gather, homogeneous transform, record build
+# ---------------------------------------------------------------------------
+def homo_transform(tf, points):
+    """datasets/nuscenes_utils.py:46-60."""
+    assert tf.shape == (4, 4), f"{tf.shape} is not (4, 4)"
+    assert points.shape == (points.shape[0], 3), \
+        f"{points.shape} is not (N, 3)"
+    if points.shape[0] == 1:
+        # single-point products take numpy's matrix-vector path, whose
+        # arithmetic differs from the FMA chain (DESIGN.md "N=1"): mirror it
+        _p = np.concatenate([points, np.ones((1, 1))], axis=1)
+        return (tf @ _p.T)[:3, :].T
+    return affine(tf, points)
+
+
+def pts_feat_nearest(pts_uv, img):
+    """datasets/nuscenes_utils.py:181-214 with method='nearest'."""
+    img_wh = np.array([img.shape[1], img.shape[0]], dtype=float)
+    inside = (pts_uv > 1) & (pts_uv < img_wh - 1)
+    assert np.all(inside), "pts_uv must be all inside image"
+    uv = np.round(pts_uv).astype(int)
+    return img[uv[:, 1], uv[:, 0]]
+
+
+def nusc_obs2sem(pc, pc_cam_idx, rgbs, class_maps, T_ego_world, filters):
+    """nuscenes_oracle_sem_pc_accum.py:454-501 — (M,10) f64 world-frame
+    records; also returns the boolean keep mask over the N inputs."""
+    feat = -np.ones((pc.shape[0], 4), dtype=float)
+    for cam_idx, (rgb, cls) in enumerate(zip(rgbs, class_maps)):
+        m = pc_cam_idx == cam_idx
+        img = np.concatenate([np.asarray(rgb), cls[..., None]], axis=2)
+        feat[m] = pts_feat_nearest(pc[m, 4:6], img)
+    invalid = np.any(feat < 0, axis=1)
+    for c in filters:
+        invalid |= feat[:, -1] == c
+    keep = ~invalid
+    pc_k, feat_k = pc[keep], feat[keep]
+    xyz = homo_transform(T_ego_world, pc_k[:, :3])
+    rec = np.concatenate([xyz, pc_k[:, 3:4] / 255., feat_k, pc_k[:, 6:7],
+                          np.zeros((pc_k.shape[0], 1))], axis=1)
+    return rec, keep
+
+
+# ---------------------------------------------------------------------------
+#  a14-a20: the BEV generator
+# ---------------------------------------------------------------------------
+def rotation_matrix_3d(ang):
+    """bev_generator/bev_generator.py:732-735."""
+    return np.array([[np.cos(ang), -np.sin(ang), 0],
+                     [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+
+
+def heading_rot_ang(ego_traj_present):
+    """bev_generator/bev_generator.py:87-93."""
+    rot_ang = 0.5 * np.pi
+    if len(ego_traj_present) > 1:
+        dx = ego_traj_present[-1][0] - ego_traj_present[-2][0]
+        dy = ego_traj_present[-1][1] - ego_traj_present[-2][1]
+        rot_ang += np.arctan2(dy, dx)
+    return np.pi - rot_ang
+
+
+def point_in_box(x, y, bx0, by0, bx1, by1):
+    """bev_generator/bev_generator.py:317-320."""
+    return (bx0 < x and x < bx1) and (by0 < y and y < by1)
+
+
+def bisect_boundary(x0, y0, x1, y1, bbox, thresh=1e-4):
+    """bev_generator/bev_generator.py:322-371 — midpoint refinement until the
+    replaced end moved by <= thresh."""
+    bx0, by0, bx1, by1 = bbox
+    diff = np.inf
+    while diff > thresh:
+        xm = 0.5 * (x0 + x1)
+        ym = 0.5 * (y0 + y1)
+        p0_in = point_in_box(x0, y0, bx0, by0, bx1, by1)
+        mid_in = point_in_box(xm, ym, bx0, by0, bx1, by1)
+        if mid_in == p0_in:
+            diff = np.sqrt((xm - x0) ** 2 + (ym - y0) ** 2)
+            x0, y0 = xm, ym
+        else:
+            diff = np.sqrt((xm - x1) ** 2 + (ym - y1) ** 2)
+            x1, y1 = xm, ym
+    return xm, ym
+
+
+def crop_trajectory(traj, view, thresh=1e-4):
+    """bev_generator/bev_generator.py:257-315."""
+    b = (-0.5 * view, -0.5 * view, 0.5 * view, 0.5 * view)
+    out = []
+    for k in range(traj.shape[0] - 1):
+        x0, y0 = list(traj[k][:2])
+        x1, y1 = list(traj[k + 1][:2])
+        z0 = traj[k][2]
+        in0 = point_in_box(x0, y0, *b)
+        in1 = point_in_box(x1, y1, *b)
+        if not in0 and not in1:
+            continue
+        if in0:
+            out.append([x0, y0, z0])
+        if in0 != in1:
+            xi, yi = bisect_boundary(x0, y0, x1, y1, list(b), thresh)
+            out.append([xi, yi, z0])
+    return np.array(out) if out else np.zeros((0, 3))
+
+
+def pos2grid(mat, view, P):
+    """bev_generator/bev_generator.py:737-747 (in place on columns 0:2)."""
+    mat[:, 0:2] = np.floor(mat[:, 0:2] / view * P + 0.5 * P)
+    return mat
+
+
+def transform_traj(traj, R, dx, dy, view, P):
+    """geometric_transform(is_traj=True) + pos2grid,
+    bev_generator/bev_generator.py:141-158,224-237."""
+    t = np.array(traj, dtype=float)
+    t = t.reshape(-1, 3) if t.size else np.zeros((0, 3))
+    t[:, :3] = np.matmul(R, t[:, :3].T).T
+    t[:, 0] += dx
+    t[:, 1] += dy
+    t = crop_trajectory(t, view)
+    return pos2grid(t, view, P)
+
+
+def preprocess_pc(pc, R, dx, dy, view, P, height_filter):
+    """bev_generator/bev_generator.py:127-160,207-255 for the point cloud:
+    rotate (FMA chain), translate, strict crop, height filter, pos2grid.
+    Returns the (Mc,10) cloud with integer-valued xy."""
+    pc = pc.copy()
+    pc[:, :3] = rot33(R, pc[:, :3]) if pc.shape[0] != 1 else \
+        np.matmul(R, pc[:, :3].T).T
+    pc[:, 0] += dx
+    pc[:, 1] += dy
+    m = (pc[:, 0] > -0.5 * view) & (pc[:, 0] < 0.5 * view)
+    pc = pc[m]
+    m = (pc[:, 1] > -0.5 * view) & (pc[:, 1] < 0.5 * view)
+    pc = pc[m]
+    if height_filter is not None:
+        pc = pc[pc[:, 2] < height_filter]
+    return pos2grid(pc, view, P)
+
+
+def _segment_median(cell, val, P2):
+    """Per-cell np.median (mean of the two middle values for even counts),
+    bev_generator/sem_bev.py:657-667; NaN where the cell is empty."""
+    out = np.full(P2, np.nan)
+    if cell.size == 0:
+        return out
+    order = np.lexsort((val, cell))
+    c = cell[order]
+    v = val[order]
+    starts = np.flatnonzero(np.r_[True, c[1:] != c[:-1]])
+    counts = np.diff(np.r_[starts, c.size])
+    hi = starts + counts // 2
+    lo = np.where(counts % 2 == 1, hi, hi - 1)
+    out[c[starts]] = (v[lo] + v[hi]) / 2.0
+    return out
+
+
+def raster_window(pc_grid, P, sem_idxs, int_scaler, int_sep_scaler,
+                  int_mid_threshold, rgb_fill=0, return_f64=False,
+                  elevation_mode='min'):
+    """One window of SemBEVGenerator.generate_bev
+    (bev_generator/sem_bev.py:54-118,196-257) on a preprocessed cloud:
+    7 planes (road, intensity, r, g, b, dynamic, elevation), each (P,P).
+
+    `pc_grid` columns: [i, j, z, intensity, r, g, b, sem, inst, dyn] with
+    integer-valued i, j (output of preprocess_pc)."""
+    P2 = P * P
+    pc = pc_grid[pc_grid[:, 9] != 1]                       # sem_bev.py:54-58
+    col = pc[:, 0].astype(np.int64)
+    row = P - 1 - pc[:, 1].astype(np.int64)                # flip, :453 / :546
+    ok = (col >= 0) & (col < P) & (row >= 0) & (row < P)
+    pc, col, row = pc[ok], col[ok], row[ok]
+    cell = row * P + col
+    sem = pc[:, 7]
+
+    n = np.bincount(cell, minlength=P2).astype(np.float64)
+    road = sem == sem_idxs['road']
+    veh = np.zeros(sem.shape, dtype=bool)
+    for name in ('car', 'truck', 'bus', 'motorcycle'):     # sem_bev.py:55
+        veh |= sem == sem_idxs[name]
+    n_road = np.bincount(cell[road], minlength=P2).astype(np.float64)
+    n_veh = np.bincount(cell[veh], minlength=P2).astype(np.float64)
+
+    # Dirichlet expectation with a uniform prior, bev_generator.py:457-480
+    p_road = (n_road + 1.) / ((n_road + 1.) + ((n - n_road) + 1.))
+    p_veh = (n_veh + 1.) / ((n_veh + 1.) + ((n - n_veh) + 1.))
+
+    # intensity: sequential f64 sum in point order, bev_generator.py:396-415
+    int_sum = np.bincount(cell[road], weights=pc[road, 3], minlength=P2)
+    inten = int_sum / (n_road + 1.)
+    # road_marking_transform, sem_bev.py:593-617
+    inten = int_scaler * (1 / (1 + np.exp(-(int_sep_scaler *
+                                            (inten - int_mid_threshold)))))
+    inten[inten > 1.] = 1.
+
+    # elevation: per-cell min z, 0 where unobserved, sem_bev.py:535-554
+    elev = np.zeros(P2)
+    if cell.size:
+        if elevation_mode == 'min':
+            ext = np.full(P2, np.inf)
+            np.minimum.at(ext, cell, pc[:, 2])
+        else:                       # north-star variant, not the reference
+            ext = np.full(P2, -np.inf)
+            np.maximum.at(ext, cell, pc[:, 2])
+        obs = n > 0
+        elev[obs] = ext[obs]
+
+    # rgb: per-cell per-channel median, fill where empty, /255
+    planes = [p_road, inten]
+    for ch in (4, 5, 6):
+        med = _segment_median(cell, pc[:, ch], P2)
+        med[np.isnan(med)] = rgb_fill
+        planes.append(med / 255.)
+    planes += [p_veh, elev]
+    out = np.stack([p.reshape(P, P) for p in planes])
+    return out if return_f64 else out.astype(np.float16)
+
+
+PLANES = ('road', 'intensity', 'r', 'g', 'b', 'dynamic', 'elevation')
+
+
+def generate(pcs, trajs, gen_params, rot_ang=0., trans_dx=0., trans_dy=0.,
+             zoom_scalar=1., do_warping=False, return_f64=False):
+    """BEVGenerator.generate + SemBEVGenerator.generate_bev
+    (bev_generator/bev_generator.py:63-125, sem_bev.py:36-262), warp excluded.
+
+    gen_params: dict(sem_idxs, view_size, pixel_size, int_scaler,
+                     int_sep_scaler, int_mid_threshold, height_filter,
+                     rgb_fill)
+    Returns the 18-key dict; with return_f64 also '<name>_f64' stacks
+    (3 windows x 7 planes before the fp16 cast) and 'cells_<w>' index lists.
+    """
+    P = gen_params['pixel_size']
+    view = zoom_scalar * gen_params['view_size']
+    ego_present = trajs['ego_traj_present']
+    if do_warping is False:
+        rot_ang = heading_rot_ang(ego_present)
+    R = rotation_matrix_3d(rot_ang)
+
+    bev = {}
+    dbg = {}
+    for w in ('present', 'future', 'full'):
+        pc = pcs[f'pc_{w}']
+        if pc is None:
+            continue
+        pcg = preprocess_pc(pc, R, trans_dx, trans_dy, view, P,
+                            gen_params.get('height_filter'))
+        tr = [trajs[f'ego_traj_{w}']] + list(trajs[f'other_trajs_{w}'])
+        tr = [transform_traj(t, R, trans_dx, trans_dy, view, P) for t in tr]
+        planes = raster_window(
+            pcg, P, gen_params['sem_idxs'], gen_params['int_scaler'],
+            gen_params['int_sep_scaler'], gen_params['int_mid_threshold'],
+            gen_params.get('rgb_fill', 0), return_f64=True,
+            elevation_mode=gen_params.get('elevation_mode', 'min'))
+        h = planes.astype(np.float16)
+        bev[f'road_{w}'] = h[0]
+        bev[f'trajs_{w}'] = tr
+        bev[f'intensity_{w}'] = h[1]
+        bev[f'rgb_{w}'] = h[2:5]
+        bev[f'dynamic_{w}'] = h[5]
+        bev[f'elevation_{w}'] = h[6]
+        if return_f64:
+            dbg[f'planes_f64_{w}'] = planes
+            st = pcg[pcg[:, 9] != 1]
+            dbg[f'cells_{w}'] = np.stack(
+                [P - 1 - st[:, 1].astype(np.int64), st[:, 0].astype(np.int64)],
+                axis=1)
+    if 'gt_lanes' in trajs:
+        lanes = [transform_traj(t, R, trans_dx, trans_dy, view, P)
+                 for t in trajs['gt_lanes']]
+        bev['gt_lanes'] = [l for l in lanes if l.shape[0] > 0]
+    if return_f64:
+        bev['_debug'] = dbg
+    return bev
+
+
+def split_windows(sem_pcs, poses, present_idx, other_trajs=None):
+    """generate_bev of the accumulators (kitti360_sem_pc_accum.py:179-228,
+    nuscenes_oracle_sem_pc_accum.py:521-595): window split + origin shift."""
+    origin = np.array(poses[-1] if present_idx is None else poses[present_idx])
+    pcs, trajs = {}, {}
+    if other_trajs is None:
+        other_trajs = ([], [], [])
+    for w, sl, ot in (('present', slice(None, present_idx), other_trajs[0]),
+                      ('future', slice(present_idx, None), other_trajs[1]),
+                      ('full', slice(None), other_trajs[2])):
+        pc = np.concatenate(sem_pcs[sl])
+        pc[:, :3] = pc[:, :3] - origin
+        pcs[f'pc_{w}'] = pc
+        trajs[f'ego_traj_{w}'] = np.concatenate([poses[sl]]) - origin
+        trajs[f'other_trajs_{w}'] = [np.concatenate([t]) - origin for t in ot]
+    return pcs, trajs
+
+
+# ---------------------------------------------------------------------------
+#  a5-a8, a13: KITTI-360 accumulator (ICP replaced by an injected transform)
+# ---------------------------------------------------------------------------
+class KittiOracle:
+    """Restates Kitti360SemanticPointCloudAccumulator
+    (kitti360_sem_pc_accum.py:41-243 over sem_pc_accum.py:156-228) with the
+    ICP result `T_new_prev` injected per frame."""
+
+    def __init__(self, horizon_dist, P_velo_frame, filters, gen_params,
+                 use_gt_sem=False):
+        self.horizon_dist = horizon_dist
+        self.P = np.asarray(P_velo_frame, dtype=np.float64)
+        self.filters = list(filters)
+        self.gen_params = gen_params
+        self.use_gt_sem = use_gt_sem
+        self.sem_pcs, self.poses, self.seg_dists = [], [], []
+
+    def integrate(self, pc, rgb, class_map, T_new_prev, sem_gt=None):
+        rec = kitti_obs2sem(pc, rgb, class_map, self.P, self.filters,
+                            sem_gt if self.use_gt_sem else None)
+        if len(self.poses) > 0:
+            # update_poses, sem_pc_accum.py:156-165 (one 4x1 product per pose)
+            self.poses = [
+                list(np.matmul(T_new_prev, np.array([p + [1]]).T)[:, 0][:-1])
+                for p in self.poses]
+            # update_sem_pcs, sem_pc_accum.py:167-183
+            for s in self.sem_pcs:
+                if s.shape[0] == 0:
+                    continue
+                if s.shape[0] == 1:
+                    h = np.concatenate((s[:, :3], np.ones((1, 1))), axis=1)
+                    s[:, :3] = np.matmul(T_new_prev, h.T).T[:, :3]
+                else:
+                    s[:, :3] = affine(T_new_prev, s[:, :3])
+        self.sem_pcs.append(rec)
+        self.poses.append([0., 0., 0.])
+        idx = 0
+        if len(self.poses) > 1:
+            idx = self._remove_observations()
+        return idx
+
+    def _remove_observations(self):
+        """sem_pc_accum.py:185-209."""
+        idx = 0
+        d = np.sqrt(np.sum((np.array(self.poses[-2])
+                            - np.array(self.poses[-1])) ** 2))
+        self.seg_dists.append(d)
+        path_length = np.sum(self.seg_dists)
+        if path_length > self.horizon_dist:
+            incr = np.matmul(np.tri(len(self.seg_dists)),
+                             np.array(self.seg_dists))
+            incr -= path_length - self.horizon_dist
+            idx = (incr > 0.).argmax()
+            self.sem_pcs = self.sem_pcs[idx:]
+            self.poses = self.poses[idx:]
+            self.seg_dists = self.seg_dists[idx:]
+        return idx
+
+    def generate_bev(self, present_idx=None, return_f64=False, **aug):
+        pcs, trajs = split_windows(self.sem_pcs, self.poses, present_idx)
+        return generate(pcs, trajs, self.gen_params, return_f64=return_f64,
+                        **aug)
+
+
+# ---------------------------------------------------------------------------
+#  a11-a13: nuScenes oracle-pose accumulator
+# ---------------------------------------------------------------------------
+class NuscOracle:
+    """Restates NuScenesOracleSemanticPointCloudAccumulator
+    (nuscenes_oracle_sem_pc_accum.py:139-270,272-414,416-610)."""
+
+    TRACKED = [0, 1, 2, 3, 5]
+    DYN_THRESH = 1.0
+
+    def __init__(self, filters, gen_params, ego_pose_z=1.):
+        self.filters = list(filters)
+        self.gen_params = gen_params
+        self.ego_pose_z = ego_pose_z
+        self.T_global_world = None
+        self.sem_pcs, self.poses, self.seg_dists = [], [], []
+        self.instances, self.dyn_instances, self.token2idx = {}, [], []
+        self.ts = 0
+
+    def integrate(self, obs, class_maps):
+        T_ego_global = obs['ego_at_lidar_ts']
+        if self.T_global_world is None:
+            self.T_global_world = np.linalg.inv(T_ego_global)
+        T_ego_world = self.T_global_world @ T_ego_global
+        pose = T_ego_world[:3, -1].tolist()
+        pose[2] += self.ego_pose_z
+        rec, _ = nusc_obs2sem(obs['pc'], obs['pc_cam_idx'], obs['images'],
+                              class_maps, T_ego_world, self.filters)
+        self.sem_pcs.append(rec)
+        self.poses.append(pose)
+
+        # fake detector / tracker, :191-250
+        self.token2idx.append({'ts': self.ts})
+        for idx, token in enumerate(obs['inst_tokens']):
+            if obs['inst_cls'][idx] not in self.TRACKED:
+                continue
+            c = homo_transform(self.T_global_world,
+                               np.expand_dims(obs['inst_center'][idx], 0))[0]
+            self.instances.setdefault(token, []).append((c, self.ts))
+            self.token2idx[-1][token] = idx
+            if token in self.dyn_instances:
+                s = self.sem_pcs[-1]
+                s[s[:, 8] == idx, 9] = 1
+                continue
+            obs_list = self.instances[token]
+            if len(obs_list) < 2:
+                continue
+            d = obs_list[-1][0][:2] - obs_list[0][0][:2]
+            if np.linalg.norm(d) > self.DYN_THRESH:
+                self.dyn_instances.append(token)
+                for ts, s in enumerate(self.sem_pcs):
+                    if token in self.token2idx[ts]:
+                        s[s[:, 8] == self.token2idx[ts][token], 9] = 1
+        if len(self.poses) > 1:
+            self.seg_dists.append(np.sqrt(np.sum(
+                (np.array(self.poses[-1]) - np.array(self.poses[-2])) ** 2)))
+        self.ts += 1
+
+    # trajectory bookkeeping, :272-414
+    def dyn_obj_trajs(self, ts_start=0, ts_end=None):
+        out = []
+        for token, obs_list in self.instances.items():
+            if token not in self.dyn_instances:
+                continue
+            poses, tss = zip(*obs_list)
+            ge = [k for k, t in enumerate(tss) if t >= ts_start]
+            if not ge:
+                continue
+            i0 = ge[0]
+            if ts_end is None:
+                i1 = None
+            else:
+                if tss[0] > ts_end:
+                    continue
+                le = [k for k in range(len(tss) - 1) if tss[k + 1] > ts_end]
+                i1 = (le[0] if le else len(tss) - 1) + 1
+            poses, tss = poses[i0:i1], tss[i0:i1]
+            if len(tss) == 0:
+                # reference: parse_seq_into_coherent_seqs reads ts[0] ->
+                # IndexError propagates; generators avoid empty splices
+                raise IndexError('tuple index out of range')
+            seqs, prev = [[]], tss[0] - 1
+            for k, t in enumerate(tss):
+                if t - prev != 1:
+                    seqs.append([])
+                seqs[-1].append(poses[k].tolist())
+                prev = t
+            out += [s for s in seqs if len(s) >= 2]
+        return out
+
+    def generate_bev(self, present_idx=None, return_f64=False, **aug):
+        other = (self.dyn_obj_trajs(ts_end=present_idx),
+                 self.dyn_obj_trajs(ts_start=present_idx),
+                 self.dyn_obj_trajs())
+        pcs, trajs = split_windows(self.sem_pcs, self.poses, present_idx,
+                                   other)
+        return generate(pcs, trajs, self.gen_params, return_f64=return_f64,
+                        **aug)

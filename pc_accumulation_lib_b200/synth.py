@@ -1,0 +1,339 @@
+"""Seeded synthetic inputs of the shapes named in BASELINE.json / SURVEY.md §8(d).
+
+The reference reads KITTI-360 / nuScenes from disk (obs_dataloaders/*, out of
+scope); these generators stand in for that I/O so that the reference (when
+importable), the oracle and the CUDA path all see identical bytes.  Nothing in
+here computes anything on the hot path: it only fabricates observations in the
+input contract of `integrate()`:
+
+  KITTI-360   observations[0] = (rgb, pc (N,4) f32, sem_gt (N,1) int16 | None)
+              (reference: kitti360_sem_pc_accum.py:61-67,
+               obs_dataloaders/kitti360_obs_dataloader.py:87-106)
+  nuScenes    observations[0] = dict(images, pc (N,7) f64, pc_cam_idx, ...)
+              (reference: obs_dataloaders/nuscenes_obs_dataloader.py:103-220)
+
+Seeds follow SURVEY.md §8(d): seed = 20260 + 1000*config + frame id.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ---------------------------------------------------------------------------
+#  Constants of the two dataset shapes
+# ---------------------------------------------------------------------------
+KITTI_IMG_W, KITTI_IMG_H = 1408, 376
+KITTI_FX = KITTI_FY = 552.554261
+KITTI_CX, KITTI_CY = 682.049453, 238.769549
+KITTI_N_CLASSES = 19
+# run_kitti360_bev_gen.py:98-99 / run_nuscenes_bev_gen.py:125
+KITTI_FILTERS = [10, 11, 12, 16, 18, 255]
+NUSC_FILTERS = [10, 11, 12, 16, 18]
+SEM_IDXS = {'road': 0, 'car': 13, 'truck': 14, 'bus': 15, 'motorcycle': 17}
+
+NUSC_IMG_W, NUSC_IMG_H = 1600, 900
+NUSC_K = np.array([[1266.417203046554, 0.0, 816.2670197447984],
+                   [0.0, 1266.417203046554, 491.50706579294757],
+                   [0.0, 0.0, 1.0]])
+
+
+def seed_for(config: int, idx: int) -> int:
+    return 20260 + 1000 * config + idx
+
+
+def kitti_bev_params(pixel_size: int = 256, view_size=80, height_filter=None):
+    # defaults of run_kitti360_bev_gen.py:25-73,128-139
+    return {
+        'type': 'sem', 'view_size': view_size, 'pixel_size': pixel_size,
+        'max_trans_radius': 0., 'zoom_thresh': 0., 'do_warp': False,
+        'int_scaler': 20., 'int_sep_scaler': 20., 'int_mid_threshold': 0.5,
+        'height_filter': height_filter,
+    }
+
+
+def nusc_bev_params(pixel_size: int = 256):
+    # defaults of run_nuscenes_bev_gen.py:71-85
+    return {
+        'type': 'sem', 'view_size': 51.2, 'pixel_size': pixel_size,
+        'max_trans_radius': 0., 'zoom_thresh': 0., 'do_warp': False,
+        'int_scaler': 1., 'int_sep_scaler': 30., 'int_mid_threshold': 0.12,
+        'height_filter': 3.,
+    }
+
+
+# ---------------------------------------------------------------------------
+#  KITTI-360-shaped
+# ---------------------------------------------------------------------------
+def kitti_calib() -> dict:
+    """Calibration dict in the layout of run_kitti360_bev_gen.py:104-119."""
+    p_cam_frame = np.array([[KITTI_FX, 0., KITTI_CX, 0.],
+                            [0., KITTI_FY, KITTI_CY, 0.],
+                            [0., 0., 1., 0.]])
+    # velodyne (x fwd, y left, z up) -> camera (x right, y down, z fwd)
+    h_velo_cam = np.array([[0.0371, -0.9993, 0.0026, 0.2628],
+                           [-0.0089, -0.0029, -0.9999, -0.1121],
+                           [0.9993, 0.0371, -0.0090, -0.8296],
+                           [0., 0., 0., 1.]])
+    p_velo_frame = np.matmul(p_cam_frame, h_velo_cam)
+    return {
+        'h_velo_cam': h_velo_cam, 'p_cam_frame': p_cam_frame,
+        'p_velo_frame': p_velo_frame, 'c_x': KITTI_CX, 'c_y': KITTI_CY,
+        'f_x': KITTI_FX, 'f_y': KITTI_FY,
+    }
+
+
+def kitti_lidar(seed: int, n_beams: int = 64, n_azimuth: int = 1875,
+                dtype=np.float32) -> np.ndarray:
+    """64-beam sweep hitting a ground plane 1.73 m below the sensor or an
+    obstacle at U(8,70) m, whichever is nearer.  Returns (N,4) [x,y,z,i]."""
+    rng = np.random.default_rng(seed)
+    elev = np.deg2rad(np.linspace(-24.8, 2.0, n_beams))
+    azim = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)
+    el, az = np.meshgrid(elev, azim, indexing='ij')
+    el = el.ravel()
+    az = az.ravel() + rng.normal(0., 1e-4, el.size)
+    r_obst = rng.uniform(8., 70., el.size)
+    with np.errstate(divide='ignore'):
+        r_ground = np.where(el < -1e-3, 1.73 / np.sin(-el), np.inf)
+    r = np.minimum(r_ground, r_obst)
+    pc = np.empty((el.size, 4), dtype=np.float64)
+    pc[:, 0] = r * np.cos(el) * np.cos(az)
+    pc[:, 1] = r * np.cos(el) * np.sin(az)
+    pc[:, 2] = r * np.sin(el)
+    pc[:, 3] = rng.uniform(0., 1., el.size)
+    return pc.astype(dtype)
+
+
+def kitti_rgb(seed: int, h: int = KITTI_IMG_H, w: int = KITTI_IMG_W):
+    rng = np.random.default_rng(seed + 500_000)
+    return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def kitti_prob_map(seed: int, h: int = KITTI_IMG_H, w: int = KITTI_IMG_W,
+                   k: int = KITTI_N_CLASSES) -> np.ndarray:
+    """(h,w,k) f32 softmax of seeded logits with a row-dependent road prior
+    (stand-in for the ONNX network's per-pixel class probabilities)."""
+    rng = np.random.default_rng(seed + 700_000)
+    logits = rng.normal(0., 1., (h, w, k)).astype(np.float32)
+    rows = np.linspace(0., 1., h, dtype=np.float32)[:, None]
+    logits[:, :, 0] += 4.0 * rows - 1.0          # road towards the bottom
+    logits[:, :, 13] += 1.5 * (1.0 - rows)       # some cars higher up
+    logits -= logits.max(axis=2, keepdims=True)
+    e = np.exp(logits)
+    return (e / e.sum(axis=2, keepdims=True)).astype(np.float32)
+
+
+def kitti_class_map(seed: int, h: int = KITTI_IMG_H, w: int = KITTI_IMG_W,
+                    k: int = KITTI_N_CLASSES) -> np.ndarray:
+    """(h,w) int64 class-index map: argmax of `kitti_prob_map`."""
+    return np.argmax(kitti_prob_map(seed, h, w, k), axis=2).astype(np.int64)
+
+
+def kitti_class_map_fast(seed: int, h: int = KITTI_IMG_H,
+                         w: int = KITTI_IMG_W) -> np.ndarray:
+    """Cheap (h,w) uint8 class map for large benches (no softmax)."""
+    rng = np.random.default_rng(seed + 700_000)
+    cls = rng.integers(0, KITTI_N_CLASSES, (h, w), dtype=np.uint8)
+    road = rng.random((h, w)) < np.linspace(0.05, 0.9, h)[:, None]
+    cls[road] = 0
+    return cls
+
+
+def kitti_sem_gt(seed: int, n: int, unfiltered_only: bool = True):
+    """(n,1) int16 per-point GT classes for the `use_gt_sem` path
+    (kitti360_sem_pc_accum.py:138-144)."""
+    rng = np.random.default_rng(seed + 900_000)
+    if unfiltered_only:
+        allowed = np.array([c for c in range(KITTI_N_CLASSES)
+                            if c not in KITTI_FILTERS], dtype=np.int16)
+    else:
+        allowed = np.array(list(range(KITTI_N_CLASSES)) + [255],
+                           dtype=np.int16)
+    cls = allowed[rng.integers(0, allowed.size, n)]
+    cls[rng.random(n) < 0.45] = 0
+    return cls.reshape(n, 1).astype(np.int16)
+
+
+def kitti_step_transform(seed: int) -> np.ndarray:
+    """T_new_prev (4,4): maps points of the previous ego frame into the new
+    one after driving forward 1-4.5 m with |yaw| <= 0.01 rad.  Stands in for
+    the ICP result at kitti360_sem_pc_accum.py:123-126."""
+    rng = np.random.default_rng(seed + 300_000)
+    fwd = rng.uniform(1.0, 4.5)
+    lat = rng.normal(0., 0.02)
+    yaw = rng.uniform(-0.01, 0.01)
+    pitch = rng.normal(0., 0.001)
+    cy, sy = np.cos(yaw), np.sin(yaw)
+    cp, sp = np.cos(pitch), np.sin(pitch)
+    rz = np.array([[cy, -sy, 0.], [sy, cy, 0.], [0., 0., 1.]])
+    ry = np.array([[cp, 0., sp], [0., 1., 0.], [-sp, 0., cp]])
+    t_prev_new = np.eye(4)            # pose of the new frame in the old one
+    t_prev_new[:3, :3] = rz @ ry
+    t_prev_new[:3, 3] = [fwd, lat, rng.normal(0., 0.01)]
+    return np.linalg.inv(t_prev_new)
+
+
+class FakeSemseg:
+    """Object with the `.pred(rgb) -> (1,1,H,W)` contract of
+    utils/onnx_utils.py:32-44; returns pre-generated class maps in turn."""
+
+    def __init__(self, class_maps):
+        self._maps = list(class_maps)
+        self._i = 0
+
+    def pred(self, rgb):
+        m = self._maps[self._i % len(self._maps)]
+        self._i += 1
+        return m[None, None]
+
+
+# ---------------------------------------------------------------------------
+#  nuScenes-shaped (oracle pose)
+# ---------------------------------------------------------------------------
+def _rot_z(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]])
+
+
+def nusc_ego_poses(seed: int, n: int) -> list:
+    """n SE(3) `ego_at_lidar_ts` matrices (ego -> global), ~5 m per step."""
+    rng = np.random.default_rng(seed + 100_000)
+    yaw = rng.uniform(-np.pi, np.pi)
+    pos = np.array([rng.uniform(300., 2000.), rng.uniform(300., 2000.), 0.])
+    out = []
+    for _ in range(n):
+        T = np.eye(4)
+        T[:3, :3] = _rot_z(yaw)
+        T[:3, 3] = pos
+        out.append(T)
+        step = rng.uniform(4.0, 6.0)
+        pos = pos + np.array([step * np.cos(yaw), step * np.sin(yaw),
+                              rng.normal(0., 0.02)])
+        yaw += rng.uniform(-0.03, 0.03)
+    return out
+
+
+def nusc_project_pts3d(pc_cam, cam_k, img_wh, depth_thres=1e-3):
+    """Restatement of NuScenesCamera.project_pts3d
+    (datasets/nuscenes_utils.py:112-136; nuscenes-devkit view_points with
+    normalize=True is uv = (K p)[:2] / (K p)[2])."""
+    valid = pc_cam[:, 2] > depth_thres
+    out = np.zeros((pc_cam.shape[0], 2)) - 10.
+    kp = (cam_k @ pc_cam[valid].T)
+    out[valid] = (kp[:2] / kp[2:3]).T
+    inside = (out > 1) & (out < np.asarray(img_wh, dtype=float) - 1)
+    return out, np.all(inside, axis=1) & valid
+
+
+def nusc_boxes(seed: int, n_boxes: int = 10, n_moving: int = 3):
+    """Static description of the scene's annotated boxes (global frame)."""
+    rng = np.random.default_rng(seed + 200_000)
+    boxes = []
+    clss = [0, 1, 3, 5, 0, 7, 0, 4, 0, 2, 6, 0]
+    for b in range(n_boxes):
+        boxes.append({
+            'token': f'inst_{seed}_{b:03d}',
+            'cls': clss[b % len(clss)],
+            'offset': np.array([rng.uniform(8., 25.), rng.uniform(-6., 6.), 0.8]),
+            'vel': (np.array([rng.uniform(1.5, 3.0), rng.uniform(-.3, .3), 0.])
+                    if b < n_moving else np.zeros(3)),
+            'size': np.array([4.2, 1.9, 1.6]),
+        })
+    return boxes
+
+
+def nusc_obs(seed: int, T_ego_global: np.ndarray, ts: int, boxes=None,
+             anchor_global=None, n_beams: int = 32, n_azimuth: int = 1084,
+             img_h: int = NUSC_IMG_H, img_w: int = NUSC_IMG_W,
+             with_images: bool = True) -> dict:
+    """One observation dict in the nuScenes dataloader's output contract.
+
+    CAM_FRONT only (the reference's commented single-camera option,
+    obs_dataloaders/nuscenes_obs_dataloader.py:31).  `images` holds uint8
+    (H,W,3) arrays (np.array(PIL) yields the same)."""
+    rng = np.random.default_rng(seed)
+    elev = np.deg2rad(np.linspace(-30.0, 10.0, n_beams))
+    azim = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)
+    el, az = np.meshgrid(elev, azim, indexing='ij')
+    el = el.ravel()
+    az = az.ravel() + rng.normal(0., 1e-4, el.size)
+    n = el.size
+    r_obst = rng.uniform(4., 60., n)
+    with np.errstate(divide='ignore'):
+        r_ground = np.where(el < -1e-3, 1.84 / np.sin(-el), np.inf)
+    r = np.minimum(r_ground, r_obst)
+    xyz = np.empty((n, 3))
+    xyz[:, 0] = r * np.cos(el) * np.cos(az)
+    xyz[:, 1] = r * np.cos(el) * np.sin(az)
+    xyz[:, 2] = r * np.sin(el) + 1.84
+    intensity = rng.integers(0, 256, n).astype(np.float64)
+
+    # camera: ego (x fwd, y left, z up) -> cam (x right, y down, z fwd)
+    r_cam_ego = np.array([[0., -1., 0.], [0., 0., -1.], [1., 0., 0.]])
+    t_cam = np.array([1.70, 0.016, 1.51])
+    pc_cam = (r_cam_ego @ (xyz - t_cam).T).T
+    uv, in_img = nusc_project_pts3d(pc_cam, NUSC_K, (img_w, img_h))
+    pc_uv = np.zeros((n, 2))
+    pc_uv[in_img] = uv[in_img]
+    pc_cam_idx = -np.ones(n, dtype=int)
+    pc_cam_idx[in_img] = 0
+
+    # boxes: assign instance index to points inside axis-aligned boxes
+    inst = -np.ones(n)
+    inst_tokens, inst_cls, inst_center = [], [], []
+    if boxes:
+        T_global_ego = np.linalg.inv(T_ego_global)
+        for b in boxes:
+            center_g = anchor_global + b['offset'] + b['vel'] * ts
+            c_e = (T_global_ego @ np.append(center_g, 1.))[:3]
+            half = 0.5 * b['size']
+            inside = np.all(np.abs(xyz - c_e) < half, axis=1)
+            idx = len(inst_tokens)
+            inst[inside] = idx
+            inst_tokens.append(b['token'])
+            inst_cls.append(int(b['cls']))
+            inst_center.append(center_g.copy())
+
+    obs = {
+        'pc': np.concatenate([xyz, intensity[:, None], pc_uv, inst[:, None]],
+                             axis=1),
+        'pc_cam_idx': pc_cam_idx,
+        'ego_at_lidar_ts': T_ego_global,
+        'ego_global_x': float(T_ego_global[0, 3]),
+        'ego_global_y': float(T_ego_global[1, 3]),
+        'inst_tokens': inst_tokens,
+        'inst_cls': inst_cls,
+        'inst_center': inst_center,
+        'meta': {'cam_channels': ['CAM_FRONT']},
+    }
+    if with_images:
+        obs['images'] = [rng.integers(0, 256, (img_h, img_w, 3),
+                                      dtype=np.uint8)]
+        cls = rng.integers(0, KITTI_N_CLASSES, (img_h, img_w)).astype(np.int64)
+        road = rng.random((img_h, img_w)) < np.linspace(0.05, 0.9, img_h)[:, None]
+        cls[road] = 0
+        obs['_semseg'] = [cls]     # consumed by the stand-in semseg model
+    return obs
+
+
+def nusc_scene(seed: int, n_samples: int = 40, **kw) -> list:
+    """List of observation dicts for one scene."""
+    poses = nusc_ego_poses(seed, n_samples)
+    boxes = nusc_boxes(seed)
+    anchor = poses[0][:3, 3].copy()
+    return [nusc_obs(seed + 1 + ts, poses[ts], ts, boxes, anchor, **kw)
+            for ts in range(n_samples)]
+
+
+class SceneSemseg:
+    """Stand-in semseg for nuScenes scenes: `.pred(rgb)` returns the class map
+    that `nusc_obs` generated for the image with the same id()."""
+
+    def __init__(self):
+        self._by_id = {}
+
+    def register(self, obs: dict):
+        for img, cls in zip(obs['images'], obs['_semseg']):
+            self._by_id[id(img)] = cls
+
+    def pred(self, rgb):
+        return self._by_id[id(rgb)][None, None]

@@ -1,0 +1,194 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_loader.py) on the seeded inputs
+of tests/golden/cases.py.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these
+outputs of the reference itself are what pins the oracle and the CUDA path.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_loader                      # noqa: E402
+from pc_accumulation_lib_b200 import synth         # noqa: E402
+from tests.golden import cases                     # noqa: E402
+
+WINDOWS = ('present', 'future', 'full')
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def pack_bev(bev: dict, prefix: str, out: dict):
+    for k, v in bev.items():
+        if k.startswith('trajs_') or k == 'gt_lanes':
+            out[f'{prefix}{k}_n'] = np.int64(len(v))
+            for i, t in enumerate(v):
+                out[f'{prefix}{k}_{i}'] = np.asarray(t, dtype=np.float64)
+        else:
+            out[f'{prefix}{k}'] = v
+
+
+def pack_sem_pcs(sem_pcs, prefix, out):
+    out[f'{prefix}n_frames'] = np.int64(len(sem_pcs))
+    for i, s in enumerate(sem_pcs):
+        out[f'{prefix}xyzi_{i}'] = s[:, :4].copy()
+        out[f'{prefix}attr_{i}'] = s[:, 4:].astype(np.int32)
+        assert np.array_equal(out[f'{prefix}attr_{i}'], s[:, 4:])
+
+
+def save(name, out):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(out)} arrays')
+
+
+def gen_kitti_project(ref):
+    inp = cases.kitti_project_inputs()
+    acc = ref_loader.make_kitti_accum(
+        ref, 1e9, synth.kitti_calib(), synth.KITTI_FILTERS, synth.SEM_IDXS,
+        synth.kitti_bev_params(pixel_size=32))
+    pc, P = inp['pc'], inp['P']
+    n = pc.shape[0]
+    pc5 = np.concatenate([pc, np.arange(n, dtype=np.float32)[:, None]], axis=1)
+    img = acc.velo2img(pc5, P, synth.KITTI_IMG_H, synth.KITTI_IMG_W)
+    out = {
+        'input_sha256': np.array(cases.digest(pc, P, inp['rgb'], inp['prob'])),
+        'kept_idx': img[:, 4].astype(np.int32),
+        'u': img[:, 5].astype(np.int32), 'v': img[:, 6].astype(np.int32),
+    }
+    assert np.array_equal(img[:, :4], pc[out['kept_idx']].astype(np.float64))
+    sem_rgb = acc.gen_semantic_pc(pc, inp['rgb'], P)
+    sem_cls = acc.gen_semantic_pc(pc, inp['cls'][..., None], P)
+    sem_prob = acc.gen_semantic_pc(pc, inp['prob'], P)
+    assert np.array_equal(sem_rgb[:, :4], img[:, :4])
+    out['gather_rgb'] = sem_rgb[:, 4:].astype(np.uint8)
+    out['gather_cls'] = sem_cls[:, 4].astype(np.int32)
+    out['gather_prob'] = sem_prob[:, 4:].astype(np.float32)
+    assert np.array_equal(out['gather_prob'].astype(np.float64),
+                          sem_prob[:, 4:])
+    # max_depth variant
+    img_d = acc.velo2img(pc5, P, synth.KITTI_IMG_H, synth.KITTI_IMG_W,
+                         max_depth=30.0)
+    out['kept_idx_maxdepth30'] = img_d[:, 4].astype(np.int32)
+    save('kitti_project.npz', out)
+
+
+def gen_kitti_seq(ref, name, use_gt_sem, P, horizon, present_idx, **kw):
+    frames = cases.kitti_seq_inputs(use_gt_sem=use_gt_sem, **kw)
+    bev_params = synth.kitti_bev_params(pixel_size=P)
+    sem = None if use_gt_sem else synth.FakeSemseg(
+        [f['cls'] for f in frames])
+    acc = ref_loader.make_kitti_accum(
+        ref, horizon, synth.kitti_calib(), synth.KITTI_FILTERS,
+        synth.SEM_IDXS, bev_params, sem, use_gt_sem=use_gt_sem)
+    evicted = []
+    n_kept = []
+    for fr in frames:
+        ref_loader.ICP_QUEUE.append(fr['T'])
+        with quiet():
+            evicted.append(acc.integrate(
+                [(fr['rgb'], fr['pc'], fr['sem_gt'])]))
+        n_kept.append(acc.sem_pcs[-1].shape[0])
+    out = {'input_sha256': np.array(cases.kitti_seq_digest(frames)),
+           'evicted': np.array(evicted, dtype=np.int64),
+           'n_kept': np.array(n_kept, dtype=np.int64),
+           'poses': np.array(acc.poses, dtype=np.float64),
+           'seg_dists': np.array(acc.seg_dists, dtype=np.float64),
+           'present_idx': np.int64(present_idx), 'P': np.int64(P),
+           'horizon': np.float64(horizon)}
+    pack_sem_pcs(acc.sem_pcs, 'sem_pcs_', out)
+    t = time.time()
+    with quiet():
+        bev = acc.generate_bev(present_idx, 1, True)[0]
+    print(f'  reference generate_bev: {time.time() - t:.2f} s')
+    pack_bev(bev, 'bev_', out)
+    save(name, out)
+
+
+def gen_nusc_seq(ref, name, P, present_idx, **kw):
+    scene = cases.nusc_seq_inputs(**kw)
+    semseg = synth.SceneSemseg()
+    for o in scene:
+        semseg.register(o)
+    acc = ref_loader.make_nusc_accum(ref, synth.NUSC_FILTERS, synth.SEM_IDXS,
+                                     synth.nusc_bev_params(pixel_size=P),
+                                     semseg)
+    for o in scene:
+        with quiet():
+            acc.integrate([o])
+    out = {'input_sha256': np.array(cases.nusc_seq_digest(scene)),
+           'poses': np.array(acc.poses, dtype=np.float64),
+           'seg_dists': np.array(acc.seg_dists, dtype=np.float64),
+           'dyn_instances': np.array(acc.dyn_instances),
+           'present_idx': np.int64(present_idx), 'P': np.int64(P)}
+    pack_sem_pcs(acc.sem_pcs, 'sem_pcs_', out)
+    n_dyn = sum(int((s[:, 9] == 1).sum()) for s in acc.sem_pcs)
+    print(f'  dynamic tokens {acc.dyn_instances}, dyn points {n_dyn}')
+    with quiet():
+        bev = acc.generate_bev(present_idx, 1, True)[0]
+    pack_bev(bev, 'bev_', out)
+    save(name, out)
+
+
+def gen_bev_direct(ref, name, **kw):
+    pcs, trajs, aug, gen = cases.bev_direct_inputs(**kw)
+    g = ref.SemBEVGenerator(gen['sem_idxs'], gen['view_size'],
+                            gen['pixel_size'], 0., 0., False,
+                            gen['int_scaler'], gen['int_sep_scaler'],
+                            gen['int_mid_threshold'], gen['height_filter'],
+                            gen['rgb_fill'])
+    out = {'input_sha256': np.array(cases.digest(
+        pcs['pc_present'], pcs['pc_future'], trajs['ego_traj_full']))}
+    p, t = cases.copy_pcs_trajs(pcs, trajs)
+    with quiet():
+        bev = g.generate(p, t, **aug)
+    pack_bev(bev, 'bev_', out)
+    # heading-aligned variant (do_warping False -> angle from the ego track)
+    p, t = cases.copy_pcs_trajs(pcs, trajs)
+    with quiet():
+        bev = g.generate(p, t)
+    pack_bev(bev, 'bevhead_', out)
+    # preprocessed clouds (cell indices) of the explicit-angle variant
+    p, t = cases.copy_pcs_trajs(pcs, trajs)
+    view = aug['zoom_scalar'] * gen['view_size']
+    for w in WINDOWS:
+        with quiet():
+            pcg, _ = g.preprocess_pc_and_trajs(
+                p[f'pc_{w}'], [], aug['rot_ang'], aug['trans_dx'],
+                aug['trans_dy'], view)
+        out[f'grid_ij_{w}'] = pcg[:, :2].astype(np.int32)
+        out[f'grid_z_{w}'] = pcg[:, 2].copy()
+    save(name, out)
+
+
+def main():
+    ref = ref_loader.load()
+    gen_kitti_project(ref)
+    gen_kitti_seq(ref, 'kitti_seq.npz', use_gt_sem=False, P=64, horizon=14.0,
+                  present_idx=3, n_frames=9)
+    gen_kitti_seq(ref, 'kitti_seq_p256.npz', use_gt_sem=False, P=256,
+                  horizon=1e9, present_idx=3, n_frames=6)
+    gen_kitti_seq(ref, 'kitti_gtsem_seq.npz', use_gt_sem=True, P=64,
+                  horizon=1e9, present_idx=2, n_frames=5, n_beams=8,
+                  n_azimuth=300, config=3)
+    gen_nusc_seq(ref, 'nusc_seq.npz', P=64, present_idx=4)
+    gen_bev_direct(ref, 'bev_direct.npz')
+    gen_bev_direct(ref, 'bev_direct_p128.npz', n=20000, seed=78, P=128,
+                   view=51.2)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,141 @@
+"""The CPU oracle (oracle/oracle.py) against the golden vectors produced by
+the literal reference (tests/golden/make_golden.py).  Everything here is
+bit-exact: same host arithmetic, restated."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from pc_accumulation_lib_b200 import synth
+from tests.conftest import (assert_bev_equal, load_golden, unpack_bev,
+                            unpack_sem_pcs)
+from tests.golden import cases
+
+
+def test_matmul_equals_fma_chain_on_this_host():
+    """The premise of SURVEY.md §0: numpy's f64 matmul (N>=2) for the shapes
+    on the path is a sequential FMA chain over k."""
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 17, 4097):
+        T = np.eye(4)
+        T[:3, :3] += rng.normal(0, 0.3, (3, 3))
+        T[:3, 3] = rng.normal(0, 5, 3)
+        p = rng.normal(0, 30, (n, 3))
+        ref = np.matmul(T, np.concatenate([p, np.ones((n, 1))], 1).T).T[:, :3]
+        np.testing.assert_array_equal(orc.affine(T, p), ref)
+        P = rng.normal(0, 100, (3, 4))
+        p32 = p.astype(np.float32)
+        ref = np.matmul(P, np.concatenate([p32, np.ones((n, 1))], 1).T).T
+        np.testing.assert_array_equal(orc.affine(P, p32), ref)
+        R = orc.rotation_matrix_3d(0.7)
+        big = rng.normal(0, 30, (n, 10))
+        ref = np.matmul(R, big[:, :3].T).T
+        np.testing.assert_array_equal(orc.rot33(R, big[:, :3]), ref)
+
+
+def test_kitti_project_golden():
+    g = load_golden('kitti_project.npz')
+    inp = cases.kitti_project_inputs()
+    assert str(g['input_sha256']) == cases.digest(inp['pc'], inp['P'],
+                                                  inp['rgb'], inp['prob'])
+    u, v, mask = orc.project(inp['pc'], inp['P'], synth.KITTI_IMG_H,
+                             synth.KITTI_IMG_W)
+    kept = np.flatnonzero(mask)
+    np.testing.assert_array_equal(kept, g['kept_idx'])
+    np.testing.assert_array_equal(u[kept], g['u'])
+    np.testing.assert_array_equal(v[kept], g['v'])
+    sem = orc.gen_semantic_pc(inp['pc'], inp['rgb'], inp['P'])
+    np.testing.assert_array_equal(sem[:, 4:], g['gather_rgb'])
+    sem = orc.gen_semantic_pc(inp['pc'], inp['cls'][..., None], inp['P'])
+    np.testing.assert_array_equal(sem[:, 4], g['gather_cls'])
+    sem = orc.gen_semantic_pc(inp['pc'], inp['prob'], inp['P'])
+    np.testing.assert_array_equal(sem[:, 4:], g['gather_prob'])
+    _, _, m30 = orc.project(inp['pc'], inp['P'], synth.KITTI_IMG_H,
+                            synth.KITTI_IMG_W, max_depth=30.0)
+    np.testing.assert_array_equal(np.flatnonzero(m30),
+                                  g['kept_idx_maxdepth30'])
+
+
+def _gen_params(bev_params):
+    return dict(sem_idxs=synth.SEM_IDXS, view_size=bev_params['view_size'],
+                pixel_size=bev_params['pixel_size'],
+                int_scaler=bev_params['int_scaler'],
+                int_sep_scaler=bev_params['int_sep_scaler'],
+                int_mid_threshold=bev_params['int_mid_threshold'],
+                height_filter=bev_params['height_filter'], rgb_fill=0)
+
+
+@pytest.mark.parametrize('name,kw,gt', [
+    ('kitti_seq.npz', dict(n_frames=9), False),
+    ('kitti_seq_p256.npz', dict(n_frames=6), False),
+    ('kitti_gtsem_seq.npz',
+     dict(n_frames=5, n_beams=8, n_azimuth=300, config=3), True),
+])
+def test_kitti_sequence_golden(name, kw, gt):
+    g = load_golden(name)
+    frames = cases.kitti_seq_inputs(use_gt_sem=gt, **kw)
+    assert str(g['input_sha256']) == cases.kitti_seq_digest(frames)
+    P = int(g['P'])
+    acc = orc.KittiOracle(float(g['horizon']),
+                          synth.kitti_calib()['p_velo_frame'],
+                          synth.KITTI_FILTERS,
+                          _gen_params(synth.kitti_bev_params(pixel_size=P)),
+                          use_gt_sem=gt)
+    evicted, n_kept = [], []
+    for fr in frames:
+        evicted.append(acc.integrate(fr['pc'], fr['rgb'], fr['cls'], fr['T'],
+                                     fr['sem_gt']))
+        n_kept.append(acc.sem_pcs[-1].shape[0])
+    np.testing.assert_array_equal(evicted, g['evicted'])
+    np.testing.assert_array_equal(n_kept, g['n_kept'])
+    np.testing.assert_array_equal(np.array(acc.poses), g['poses'])
+    np.testing.assert_array_equal(np.array(acc.seg_dists), g['seg_dists'])
+    want = unpack_sem_pcs(g)
+    assert len(want) == len(acc.sem_pcs)
+    for a, b in zip(acc.sem_pcs, want):
+        np.testing.assert_array_equal(a, b)
+    bev = acc.generate_bev(int(g['present_idx']))
+    assert_bev_equal(bev, unpack_bev(g))
+
+
+def test_nusc_sequence_golden():
+    g = load_golden('nusc_seq.npz')
+    scene = cases.nusc_seq_inputs()
+    assert str(g['input_sha256']) == cases.nusc_seq_digest(scene)
+    P = int(g['P'])
+    acc = orc.NuscOracle(synth.NUSC_FILTERS,
+                         _gen_params(synth.nusc_bev_params(pixel_size=P)))
+    for o in scene:
+        acc.integrate(o, o['_semseg'])
+    np.testing.assert_array_equal(np.array(acc.poses), g['poses'])
+    np.testing.assert_array_equal(np.array(acc.seg_dists), g['seg_dists'])
+    assert list(g['dyn_instances']) == acc.dyn_instances
+    for a, b in zip(acc.sem_pcs, unpack_sem_pcs(g)):
+        np.testing.assert_array_equal(a, b)
+    bev = acc.generate_bev(int(g['present_idx']))
+    assert_bev_equal(bev, unpack_bev(g))
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bev_direct.npz', {}),
+    ('bev_direct_p128.npz', dict(n=20000, seed=78, P=128, view=51.2)),
+])
+def test_bev_direct_golden(name, kw):
+    g = load_golden(name)
+    pcs, trajs, aug, gen = cases.bev_direct_inputs(**kw)
+    assert str(g['input_sha256']) == cases.digest(
+        pcs['pc_present'], pcs['pc_future'], trajs['ego_traj_full'])
+    bev = orc.generate(pcs, trajs, gen, return_f64=True, **aug)
+    dbg = bev.pop('_debug')
+    assert_bev_equal(bev, unpack_bev(g, 'bev_'))
+    for w in ('present', 'future', 'full'):
+        ij = g[f'grid_ij_{w}']
+        st = pcs[f'pc_{w}']
+        # golden holds all cropped points; oracle debug holds static ones
+        pcg = orc.preprocess_pc(st, orc.rotation_matrix_3d(aug['rot_ang']),
+                                aug['trans_dx'], aug['trans_dy'],
+                                aug['zoom_scalar'] * gen['view_size'],
+                                gen['pixel_size'], gen['height_filter'])
+        np.testing.assert_array_equal(pcg[:, :2].astype(np.int32), ij)
+        np.testing.assert_array_equal(pcg[:, 2], g[f'grid_z_{w}'])
+    bev = orc.generate(pcs, trajs, gen)
+    assert_bev_equal(bev, unpack_bev(g, 'bevhead_'))
