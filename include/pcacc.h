@@ -1,0 +1,219 @@
+/* pcacc.h — C ABI of libpcacc.so: the sm_100a implementation of the per-frame
+ * semantic fusion + BEV rasterisation path of robin-karlsson0/pc-accumulation-lib.
+ *
+ * The reference has no FFI of its own (it is pure Python/numpy);
+ * its boundary for this path is the Python class API.  Each entry point below
+ * names the reference function(s) it replaces (paths relative to the reference
+ * root).  The Python mirror of that class API (pc_accumulation_lib_b200/*.py)
+ * binds these symbols with ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every bulk pointer named *_dev is a DEVICE pointer; small parameter
+ *     blocks (matrices, filter lists, pcacc_bev_params) are HOST pointers and
+ *     are consumed before the call returns;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises unless the comment says so;
+ *   - return value: PCACC_OK (0) or a negative pcacc_status; pcacc_strerror()
+ *     gives text, pcacc_last_error() the detail of the last failure;
+ *   - there is no CPU fallback: without a CUDA device every call fails with
+ *     PCACC_ERR_CUDA.
+ */
+#ifndef PCACC_H_
+#define PCACC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCACC_ABI_VERSION 1
+
+typedef struct pcacc_s *pcacc_t;
+
+typedef enum {
+    PCACC_OK = 0,
+    PCACC_ERR_ARG = -1,       /* bad argument */
+    PCACC_ERR_CUDA = -2,      /* CUDA runtime error (see pcacc_last_error) */
+    PCACC_ERR_CAPACITY = -3,  /* ring or frame table full */
+    PCACC_ERR_NOMEM = -4,     /* device allocation failed */
+    PCACC_ERR_STATE = -5      /* call not valid in the current state */
+} pcacc_status;
+
+/* device-side data error flags, OR-ed into the word read by pcacc_sync() */
+#define PCACC_FLAG_UV_OUT_OF_IMAGE 1u  /* pts_feat_from_img assertion, datasets/nuscenes_utils.py:194-195 */
+#define PCACC_FLAG_INTENSITY_F32   2u  /* informational: an intensity was rounded to float32 (6e-8 relative; the ring stores f32) */
+#define PCACC_FLAG_ATTR_RANGE      4u  /* r/g/b/sem outside 0..255 or inst outside int32 */
+#define PCACC_FLAG_CELL_OVERFLOW   8u  /* internal: scatter cursor ran past its segment */
+
+/* dtype codes for semantic maps */
+#define PCACC_SEM_U8 0
+#define PCACC_SEM_I32 1
+#define PCACC_SEM_I64 2
+#define PCACC_SEM_F32_PROB 3 /* (H,W,K) float32 class probabilities: class = first argmax over K */
+
+const char *pcacc_strerror(int status);
+const char *pcacc_last_error(pcacc_t h);
+int pcacc_abi_version(void);
+
+/* ---- lifetime ----------------------------------------------------------
+ * The accumulated cloud (the reference's `self.sem_pcs` list of (M,10) float64
+ * arrays, sem_pc_accum.py:100) lives in a device-resident SoA ring of
+ * `capacity_pts` records: x,y,z float64 | intensity float32 | r,g,b,sem uint8x4
+ * | inst int32 | dyn uint8 (37 B/point), plus a table of `max_frames` frame
+ * segments.  `device` is the CUDA ordinal. */
+int pcacc_create(int device, int64_t capacity_pts, int max_frames, pcacc_t *out);
+int pcacc_destroy(pcacc_t h);
+/* drop all frames (new scene) */
+int pcacc_reset(pcacc_t h, void *stream);
+
+/* ---- stand-alone operators (helpers the reference exposes) --------------
+ * velo2frame + velo2img, sem_pc_accum.py:347-402: for ALL n points writes
+ * u, v (int32; value of np.round(...).astype(int) when it fits) and the
+ * in-image mask (1/0).  pts_dev: (n, pts_stride) float32, columns 0..2 = xyz.
+ * P: host (3,4) float64 row-major. */
+int pcacc_project(const float *pts_dev, int64_t n, int pts_stride, const double *P,
+                  int img_h, int img_w, double max_depth,
+                  int32_t *u_dev, int32_t *v_dev, uint8_t *mask_dev, void *stream);
+
+/* gen_semantic_pc, sem_pc_accum.py:323-345: projection, order-preserving
+ * compaction of in-image points and the K-channel gather map[v,u,:].
+ * out_dev: (n, 4+K) float64 (only the first *n_kept rows are written),
+ * n_kept_dev: device int64.  map_dtype: PCACC_SEM_U8 / I32 / I64 or
+ * PCACC_SEM_F32_PROB (plain float32 copy here, no argmax). */
+int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n, const double *P,
+                          const void *map_dev, int map_dtype, int img_h, int img_w, int K,
+                          double *out_dev, int64_t *n_kept_dev, void *stream);
+
+/* ---- integrate: append one frame to the ring ----------------------------
+ * All three are asynchronous; the frame's kept count lands in the device
+ * frame table and is fetched by pcacc_sync().  Each returns the new frame's
+ * absolute id in *frame_id (ids count up from 0 after create/reset).
+ *
+ * KITTI-360 frustum path — Kitti360SemanticPointCloudAccumulator
+ * .obs2sem_vec_space with sem_gt=None, kitti360_sem_pc_accum.py:129-156 over
+ * sem_pc_accum.py:317-402: projection, in-image mask, RGB + class gather,
+ * class filter, inst=0, dyn=0, order-preserving append.
+ *   pts_dev (n,4) float32 [x,y,z,intensity]; rgb_dev (H,W,3) uint8;
+ *   sem_dev (H,W) class indices of sem_dtype, or (H,W,K) float32 probabilities
+ *   (PCACC_SEM_F32_PROB, class = argmax); filters: host list of class ids. */
+int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t n, const double *P,
+                            const uint8_t *rgb_dev, const void *sem_dev, int sem_dtype, int K,
+                            int img_h, int img_w, double max_depth,
+                            const int32_t *filters, int n_filters,
+                            int64_t *frame_id, void *stream);
+
+/* KITTI-360 `use_gt_sem` path, kitti360_sem_pc_accum.py:138-156: no
+ * projection, rgb = 0, class from sem_gt (n,) int16, class filter. */
+int pcacc_integrate_gt(pcacc_t h, const float *pts_dev, int64_t n, const int16_t *sem_gt_dev,
+                       const int32_t *filters, int n_filters,
+                       int64_t *frame_id, void *stream);
+
+/* nuScenes oracle-pose path — NuScenesOracleSemanticPointCloudAccumulator
+ * .obs2sem_vec_space, nuscenes_oracle_sem_pc_accum.py:454-501 with
+ * pts_feat_from_img(method='nearest') (datasets/nuscenes_utils.py:181-214)
+ * and homo_transform (datasets/nuscenes_utils.py:46-60).
+ *   pc_dev (n,7) float64 [x,y,z,intensity,u,v,inst] (the dataloader's layout,
+ *   obs_dataloaders/nuscenes_obs_dataloader.py:103-123); cam_idx_dev (n,) int64
+ *   (-1 = seen by no camera); rgb_maps/sem_maps: host arrays of n_cams device
+ *   pointers ((H,W,3) uint8 and (H,W) sem_dtype); T_ego_world: host (4,4)
+ *   float64; intensity is stored raw (float32) and divided by intensity_div
+ *   (255.) in float64 wherever it is used; one ring holds one divisor
+ *   (PCACC_ERR_STATE otherwise; the frustum / gt / cloud paths use 1). */
+int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const int64_t *cam_idx_dev, int64_t n,
+                            const uint8_t *const *rgb_maps, const void *const *sem_maps,
+                            int n_cams, int sem_dtype, int img_h, int img_w,
+                            const double *T_ego_world, double intensity_div,
+                            const int32_t *filters, int n_filters,
+                            int64_t *frame_id, void *stream);
+
+/* Append an already-built (n,10) float64 cloud [x,y,z,i,r,g,b,sem,inst,dyn]
+ * as one frame (used by BEVGenerator.generate(pcs, ...) when it is handed host
+ * clouds, bev_generator/bev_generator.py:63-125).  Rows are stored unchanged. */
+int pcacc_integrate_cloud(pcacc_t h, const double *rec_dev, int64_t n,
+                          int64_t *frame_id, void *stream);
+
+/* ---- ego-motion re-basing: update_sem_pcs, sem_pc_accum.py:167-183 ------
+ * T_new_prev: host (4,4) float64 applied to every stored point of every live
+ * frame.  eager=1 rewrites xyz in place (exactly what the reference does);
+ * eager=0 records T in the per-frame chain and folds it into the frame's
+ * composed matrix — points stay in their source frame and the rasteriser
+ * applies the composed matrix, replaying the exact chain for any point within
+ * a guard band of a cell / crop / height boundary (DESIGN.md "lazy re-base"). */
+int pcacc_rebase(pcacc_t h, const double *T_new_prev, int eager, void *stream);
+
+/* horizon eviction, remove_observations sem_pc_accum.py:185-209: drop the
+ * n_frames oldest live frames (host bookkeeping only). */
+int pcacc_evict(pcacc_t h, int n_frames);
+
+/* fake-tracker dynamic flags, nuscenes_oracle_sem_pc_accum.py:223-230,243-250:
+ * for each pair k: dyn = 1 on points of frame frame_ids[k] whose inst equals
+ * inst_idx[k].  Host arrays. */
+int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int32_t *inst_idx, int n_pairs,
+                       void *stream);
+
+/* ---- table / export -------------------------------------------------------
+ * Synchronises `stream`, fetches the frame table and the data-error flags.
+ * *flags (optional) receives the OR of PCACC_FLAG_* raised since the last
+ * sync and clears them. */
+int pcacc_sync(pcacc_t h, uint32_t *flags, void *stream);
+int pcacc_num_frames(pcacc_t h, int64_t *first_frame_id, int *n_live);
+/* kept-point count of a live frame (requires a pcacc_sync after its integrate) */
+int pcacc_frame_count(pcacc_t h, int64_t frame_id, int64_t *count);
+int64_t pcacc_resident_points(pcacc_t h); /* sum over live frames (after sync) */
+/* one frame as the reference's (M,10) float64 record array, `self.sem_pcs[i]`;
+ * lazy re-base chains are replayed exactly. out_dev: (count,10) float64. */
+int pcacc_export_frame(pcacc_t h, int64_t frame_id, double *out_dev, void *stream);
+
+/* ---- BEV rasterisation ----------------------------------------------------
+ * One pcacc_bev_params per BEV variant; a call rasterises n_variants BEVs of
+ * the resident cloud in one batch of launches.  Replaces
+ *   accumulators' generate_bev window split + origin shift
+ *     (kitti360_sem_pc_accum.py:179-213, nuscenes_oracle_sem_pc_accum.py:521-560),
+ *   BEVGenerator.preprocess_pc_and_trajs / geometric_transform / crop_view /
+ *     pos2grid for the point cloud (bev_generator/bev_generator.py:127-160,
+ *     207-255,737-747),
+ *   SemBEVGenerator.generate_bev's grids (bev_generator/sem_bev.py:54-118,
+ *     196-257): partition_semantic_pc, gen_sem_probmap, gen_intensity_map,
+ *     road_marking_transform, get_elevation_map, get_rgb_maps, astype(float16).
+ * Trajectories stay on the host (Python mirror). */
+typedef struct {
+    int64_t frame_begin;   /* absolute ids: present = [frame_begin, frame_split) */
+    int64_t frame_split;   /*               future  = [frame_split, frame_end)   */
+    int64_t frame_end;     /*               full    = [frame_begin, frame_end)   */
+    double origin[3];      /* poses[present_idx], subtracted from xyz */
+    double R[9];           /* rotation_matrix_3d(rot_ang), computed on the host with numpy */
+    double trans_dx, trans_dy;
+    double view;           /* zoom_scalar * view_size */
+    double height_filter;  /* NaN = none */
+    double int_scaler, int_sep_scaler, int_mid_threshold;
+    double rgb_fill;
+    int32_t road_cls;      /* sem_idxs['road'] */
+    int32_t veh_cls[4];    /* car, truck, bus, motorcycle */
+    int32_t elevation_max; /* 0 = reference (per-cell min z); 1 = north-star variant (max z) */
+} pcacc_bev_params;
+
+#define PCACC_BEV_PLANES 7 /* road, intensity, r, g, b, dynamic, elevation */
+#define PCACC_BEV_WINDOWS 3 /* present, future, full */
+
+/* out_f16_dev: (n_variants, 3 windows, 7 planes, P, P) float16.
+ * out_f64_dev: optional, same shape in float64 (values before the cast).
+ * dbg_cell_dev: optional (ring capacity,) int32 indexed by ring position: for
+ *   variant 0, row*P+col of each point that survives crop/height/static
+ *   filtering, -1 otherwise (parity tests). */
+int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_variants, int P,
+                    void *out_f16_dev, double *out_f64_dev, int32_t *dbg_cell_dev,
+                    void *stream);
+
+/* ring position (record index) of a live frame's first point, for dbg_cell_dev */
+int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset);
+
+/* counters of the last pcacc_rasterise on this handle (after a sync):
+ * [0] points visited, [1] points binned (in view, static), [2] exact-chain replays */
+int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCACC_H_ */

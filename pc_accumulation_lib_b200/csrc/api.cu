@@ -1,0 +1,270 @@
+// api.cu — handle lifetime, frame-table bookkeeping and error plumbing of libpcacc.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int pcacc_fail(pcacc_t h, int status, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (h) memcpy(h->err, g_err, sizeof(h->err));
+    return status;
+}
+
+int pcacc_cuda_check(pcacc_t h, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return PCACC_OK;
+    return pcacc_fail(h, PCACC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+uint32_t pcacc_next_epoch(pcacc_t h) {
+    h->launch_epoch = (h->launch_epoch + 1u) & 0x3fffffffu;
+    if (h->launch_epoch == 0) h->launch_epoch = 1;
+    return h->launch_epoch;
+}
+
+int pcacc_ensure_tiles(pcacc_t h, int64_t n_tiles) {
+    if (n_tiles <= h->tile_cap) return PCACC_OK;
+    int64_t want = n_tiles * 2;
+    if (want < 4096) want = 4096;
+    if (h->d_tile_state) {
+        PCACC_CUDA(h, cudaDeviceSynchronize());
+        cudaFree(h->d_tile_state);
+        h->d_tile_state = nullptr;
+        h->tile_cap = 0;
+    }
+    PCACC_CUDA(h, cudaMalloc(&h->d_tile_state, (size_t)want * 8));
+    PCACC_CUDA(h, cudaMemset(h->d_tile_state, 0, (size_t)want * 8));
+    h->tile_cap = want;
+    return PCACC_OK;
+}
+
+int pcacc_arena_put(pcacc_t h, const void *src, size_t bytes, void **dev, cudaStream_t st) {
+    size_t need = (bytes + 255) / 256 * 256;
+    if (need > h->arena_size) return pcacc_fail(h, PCACC_ERR_ARG, "parameter block of %zu bytes too large", bytes);
+    if (h->arena_pos + need > h->arena_size) {
+        // recycle: everything enqueued so far must have consumed its parameters
+        PCACC_CUDA(h, cudaDeviceSynchronize());
+        h->arena_pos = 0;
+    }
+    memcpy(h->h_arena + h->arena_pos, src, bytes);
+    PCACC_CUDA(h, cudaMemcpyAsync(h->d_arena + h->arena_pos, h->h_arena + h->arena_pos, bytes,
+                                  cudaMemcpyHostToDevice, st));
+    *dev = h->d_arena + h->arena_pos;
+    h->arena_pos += need;
+    return PCACC_OK;
+}
+
+FrameHost *pcacc_frame(pcacc_t h, int64_t frame_id) {
+    if (frame_id < h->first_id || frame_id >= h->next_id) return nullptr;
+    return &h->frames[(int)(frame_id % h->max_frames)];
+}
+
+extern "C" const char *pcacc_strerror(int status) {
+    switch (status) {
+        case PCACC_OK: return "ok";
+        case PCACC_ERR_ARG: return "invalid argument";
+        case PCACC_ERR_CUDA: return "CUDA error";
+        case PCACC_ERR_CAPACITY: return "ring or frame table capacity exceeded";
+        case PCACC_ERR_NOMEM: return "device memory allocation failed";
+        case PCACC_ERR_STATE: return "call not valid in the current state";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *pcacc_last_error(pcacc_t h) { return h ? h->err : g_err; }
+
+extern "C" int pcacc_abi_version(void) { return PCACC_ABI_VERSION; }
+
+static void free_all(pcacc_t h) {
+    cudaFree(h->ring.x);
+    cudaFree(h->ring.y);
+    cudaFree(h->ring.z);
+    cudaFree(h->ring.inten);
+    cudaFree(h->ring.rgbs);
+    cudaFree(h->ring.inst);
+    cudaFree(h->ring.dyn);
+    cudaFree(h->d_frame_off);
+    cudaFree(h->d_frame_cnt);
+    cudaFree(h->d_frame_epoch);
+    cudaFree(h->d_comp);
+    cudaFree(h->d_chain);
+    cudaFree(h->d_flags);
+    cudaFree(h->d_tile_state);
+    cudaFree(h->d_ticket);
+    cudaFree(h->d_arena);
+    cudaFree(h->d_ws);
+    cudaFree(h->d_rstats);
+    if (h->h_mail) cudaFreeHost(h->h_mail);
+    if (h->h_arena) cudaFreeHost(h->h_arena);
+}
+
+extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pcacc_t *out) {
+    if (!out || capacity_pts <= 0 || max_frames < 4 || capacity_pts > 0x7fffffff00ll)
+        return pcacc_fail(nullptr, PCACC_ERR_ARG, "pcacc_create: capacity_pts > 0 and max_frames >= 4 required");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return pcacc_fail(nullptr, PCACC_ERR_CUDA, "no CUDA device (%s): libpcacc has no CPU fallback",
+                          e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev)
+        return pcacc_fail(nullptr, PCACC_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
+    pcacc_t h = new (std::nothrow) pcacc_s();
+    if (!h) return PCACC_ERR_NOMEM;
+    h->device = device;
+    // records are addressed in groups of PCACC_ALIGN_PTS
+    h->capacity = (capacity_pts + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS * PCACC_ALIGN_PTS;
+    h->max_frames = max_frames;
+    h->frames.resize((size_t)max_frames);
+    h->launch_epoch = 0;
+    h->arena_size = 1u << 20;
+    size_t cap = (size_t)h->capacity;
+#define TRY(call)                                                           \
+    do {                                                                    \
+        cudaError_t e2 = (call);                                            \
+        if (e2 != cudaSuccess) {                                            \
+            int rc = pcacc_fail(nullptr, e2 == cudaErrorMemoryAllocation ? PCACC_ERR_NOMEM : PCACC_ERR_CUDA, \
+                                "%s: %s", #call, cudaGetErrorString(e2));   \
+            cudaGetLastError();                                             \
+            free_all(h);                                                    \
+            delete h;                                                       \
+            return rc;                                                      \
+        }                                                                   \
+    } while (0)
+    TRY(cudaSetDevice(device));
+    TRY(cudaMalloc(&h->ring.x, cap * 8));
+    TRY(cudaMalloc(&h->ring.y, cap * 8));
+    TRY(cudaMalloc(&h->ring.z, cap * 8));
+    TRY(cudaMalloc(&h->ring.inten, cap * 4));
+    TRY(cudaMalloc(&h->ring.rgbs, cap * 4));
+    TRY(cudaMalloc(&h->ring.inst, cap * 4));
+    TRY(cudaMalloc(&h->ring.dyn, cap));
+    TRY(cudaMalloc(&h->d_frame_off, (size_t)max_frames * 8));
+    TRY(cudaMalloc(&h->d_frame_cnt, (size_t)max_frames * 8));
+    TRY(cudaMalloc(&h->d_frame_epoch, (size_t)max_frames * 8));
+    TRY(cudaMalloc(&h->d_comp, (size_t)max_frames * 12 * 8));
+    TRY(cudaMalloc(&h->d_chain, (size_t)max_frames * 12 * 8));
+    TRY(cudaMalloc(&h->d_flags, 4));
+    TRY(cudaMalloc(&h->d_ticket, 4));
+    TRY(cudaMalloc(&h->d_rstats, 4 * 8));
+    TRY(cudaMalloc(&h->d_arena, h->arena_size));
+    TRY(cudaMemset(h->d_frame_off, 0, (size_t)max_frames * 8));
+    TRY(cudaMemset(h->d_frame_cnt, 0, (size_t)max_frames * 8));
+    TRY(cudaMemset(h->d_frame_epoch, 0, (size_t)max_frames * 8));
+    TRY(cudaMemset(h->d_comp, 0, (size_t)max_frames * 12 * 8));
+    TRY(cudaMemset(h->d_chain, 0, (size_t)max_frames * 12 * 8));
+    TRY(cudaMemset(h->d_flags, 0, 4));
+    TRY(cudaMemset(h->d_ticket, 0, 4));
+    TRY(cudaMemset(h->d_rstats, 0, 4 * 8));
+    TRY(cudaMallocHost(&h->h_mail, (size_t)(3 * max_frames + 8) * 8));
+    TRY(cudaMallocHost(&h->h_arena, h->arena_size));
+#undef TRY
+    int rc = pcacc_ensure_tiles(h, 4096);
+    if (rc) {
+        free_all(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_destroy(pcacc_t h) {
+    if (!h) return PCACC_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_all(h);
+    delete h;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_reset(pcacc_t h, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    (void)stream;
+    h->first_id = h->next_id;  // ids keep counting; nothing is live
+    h->wrapped = false;
+    h->any_lazy = false;
+    h->inten_div = 0.0;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_evict(pcacc_t h, int n_frames) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n_frames < 0 || n_frames > (int)(h->next_id - h->first_id))
+        return pcacc_fail(h, PCACC_ERR_ARG, "cannot evict %d of %d live frames", n_frames,
+                          (int)(h->next_id - h->first_id));
+    h->first_id += n_frames;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_sync(pcacc_t h, uint32_t *flags, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    const int mf = h->max_frames;
+    PCACC_CUDA(h, cudaMemcpyAsync(h->h_mail, h->d_frame_off, (size_t)mf * 8, cudaMemcpyDeviceToHost, st));
+    PCACC_CUDA(h, cudaMemcpyAsync(h->h_mail + mf, h->d_frame_cnt, (size_t)mf * 8, cudaMemcpyDeviceToHost, st));
+    PCACC_CUDA(h, cudaMemcpyAsync(h->h_mail + 2 * mf, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
+    PCACC_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, st));
+    PCACC_CUDA(h, cudaStreamSynchronize(st));
+    for (int64_t id = h->first_id; id < h->next_id; id++) {
+        int slot = (int)(id % mf);
+        FrameHost &f = h->frames[slot];
+        f.off = h->h_mail[slot];
+        f.cnt = h->h_mail[mf + slot];
+        f.off_ub = f.off;
+        f.n_in = f.cnt;
+        f.exact = true;
+    }
+    uint32_t fl = *(uint32_t *)(h->h_mail + 2 * mf);
+    h->pending_flags |= fl;
+    if (flags) {
+        *flags = h->pending_flags;
+        h->pending_flags = 0;
+    }
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_num_frames(pcacc_t h, int64_t *first_frame_id, int *n_live) {
+    if (!h) return PCACC_ERR_ARG;
+    if (first_frame_id) *first_frame_id = h->first_id;
+    if (n_live) *n_live = (int)(h->next_id - h->first_id);
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_frame_count(pcacc_t h, int64_t frame_id, int64_t *count) {
+    if (!h || !count) return PCACC_ERR_ARG;
+    FrameHost *f = pcacc_frame(h, frame_id);
+    if (!f) return pcacc_fail(h, PCACC_ERR_ARG, "frame %lld is not live", (long long)frame_id);
+    if (!f->exact) return pcacc_fail(h, PCACC_ERR_STATE, "pcacc_sync() needed after integrate");
+    *count = f->cnt;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset) {
+    if (!h || !offset) return PCACC_ERR_ARG;
+    FrameHost *f = pcacc_frame(h, frame_id);
+    if (!f) return pcacc_fail(h, PCACC_ERR_ARG, "frame %lld is not live", (long long)frame_id);
+    if (!f->exact) return pcacc_fail(h, PCACC_ERR_STATE, "pcacc_sync() needed after integrate");
+    *offset = f->off;
+    return PCACC_OK;
+}
+
+extern "C" int64_t pcacc_resident_points(pcacc_t h) {
+    if (!h) return 0;
+    int64_t s = 0;
+    for (int64_t id = h->first_id; id < h->next_id; id++) {
+        FrameHost &f = h->frames[(int)(id % h->max_frames)];
+        s += f.exact ? f.cnt : f.n_in;
+    }
+    return s;
+}

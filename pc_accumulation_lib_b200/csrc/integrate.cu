@@ -1,0 +1,866 @@
+// integrate.cu — per-frame fusion kernels: projection, in-image mask, map
+// gathers, class filter, pose transform and order-preserving append into the
+// device-resident SoA ring; plus re-basing, dynamic flags and frame export.
+//
+// Reference behaviour restated (paths relative to the reference root):
+//   sem_pc_accum.py:317-402   velo2frame / velo2img / gen_semantic_pc / filter_semseg_pc
+//   kitti360_sem_pc_accum.py:129-156   record build (inst = 0, dyn = 0)
+//   nuscenes_oracle_sem_pc_accum.py:454-501, datasets/nuscenes_utils.py:46-60,181-214
+//   sem_pc_accum.py:167-183   update_sem_pcs
+//   nuscenes_oracle_sem_pc_accum.py:223-230,243-250   dynamic flags
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+#define IBLOCK 256
+
+struct FrameSlots {
+    int64_t *frame_off, *frame_cnt, *frame_epoch;
+    double *comp;  // this frame's composed matrix (12 doubles), reset to identity
+    int slot, next_slot;
+    int64_t base_override;  // >= 0: use this ring offset instead of frame_off[slot]
+    int64_t epoch;
+    int64_t capacity;
+};
+
+struct Filters {
+    int32_t v[PCACC_MAX_FILTERS];
+    int n;
+};
+
+struct LookBack {
+    unsigned long long *state;
+    uint32_t *ticket;
+    uint32_t epoch;
+    uint32_t n_tiles;
+};
+
+__device__ __forceinline__ bool class_filtered(const Filters &f, int cls) {
+    bool hit = false;
+#pragma unroll 4
+    for (int k = 0; k < f.n; k++) hit |= (cls == f.v[k]);
+    return hit;
+}
+
+// the tile that ends the frame records its size and the next frame's offset
+__device__ __forceinline__ void finish_frame(const FrameSlots &fs, int64_t base, uint32_t total) {
+    fs.frame_off[fs.slot] = base;
+    fs.frame_cnt[fs.slot] = (int64_t)total;
+    fs.frame_epoch[fs.slot] = fs.epoch;
+    int64_t nxt = base + (((int64_t)total + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
+    fs.frame_off[fs.next_slot] = nxt;
+    for (int k = 0; k < 12; k++) fs.comp[k] = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ int64_t frame_base(const FrameSlots &fs) {
+    return fs.base_override >= 0 ? fs.base_override : fs.frame_off[fs.slot];
+}
+
+template <int DT>
+__device__ __forceinline__ int load_class(const void *map, int64_t pix, int K) {
+    if (DT == PCACC_SEM_U8) return (int)((const uint8_t *)map)[pix];
+    if (DT == PCACC_SEM_I32) return ((const int32_t *)map)[pix];
+    if (DT == PCACC_SEM_I64) {
+        long long v = ((const long long *)map)[pix];
+        return (v < -2147483647ll || v > 2147483647ll) ? -2147483647 : (int)v;
+    }
+    // float32 probabilities: first index of the maximum (np.argmax)
+    const float *p = (const float *)map + pix * K;
+    float best = p[0];
+    int arg = 0;
+    for (int k = 1; k < K; k++) {
+        float v = p[k];
+        if (v > best) {
+            best = v;
+            arg = k;
+        }
+    }
+    return arg;
+}
+
+// projection of one point: sem_pc_accum.py:358-396
+struct Proj {
+    double u, v, d;
+    bool in_img;
+};
+__device__ __forceinline__ Proj project_point(const double *P, float x, float y, float z, int img_h,
+                                              int img_w, double max_depth) {
+    double X0, X1, X2;
+    affine_chain(P, 4, (double)x, (double)y, (double)z, X0, X1, X2);
+    double d = X2;
+    if (d == 0.0) d = -1e-6;
+    double ad = fabs(d);
+    Proj r;
+    r.u = rint_even(__ddiv_rn(X0, ad));
+    r.v = rint_even(__ddiv_rn(X1, ad));
+    r.d = d;
+    // integer compares of the reference done on the (integral) doubles: NaN /
+    // inf / out-of-int64 values fail them exactly as astype(int) garbage does
+    r.in_img = (r.u >= 0.0) && (r.u < (double)img_w) && (r.v >= 0.0) && (r.v < (double)img_h) &&
+               (d > 0.0) && (d < max_depth);
+    return r;
+}
+
+struct PMat {
+    double m[12];
+};
+
+// ---------------------------------------------------------------------------
+// stand-alone projection (all points)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBLOCK)
+k_project(const float *__restrict__ pts, int64_t n, int stride, PMat P, int img_h, int img_w,
+          double max_depth, int32_t *__restrict__ u, int32_t *__restrict__ v,
+          uint8_t *__restrict__ mask) {
+    int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    if (i >= n) return;
+    const float *p = pts + i * stride;
+    Proj r = project_point(P.m, p[0], p[1], p[2], img_h, img_w, max_depth);
+    u[i] = sat_i32(r.u);
+    v[i] = sat_i32(r.v);
+    mask[i] = r.in_img ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// gen_semantic_pc: generic K-channel gather into (M,4+K) float64
+// ---------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(IBLOCK)
+k_gen_semantic_pc(const float4 *__restrict__ pts, int64_t n, PMat P, const void *__restrict__ map,
+                  int img_h, int img_w, int K, double *__restrict__ out,
+                  int64_t *__restrict__ n_kept, LookBack lb) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0);
+    Proj r;
+    r.u = r.v = 0;
+    if (i < n) {
+        p = pts[i];
+        r = project_point(P.m, p.x, p.y, p.z, img_h, img_w, INFINITY);
+        keep = r.in_img;
+    }
+    uint32_t tile_end;
+    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        double *o = out + (int64_t)rank * (4 + K);
+        o[0] = (double)p.x;
+        o[1] = (double)p.y;
+        o[2] = (double)p.z;
+        o[3] = (double)p.w;
+        int64_t pix = ((int64_t)r.v * img_w + (int64_t)r.u) * K;
+        for (int k = 0; k < K; k++) {
+            double f;
+            if (DT == PCACC_SEM_U8) f = (double)((const uint8_t *)map)[pix + k];
+            else if (DT == PCACC_SEM_I32) f = (double)((const int32_t *)map)[pix + k];
+            else if (DT == PCACC_SEM_I64) f = (double)((const long long *)map)[pix + k];
+            else f = (double)((const float *)map)[pix + k];
+            o[4 + k] = f;
+        }
+    }
+    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) *n_kept = (int64_t)tile_end;
+}
+
+// ---------------------------------------------------------------------------
+// KITTI-360 frustum integrate (K1-K4 fused)
+// ---------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(IBLOCK)
+k_integrate_frustum(const float4 *__restrict__ pts, int64_t n, PMat P,
+                    const uint8_t *__restrict__ rgb, const void *__restrict__ sem, int K, int img_h,
+                    int img_w, double max_depth, Filters filt, RingDev ring, FrameSlots fs,
+                    LookBack lb, uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const int64_t base = frame_base(fs);
+    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0);
+    uint32_t packed = 0;
+    if (i < n) {
+        p = pts[i];
+        Proj r = project_point(P.m, p.x, p.y, p.z, img_h, img_w, max_depth);
+        if (r.in_img) {
+            int64_t pix = (int64_t)r.v * img_w + (int64_t)r.u;
+            int cls = load_class<DT>(sem, pix, K);
+            keep = !class_filtered(filt, cls);
+            if (keep) {
+                if (cls < 0 || cls > 255) {
+                    atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                    cls &= 255;
+                }
+                const uint8_t *c = rgb + pix * 3;
+                packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
+                         ((uint32_t)cls << 24);
+            }
+        }
+    }
+    uint32_t tile_end;
+    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        int64_t o = base + rank;
+        if (o < fs.capacity) {
+            ring.x[o] = (double)p.x;
+            ring.y[o] = (double)p.y;
+            ring.z[o] = (double)p.z;
+            ring.inten[o] = p.w;
+            ring.rgbs[o] = packed;
+            ring.inst[o] = 0;
+            ring.dyn[o] = 0;
+        }
+    }
+    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
+}
+
+// KITTI-360 use_gt_sem path: all points, class from sem_gt, rgb = 0
+__global__ void __launch_bounds__(IBLOCK)
+k_integrate_gt(const float4 *__restrict__ pts, int64_t n, const int16_t *__restrict__ sem_gt,
+               Filters filt, RingDev ring, FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const int64_t base = frame_base(fs);
+    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0);
+    int cls = 0;
+    if (i < n) {
+        p = pts[i];
+        cls = (int)sem_gt[i];
+        keep = !class_filtered(filt, cls);
+        if (keep && (cls < 0 || cls > 255)) {
+            atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+            cls &= 255;
+        }
+    }
+    uint32_t tile_end;
+    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        int64_t o = base + rank;
+        if (o < fs.capacity) {
+            ring.x[o] = (double)p.x;
+            ring.y[o] = (double)p.y;
+            ring.z[o] = (double)p.z;
+            ring.inten[o] = p.w;
+            ring.rgbs[o] = (uint32_t)cls << 24;
+            ring.inst[o] = 0;
+            ring.dyn[o] = 0;
+        }
+    }
+    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
+}
+
+// ---------------------------------------------------------------------------
+// nuScenes oracle-pose integrate (a9-a11)
+// ---------------------------------------------------------------------------
+struct CamMaps {
+    const uint8_t *rgb[PCACC_MAX_CAMS];
+    const void *sem[PCACC_MAX_CAMS];
+    int n;
+};
+struct TMat {
+    double m[16];
+};
+
+template <int DT>
+__global__ void __launch_bounds__(IBLOCK)
+k_integrate_records(const double *__restrict__ pc, const long long *__restrict__ cam_idx, int64_t n,
+                    CamMaps maps, int img_h, int img_w, TMat T, Filters filt, RingDev ring,
+                    FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const int64_t base = frame_base(fs);
+    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    double x = 0, y = 0, z = 0, inten = 0, inst_f = 0;
+    uint32_t packed = 0;
+    if (i < n) {
+        long long cam = cam_idx[i];
+        if (cam >= 0 && cam < maps.n) {
+            const double *row = pc + i * 7;
+            double uf = row[4], vf = row[5];
+            // pts_feat_from_img bounds assertion, datasets/nuscenes_utils.py:190-195
+            bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
+                          (vf < (double)img_h - 1.0);
+            if (!inside) {
+                atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
+            } else {
+                int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
+                int cls = load_class<DT>(maps.sem[cam], pix, 1);
+                keep = (cls >= 0) && !class_filtered(filt, cls);
+                if (keep) {
+                    if (cls > 255) {
+                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                        cls &= 255;
+                    }
+                    const uint8_t *c = maps.rgb[cam] + pix * 3;
+                    packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
+                             ((uint32_t)cls << 24);
+                    x = row[0];
+                    y = row[1];
+                    z = row[2];
+                    inten = row[3];
+                    inst_f = row[6];
+                }
+            }
+        }
+    }
+    uint32_t tile_end;
+    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        int64_t o = base + rank;
+        if (o < fs.capacity) {
+            double wx, wy, wz;
+            affine_chain(T.m, 4, x, y, z, wx, wy, wz);
+            ring.x[o] = wx;
+            ring.y[o] = wy;
+            ring.z[o] = wz;
+            float fi = (float)inten;
+            if ((double)fi != inten) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
+            ring.inten[o] = fi;
+            ring.rgbs[o] = packed;
+            int32_t ii = sat_i32(inst_f);
+            if ((double)ii != inst_f) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+            ring.inst[o] = ii;
+            ring.dyn[o] = 0;
+        }
+    }
+    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
+}
+
+// ---------------------------------------------------------------------------
+// import of a ready-made (n,10) float64 cloud
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBLOCK)
+k_integrate_cloud(const double *__restrict__ rec, int64_t n, RingDev ring, FrameSlots fs,
+                  uint32_t *__restrict__ flags) {
+    const int64_t base = frame_base(fs);
+    int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    if (i < n) {
+        const double *r = rec + i * 10;
+        int64_t o = base + i;
+        if (o < fs.capacity) {
+            ring.x[o] = r[0];
+            ring.y[o] = r[1];
+            ring.z[o] = r[2];
+            float fi = (float)r[3];
+            if ((double)fi != r[3]) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
+            ring.inten[o] = fi;
+            uint32_t packed = 0;
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                double c = r[4 + k];
+                int ci = (int)c;
+                if (!((double)ci == c) || ci < 0 || ci > 255) {
+                    bad = true;
+                    ci &= 255;
+                }
+                packed |= (uint32_t)ci << (8 * k);
+            }
+            ring.rgbs[o] = packed;
+            int32_t ii = sat_i32(r[8]);
+            if ((double)ii != r[8]) bad = true;
+            ring.inst[o] = ii;
+            double dy = r[9];
+            if (dy != 0.0 && dy != 1.0) bad = true;
+            ring.dyn[o] = (dy == 1.0) ? 1 : 0;
+            if (bad) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_frame(fs, base, (uint32_t)n);
+}
+
+// ---------------------------------------------------------------------------
+// re-basing
+// ---------------------------------------------------------------------------
+// lazy: chain[epoch] = T; comp[f] = T @ comp[f] for every live frame
+__global__ void k_rebase_lazy(double *__restrict__ chain_slot, double *__restrict__ comp, TMat T,
+                              int first_slot, int n_live, int max_frames) {
+    int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t < 12) chain_slot[t] = T.m[(t / 4) * 4 + (t % 4)];
+    if (t < n_live) {
+        double *c = comp + (int64_t)((first_slot + t) % max_frames) * 12;
+        double o[12];
+        // 3x4 affine composition: rows of T times [c; 0 0 0 1]
+        for (int r = 0; r < 3; r++) {
+            for (int k = 0; k < 4; k++) {
+                double a = __dmul_rn(T.m[r * 4 + 0], c[0 * 4 + k]);
+                a = __fma_rn(T.m[r * 4 + 1], c[1 * 4 + k], a);
+                a = __fma_rn(T.m[r * 4 + 2], c[2 * 4 + k], a);
+                if (k == 3) a = __dadd_rn(a, T.m[r * 4 + 3]);
+                o[r * 4 + k] = a;
+            }
+        }
+        for (int k = 0; k < 12; k++) c[k] = o[k];
+    }
+}
+
+// exact sequential replay of the re-base chain for one point
+__device__ __forceinline__ void replay_chain(const double *__restrict__ chain, int max_frames,
+                                             int64_t e0, int64_t e1, double &x, double &y, double &z) {
+    for (int64_t e = e0; e < e1; e++) {
+        const double *T = chain + (e % max_frames) * 12;
+        double nx, ny, nz;
+        affine_chain(T, 4, x, y, z, nx, ny, nz);
+        x = nx;
+        y = ny;
+        z = nz;
+    }
+}
+
+// materialise: apply every pending transform of each live frame in place
+__global__ void __launch_bounds__(IBLOCK)
+k_materialise(RingDev ring, const int64_t *__restrict__ frame_off,
+              const int64_t *__restrict__ frame_cnt, const int64_t *__restrict__ frame_epoch,
+              const double *__restrict__ chain, int first_slot, int max_frames, int64_t epoch_now) {
+    int slot = (first_slot + blockIdx.y) % max_frames;
+    int64_t cnt = frame_cnt[slot], off = frame_off[slot], e0 = frame_epoch[slot];
+    if (e0 >= epoch_now) return;
+    for (int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x; i < cnt;
+         i += (int64_t)gridDim.x * IBLOCK) {
+        double x = ring.x[off + i], y = ring.y[off + i], z = ring.z[off + i];
+        replay_chain(chain, max_frames, e0, epoch_now, x, y, z);
+        ring.x[off + i] = x;
+        ring.y[off + i] = y;
+        ring.z[off + i] = z;
+    }
+}
+__global__ void k_materialise_done(int64_t *__restrict__ frame_epoch, double *__restrict__ comp,
+                                   int first_slot, int n_live, int max_frames, int64_t epoch_now) {
+    int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= n_live) return;
+    int slot = (first_slot + t) % max_frames;
+    frame_epoch[slot] = epoch_now;
+    double *c = comp + (int64_t)slot * 12;
+    for (int k = 0; k < 12; k++) c[k] = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// dynamic flags
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBLOCK)
+k_mark_dynamic(RingDev ring, const int64_t *__restrict__ frame_off,
+               const int64_t *__restrict__ frame_cnt, const int32_t *__restrict__ pair_slot,
+               const int32_t *__restrict__ pair_inst) {
+    int slot = pair_slot[blockIdx.y];
+    int32_t want = pair_inst[blockIdx.y];
+    int64_t cnt = frame_cnt[slot], off = frame_off[slot];
+    for (int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x; i < cnt;
+         i += (int64_t)gridDim.x * IBLOCK)
+        if (ring.inst[off + i] == want) ring.dyn[off + i] = 1;
+}
+
+// ---------------------------------------------------------------------------
+// export one frame as (M,10) float64
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBLOCK)
+k_export_frame(RingDev ring, const int64_t *__restrict__ frame_off,
+               const int64_t *__restrict__ frame_cnt, const int64_t *__restrict__ frame_epoch,
+               const double *__restrict__ chain, int slot, int max_frames, int64_t epoch_now,
+               double intensity_div, double *__restrict__ out) {
+    int64_t cnt = frame_cnt[slot], off = frame_off[slot], e0 = frame_epoch[slot];
+    int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    if (i >= cnt) return;
+    double x = ring.x[off + i], y = ring.y[off + i], z = ring.z[off + i];
+    replay_chain(chain, max_frames, e0, epoch_now, x, y, z);
+    double *o = out + i * 10;
+    uint32_t c = ring.rgbs[off + i];
+    o[0] = x;
+    o[1] = y;
+    o[2] = z;
+    o[3] = __ddiv_rn((double)ring.inten[off + i], intensity_div);
+    o[4] = (double)(c & 255u);
+    o[5] = (double)((c >> 8) & 255u);
+    o[6] = (double)((c >> 16) & 255u);
+    o[7] = (double)(c >> 24);
+    o[8] = (double)ring.inst[off + i];
+    o[9] = (double)ring.dyn[off + i];
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+static int fill_filters(pcacc_t h, const int32_t *filters, int n, Filters *f) {
+    if (n < 0 || n > PCACC_MAX_FILTERS || (n > 0 && !filters))
+        return pcacc_fail(h, PCACC_ERR_ARG, "n_filters must be 0..%d", PCACC_MAX_FILTERS);
+    f->n = n;
+    for (int k = 0; k < PCACC_MAX_FILTERS; k++) f->v[k] = k < n ? filters[k] : 0;
+    return PCACC_OK;
+}
+
+static int set_inten_div(pcacc_t h, double div) {
+    if (!(div > 0.0)) return pcacc_fail(h, PCACC_ERR_ARG, "intensity_div must be positive");
+    if (h->next_id == h->first_id || h->inten_div == 0.0) h->inten_div = div;
+    if (h->inten_div != div)
+        return pcacc_fail(h, PCACC_ERR_STATE, "ring holds intensity/%g frames; cannot add intensity/%g",
+                          h->inten_div, div);
+    return PCACC_OK;
+}
+
+static int make_lookback(pcacc_t h, int64_t n_tiles, LookBack *lb) {
+    int rc = pcacc_ensure_tiles(h, n_tiles);
+    if (rc) return rc;
+    lb->state = h->d_tile_state;
+    lb->ticket = h->d_ticket;
+    lb->epoch = pcacc_next_epoch(h);
+    lb->n_tiles = (uint32_t)n_tiles;
+    return PCACC_OK;
+}
+
+// Reserve a frame slot for up to n_in records. Decides the ring offset policy
+// on the host from upper bounds; syncs the table only when it has to.
+static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs, int64_t *frame_id) {
+    if (n_in < 0) return pcacc_fail(h, PCACC_ERR_ARG, "negative point count");
+    if (n_in > h->capacity)
+        return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame of %lld points exceeds ring capacity %lld",
+                          (long long)n_in, (long long)h->capacity);
+    int n_live = (int)(h->next_id - h->first_id);
+    if (n_live >= h->max_frames - 1)
+        return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame table full (%d live frames)", n_live);
+    int64_t id = h->next_id;
+    int slot = (int)(id % h->max_frames);
+    FrameHost &f = h->frames[slot];
+    int64_t override_base = -1;
+    int64_t ub = 0;
+    if (n_live == 0) {
+        override_base = 0;
+        ub = 0;
+        h->wrapped = false;
+    } else {
+        FrameHost &prev = h->frames[(int)((id - 1) % h->max_frames)];
+        ub = prev.off_ub + ((prev.n_in + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
+        if (h->wrapped || ub + n_in > h->capacity) {
+            // need exact numbers
+            int rc = pcacc_sync(h, nullptr, (void *)st);
+            if (rc) return rc;
+            FrameHost &pv = h->frames[(int)((id - 1) % h->max_frames)];
+            int64_t nxt = pv.off + ((pv.cnt + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
+            if (nxt + n_in > h->capacity) {
+                nxt = 0;
+                h->wrapped = true;
+            }
+            // the new region must not touch any live frame
+            bool any_after = false;
+            for (int64_t k = h->first_id; k < h->next_id; k++) {
+                FrameHost &g = h->frames[(int)(k % h->max_frames)];
+                if (g.cnt > 0 && g.off < nxt + n_in && nxt < g.off + g.cnt)
+                    return pcacc_fail(h, PCACC_ERR_CAPACITY,
+                                      "ring full: %lld resident points, capacity %lld",
+                                      (long long)pcacc_resident_points(h), (long long)h->capacity);
+                if (g.off >= nxt) any_after = true;
+            }
+            if (!any_after) h->wrapped = false;
+            override_base = nxt;
+            ub = nxt;
+        }
+    }
+    f.n_in = n_in;
+    f.off_ub = ub;
+    f.off = override_base >= 0 ? override_base : -1;
+    f.cnt = -1;
+    f.epoch = h->rebase_epoch;
+    f.exact = false;
+    fs->frame_off = h->d_frame_off;
+    fs->frame_cnt = h->d_frame_cnt;
+    fs->frame_epoch = h->d_frame_epoch;
+    fs->comp = h->d_comp + (int64_t)slot * 12;
+    fs->slot = slot;
+    fs->next_slot = (int)((id + 1) % h->max_frames);
+    fs->base_override = override_base;
+    fs->epoch = h->rebase_epoch;
+    fs->capacity = h->capacity;
+    h->next_id = id + 1;
+    if (frame_id) *frame_id = id;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_project(const float *pts_dev, int64_t n, int pts_stride, const double *P,
+                             int img_h, int img_w, double max_depth, int32_t *u_dev, int32_t *v_dev,
+                             uint8_t *mask_dev, void *stream) {
+    if (n < 0 || !P || pts_stride < 3) return PCACC_ERR_ARG;
+    if (n == 0) return PCACC_OK;
+    PMat pm;
+    memcpy(pm.m, P, sizeof(pm.m));
+    int64_t blocks = (n + IBLOCK - 1) / IBLOCK;
+    k_project<<<(unsigned)blocks, IBLOCK, 0, (cudaStream_t)stream>>>(
+        pts_dev, n, pts_stride, pm, img_h, img_w, max_depth, u_dev, v_dev, mask_dev);
+    return cudaGetLastError() == cudaSuccess ? PCACC_OK : PCACC_ERR_CUDA;
+}
+
+extern "C" int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n, const double *P,
+                                     const void *map_dev, int map_dtype, int img_h, int img_w, int K,
+                                     double *out_dev, int64_t *n_kept_dev, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || !P || K < 1) return pcacc_fail(h, PCACC_ERR_ARG, "bad gen_semantic_pc arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    if (n == 0) {
+        PCACC_CUDA(h, cudaMemsetAsync(n_kept_dev, 0, sizeof(int64_t), st));
+        return PCACC_OK;
+    }
+    PMat pm;
+    memcpy(pm.m, P, sizeof(pm.m));
+    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    LookBack lb;
+    int rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    const float4 *p4 = (const float4 *)pts_dev;
+#define LAUNCH_GSP(DT)                                                                      \
+    k_gen_semantic_pc<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(p4, n, pm, map_dev, img_h, img_w, K, \
+                                                               out_dev, n_kept_dev, lb)
+    switch (map_dtype) {
+        case PCACC_SEM_U8: LAUNCH_GSP(PCACC_SEM_U8); break;
+        case PCACC_SEM_I32: LAUNCH_GSP(PCACC_SEM_I32); break;
+        case PCACC_SEM_I64: LAUNCH_GSP(PCACC_SEM_I64); break;
+        case PCACC_SEM_F32_PROB: LAUNCH_GSP(PCACC_SEM_F32_PROB); break;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown map dtype %d", map_dtype);
+    }
+#undef LAUNCH_GSP
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t n, const double *P,
+                                       const uint8_t *rgb_dev, const void *sem_dev, int sem_dtype,
+                                       int K, int img_h, int img_w, double max_depth,
+                                       const int32_t *filters, int n_filters, int64_t *frame_id,
+                                       void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (!P || img_h <= 0 || img_w <= 0 || K < 1)
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad integrate_frustum arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    Filters filt;
+    int rc = fill_filters(h, filters, n_filters, &filt);
+    if (rc) return rc;
+    rc = set_inten_div(h, 1.0);
+    if (rc) return rc;
+    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    if (tiles == 0) tiles = 1;
+    LookBack lb;
+    rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    FrameSlots fs;
+    rc = begin_frame(h, n, st, &fs, frame_id);
+    if (rc) return rc;
+    PMat pm;
+    memcpy(pm.m, P, sizeof(pm.m));
+    const float4 *p4 = (const float4 *)pts_dev;
+#define LAUNCH_IF(DT)                                                                          \
+    k_integrate_frustum<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(p4, n, pm, rgb_dev, sem_dev, K, img_h, \
+                                                                 img_w, max_depth, filt, h->ring, fs, \
+                                                                 lb, h->d_flags)
+    switch (sem_dtype) {
+        case PCACC_SEM_U8: LAUNCH_IF(PCACC_SEM_U8); break;
+        case PCACC_SEM_I32: LAUNCH_IF(PCACC_SEM_I32); break;
+        case PCACC_SEM_I64: LAUNCH_IF(PCACC_SEM_I64); break;
+        case PCACC_SEM_F32_PROB: LAUNCH_IF(PCACC_SEM_F32_PROB); break;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown sem dtype %d", sem_dtype);
+    }
+#undef LAUNCH_IF
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_integrate_gt(pcacc_t h, const float *pts_dev, int64_t n,
+                                  const int16_t *sem_gt_dev, const int32_t *filters, int n_filters,
+                                  int64_t *frame_id, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    Filters filt;
+    int rc = fill_filters(h, filters, n_filters, &filt);
+    if (rc) return rc;
+    rc = set_inten_div(h, 1.0);
+    if (rc) return rc;
+    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    if (tiles == 0) tiles = 1;
+    LookBack lb;
+    rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    FrameSlots fs;
+    rc = begin_frame(h, n, st, &fs, frame_id);
+    if (rc) return rc;
+    k_integrate_gt<<<(unsigned)tiles, IBLOCK, 0, st>>>((const float4 *)pts_dev, n, sem_gt_dev, filt,
+                                                       h->ring, fs, lb, h->d_flags);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const int64_t *cam_idx_dev,
+                                       int64_t n, const uint8_t *const *rgb_maps,
+                                       const void *const *sem_maps, int n_cams, int sem_dtype,
+                                       int img_h, int img_w, const double *T_ego_world,
+                                       double intensity_div, const int32_t *filters, int n_filters,
+                                       int64_t *frame_id, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n_cams < 0 || n_cams > PCACC_MAX_CAMS || !T_ego_world)
+        return pcacc_fail(h, PCACC_ERR_ARG, "n_cams must be 0..%d", PCACC_MAX_CAMS);
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    Filters filt;
+    int rc = fill_filters(h, filters, n_filters, &filt);
+    if (rc) return rc;
+    rc = set_inten_div(h, intensity_div);  // applied where intensity is read (export, rasterise)
+    if (rc) return rc;
+    CamMaps maps;
+    maps.n = n_cams;
+    for (int k = 0; k < PCACC_MAX_CAMS; k++) {
+        maps.rgb[k] = k < n_cams ? rgb_maps[k] : nullptr;
+        maps.sem[k] = k < n_cams ? sem_maps[k] : nullptr;
+    }
+    TMat T;
+    memcpy(T.m, T_ego_world, sizeof(T.m));
+    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    if (tiles == 0) tiles = 1;
+    LookBack lb;
+    rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    FrameSlots fs;
+    rc = begin_frame(h, n, st, &fs, frame_id);
+    if (rc) return rc;
+#define LAUNCH_IR(DT)                                                                           \
+    k_integrate_records<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(                                \
+        pc_dev, (const long long *)cam_idx_dev, n, maps, img_h, img_w, T, filt, h->ring, fs, lb, \
+        h->d_flags)
+    switch (sem_dtype) {
+        case PCACC_SEM_U8: LAUNCH_IR(PCACC_SEM_U8); break;
+        case PCACC_SEM_I32: LAUNCH_IR(PCACC_SEM_I32); break;
+        case PCACC_SEM_I64: LAUNCH_IR(PCACC_SEM_I64); break;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
+    }
+#undef LAUNCH_IR
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_integrate_cloud(pcacc_t h, const double *rec_dev, int64_t n, int64_t *frame_id,
+                                     void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    int rc = set_inten_div(h, 1.0);
+    if (rc) return rc;
+    FrameSlots fs;
+    rc = begin_frame(h, n, st, &fs, frame_id);
+    if (rc) return rc;
+    int64_t blocks = (n + IBLOCK - 1) / IBLOCK;
+    if (blocks == 0) blocks = 1;
+    k_integrate_cloud<<<(unsigned)blocks, IBLOCK, 0, st>>>(rec_dev, n, h->ring, fs, h->d_flags);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+// apply every pending transform of every live frame in place (exact chain)
+static int materialise_all(pcacc_t h, cudaStream_t st) {
+    int n_live = (int)(h->next_id - h->first_id);
+    if (n_live == 0 || !h->any_lazy) return PCACC_OK;
+    int first_slot = (int)(h->first_id % h->max_frames);
+    int64_t max_n = 0;
+    for (int64_t k = h->first_id; k < h->next_id; k++) {
+        FrameHost &f = h->frames[(int)(k % h->max_frames)];
+        int64_t c = f.exact ? f.cnt : f.n_in;
+        if (c > max_n) max_n = c;
+    }
+    int64_t bx = (max_n + IBLOCK - 1) / IBLOCK;
+    if (bx < 1) bx = 1;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_live);
+    k_materialise<<<grid, IBLOCK, 0, st>>>(h->ring, h->d_frame_off, h->d_frame_cnt, h->d_frame_epoch,
+                                           h->d_chain, first_slot, h->max_frames, h->rebase_epoch);
+    PCACC_CUDA(h, cudaGetLastError());
+    k_materialise_done<<<(n_live + 127) / 128, 128, 0, st>>>(h->d_frame_epoch, h->d_comp, first_slot,
+                                                             n_live, h->max_frames, h->rebase_epoch);
+    PCACC_CUDA(h, cudaGetLastError());
+    for (int64_t k = h->first_id; k < h->next_id; k++)
+        h->frames[(int)(k % h->max_frames)].epoch = h->rebase_epoch;
+    h->any_lazy = false;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_rebase(pcacc_t h, const double *T_new_prev, int eager, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (!T_new_prev) return pcacc_fail(h, PCACC_ERR_ARG, "T_new_prev is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    int n_live = (int)(h->next_id - h->first_id);
+    if (n_live == 0) return PCACC_OK;  // nothing stored: the reference loop is empty too
+    // the chain ring holds max_frames transforms: epochs [oldest live, now]
+    int64_t oldest = h->rebase_epoch;
+    for (int64_t k = h->first_id; k < h->next_id; k++) {
+        int64_t e = h->frames[(int)(k % h->max_frames)].epoch;
+        if (e < oldest) oldest = e;
+    }
+    if (h->rebase_epoch + 1 - oldest > h->max_frames) {
+        int rc = materialise_all(h, st);  // fold the pending chain before it is overwritten
+        if (rc) return rc;
+    }
+    TMat T;
+    memcpy(T.m, T_new_prev, sizeof(T.m));
+    int first_slot = (int)(h->first_id % h->max_frames);
+    double *slot = h->d_chain + (h->rebase_epoch % h->max_frames) * 12;
+    int threads = n_live < 12 ? 12 : n_live;
+    k_rebase_lazy<<<(threads + 127) / 128, 128, 0, st>>>(slot, h->d_comp, T, first_slot, n_live,
+                                                         h->max_frames);
+    PCACC_CUDA(h, cudaGetLastError());
+    h->rebase_epoch += 1;
+    h->any_lazy = true;
+    if (eager) return materialise_all(h, st);
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int32_t *inst_idx,
+                                  int n_pairs, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n_pairs <= 0) return PCACC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<int32_t> buf(2 * (size_t)n_pairs);
+    int64_t max_n = 0;
+    for (int k = 0; k < n_pairs; k++) {
+        FrameHost *f = pcacc_frame(h, frame_ids[k]);
+        if (!f) return pcacc_fail(h, PCACC_ERR_ARG, "frame %lld is not live", (long long)frame_ids[k]);
+        buf[k] = (int32_t)(frame_ids[k] % h->max_frames);
+        buf[n_pairs + k] = inst_idx[k];
+        int64_t c = f->exact ? f->cnt : f->n_in;
+        if (c > max_n) max_n = c;
+    }
+    void *dev = nullptr;
+    int rc = pcacc_arena_put(h, buf.data(), buf.size() * sizeof(int32_t), &dev, st);
+    if (rc) return rc;
+    int64_t bx = (max_n + IBLOCK - 1) / IBLOCK;
+    if (bx < 1) bx = 1;
+    if (bx > 1024) bx = 1024;
+    for (int k0 = 0; k0 < n_pairs; k0 += 32768) {
+        int ny = n_pairs - k0 < 32768 ? n_pairs - k0 : 32768;
+        dim3 grid((unsigned)bx, (unsigned)ny);
+        k_mark_dynamic<<<grid, IBLOCK, 0, st>>>(h->ring, h->d_frame_off, h->d_frame_cnt,
+                                                (const int32_t *)dev + k0,
+                                                (const int32_t *)dev + n_pairs + k0);
+        PCACC_CUDA(h, cudaGetLastError());
+    }
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_export_frame(pcacc_t h, int64_t frame_id, double *out_dev, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    FrameHost *f = pcacc_frame(h, frame_id);
+    if (!f) return pcacc_fail(h, PCACC_ERR_ARG, "frame %lld is not live", (long long)frame_id);
+    if (!f->exact) return pcacc_fail(h, PCACC_ERR_STATE, "pcacc_sync() needed before export");
+    if (f->cnt == 0) return PCACC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    int64_t blocks = (f->cnt + IBLOCK - 1) / IBLOCK;
+    k_export_frame<<<(unsigned)blocks, IBLOCK, 0, st>>>(
+        h->ring, h->d_frame_off, h->d_frame_cnt, h->d_frame_epoch, h->d_chain,
+        (int)(frame_id % h->max_frames), h->max_frames, h->rebase_epoch,
+        h->inten_div > 0.0 ? h->inten_div : 1.0, out_dev);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}

@@ -1,0 +1,351 @@
+"""Device-resident accumulated cloud: the thin host layer between the Python
+mirror of the reference classes and libpcacc's C ABI.
+
+PyTorch is plumbing here (pinned staging, device buffers for inputs/outputs,
+the current stream); every computation happens in libpcacc's sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BevParams, PcaccError, check
+
+_SEM_DTYPES = {np.dtype(np.uint8): _lib.SEM_U8, np.dtype(np.int32): _lib.SEM_I32,
+               np.dtype(np.int64): _lib.SEM_I64}
+_TORCH_SEM = {torch.uint8: _lib.SEM_U8, torch.int32: _lib.SEM_I32,
+              torch.int64: _lib.SEM_I64}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise PcaccError(_lib.ERR_CUDA,
+                         'no CUDA device: pc_accumulation_lib_b200 has no CPU path')
+
+
+class Stager:
+    """Reusable pinned-host + device buffer pairs for host->device inputs."""
+
+    def __init__(self, device):
+        self.device = device
+        self._pin = {}
+        self._dev = {}
+
+    def _buffers(self, key, nbytes):
+        pin = self._pin.get(key)
+        if pin is None or pin.numel() < nbytes:
+            cap = max(nbytes, 1) * 5 // 4 + 64
+            pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._pin[key] = pin
+            self._dev[key] = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        return pin, self._dev[key]
+
+    def put(self, key, arr):
+        """numpy array (any dtype, C-contiguous after this call) or torch tensor
+        -> device tensor of the same dtype/shape on the current stream."""
+        if isinstance(arr, torch.Tensor):
+            if arr.is_cuda:
+                return arr.contiguous()
+            arr = arr.contiguous().numpy()
+        arr = np.ascontiguousarray(arr)
+        nbytes = arr.nbytes
+        pin, dev = self._buffers(key, nbytes)
+        src = torch.from_numpy(arr.reshape(-1).view(np.uint8)) if nbytes else None
+        if nbytes:
+            # the previous async copy out of this pinned buffer must be done
+            ev = getattr(self, '_ev_' + key, None)
+            if ev is not None:
+                ev.synchronize()
+            pin[:nbytes].copy_(src)
+            dev[:nbytes].copy_(pin[:nbytes], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            setattr(self, '_ev_' + key, ev)
+        tdt = torch.from_numpy(np.empty(0, dtype=arr.dtype)).dtype
+        return dev[:nbytes].view(tdt).view(arr.shape)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
+
+
+def _hostd(a, n):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    assert a.size == n, (a.size, n)
+    return a
+
+
+class DeviceCloud:
+    """Owns one pcacc handle: the SoA ring with its frame table on `device`."""
+
+    def __init__(self, capacity_pts: int, max_frames: int = 1024, device: int | None = None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device('cuda', self.device_index)
+        self.capacity = int(capacity_pts)
+        self.max_frames = int(max_frames)
+        h = C.c_void_p()
+        check(self.lib.pcacc_create(self.device_index, self.capacity, self.max_frames,
+                                    C.byref(h)))
+        self.h = h
+        self.stage = Stager(self.device)
+        self._keep = []      # device tensors that in-flight kernels still read
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.pcacc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------
+    def _check(self, status):
+        check(status, self.h)
+
+    def _filters(self, filters):
+        f = np.ascontiguousarray(np.asarray(list(filters or []), dtype=np.int32))
+        return f, f.ctypes.data_as(C.c_void_p), int(f.size)
+
+    def _sem_arg(self, sem, key):
+        """class map (H,W) of u8/i32/i64, or (H,W,K) float32 probabilities."""
+        if isinstance(sem, torch.Tensor):
+            if sem.dtype == torch.float32:
+                return self.stage.put(key, sem), _lib.SEM_F32_PROB, int(sem.shape[-1])
+            if sem.dtype not in _TORCH_SEM:
+                sem = sem.to(torch.int64)
+            return self.stage.put(key, sem), _TORCH_SEM[sem.dtype], 1
+        sem = np.asarray(sem)
+        if sem.dtype == np.float32 and sem.ndim == 3:
+            return self.stage.put(key, sem), _lib.SEM_F32_PROB, int(sem.shape[-1])
+        if sem.dtype not in _SEM_DTYPES:
+            sem = sem.astype(np.int64)
+        return self.stage.put(key, sem), _SEM_DTYPES[sem.dtype], 1
+
+    # -- lifetime --------------------------------------------------------------
+    def reset(self):
+        self._check(self.lib.pcacc_reset(self.h, _stream()))
+
+    def sync(self) -> int:
+        """Waits for the stream, refreshes the frame table, returns and clears
+        the data-error flags."""
+        fl = C.c_uint32(0)
+        self._check(self.lib.pcacc_sync(self.h, C.byref(fl), _stream()))
+        self._keep.clear()
+        return int(fl.value)
+
+    def live_frames(self):
+        first, n = C.c_int64(0), C.c_int(0)
+        self._check(self.lib.pcacc_num_frames(self.h, C.byref(first), C.byref(n)))
+        return int(first.value), int(n.value)
+
+    def frame_count(self, fid: int) -> int:
+        c = C.c_int64(0)
+        self._check(self.lib.pcacc_frame_count(self.h, int(fid), C.byref(c)))
+        return int(c.value)
+
+    def frame_offset(self, fid: int) -> int:
+        c = C.c_int64(0)
+        self._check(self.lib.pcacc_frame_offset(self.h, int(fid), C.byref(c)))
+        return int(c.value)
+
+    def resident_points(self) -> int:
+        return int(self.lib.pcacc_resident_points(self.h))
+
+    # -- integrate ---------------------------------------------------------------
+    def integrate_frustum(self, pc, P, rgb, sem, filters, max_depth=np.inf) -> int:
+        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
+                             if not isinstance(pc, torch.Tensor) else pc)
+        assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
+        rgb_d = self.stage.put('rgb', rgb if isinstance(rgb, torch.Tensor)
+                               else np.asarray(rgb, dtype=np.uint8))
+        sem_d, sem_dt, K = self._sem_arg(sem, 'sem')
+        h, w = int(rgb_d.shape[0]), int(rgb_d.shape[1])
+        assert tuple(sem_d.shape[:2]) == (h, w), (sem_d.shape, rgb_d.shape)
+        Pm = _hostd(P, 12)
+        f, fp, nf = self._filters(filters)
+        fid = C.c_int64(-1)
+        self._check(self.lib.pcacc_integrate_frustum(
+            self.h, _ptr(pts), int(pts.shape[0]), Pm.ctypes.data_as(C.c_void_p), _ptr(rgb_d),
+            _ptr(sem_d), sem_dt, K, h, w, float(max_depth), fp, nf, C.byref(fid), _stream()))
+        self._keep += [pts, rgb_d, sem_d]
+        return int(fid.value)
+
+    def integrate_gt(self, pc, sem_gt, filters) -> int:
+        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
+                             if not isinstance(pc, torch.Tensor) else pc)
+        assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
+        if isinstance(sem_gt, torch.Tensor):
+            sg = self.stage.put('sem_gt', sem_gt.reshape(-1).to(torch.int16))
+        else:
+            sg = self.stage.put('sem_gt', np.asarray(sem_gt)[:, -1].astype(np.int16))
+        assert sg.numel() == pts.shape[0]
+        f, fp, nf = self._filters(filters)
+        fid = C.c_int64(-1)
+        self._check(self.lib.pcacc_integrate_gt(self.h, _ptr(pts), int(pts.shape[0]), _ptr(sg),
+                                                fp, nf, C.byref(fid), _stream()))
+        self._keep += [pts, sg]
+        return int(fid.value)
+
+    def integrate_records(self, pc, cam_idx, rgbs, sems, T_ego_world, filters,
+                          intensity_div=255.) -> int:
+        pcd = self.stage.put('pc', pc if isinstance(pc, torch.Tensor)
+                             else np.asarray(pc, dtype=np.float64))
+        assert pcd.dim() == 2 and pcd.shape[1] == 7 and pcd.dtype == torch.float64
+        cam = self.stage.put('cam', cam_idx if isinstance(cam_idx, torch.Tensor)
+                             else np.asarray(cam_idx, dtype=np.int64))
+        assert cam.dtype == torch.int64 and cam.numel() == pcd.shape[0]
+        n_cams = len(rgbs)
+        rgb_d, sem_d, sem_dt = [], [], None
+        for k in range(n_cams):
+            r = self.stage.put(f'rgb{k}', rgbs[k] if isinstance(rgbs[k], torch.Tensor)
+                               else np.asarray(rgbs[k], dtype=np.uint8))
+            s, dt, K = self._sem_arg(sems[k], f'sem{k}')
+            assert K == 1 and dt != _lib.SEM_F32_PROB
+            assert sem_dt in (None, dt), 'all class maps must share one dtype'
+            sem_dt = dt
+            rgb_d.append(r)
+            sem_d.append(s)
+        h, w = (int(rgb_d[0].shape[0]), int(rgb_d[0].shape[1])) if n_cams else (1, 1)
+        rp = (C.c_void_p * max(n_cams, 1))(*[r.data_ptr() for r in rgb_d])
+        sp = (C.c_void_p * max(n_cams, 1))(*[s.data_ptr() for s in sem_d])
+        T = _hostd(T_ego_world, 16)
+        f, fp, nf = self._filters(filters)
+        fid = C.c_int64(-1)
+        self._check(self.lib.pcacc_integrate_records(
+            self.h, _ptr(pcd), _ptr(cam), int(pcd.shape[0]), C.cast(rp, C.c_void_p),
+            C.cast(sp, C.c_void_p), n_cams, sem_dt if sem_dt is not None else _lib.SEM_U8, h, w,
+            T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf, C.byref(fid), _stream()))
+        self._keep += [pcd, cam] + rgb_d + sem_d
+        return int(fid.value)
+
+    def integrate_cloud(self, rec) -> int:
+        r = self.stage.put('cloud', rec if isinstance(rec, torch.Tensor)
+                           else np.asarray(rec, dtype=np.float64))
+        assert r.dim() == 2 and r.shape[1] == 10 and r.dtype == torch.float64
+        fid = C.c_int64(-1)
+        self._check(self.lib.pcacc_integrate_cloud(self.h, _ptr(r), int(r.shape[0]),
+                                                   C.byref(fid), _stream()))
+        self._keep.append(r)
+        return int(fid.value)
+
+    # -- state updates -------------------------------------------------------------
+    def rebase(self, T_new_prev, eager=False):
+        T = _hostd(T_new_prev, 16)
+        self._check(self.lib.pcacc_rebase(self.h, T.ctypes.data_as(C.c_void_p),
+                                          1 if eager else 0, _stream()))
+
+    def evict(self, n_frames: int):
+        self._check(self.lib.pcacc_evict(self.h, int(n_frames)))
+
+    def mark_dynamic(self, frame_ids, inst_idx):
+        fi = np.ascontiguousarray(np.asarray(frame_ids, dtype=np.int64))
+        ii = np.ascontiguousarray(np.asarray(inst_idx, dtype=np.int32))
+        assert fi.size == ii.size
+        if fi.size == 0:
+            return
+        self._check(self.lib.pcacc_mark_dynamic(self.h, fi.ctypes.data_as(C.c_void_p),
+                                                ii.ctypes.data_as(C.c_void_p), int(fi.size),
+                                                _stream()))
+
+    # -- export ----------------------------------------------------------------------
+    def export_frame(self, fid: int, to_host=True):
+        n = self.frame_count(fid)
+        out = torch.empty((n, 10), dtype=torch.float64, device=self.device)
+        self._check(self.lib.pcacc_export_frame(self.h, int(fid), _ptr(out), _stream()))
+        return out.cpu().numpy() if to_host else out
+
+    # -- stand-alone operators -----------------------------------------------------------
+    def project(self, pc, P, img_h, img_w, max_depth=np.inf):
+        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
+                             if not isinstance(pc, torch.Tensor) else pc)
+        n, stride = int(pts.shape[0]), int(pts.shape[1])
+        u = torch.empty(n, dtype=torch.int32, device=self.device)
+        v = torch.empty(n, dtype=torch.int32, device=self.device)
+        m = torch.empty(n, dtype=torch.uint8, device=self.device)
+        Pm = _hostd(P, 12)
+        self._check(self.lib.pcacc_project(_ptr(pts), n, stride, Pm.ctypes.data_as(C.c_void_p),
+                                           int(img_h), int(img_w), float(max_depth), _ptr(u),
+                                           _ptr(v), _ptr(m), _stream()))
+        return u, v, m
+
+    def gen_semantic_pc(self, pc, semantic_map, P):
+        """(M,4+K) float64 device tensor, rows in input order."""
+        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
+                             if not isinstance(pc, torch.Tensor) else pc)
+        assert pts.shape[1] == 4 and pts.dtype == torch.float32
+        sm = semantic_map
+        if not isinstance(sm, torch.Tensor):
+            sm = np.asarray(sm)
+            if sm.dtype not in _SEM_DTYPES and sm.dtype != np.float32:
+                sm = sm.astype(np.float32 if sm.dtype.kind == 'f' else np.int64)
+        mp = self.stage.put('map', sm)
+        if mp.dtype == torch.float32:
+            dt = _lib.SEM_F32_PROB
+        else:
+            dt = _TORCH_SEM[mp.dtype]
+        h, w, K = int(mp.shape[0]), int(mp.shape[1]), int(mp.shape[2])
+        n = int(pts.shape[0])
+        out = torch.empty((n, 4 + K), dtype=torch.float64, device=self.device)
+        nk = torch.zeros(1, dtype=torch.int64, device=self.device)
+        Pm = _hostd(P, 12)
+        self._check(self.lib.pcacc_gen_semantic_pc(
+            self.h, _ptr(pts), n, Pm.ctypes.data_as(C.c_void_p), _ptr(mp), dt, h, w, K, _ptr(out),
+            _ptr(nk), _stream()))
+        return out[:int(nk.item())]
+
+    # -- rasterise ------------------------------------------------------------------------
+    def rasterise(self, params, P: int, want_f64=False, want_cells=False, out=None):
+        """params: list of BevParams. Returns (planes f16 (V,3,7,P,P) device
+        tensor, planes f64 or None, per-ring-position cell index or None)."""
+        V = len(params)
+        arr = (BevParams * V)(*params)
+        if out is None:
+            out = torch.empty((V, 3, 7, P, P), dtype=torch.float16, device=self.device)
+        o64 = (torch.empty((V, 3, 7, P, P), dtype=torch.float64, device=self.device)
+               if want_f64 else None)
+        cells = (torch.full((self.capacity + 4,), -2, dtype=torch.int32, device=self.device)
+                 if want_cells else None)
+        self._check(self.lib.pcacc_rasterise(self.h, arr, V, int(P), _ptr(out), _ptr(o64),
+                                             _ptr(cells), _stream()))
+        return out, o64, cells
+
+    def raster_stats(self):
+        s = (C.c_int64 * 3)()
+        self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))
+        return {'visited': int(s[0]), 'binned': int(s[1]), 'replays': int(s[2])}
+
+
+def make_bev_params(frame_begin, frame_split, frame_end, origin, R, trans_dx, trans_dy, view,
+                    height_filter, int_scaler, int_sep_scaler, int_mid_threshold, rgb_fill,
+                    sem_idxs, elevation_max=False) -> BevParams:
+    p = BevParams()
+    p.frame_begin, p.frame_split, p.frame_end = int(frame_begin), int(frame_split), int(frame_end)
+    o = np.asarray(origin, dtype=np.float64).reshape(3)
+    Rm = np.asarray(R, dtype=np.float64).reshape(9)
+    for k in range(3):
+        p.origin[k] = float(o[k])
+    for k in range(9):
+        p.R[k] = float(Rm[k])
+    p.trans_dx, p.trans_dy = float(trans_dx), float(trans_dy)
+    p.view = float(view)
+    p.height_filter = float('nan') if height_filter is None else float(height_filter)
+    p.int_scaler, p.int_sep_scaler = float(int_scaler), float(int_sep_scaler)
+    p.int_mid_threshold = float(int_mid_threshold)
+    p.rgb_fill = float(rgb_fill)
+    p.road_cls = int(sem_idxs['road'])
+    for k, name in enumerate(('car', 'truck', 'bus', 'motorcycle')):
+        p.veh_cls[k] = int(sem_idxs[name])
+    p.elevation_max = 1 if elevation_max else 0
+    return p
