@@ -1,0 +1,560 @@
+#!/usr/bin/env python
+"""bench.py — the contract benchmark of the fusion + BEV rasterisation path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libpcacc, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the path on the host CPU
+
+Workload (BASELINE.json configs[1] shape, batched as configs[3]): nuScenes-shaped
+oracle-pose scenes — 40 sweeps x 34,688 points, CAM_FRONT 1600x900, seeded
+synthetic class maps standing in for the ONNX network — each scene accumulated
+and rasterised into 32 BEVs (8 present indices x 4 augmentation variants,
+256x256, present / future / full).  A *step* is SCENES_PER_STEP such scenes on
+every GPU; scenes are sharded by rank with no data-path collective (weak
+scaling).  metric = input lidar points fused + rasterised per second.
+
+value : libpcacc's C ABI driven with inputs already resident in HBM.
+e2e   : the reference-facing Python API (accumulator.integrate / generate_bev)
+        with HOST numpy buffers in and out, copies inside the timed region.
+Extra lines in the same JSON object: roofline (dominant kernel, CUDA-event
+timed inside the timed region), roofline_path, cpu_baseline, clocks, and (N=1)
+the long-horizon KITTI-360 window of BASELINE.json configs[2].
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pc_accumulation_lib_b200 import synth  # noqa: E402
+
+N_SWEEPS = 40
+PRESENT_IDXS = [6, 10, 14, 18, 22, 26, 30, 34]
+BEVS_PER_PRESENT = 4
+P = 256
+N_DISTINCT = 4            # distinct synthetic scenes per rank (replicated on the device)
+METRIC = 'lidar_points_fused_and_rasterised_per_s'
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+def bev_setup():
+    bp = synth.nusc_bev_params(pixel_size=P)
+    bp['max_trans_radius'] = 5.0       # run_nuscenes_bev_gen.py augmentation defaults
+    bp['zoom_thresh'] = 0.1
+    return bp
+
+
+def make_scenes(rank, n):
+    return [synth.nusc_scene(synth.seed_for(4, 100 * rank + k), N_SWEEPS) for k in range(n)]
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(mx)) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------
+class HostSemseg:
+    """Stand-in for the ONNX network (out of scope): returns the pre-generated
+    class map of the image it is handed (utils/onnx_utils.py:32-44 contract)."""
+
+    def __init__(self):
+        self.by_id = {}
+
+    def pred(self, rgb):
+        return self.by_id[id(rgb)][None, None]
+
+
+def variant_params(acc, rng):
+    """The 32 pcacc_bev_params of one scene, exactly what generate_bev would use."""
+    gen = acc.sem_bev_generator
+    first, n = acc._fids[0], len(acc._fids)
+    out = []
+    for p in PRESENT_IDXS:
+        origin = np.array(acc.poses[p])
+        ego_present = np.concatenate([acc.poses[:p]]) - origin
+        for _ in range(BEVS_PER_PRESENT):
+            gen.rng = rng
+            a = gen.rand_aug_params()
+            out.append(gen._bev_params(first + 0, first + p, first + n, origin, a['rot_ang'],
+                                       a['trans_dx'], a['trans_dy'],
+                                       a['zoom_scalar'] * gen.view_size))
+        del ego_present
+    return out
+
+
+def run_ours(args, rank, world, local_rank, dist):
+    import torch
+    from pc_accumulation_lib_b200 import NuScenesOracleSemanticPointCloudAccumulator
+    from pc_accumulation_lib_b200.device import DeviceCloud
+    dev = torch.device('cuda', local_rank)
+    pk, pk_kind = peaks()
+
+    scenes = make_scenes(rank, N_DISTINCT)
+    n_in_scene = sum(o['pc'].shape[0] for o in scenes[0])
+    S = args.scenes_per_step
+    bevs_per_scene = len(PRESENT_IDXS) * BEVS_PER_PRESENT
+
+    # ---- e2e objects: public API, host buffers ---------------------------------
+    semseg = HostSemseg()
+    for sc in scenes:
+        for o in sc:
+            for img, cls in zip(o['images'], o['_semseg']):
+                semseg.by_id[id(img)] = cls
+    acc = NuScenesOracleSemanticPointCloudAccumulator(
+        semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None, bev_setup(),
+        ring_capacity_pts=n_in_scene + 4096, ring_max_frames=N_SWEEPS + 8, device=local_rank)
+
+    def new_scene_state():
+        acc.cloud.reset()
+        acc._fids, acc.poses, acc.seg_dists, acc.rgbs, acc.semsegs = [], [], [], [], []
+        acc.T_global_world = None
+        acc.instances, acc.dyn_instances, acc.token2idx, acc.ts = {}, [], [], 0
+        acc.ego_global_xs, acc.ego_global_ys = [], []
+
+    marks = []          # per distinct scene: per sweep (rel frame ids, inst idx)
+    params = []         # per distinct scene: 32 BevParams (frame ids relative to 0)
+    n_keep = []
+
+    def e2e_scene(k, record=False):
+        """One scene through the reference-facing API; returns #BEVs produced."""
+        new_scene_state()
+        sc = scenes[k]
+        log = []
+        if record:
+            orig = acc.cloud.mark_dynamic
+            acc.cloud.mark_dynamic = lambda f, i: (log.append((list(f), list(i))), orig(f, i))[1]
+        for o in sc:
+            acc.integrate([o])
+        if record:
+            acc.cloud.mark_dynamic = orig
+            first = acc._fids[0]
+            marks.append([([f - first for f in fs], ii) for fs, ii in log])
+            rng = np.random.RandomState(1234 + k)
+            ps = variant_params(acc, rng)
+            for q in ps:
+                q.frame_begin -= first
+                q.frame_split -= first
+                q.frame_end -= first
+            params.append(ps)
+            n_keep.append(acc.cloud.resident_points())
+        n = 0
+        acc.sem_bev_generator.rng = np.random.RandomState(99 + k)
+        for p in PRESENT_IDXS:
+            bevs = acc.generate_bev(p, BEVS_PER_PRESENT, True)
+            n += len(bevs)
+            assert bevs[0]['rgb_full'].shape == (3, P, P)
+        return n
+
+    for k in range(N_DISTINCT):            # also the e2e warm-up
+        assert e2e_scene(k, record=True) == bevs_per_scene
+
+    # ---- device-resident copies of the inputs (value path) ------------------------
+    def to_dev(sc):
+        out = []
+        for o in sc:
+            out.append(dict(
+                pc=torch.from_numpy(o['pc']).to(dev), cam=torch.from_numpy(o['pc_cam_idx']).to(dev),
+                rgb=[torch.from_numpy(np.ascontiguousarray(i)).to(dev) for i in o['images']],
+                sem=[torch.from_numpy(c.astype(np.uint8)).to(dev) for c in o['_semseg']],
+                T=None))
+        T_gw = np.linalg.inv(sc[0]['ego_at_lidar_ts'])
+        for o, d in zip(sc, out):
+            d['T'] = T_gw @ o['ego_at_lidar_ts']
+        return out
+
+    dev_scenes = []
+    for s in range(S):                      # S resident copies: the step's inputs exceed L2
+        dev_scenes.append(to_dev(scenes[s % N_DISTINCT]))
+    cloud = DeviceCloud(n_in_scene + 4096, N_SWEEPS + 8, local_rank)
+    out_planes = torch.empty((bevs_per_scene, 3, 7, P, P), dtype=torch.float16, device=dev)
+
+    def device_step():
+        for s in range(S):
+            k = s % N_DISTINCT
+            cloud.reset()
+            first = None
+            for t, d in enumerate(dev_scenes[s]):
+                fid = cloud.integrate_records(d['pc'], d['cam'], d['rgb'], d['sem'], d['T'],
+                                              synth.NUSC_FILTERS, 255.)
+                if first is None:
+                    first = fid
+                fs, ii = marks[k][t]
+                if fs:
+                    cloud.mark_dynamic([first + f for f in fs], ii)
+            ps = params[k]
+            for q in ps:
+                q.frame_begin += first
+                q.frame_split += first
+                q.frame_end += first
+            cloud.rasterise(ps, P, out=out_planes)
+            for q in ps:
+                q.frame_begin -= first
+                q.frame_split -= first
+                q.frame_end -= first
+        cloud._keep.clear()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    cloud.profile(True)
+    cloud.profile_read()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    prof = cloud.profile_read()
+    cloud.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    pts_step_rank = S * n_in_scene
+    value = world * pts_step_rank * args.steps / (ms_max * 1e-3)
+    bevs_per_s = world * S * bevs_per_scene * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (CUDA events inside the timed region) ------
+    n_res = float(np.mean([n_keep[s % N_DISTINCT] for s in range(S)]))
+    n_vis = float(np.mean([sum(int((o['pc_cam_idx'] >= 0).sum()) for o in scenes[s % N_DISTINCT])
+                           for s in range(S)])) / N_SWEEPS
+    alg = {  # algorithmic bytes per launch, SURVEY.md §8(d) / DESIGN.md "Bytes"
+        'integrate': 49.0 * (n_in_scene / N_SWEEPS) + 7.0 * n_vis + 37.0 * n_res / N_SWEEPS,
+        'bev_bin': 33.0 * n_res * bevs_per_scene,
+        'bev_reduce': 42.0 * P * P * bevs_per_scene,
+    }
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    peak = pk['hbm_gbs']
+    ach = (alg.get(dom, 0.0) / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n and dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
+    except Exception:
+        pass
+    roofline = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' (burst copy)',
+                'launch_us': dom_ms / max(dom_n, 1) * 1e3,
+                'share_of_step': dom_ms / ms_total,
+                'kernel_ms': {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+                'kernel_launches': {k: v[1] for k, v in prof.items() if v[1]}}
+    b_step = S * (N_SWEEPS * alg['integrate'] + alg['bev_bin'] + alg['bev_reduce'])
+    path_ach = b_step * args.steps / (ms_total * 1e-3) / 1e9
+    roofline_path = {'achieved': path_ach, 'peak': peak, 'unit': 'GB/s', 'frac': path_ach / peak,
+                     'bytes_per_step': b_step,
+                     'note': 'all algorithmic bytes of the step (integrate + rasterise) / step time'}
+    gpu_launches = int(sum(v[1] for v in prof.values()))
+
+    # ---- e2e: public API, host buffers, copies inside the timed region ---------------
+    e2e_scenes = max(1, min(S, args.e2e_scenes))
+    barrier()
+    t0 = time.perf_counter()
+    n_b = 0
+    for _ in range(args.e2e_steps):
+        for s in range(e2e_scenes):
+            n_b += e2e_scene(s % N_DISTINCT)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    e2e_pts = world * e2e_scenes * args.e2e_steps * n_in_scene / dt
+    h2d = sum(o['pc'].nbytes + o['pc_cam_idx'].nbytes + sum(i.nbytes for i in o['images'])
+              + sum(c.nbytes for c in o['_semseg']) for o in scenes[0]) * e2e_scenes
+    d2h = e2e_scenes * bevs_per_scene * 21 * P * P * 2
+    e2e = {'value': e2e_pts, 'unit': 'points/s', 'h2d_bytes_per_step': int(h2d),
+           'd2h_bytes_per_step': int(d2h), 'bevs_per_s': n_b * world / dt,
+           'scenes_per_step': e2e_scenes, 'steps': args.e2e_steps,
+           'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev, numpy in/out'}
+
+    # ---- CPU baseline + long-horizon extra (rank 0, N = 1) ---------------------------
+    cpu = None
+    extra = {}
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(scenes[0])
+        if not args.no_c3:
+            del dev_scenes, out_planes
+            torch.cuda.empty_cache()
+            extra['kitti360_long_horizon'] = c3_extra(torch, DeviceCloud, pk)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_max / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'nuscenes-shaped oracle-pose scenes (BASELINE configs[1]) batched as '
+                                   'configs[3]: 40 sweeps x 34688 pts, CAM_FRONT 1600x900, '
+                                   '32 BEVs/scene (8 present idx x 4 aug), 256x256, present/future/full',
+                       'scenes_per_step_per_gpu': S, 'points_per_step_per_gpu': pts_step_rank,
+                       'bevs_per_step_per_gpu': S * bevs_per_scene, 'sharding': 'scenes by rank',
+                       'l2': 'step inputs (%.1f GB resident copies) exceed the 126 MB L2'
+                             % (S * 0.32)},
+            'bevs_per_s': bevs_per_s, 'e2e': e2e, 'gpu_launches': gpu_launches,
+            'roofline': roofline, 'roofline_path': roofline_path, 'clocks': clk,
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        if extra:
+            line['extra'] = extra
+        print(json.dumps(line))
+
+
+def c3_extra(torch, DeviceCloud, pk):
+    """BASELINE.json configs[2]: 200 all-points KITTI-360-shaped frames (24 M
+    resident points, use_gt_sem path, lazy re-base), one 256x256 BEV at frame
+    100 — the primary roofline configuration of SURVEY.md §8(d)."""
+    from pc_accumulation_lib_b200.device import make_bev_params
+    F, n_distinct = 200, 8
+    pcs = [torch.from_numpy(synth.kitti_lidar(synth.seed_for(3, f))).cuda() for f in range(n_distinct)]
+    sgs = [torch.from_numpy(synth.kitti_sem_gt(synth.seed_for(3, f), pcs[0].shape[0])[:, 0].copy()).cuda()
+           for f in range(n_distinct)]
+    Ts = [synth.kitti_step_transform(synth.seed_for(3, f)) for f in range(F)]
+    N = int(pcs[0].shape[0])
+    cloud = DeviceCloud(F * N + 1024, F + 8)
+    poses = []
+    for f in range(F):
+        if f:
+            poses = [list(np.matmul(Ts[f], np.array([p + [1]]).T)[:, 0][:-1]) for p in poses]
+        poses.append([0., 0., 0.])
+
+    def integrate_all():
+        cloud.reset()
+        for f in range(F):
+            if f:
+                cloud.rebase(Ts[f], eager=False)
+            cloud.integrate_gt(pcs[f % n_distinct], sgs[f % n_distinct], synth.KITTI_FILTERS)
+        cloud._keep.clear()
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_int = timed(integrate_all, 3)
+    cloud.sync()
+    first, n_live = cloud.live_frames()
+    p = F // 2
+    origin = np.array(poses[p])
+    d = np.array(poses[p - 1]) - np.array(poses[p - 2])
+    rot = np.pi - (0.5 * np.pi + np.arctan2(d[1], d[0]))
+    R = np.array([[np.cos(rot), -np.sin(rot), 0], [np.sin(rot), np.cos(rot), 0], [0, 0, 1]])
+    bp = make_bev_params(first, first + p, first + n_live, origin, R, 0., 0., 80., None, 20., 20., .5,
+                         0, synth.SEM_IDXS)
+    out = torch.empty((1, 3, 7, P, P), dtype=torch.float16, device='cuda')
+    n_res = cloud.resident_points()
+    cloud.profile(True)
+    cloud.profile_read()
+    ms_ras = timed(lambda: cloud.rasterise([bp], P, out=out), 10)
+    prof = cloud.profile_read()
+    cloud.profile(False)
+    st = cloud.raster_stats()
+    b_int = 18.0 * N + 37.0 * N
+    b_ras = 33.0 * n_res + 42.0 * P * P
+    res = {
+        'frames': F, 'resident_points': n_res, 'points_in_view': st['binned'],
+        'exact_chain_replays': st['replays'],
+        'integrate_ms_per_frame': ms_int / F, 'integrate_points_per_s': F * N / (ms_int * 1e-3),
+        'integrate_alg_GBps': b_int * F / (ms_int * 1e-3) / 1e9,
+        'rasterise_ms_per_bev': ms_ras, 'bevs_per_s': 1e3 / ms_ras,
+        'rasterise_alg_GBps': b_ras / (ms_ras * 1e-3) / 1e9,
+        'rasterise_frac_of_hbm_peak': b_ras / (ms_ras * 1e-3) / 1e9 / pk['hbm_gbs'],
+        'kernel_us_per_bev': {k: round(v[0] / 11 * 1e3, 1) for k, v in prof.items() if v[1]},
+        'note': 'inputs (0.9 GB ring) exceed L2; 33 B/resident point + 42 B/cell algorithmic',
+    }
+    cloud.close()
+    return res
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# ---------------------------------------------------------------------------
+def cpu_scene(scene, n_sweeps, present_idxs, rng):
+    """One bounded sample of the workload on the CPU port (oracle/oracle.py):
+    returns (points integrated, BEVs, seconds)."""
+    from oracle import oracle as orc
+    bp = bev_setup()
+    gp = dict(sem_idxs=synth.SEM_IDXS, view_size=bp['view_size'], pixel_size=P,
+              int_scaler=bp['int_scaler'], int_sep_scaler=bp['int_sep_scaler'],
+              int_mid_threshold=bp['int_mid_threshold'], height_filter=bp['height_filter'],
+              rgb_fill=0)
+    t0 = time.perf_counter()
+    acc = orc.NuscOracle(synth.NUSC_FILTERS, gp)
+    pts = 0
+    for o in scene[:n_sweeps]:
+        acc.integrate(o, o['_semseg'])
+        pts += o['pc'].shape[0]
+    n_b = 0
+    for p in present_idxs:
+        for _ in range(BEVS_PER_PRESENT):
+            rot = 2 * np.pi * rng.random_sample()
+            r, a = 5.0 * rng.random_sample(), 2 * np.pi * rng.random_sample()
+            z = 1 + min(max(rng.normal(0, 0.1), -0.1), 0.1)
+            acc.generate_bev(p, rot_ang=rot, trans_dx=r * np.cos(a), trans_dy=r * np.sin(a),
+                             zoom_scalar=z, do_warping=True)
+            n_b += 1
+    return pts, n_b, time.perf_counter() - t0
+
+
+def cpu_baseline_sample(scene):
+    rng = np.random.RandomState(5)
+    pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng)
+    return {'value': pts / dt, 'unit': 'points/s', 'cores': 1, 'kind': 'port',
+            'bevs_per_s': n_b / dt, 'seconds': dt,
+            'sample': f'1 scene: {N_SWEEPS} sweeps ({pts} pts) + {n_b} BEVs through oracle/oracle.py '
+                      '(vectorised numpy + C FMA-chain restatement of the reference, 1 thread; the '
+                      'literal reference is ~100x slower per BEV, BASELINE.md)',
+            'host_cpus': os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    scene = make_scenes(0, 1)[0]
+    rng = np.random.RandomState(5)
+    for _ in range(min(args.warmup, 1)):
+        cpu_scene(scene, 8, PRESENT_IDXS[:1], rng)
+    tot_pts, tot_b, tot_t = 0, 0, 0.0
+    for _ in range(args.steps):
+        pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng)
+        tot_pts, tot_b, tot_t = tot_pts + pts, tot_b + n_b, tot_t + dt
+    v = tot_pts / tot_t
+    sample = (f'each step = 1 scene: {N_SWEEPS} sweeps + {len(PRESENT_IDXS) * BEVS_PER_PRESENT} BEVs '
+              'on the CPU port of the reference algorithm (oracle/oracle.py); the reference itself is '
+              'pure Python and /root/reference is not present on the GPU box')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'points/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': tot_t / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'bevs_per_s': tot_b / tot_t,
+        'config': {'workload': 'nuscenes-shaped oracle-pose scenes (BASELINE configs[1]) batched as '
+                               'configs[3]: 40 sweeps x 34688 pts, CAM_FRONT 1600x900, '
+                               '32 BEVs/scene (8 present idx x 4 aug), 256x256, present/future/full',
+                   'scenes_per_step': 1},
+        'cpu_baseline': {'value': v, 'unit': 'points/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+                         'host_cpus': os.cpu_count()},
+        'e2e': {'value': v, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scenes-per-step', type=int, default=16)
+    ap.add_argument('--e2e-scenes', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-c3', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product has no CPU path '
+                         '(use --impl reference for the host baseline)')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -4,7 +4,7 @@
  * The reference has no FFI of its own (it is pure Python/numpy);
  * its boundary for this path is the Python class API.  Each entry point below
  * names the reference function(s) it replaces (paths relative to the reference
- * root).  The Python mirror of that class API (pc_accumulation_lib_b200/*.py)
+ * root).  The Python mirror of that class API (the .py files of pc_accumulation_lib_b200/)
  * binds these symbols with ctypes; INTEGRATION.md shows the binding a
  * maintainer of the reference would add.
  *
@@ -212,6 +212,26 @@ int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset);
 /* counters of the last pcacc_rasterise on this handle (after a sync):
  * [0] points visited, [1] points binned (in view, static), [2] exact-chain replays */
 int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
+
+/* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
+ * Kernel classes of this library. */
+#define PCACC_K_INTEGRATE 0 /* k_integrate_frustum / _gt / _records / _cloud, k_gen_semantic_pc, k_project */
+#define PCACC_K_REBASE 1    /* k_rebase_lazy, k_materialise */
+#define PCACC_K_MARK 2      /* k_mark_dynamic */
+#define PCACC_K_BIN 3       /* k_bev_bin */
+#define PCACC_K_SCAN 4      /* k_scan */
+#define PCACC_K_SCATTER 5   /* k_bev_scatter */
+#define PCACC_K_REDUCE 6    /* k_bev_reduce */
+#define PCACC_K_EXPORT 7    /* k_export_frame */
+#define PCACC_N_KERNELS 8
+
+/* enable=1: every kernel launch of this handle is bracketed by CUDA events on
+ * its launch stream. */
+int pcacc_profile(pcacc_t h, int enable);
+/* Synchronises, then returns and clears the accumulated per-class device time
+ * (ms, from the events) and launch counts since the last read.  launches[] is
+ * counted whether or not event timing is enabled. */
+int pcacc_profile_read(pcacc_t h, double ms[PCACC_N_KERNELS], int64_t launches[PCACC_N_KERNELS]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,350 @@
+"""Host side of the BEV generator: same class, method names and argument
+meaning as the reference's `bev_generator/bev_generator.py`, with every
+point-cloud operation (rotate / translate / crop / height filter / pos2grid and
+the per-cell reductions) executed by libpcacc on the device.
+
+What stays on the host, as in the reference, is the tiny per-BEV scalar and
+trajectory work: the heading angle (bev_generator.py:87-93), the rotation
+matrix (:732-735, numpy cos/sin so the device sees the same matrix bits as the
+reference), trajectory rotate / translate / crop with midpoint bisection
+(:224-237,257-371) and their pos2grid (:737-747).
+
+Point clouds reach `generate()` in one of two forms:
+  * `DeviceWindow` views of an accumulator's device-resident ring (what the
+    accumulators in this package pass): no cloud bytes move;
+  * numpy (M,10) arrays, exactly as the reference's callers pass them: they are
+    uploaded to a scratch ring first (drop-in path).
+"""
+from __future__ import annotations
+
+import os
+import time
+from abc import ABC, abstractmethod
+
+import numpy as np
+
+from ..device import DeviceCloud, make_bev_params
+
+WINDOWS = ('present', 'future', 'full')
+
+
+class DeviceWindow:
+    """Frames [frame_begin, frame_end) of a DeviceCloud, to be shifted by
+    `origin` — the device-resident stand-in for
+    `np.concatenate(sem_pcs[a:b])[:, :3] - bev_frame_coords`
+    (kitti360_sem_pc_accum.py:189-193)."""
+
+    def __init__(self, cloud: DeviceCloud, frame_begin: int, frame_end: int, origin):
+        self.cloud = cloud
+        self.frame_begin = int(frame_begin)
+        self.frame_end = int(frame_end)
+        self.origin = np.asarray(origin, dtype=np.float64).reshape(3)
+
+    @property
+    def shape(self):
+        self.cloud.sync()
+        n = sum(self.cloud.frame_count(f) for f in range(self.frame_begin, self.frame_end))
+        return (n, 10)
+
+
+class BEVGenerator(ABC):
+    def __init__(self,
+                 view_size: int,
+                 pixel_size: int,
+                 max_trans_radius: float = 0.,
+                 zoom_thresh: float = 0.,
+                 do_warp: bool = False,
+                 int_scaler: float = 1.,
+                 int_sep_scaler: float = 1.,
+                 int_mid_threshold: float = 0.5,
+                 height_filter=None):
+        self.view_size = view_size
+        self.pixel_size = pixel_size
+        self.max_trans_radius = max_trans_radius
+        self.zoom_thresh = zoom_thresh
+        self.do_warp = do_warp
+        self.do_aug = bool(self.max_trans_radius > 0. or self.zoom_thresh > 0.)
+        self.int_scaler = int_scaler
+        self.int_sep_scaler = int_sep_scaler
+        self.int_mid_threshold = int_mid_threshold
+        self.sem_idx = 7
+        self.height_filter = height_filter
+        # injectable RNG for generate_rand_aug (the reference seeds numpy's
+        # global RNG from pid*time, bev_generator.py:168)
+        self.rng = None
+        self.elevation_max = False      # north-star variant; reference = per-cell min z
+        self._scratch = None            # DeviceCloud for host-array inputs
+
+    # ------------------------------------------------------------------
+    # abstract parts
+    # ------------------------------------------------------------------
+    @abstractmethod
+    def generate_bev(self, *args, **kwargs):
+        pass
+
+    @abstractmethod
+    def _assemble(self, planes, v, trajs_by_window, gt_lane_trajs, has_future):
+        """Builds the output dict of variant v from the (V,3,7,P,P) planes."""
+
+    def viz_bev(self, *a, **k):
+        raise NotImplementedError('plotting is outside the B200 hot path')
+
+    # ------------------------------------------------------------------
+    # host helpers with the reference's names
+    # ------------------------------------------------------------------
+    @staticmethod
+    def rotation_matrix_3d(ang):
+        return np.array([[np.cos(ang), -np.sin(ang), 0],
+                         [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+
+    def pos2grid(self, mat, view_size):
+        mat[:, 0:2] = np.floor(mat[:, 0:2] / view_size * self.pixel_size
+                               + 0.5 * self.pixel_size)
+        return mat
+
+    @staticmethod
+    def point_in_box(x, y, bx0, by0, bx1, by1):
+        return (bx0 < x and x < bx1) and (by0 < y and y < by1)
+
+    def cal_intersec_pnt(self, x0, y0, x1, y1, bbox, thresh=1e-4):
+        """Midpoint refinement towards the view boundary; returns
+        (x_mid, y_mid, iterations)."""
+        bx0, by0, bx1, by1 = bbox
+        moved = np.inf
+        iters = 0
+        while moved > thresh:
+            xm, ym = 0.5 * (x0 + x1), 0.5 * (y0 + y1)
+            first_in = self.point_in_box(x0, y0, bx0, by0, bx1, by1)
+            mid_in = self.point_in_box(xm, ym, bx0, by0, bx1, by1)
+            if mid_in == first_in:      # midpoint on the same side as endpoint 0
+                moved = np.sqrt((xm - x0) ** 2 + (ym - y0) ** 2)
+                x0, y0 = xm, ym
+            else:
+                moved = np.sqrt((xm - x1) ** 2 + (ym - y1) ** 2)
+                x1, y1 = xm, ym
+            iters += 1
+        return xm, ym, iters
+
+    def crop_trajectory(self, traj, aug_view_size, thresh=1e-4):
+        half = 0.5 * aug_view_size
+        bbox = [-half, -half, half, half]
+        kept = []
+        for a, b in zip(traj[:-1], traj[1:]):
+            ax, ay = list(a[:2])
+            bx, by = list(b[:2])
+            a_in = self.point_in_box(ax, ay, *bbox)
+            b_in = self.point_in_box(bx, by, *bbox)
+            if a_in:
+                kept.append([ax, ay, a[2]])
+            if a_in != b_in:
+                ix, iy, _ = self.cal_intersec_pnt(ax, ay, bx, by, bbox, thresh)
+                kept.append([ix, iy, a[2]])
+        return np.array(kept) if kept else np.zeros((0, 3))
+
+    def geometric_transform(self, pc_mat, rot_ang, trans_dx, trans_dy, aug_view_size,
+                            is_traj=False):
+        """Trajectories only on the host; clouds go through generate()."""
+        if not is_traj:
+            raise NotImplementedError(
+                'point clouds are transformed on the device: use generate()')
+        R = self.rotation_matrix_3d(rot_ang)
+        pc_mat[:, :3] = np.matmul(R, pc_mat[:, :3].T).T
+        pc_mat[:, 0] += trans_dx
+        pc_mat[:, 1] += trans_dy
+        return self.crop_trajectory(pc_mat, aug_view_size)
+
+    def preprocess_trajs(self, trajs, rot_ang, trans_dx, trans_dy, aug_view_size):
+        out = []
+        for t in trajs:
+            t = np.array(t, dtype=float)
+            t = t.reshape(-1, 3) if t.size else np.zeros((0, 3))
+            t = self.geometric_transform(t, rot_ang, trans_dx, trans_dy, aug_view_size,
+                                         is_traj=True)
+            out.append(self.pos2grid(t, aug_view_size))
+        return out
+
+    @staticmethod
+    def extract_pc_dict(pcs):
+        return pcs['pc_present'], pcs['pc_future'], pcs['pc_full']
+
+    @staticmethod
+    def extract_ego_traj_dict(trajs):
+        return trajs['ego_traj_present'], trajs['ego_traj_future'], trajs['ego_traj_full']
+
+    @staticmethod
+    def extract_other_traj_dicts(trajs):
+        return (trajs['other_trajs_present'], trajs['other_trajs_future'],
+                trajs['other_trajs_full'])
+
+    @staticmethod
+    def extract_gt_lane_dicts(trajs):
+        return trajs['gt_lanes']
+
+    @staticmethod
+    def heading_angle(ego_traj_present):
+        rot_ang = 0.5 * np.pi
+        if len(ego_traj_present) > 1:
+            dx = ego_traj_present[-1][0] - ego_traj_present[-2][0]
+            dy = ego_traj_present[-1][1] - ego_traj_present[-2][1]
+            rot_ang += np.arctan2(dy, dx)
+        return np.pi - rot_ang
+
+    # ------------------------------------------------------------------
+    # device plumbing
+    # ------------------------------------------------------------------
+    def _bev_params(self, fb, fs, fe, origin, rot_ang, dx, dy, view):
+        sem_idxs = getattr(self, 'sem_idxs', None) or {
+            'road': -1, 'car': -1, 'truck': -1, 'bus': -1, 'motorcycle': -1}
+        return make_bev_params(fb, fs, fe, origin, self.rotation_matrix_3d(rot_ang), dx, dy, view,
+                               self.height_filter, self.int_scaler, self.int_sep_scaler,
+                               self.int_mid_threshold, getattr(self, 'rgb_fill', 0), sem_idxs,
+                               self.elevation_max)
+
+    def _scratch_cloud(self, n_pts):
+        if self._scratch is None or self._scratch.capacity < n_pts + 16:
+            if self._scratch is not None:
+                self._scratch.close()
+            self._scratch = DeviceCloud(int(n_pts * 1.25) + 1024, max_frames=8)
+        self._scratch.reset()
+        return self._scratch
+
+    def _rasterise_windows(self, pcs, augs):
+        """pcs: the reference's dict. Returns (planes (V,3,7,P,P) numpy f16,
+        has_future)."""
+        P = self.pixel_size
+        pp, pf, pa = self.extract_pc_dict(pcs)
+        has_future = pf is not None
+        V = len(augs)
+
+        def params(cloud, fb, fs, fe, origin):
+            return [self._bev_params(fb, fs, fe, origin, a['rot_ang'], a['trans_dx'], a['trans_dy'],
+                                     a['zoom_scalar'] * self.view_size) for a in augs]
+
+        if isinstance(pp, DeviceWindow):
+            cloud = pp.cloud
+            if has_future:
+                same = (pf.cloud is cloud and pa.cloud is cloud
+                        and pf.frame_begin == pp.frame_end and pa.frame_begin == pp.frame_begin
+                        and pa.frame_end == pf.frame_end
+                        and np.array_equal(pp.origin, pf.origin)
+                        and np.array_equal(pp.origin, pa.origin))
+                if same:        # full = present ++ future: one pass does all three
+                    planes, _, _ = cloud.rasterise(
+                        params(cloud, pp.frame_begin, pp.frame_end, pf.frame_end, pp.origin), P)
+                    return planes.cpu().numpy(), True
+                # general case: each window rasterised as a 'present' window
+                outs = []
+                for w in (pp, pf, pa):
+                    pl, _, _ = w.cloud.rasterise(
+                        params(w.cloud, w.frame_begin, w.frame_end, w.frame_end, w.origin), P)
+                    outs.append(pl[:, 0])
+                import torch
+                return torch.stack(outs, dim=1).cpu().numpy(), True
+            planes, _, _ = cloud.rasterise(
+                params(cloud, pp.frame_begin, pp.frame_end, pp.frame_end, pp.origin), P)
+            return planes.cpu().numpy(), False
+
+        # host arrays: upload into a scratch ring as frames
+        clouds = [np.asarray(pp, dtype=np.float64)]
+        if has_future:
+            clouds += [np.asarray(pf, dtype=np.float64), np.asarray(pa, dtype=np.float64)]
+        clouds = [self._pad10(c) for c in clouds]
+        cloud = self._scratch_cloud(sum(c.shape[0] for c in clouds))
+        fids = [cloud.integrate_cloud(c) for c in clouds]
+        zero = np.zeros(3)
+        pl, _, _ = cloud.rasterise(
+            params(cloud, fids[0], fids[1] if has_future else fids[0] + 1,
+                   fids[1] + 1 if has_future else fids[0] + 1, zero), P)
+        if not has_future:
+            return pl.cpu().numpy(), False
+        # pc_full is an input of its own in the reference API: rasterise it as well
+        plf, _, _ = cloud.rasterise(params(cloud, fids[2], fids[2] + 1, fids[2] + 1, zero), P)
+        pl[:, 2] = plf[:, 0]
+        return pl.cpu().numpy(), True
+
+    @staticmethod
+    def _pad10(c):
+        c = c.reshape(-1, c.shape[-1]) if c.ndim == 2 else c.reshape(0, 10)
+        if c.shape[1] < 10:
+            c = np.concatenate([c, np.zeros((c.shape[0], 10 - c.shape[1]))], axis=1)
+        return np.ascontiguousarray(c[:, :10])
+
+    # ------------------------------------------------------------------
+    # public generation API (reference names)
+    # ------------------------------------------------------------------
+    def generate_batch(self, pcs: dict, trajs: dict, augs: list) -> list:
+        """All variants in `augs` (dicts with rot_ang, trans_dx, trans_dy,
+        zoom_scalar, do_warping) rasterised in ONE batch of launches — the
+        device-side replacement of the reference's Pool(bev_num).map
+        (kitti360_sem_pc_accum.py:236-241)."""
+        ego_p, ego_f, ego_a = self.extract_ego_traj_dict(trajs)
+        oth_p, oth_f, oth_a = self.extract_other_traj_dicts(trajs)
+        _, pc_future, _ = self.extract_pc_dict(pcs)
+        if pc_future is None:
+            # the reference dies here too: trajs_future is never bound
+            # (bev_generator.py:111-123); every caller passes gen_future=True
+            raise UnboundLocalError(
+                "cannot access local variable 'trajs_future': generate() requires pc_future "
+                '(call generate_bev(..., gen_future=True))')
+        full = []
+        for a in augs:
+            a = dict(a)
+            a.setdefault('rot_ang', 0.)
+            a.setdefault('trans_dx', 0.)
+            a.setdefault('trans_dy', 0.)
+            a.setdefault('zoom_scalar', 1.)
+            if not a.get('do_warping', False):
+                a['rot_ang'] = self.heading_angle(ego_p)
+            full.append(a)
+        planes, has_future = self._rasterise_windows(pcs, full)
+        bevs = []
+        for v, a in enumerate(full):
+            view = a['zoom_scalar'] * self.view_size
+            tw = {}
+            for w, ego, oth in (('present', ego_p, oth_p), ('future', ego_f, oth_f),
+                                ('full', ego_a, oth_a)):
+                tw[w] = self.preprocess_trajs([ego] + list(oth), a['rot_ang'], a['trans_dx'],
+                                              a['trans_dy'], view)
+            lanes = None
+            if 'gt_lanes' in trajs:
+                lanes = self.preprocess_trajs(self.extract_gt_lane_dicts(trajs), a['rot_ang'],
+                                              a['trans_dx'], a['trans_dy'], view)
+                lanes = [ln for ln in lanes if ln.shape[0] > 0]
+            bevs.append(self._assemble(planes, v, tw, lanes, has_future))
+        return bevs
+
+    def generate(self, pcs: dict, trajs: dict, rot_ang: float = 0., trans_dx: float = 0.,
+                 trans_dy: float = 0., zoom_scalar: float = 1., do_warping: bool = False):
+        return self.generate_batch(pcs, trajs, [dict(
+            rot_ang=rot_ang, trans_dx=trans_dx, trans_dy=trans_dy, zoom_scalar=zoom_scalar,
+            do_warping=do_warping)])[0]
+
+    def rand_aug_params(self, do_warping: bool = True) -> dict:
+        """Draws (rot, trans, zoom) in the reference's order
+        (bev_generator.py:168-180). `self.rng` (np.random.Generator or
+        RandomState) makes it reproducible; default = the reference's seeding."""
+        rng = self.rng
+        if rng is None:
+            rng = np.random.RandomState((os.getpid() * int(time.time())) % 123456789)
+        rnd = rng.random if hasattr(rng, 'random') else rng.random_sample
+        rot_ang = 2 * np.pi * rnd()
+        trans_r = self.max_trans_radius * rnd()
+        trans_ang = 2 * np.pi * rnd()
+        zoom = rng.normal(0, 0.1)
+        zoom = min(max(zoom, -self.zoom_thresh), self.zoom_thresh)
+        return dict(rot_ang=rot_ang, trans_dx=trans_r * np.cos(trans_ang),
+                    trans_dy=trans_r * np.sin(trans_ang), zoom_scalar=1 + zoom,
+                    do_warping=do_warping)
+
+    def generate_rand_aug(self, pcs: dict, trajs: dict, do_warping: bool = True):
+        return self.generate_batch(pcs, trajs, [self.rand_aug_params(do_warping)])[0]
+
+    def generate_multiproc(self, bev_gen_inputs):
+        pcs, trajs = bev_gen_inputs
+        if self.do_aug:
+            return self.generate_rand_aug(pcs, trajs)
+        return self.generate(pcs, trajs)
+
+    def generate_rand_aug_multiproc(self, bev_gen_inputs):
+        pcs, trajs = bev_gen_inputs
+        return self.generate_rand_aug(pcs, trajs, do_warping=True)

@@ -61,6 +61,64 @@ int pcacc_arena_put(pcacc_t h, const void *src, size_t bytes, void **dev, cudaSt
     return PCACC_OK;
 }
 
+size_t pcacc_prof_begin(pcacc_t h, int kernel, cudaStream_t st) {
+    h->launches[kernel]++;
+    if (!h->prof_on) return 0;
+    if (h->prof_used + 2 > h->prof_events.size()) {
+        size_t old = h->prof_events.size();
+        h->prof_events.resize(old + 1024);
+        for (size_t k = old; k < h->prof_events.size(); k++) cudaEventCreate(&h->prof_events[k]);
+    }
+    size_t ev0 = h->prof_used;
+    h->prof_used += 2;
+    cudaEventRecord(h->prof_events[ev0], st);
+    return ev0;
+}
+
+void pcacc_prof_end(pcacc_t h, int kernel, size_t ev0, cudaStream_t st) {
+    if (!h->prof_on) return;
+    cudaEventRecord(h->prof_events[ev0 + 1], st);
+    h->prof_spans.push_back({kernel, ev0, ev0 + 1});
+    if (h->prof_spans.size() >= 16384) pcacc_prof_flush(h);
+}
+
+int pcacc_prof_flush(pcacc_t h) {
+    for (auto &sp : h->prof_spans) {
+        cudaEventSynchronize(h->prof_events[sp.ev1]);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_events[sp.ev0], h->prof_events[sp.ev1]) == cudaSuccess) {
+            h->prof_ms[sp.kernel] += ms;
+            h->prof_n[sp.kernel]++;
+        }
+    }
+    h->prof_spans.clear();
+    h->prof_used = 0;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_profile(pcacc_t h, int enable) {
+    if (!h) return PCACC_ERR_ARG;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    if (!enable && h->prof_on) pcacc_prof_flush(h);
+    h->prof_on = enable != 0;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_profile_read(pcacc_t h, double ms[PCACC_N_KERNELS], int64_t launches[PCACC_N_KERNELS]) {
+    if (!h) return PCACC_ERR_ARG;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    PCACC_CUDA(h, cudaDeviceSynchronize());
+    pcacc_prof_flush(h);
+    for (int k = 0; k < PCACC_N_KERNELS; k++) {
+        if (ms) ms[k] = h->prof_ms[k];
+        if (launches) launches[k] = h->launches[k];
+        h->prof_ms[k] = 0.0;
+        h->prof_n[k] = 0;
+        h->launches[k] = 0;
+    }
+    return PCACC_OK;
+}
+
 FrameHost *pcacc_frame(pcacc_t h, int64_t frame_id) {
     if (frame_id < h->first_id || frame_id >= h->next_id) return nullptr;
     return &h->frames[(int)(frame_id % h->max_frames)];
@@ -101,6 +159,7 @@ static void free_all(pcacc_t h) {
     cudaFree(h->d_arena);
     cudaFree(h->d_ws);
     cudaFree(h->d_rstats);
+    for (auto &e : h->prof_events) cudaEventDestroy(e);
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_arena) cudaFreeHost(h->h_arena);
 }

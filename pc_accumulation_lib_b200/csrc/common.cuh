@@ -201,8 +201,22 @@ struct pcacc_s {
     int64_t last_visit_ub;
     double inten_div;    // stored intensity / inten_div = reference intensity; 0 = not set yet
     uint32_t pending_flags;
+    // launch accounting + optional per-kernel CUDA-event timing
+    int64_t launches[PCACC_N_KERNELS];
+    bool prof_on;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used;
+    struct ProfSpan { int kernel; size_t ev0, ev1; };
+    std::vector<ProfSpan> prof_spans;
+    double prof_ms[PCACC_N_KERNELS];
+    int64_t prof_n[PCACC_N_KERNELS];
     char err[512];
 };
+
+// RAII-less span helpers: count every launch; bracket it with events when profiling
+size_t pcacc_prof_begin(pcacc_t h, int kernel, cudaStream_t st);
+void pcacc_prof_end(pcacc_t h, int kernel, size_t ev0, cudaStream_t st);
+int pcacc_prof_flush(pcacc_t h);
 
 int pcacc_fail(pcacc_t h, int status, const char *fmt, ...);
 int pcacc_cuda_check(pcacc_t h, cudaError_t e, const char *what);

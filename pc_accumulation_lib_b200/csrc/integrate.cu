@@ -611,6 +611,7 @@ extern "C" int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n,
     int rc = make_lookback(h, tiles, &lb);
     if (rc) return rc;
     const float4 *p4 = (const float4 *)pts_dev;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_GSP(DT)                                                                      \
     k_gen_semantic_pc<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(p4, n, pm, map_dev, img_h, img_w, K, \
                                                                out_dev, n_kept_dev, lb)
@@ -622,6 +623,7 @@ extern "C" int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n,
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown map dtype %d", map_dtype);
     }
 #undef LAUNCH_GSP
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
@@ -652,6 +654,7 @@ extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t 
     PMat pm;
     memcpy(pm.m, P, sizeof(pm.m));
     const float4 *p4 = (const float4 *)pts_dev;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_IF(DT)                                                                          \
     k_integrate_frustum<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(p4, n, pm, rgb_dev, sem_dev, K, img_h, \
                                                                  img_w, max_depth, filt, h->ring, fs, \
@@ -664,6 +667,7 @@ extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t 
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown sem dtype %d", sem_dtype);
     }
 #undef LAUNCH_IF
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
@@ -687,8 +691,10 @@ extern "C" int pcacc_integrate_gt(pcacc_t h, const float *pts_dev, int64_t n,
     FrameSlots fs;
     rc = begin_frame(h, n, st, &fs, frame_id);
     if (rc) return rc;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
     k_integrate_gt<<<(unsigned)tiles, IBLOCK, 0, st>>>((const float4 *)pts_dev, n, sem_gt_dev, filt,
                                                        h->ring, fs, lb, h->d_flags);
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
@@ -725,6 +731,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
     FrameSlots fs;
     rc = begin_frame(h, n, st, &fs, frame_id);
     if (rc) return rc;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_IR(DT)                                                                           \
     k_integrate_records<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(                                \
         pc_dev, (const long long *)cam_idx_dev, n, maps, img_h, img_w, T, filt, h->ring, fs, lb, \
@@ -736,6 +743,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
     }
 #undef LAUNCH_IR
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
@@ -752,7 +760,9 @@ extern "C" int pcacc_integrate_cloud(pcacc_t h, const double *rec_dev, int64_t n
     if (rc) return rc;
     int64_t blocks = (n + IBLOCK - 1) / IBLOCK;
     if (blocks == 0) blocks = 1;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
     k_integrate_cloud<<<(unsigned)blocks, IBLOCK, 0, st>>>(rec_dev, n, h->ring, fs, h->d_flags);
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
@@ -772,12 +782,15 @@ static int materialise_all(pcacc_t h, cudaStream_t st) {
     if (bx < 1) bx = 1;
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)n_live);
+    size_t pe = pcacc_prof_begin(h, PCACC_K_REBASE, st);
     k_materialise<<<grid, IBLOCK, 0, st>>>(h->ring, h->d_frame_off, h->d_frame_cnt, h->d_frame_epoch,
                                            h->d_chain, first_slot, h->max_frames, h->rebase_epoch);
     PCACC_CUDA(h, cudaGetLastError());
+    h->launches[PCACC_K_REBASE]++;
     k_materialise_done<<<(n_live + 127) / 128, 128, 0, st>>>(h->d_frame_epoch, h->d_comp, first_slot,
                                                              n_live, h->max_frames, h->rebase_epoch);
     PCACC_CUDA(h, cudaGetLastError());
+    pcacc_prof_end(h, PCACC_K_REBASE, pe, st);
     for (int64_t k = h->first_id; k < h->next_id; k++)
         h->frames[(int)(k % h->max_frames)].epoch = h->rebase_epoch;
     h->any_lazy = false;
@@ -806,9 +819,11 @@ extern "C" int pcacc_rebase(pcacc_t h, const double *T_new_prev, int eager, void
     int first_slot = (int)(h->first_id % h->max_frames);
     double *slot = h->d_chain + (h->rebase_epoch % h->max_frames) * 12;
     int threads = n_live < 12 ? 12 : n_live;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_REBASE, st);
     k_rebase_lazy<<<(threads + 127) / 128, 128, 0, st>>>(slot, h->d_comp, T, first_slot, n_live,
                                                          h->max_frames);
     PCACC_CUDA(h, cudaGetLastError());
+    pcacc_prof_end(h, PCACC_K_REBASE, pe, st);
     h->rebase_epoch += 1;
     h->any_lazy = true;
     if (eager) return materialise_all(h, st);
@@ -840,10 +855,12 @@ extern "C" int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int
     for (int k0 = 0; k0 < n_pairs; k0 += 32768) {
         int ny = n_pairs - k0 < 32768 ? n_pairs - k0 : 32768;
         dim3 grid((unsigned)bx, (unsigned)ny);
+        size_t pe = pcacc_prof_begin(h, PCACC_K_MARK, st);
         k_mark_dynamic<<<grid, IBLOCK, 0, st>>>(h->ring, h->d_frame_off, h->d_frame_cnt,
                                                 (const int32_t *)dev + k0,
                                                 (const int32_t *)dev + n_pairs + k0);
         PCACC_CUDA(h, cudaGetLastError());
+        pcacc_prof_end(h, PCACC_K_MARK, pe, st);
     }
     return PCACC_OK;
 }
@@ -857,6 +874,7 @@ extern "C" int pcacc_export_frame(pcacc_t h, int64_t frame_id, double *out_dev, 
     cudaStream_t st = (cudaStream_t)stream;
     PCACC_CUDA(h, cudaSetDevice(h->device));
     int64_t blocks = (f->cnt + IBLOCK - 1) / IBLOCK;
+    h->launches[PCACC_K_EXPORT]++;
     k_export_frame<<<(unsigned)blocks, IBLOCK, 0, st>>>(
         h->ring, h->d_frame_off, h->d_frame_cnt, h->d_frame_epoch, h->d_chain,
         (int)(frame_id % h->max_frames), h->max_frames, h->rebase_epoch,

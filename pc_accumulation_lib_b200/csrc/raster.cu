@@ -38,6 +38,8 @@
 // chains of hundreds of frames, so 1e-7 is four orders of margin
 #define GUARD_M 1e-7
 
+static_assert(sizeof(pcacc_bev_params) == 208, "pcacc_bev_params layout is part of the ABI");
+
 struct BinArgs {
     RingDev ring;
     const int64_t *frame_off, *frame_cnt, *frame_epoch;
@@ -703,8 +705,10 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
                 BinArgs b = a;
                 b.frame_lo = flo + f0;
                 dim3 grid((unsigned)((max_cnt + BIN_TILE - 1) / BIN_TILE), (unsigned)ny);
+                size_t pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
                 k_bev_bin<<<grid, BIN_BLOCK, 0, st>>>(b);
                 PCACC_CUDA(h, cudaGetLastError());
+                pcacc_prof_end(h, PCACC_K_BIN, pe, st);
             }
             // scan
             int64_t tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
@@ -715,18 +719,23 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             lb.ticket = h->d_ticket;
             lb.epoch = pcacc_next_epoch(h);
             lb.n_tiles = (uint32_t)tiles;
+            size_t pe = pcacc_prof_begin(h, PCACC_K_SCAN, st);
             k_scan<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(counts, n_keys, lb);
             PCACC_CUDA(h, cudaGetLastError());
+            pcacc_prof_end(h, PCACC_K_SCAN, pe, st);
             // scatter
             int64_t sb = (cap + 255) / 256;
             if (sb > 148 * 16) sb = 148 * 16;
+            pe = pcacc_prof_begin(h, PCACC_K_SCATTER, st);
             k_bev_scatter<<<(unsigned)sb, 256, 0, st>>>(counts, a.tmp_key, a.tmp_rank, a.tmp_rec, ctr,
                                                         cap, (uint4 *)(ws + o_sorted));
             PCACC_CUDA(h, cudaGetLastError());
+            pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
         // reduce + finalise (also correct on all-zero counters: every cell empty)
         int64_t warps = (int64_t)nv * PP / 32;
         int64_t blocks = (warps + RED_WARPS - 1) / RED_WARPS;
+        size_t pr = pcacc_prof_begin(h, PCACC_K_REDUCE, st);
         if (want_f64)
             k_bev_reduce<true><<<(unsigned)blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, nv, P,
@@ -736,10 +745,9 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, nv, P,
                 h->inten_div, o16, nullptr);
         PCACC_CUDA(h, cudaGetLastError());
+        pcacc_prof_end(h, PCACC_K_REDUCE, pr, st);
         // keep the counters of the last group for pcacc_raster_stats
         PCACC_CUDA(h, cudaMemcpyAsync(h->d_rstats + 1, ctr, 16, cudaMemcpyDeviceToDevice, st));
-        int64_t visited = cap;
-        (void)visited;
         h->last_visit_ub = cap;
     }
     return PCACC_OK;

@@ -321,6 +321,15 @@ class DeviceCloud:
                                              _ptr(cells), _stream()))
         return out, o64, cells
 
+    def profile(self, enable=True):
+        self._check(self.lib.pcacc_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel class: (device ms from CUDA events, launches)} since the last read."""
+        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        self._check(self.lib.pcacc_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     def raster_stats(self):
         s = (C.c_int64 * 3)()
         self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))

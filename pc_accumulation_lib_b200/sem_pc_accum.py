@@ -1,0 +1,250 @@
+"""SemanticPointCloudAccumulator — the reference's accumulator base class
+(`sem_pc_accum.py`) with the accumulated cloud held in a device-resident SoA
+ring (libpcacc) instead of a Python list of numpy arrays.
+
+Same constructor arguments, attributes (`poses`, `seg_dists`, `rgbs`,
+`semsegs`, `sem_pcs`) and helper names as the reference.  `sem_pcs` is a lazy
+view: indexing it exports that frame from the device as the reference's
+(M,10) float64 record array.
+
+Out of scope, as in SURVEY.md §2: the ONNX segmentation network (pass any
+object with `.pred(rgb) -> (1,1,H,W)` as `semseg_onnx_path`), Open3D ICP and
+visualisation.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+import pickle
+import time
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bev_generator import DeviceWindow, SemBEVGenerator
+from .device import DeviceCloud
+
+
+class SemPcsView(Sequence):
+    """`accumulator.sem_pcs`: list-like view of the live frames."""
+
+    def __init__(self, acc):
+        self._acc = acc
+
+    def __len__(self):
+        return len(self._acc._fids)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._acc._export(f) for f in self._acc._fids[i]]
+        return self._acc._export(self._acc._fids[i])
+
+
+class SemanticPointCloudAccumulator:
+    def __init__(self, horizon_dist: float, icp_threshold: float, semseg_onnx_path,
+                 semseg_filters: list, sem_idxs: dict, use_gt_sem: bool, bev_params: dict,
+                 ring_capacity_pts: int = 8_000_000, ring_max_frames: int = 2048,
+                 device: int | None = None):
+        self.semseg_model = None
+        if use_gt_sem is False:
+            if hasattr(semseg_onnx_path, 'pred'):
+                self.semseg_model = semseg_onnx_path
+            else:
+                raise NotImplementedError(
+                    'the ONNX semseg network is outside the B200 hot path: pass an object with '
+                    '.pred(rgb) -> (1,1,H,W) class map as semseg_onnx_path '
+                    '(utils/onnx_utils.py:32-44 contract)')
+        self.semseg_filters = semseg_filters
+        self.sem_idxs = sem_idxs
+        self.use_gt_sem = use_gt_sem
+        self.icp_threshold = icp_threshold
+        self.icp_trans_init = np.eye(4)
+        self.T_prev_origin = np.eye(4)
+        self.pcd_prev = None
+        self.horizon_dist = horizon_dist
+
+        self.poses = []
+        self.seg_dists = []
+        self.rgbs = []
+        self.semsegs = []
+
+        # device-resident cloud
+        self.cloud = DeviceCloud(ring_capacity_pts, ring_max_frames, device)
+        self._fids = []              # absolute frame ids of the live frames
+        self.eager_rebase = False    # True = rewrite xyz every frame like the reference
+        self.sync_each_integrate = True
+
+        self.sem_bev_generator = None
+        if bev_params['type'] == 'sem':
+            self.sem_bev_generator = SemBEVGenerator(
+                self.sem_idxs, bev_params['view_size'], bev_params['pixel_size'],
+                bev_params['max_trans_radius'], bev_params['zoom_thresh'], bev_params['do_warp'],
+                bev_params['int_scaler'], bev_params['int_sep_scaler'],
+                bev_params['int_mid_threshold'], bev_params['height_filter'])
+        elif bev_params['type'] == 'rgb':
+            raise NotImplementedError('Needs refactoring')
+
+    # ------------------------------------------------------------------
+    @property
+    def sem_pcs(self):
+        return SemPcsView(self)
+
+    def _export(self, fid):
+        self._sync()
+        return self.cloud.export_frame(fid)
+
+    def _sync(self):
+        flags = self.cloud.sync()
+        if flags & _lib.FLAG_UV_OUT_OF_IMAGE:
+            raise AssertionError('pts_uv must be all inside image')
+        if flags & (_lib.FLAG_ATTR_RANGE | _lib.FLAG_CELL_OVERFLOW):
+            raise ValueError(f'libpcacc data error flags 0x{flags:x} '
+                             '(class / colour outside 0..255 or instance outside int32)')
+        return flags
+
+    def integrate(self, observations: list):
+        raise NotImplementedError()
+
+    def obs2sem_vec_space(self, *a, **k):
+        raise NotImplementedError()
+
+    # -- pose / cloud updates (sem_pc_accum.py:156-209) ------------------
+    def update_poses(self, T_new_prev):
+        self.poses = [list(np.matmul(T_new_prev, np.array([p + [1]]).T)[:, 0][:-1])
+                      for p in self.poses]
+
+    def update_sem_pcs(self, T_new_prev):
+        """Every stored point <- T_new_prev @ point.  On the device this is
+        either an in-place kernel (eager) or one more link of the lazy chain."""
+        self.cloud.rebase(T_new_prev, eager=self.eager_rebase)
+
+    def remove_observations(self):
+        idx = 0
+        self.seg_dists.append(self.dist(np.array(self.poses[-1]), np.array(self.poses[-2])))
+        path_length = np.sum(self.seg_dists)
+        if path_length > self.horizon_dist:
+            incr = self.get_incremental_path_dists()
+            incr -= path_length - self.horizon_dist
+            idx = (incr > 0.).argmax()
+            self.cloud.evict(int(idx))
+            self._fids = self._fids[idx:]
+            self.poses = self.poses[idx:]
+            self.seg_dists = self.seg_dists[idx:]
+            self.rgbs = self.rgbs[idx:]
+            self.semsegs = self.semsegs[idx:]
+        return idx, path_length
+
+    @staticmethod
+    def comp_incr_path_dist(seg_dists):
+        return np.matmul(np.tri(len(seg_dists)), np.array(seg_dists))
+
+    def get_segment_dists(self):
+        return self.seg_dists
+
+    def get_incremental_path_dists(self):
+        return self.comp_incr_path_dist(np.array(self.seg_dists))
+
+    def get_pose(self, idx: int = None):
+        return np.array(self.poses) if idx is None else np.array(self.poses[idx])
+
+    def get_rgb(self, idx: int = None):
+        return self.rgbs if idx is None else [self.rgbs[idx]]
+
+    def get_semseg(self, idx: int = None):
+        return self.semsegs if idx is None else [self.semsegs[idx]]
+
+    @staticmethod
+    def dist(pose_0, pose_1):
+        return np.sqrt(np.sum((pose_1 - pose_0) ** 2))
+
+    # -- output files (sem_pc_accum.py:280-308) ----------------------------
+    @staticmethod
+    def write_compressed_pickle(obj, filename, write_dir):
+        path = os.path.join(write_dir, f'{filename}.gz')
+        try:
+            with gzip.open(path, 'wb') as f:
+                f.write(pickle.dumps(obj))
+        except IOError as error:
+            print(error)
+
+    @staticmethod
+    def read_compressed_pickle(path):
+        try:
+            with gzip.open(path, 'rb') as f:
+                return pickle.loads(f.read())
+        except IOError as error:
+            print(error)
+
+    # -- stand-alone operators (sem_pc_accum.py:317-402), device-backed ------
+    def filter_semseg_pc(self, pc):
+        t = torch.from_numpy(np.ascontiguousarray(pc)).to(self.cloud.device)
+        keep = torch.ones(t.shape[0], dtype=torch.bool, device=t.device)
+        for f in self.semseg_filters:
+            keep &= t[:, -1] != f
+        return t[keep].cpu().numpy()
+
+    def gen_semantic_pc(self, pc_velo, semantic_map, P_velo_frame):
+        return self.cloud.gen_semantic_pc(pc_velo, semantic_map, P_velo_frame).cpu().numpy()
+
+    def velo2img(self, pc_velo, P_velo_frame, img_h, img_w, max_depth=np.inf):
+        pc = np.ascontiguousarray(pc_velo, dtype=np.float32)
+        u, v, m = self.cloud.project(pc, P_velo_frame, img_h, img_w, max_depth)
+        m = m.bool()
+        pts = torch.from_numpy(np.asarray(pc_velo)).to(self.cloud.device).double()
+        out = torch.cat([pts, u.double()[:, None], v.double()[:, None]], dim=1)
+        return out[m].cpu().numpy()
+
+    def viz_sem_vec_space(self, *a, **k):
+        raise NotImplementedError('Open3D visualisation is outside the B200 hot path')
+
+    # -- shared part of generate_bev (kitti360_sem_pc_accum.py:166-243) -------
+    def _window_inputs(self, present_idx, gen_future, other_trajs=None, gt_lanes=None):
+        n = len(self.poses)
+        origin = np.array(self.poses[-1] if present_idx is None else self.poses[present_idx])
+        lo, hi, _ = slice(None, present_idx).indices(n)
+        flo, fhi, _ = slice(present_idx, None).indices(n)
+        if hi <= lo:
+            raise ValueError('need at least one array to concatenate')
+        first = self._fids[0]
+        pcs = {'pc_present': DeviceWindow(self.cloud, first + lo, first + hi, origin)}
+        trajs = {'ego_traj_present': np.concatenate([self.poses[:present_idx]]) - origin,
+                 'other_trajs_present': [np.concatenate([t]) - origin
+                                         for t in (other_trajs[0] if other_trajs else [])]}
+        if gt_lanes is not None:
+            trajs['gt_lanes'] = [lane - origin for lane in gt_lanes]
+        if gen_future:
+            if fhi <= flo:
+                raise ValueError('need at least one array to concatenate')
+            pcs['pc_future'] = DeviceWindow(self.cloud, first + flo, first + fhi, origin)
+            pcs['pc_full'] = DeviceWindow(self.cloud, first, first + n, origin)
+            trajs['ego_traj_future'] = np.concatenate([self.poses[present_idx:]]) - origin
+            trajs['ego_traj_full'] = np.concatenate([self.poses]) - origin
+            trajs['other_trajs_future'] = [np.concatenate([t]) - origin
+                                           for t in (other_trajs[1] if other_trajs else [])]
+            trajs['other_trajs_full'] = [np.concatenate([t]) - origin
+                                         for t in (other_trajs[2] if other_trajs else [])]
+        else:
+            pcs['pc_future'] = pcs['pc_full'] = None
+            for k in ('ego_traj_future', 'other_trajs_future', 'ego_traj_full',
+                      'other_trajs_full'):
+                trajs[k] = None
+        return pcs, trajs
+
+    def _generate(self, pcs, trajs, bev_num):
+        self._sync()
+        gen = self.sem_bev_generator
+        if bev_num == 1:
+            return [gen.generate_multiproc((pcs, trajs))]
+        # bev_num variants of the same sample: one batched launch instead of the
+        # reference's Pool(processes=bev_num) (kitti360_sem_pc_accum.py:236-241)
+        if gen.do_aug:
+            saved = gen.rng
+            if saved is None:       # one stream for the whole batch, seeded like the reference
+                gen.rng = np.random.RandomState((os.getpid() * int(time.time())) % 123456789)
+            augs = [gen.rand_aug_params() for _ in range(bev_num)]
+            gen.rng = saved
+        else:
+            augs = [dict(do_warping=False) for _ in range(bev_num)]
+        return gen.generate_batch(pcs, trajs, augs)

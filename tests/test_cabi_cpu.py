@@ -1,0 +1,114 @@
+"""CPU-side checks of the boundary: libpcacc.so loads, exports every symbol
+include/pcacc.h declares, refuses to run without a GPU; the host logic of the
+Python mirror (trajectories, heading, eviction bookkeeping) matches the golden
+outputs of the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, load_golden, unpack_bev
+from tests.golden import cases
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, 'include', 'pcacc.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(pcacc_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pc_accumulation_lib_b200 import _lib
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/pcacc.h but not exported'
+        assert n in _lib.SIGNATURES, f'{n} has no ctypes signature'
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.pcacc_abi_version() == 1
+    assert lib.pcacc_strerror(-3) == b'ring or frame table capacity exceeded'
+
+
+def test_bev_params_struct_layout_matches_header():
+    from pc_accumulation_lib_b200._lib import BevParams
+    # 3 int64 + 20 doubles + 6 int32 = 24 + 160 + 24 (static_assert'ed in raster.cu too)
+    assert C.sizeof(BevParams) == 208
+    assert BevParams.origin.offset == 24 and BevParams.R.offset == 48
+    assert BevParams.road_cls.offset == 184 and BevParams.elevation_max.offset == 204
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from pc_accumulation_lib_b200 import _lib
+    from pc_accumulation_lib_b200.device import DeviceCloud
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.pcacc_create(0, 1000, 8, C.byref(h)) == _lib.ERR_CUDA
+    assert b'no CPU fallback' in lib.pcacc_last_error(None)
+    with pytest.raises(_lib.PcaccError):
+        DeviceCloud(1000, 8)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may import,
+    link or execute it (bench.py's cpu_baseline legs are the only other user)."""
+    pkg = os.path.join(ROOT, 'pc_accumulation_lib_b200')
+    bad = re.compile(r'^\s*(from|import)\s+oracle\b|oracle[/.]oracle|liboracle|oracle/', re.M)
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', 'Makefile')):
+                txt = open(os.path.join(dp, f)).read()
+                assert not bad.search(txt), os.path.join(dp, f)
+
+
+def _gen():
+    from pc_accumulation_lib_b200.bev_generator import SemBEVGenerator
+    return SemBEVGenerator
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bev_direct.npz', {}),
+    ('bev_direct_p128.npz', dict(n=20000, seed=78, P=128, view=51.2)),
+])
+def test_host_trajectory_path_matches_reference(name, kw):
+    g = load_golden(name)
+    pcs, trajs, aug, gen = cases.bev_direct_inputs(**kw)
+    bg = _gen()(gen['sem_idxs'], gen['view_size'], gen['pixel_size'], 0., 0., False,
+                gen['int_scaler'], gen['int_sep_scaler'], gen['int_mid_threshold'],
+                gen['height_filter'], gen['rgb_fill'])
+    for prefix, a in (('bev_', aug), ('bevhead_', None)):
+        want = unpack_bev(g, prefix)
+        if a is None:
+            rot = bg.heading_angle(trajs['ego_traj_present'])
+            dx = dy = 0.
+            view = gen['view_size']
+        else:
+            rot, dx, dy = a['rot_ang'], a['trans_dx'], a['trans_dy']
+            view = a['zoom_scalar'] * gen['view_size']
+        for w in ('present', 'future', 'full'):
+            tr = [trajs[f'ego_traj_{w}']] + list(trajs[f'other_trajs_{w}'])
+            got = bg.preprocess_trajs([t.copy() for t in tr], rot, dx, dy, view)
+            assert len(got) == len(want[f'trajs_{w}'])
+            for x, y in zip(got, want[f'trajs_{w}']):
+                np.testing.assert_array_equal(np.asarray(x).reshape(-1, 3),
+                                              np.asarray(y).reshape(-1, 3))
+
+
+def test_rand_aug_is_injectable_and_ordered_like_the_reference():
+    bg = _gen()({'road': 0, 'car': 13, 'truck': 14, 'bus': 15, 'motorcycle': 17}, 80, 64,
+                max_trans_radius=5., zoom_thresh=0.1)
+    assert bg.do_aug
+    bg.rng = np.random.RandomState(7)
+    a = bg.rand_aug_params()
+    r = np.random.RandomState(7)
+    rot = 2 * np.pi * r.random_sample()
+    tr = 5. * r.random_sample()
+    ta = 2 * np.pi * r.random_sample()
+    z = min(max(r.normal(0, 0.1), -0.1), 0.1)
+    assert a['rot_ang'] == rot and a['trans_dx'] == tr * np.cos(ta)
+    assert a['trans_dy'] == tr * np.sin(ta) and a['zoom_scalar'] == 1 + z

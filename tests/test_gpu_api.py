@@ -1,0 +1,204 @@
+"""The drop-in Python API (same class / method names as the reference) against
+the golden outputs the UNMODIFIED reference produced for the same seeded inputs
+(tests/golden/make_golden.py).  These read like a test of the reference itself:
+construct the accumulator, integrate(), generate_bev(), compare the dict.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from pc_accumulation_lib_b200 import synth                                     # noqa: E402
+from tests.conftest import assert_bev_equal, load_golden, unpack_bev, unpack_sem_pcs  # noqa: E402
+from tests.golden import cases                                                 # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _kitti_acc(horizon, P, semseg, use_gt_sem, **kw):
+    from pc_accumulation_lib_b200 import Kitti360SemanticPointCloudAccumulator
+    return Kitti360SemanticPointCloudAccumulator(
+        horizon, synth.kitti_calib(), 1.0, semseg, synth.KITTI_FILTERS, synth.SEM_IDXS,
+        use_gt_sem, synth.kitti_bev_params(pixel_size=P), ring_capacity_pts=400_000,
+        ring_max_frames=64, **kw)
+
+
+@pytest.mark.parametrize('eager', [False, True])
+@pytest.mark.parametrize('name,kw,gt', [
+    ('kitti_seq.npz', dict(n_frames=9), False),
+    ('kitti_seq_p256.npz', dict(n_frames=6), False),
+    ('kitti_gtsem_seq.npz', dict(n_frames=5, n_beams=8, n_azimuth=300, config=3), True),
+])
+def test_kitti_accumulator_matches_reference(name, kw, gt, eager):
+    g = load_golden(name)
+    frames = cases.kitti_seq_inputs(use_gt_sem=gt, **kw)
+    sem = None if gt else synth.FakeSemseg([f['cls'] for f in frames])
+    acc = _kitti_acc(float(g['horizon']), int(g['P']), sem, gt)
+    acc.eager_rebase = eager
+    evicted, n_kept = [], []
+    for fr in frames:
+        evicted.append(acc.integrate([(fr['rgb'], fr['pc'], fr['sem_gt'], fr['T'])]))
+        n_kept.append(acc.sem_pcs[-1].shape[0])
+    np.testing.assert_array_equal(evicted, g['evicted'])
+    np.testing.assert_array_equal(n_kept, g['n_kept'])
+    np.testing.assert_array_equal(np.array(acc.poses), g['poses'])
+    np.testing.assert_array_equal(np.array(acc.seg_dists), g['seg_dists'])
+    want = unpack_sem_pcs(g)
+    assert len(acc.sem_pcs) == len(want)
+    for a, b in zip(acc.sem_pcs, want):
+        np.testing.assert_array_equal(a, b)          # (M,10) float64 records, bit-exact
+    bev = acc.generate_bev(int(g['present_idx']), 1, True)[0]
+    assert_bev_equal(bev, unpack_bev(g), exact=False)   # fp16 planes <= 1 ulp, trajs exact
+    for w in ('present', 'future', 'full'):             # index-derived planes: bit-equal
+        for k in ('road', 'rgb', 'dynamic'):
+            np.testing.assert_array_equal(bev[f'{k}_{w}'], unpack_bev(g)[f'{k}_{w}'])
+    # generate_bev must not change the accumulated state
+    for a, b in zip(acc.sem_pcs, want):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_kitti_pose_source_and_errors():
+    frames = cases.kitti_seq_inputs(n_frames=3)
+    sem = synth.FakeSemseg([f['cls'] for f in frames])
+    acc = _kitti_acc(1e9, 32, sem, False)
+    with pytest.raises(NotImplementedError):          # no ICP here: the pose is an input
+        acc.integrate([(frames[0]['rgb'], frames[0]['pc'], None)])
+    acc.pose_source = iter([f['T'] for f in frames])
+    for fr in frames:
+        acc.integrate([(fr['rgb'], fr['pc'], None)])
+    assert len(acc.poses) == 3
+    with pytest.raises(UnboundLocalError):            # reference: bev_generator.py:111-123
+        acc.generate_bev(1, 1, False)
+    with pytest.raises(ValueError):                   # np.concatenate([]) in the reference
+        acc.generate_bev(0, 1, True)
+    with pytest.raises(NotImplementedError):
+        from pc_accumulation_lib_b200 import Kitti360SemanticPointCloudAccumulator
+        bp = synth.kitti_bev_params(pixel_size=32)
+        bp['type'] = 'rgb'
+        Kitti360SemanticPointCloudAccumulator(1e9, synth.kitti_calib(), 1., sem,
+                                              synth.KITTI_FILTERS, synth.SEM_IDXS, False, bp)
+    # bev_num > 1: a batch of identical heading-aligned BEVs (no augmentation configured)
+    bevs = acc.generate_bev(2, 3, True)
+    assert len(bevs) == 3
+    for b in bevs[1:]:
+        np.testing.assert_array_equal(b['rgb_full'], bevs[0]['rgb_full'])
+
+
+def test_kitti_helpers_match_reference():
+    g = load_golden('kitti_project.npz')
+    inp = cases.kitti_project_inputs()
+    acc = _kitti_acc(1e9, 32, None, True)
+    pc5 = np.concatenate([inp['pc'], np.arange(inp['pc'].shape[0], dtype=np.float32)[:, None]], 1)
+    img = acc.velo2img(pc5, inp['P'], synth.KITTI_IMG_H, synth.KITTI_IMG_W)
+    np.testing.assert_array_equal(img[:, 4].astype(np.int32), g['kept_idx'])
+    np.testing.assert_array_equal(img[:, 5].astype(np.int32), g['u'])
+    np.testing.assert_array_equal(img[:, 6].astype(np.int32), g['v'])
+    sem = acc.gen_semantic_pc(inp['pc'], inp['cls'][..., None], inp['P'])
+    np.testing.assert_array_equal(sem[:, 4], g['gather_cls'])
+    kept = acc.filter_semseg_pc(np.concatenate([sem, sem[:, -1:]], axis=1))
+    assert not np.isin(kept[:, -1], synth.KITTI_FILTERS).any()
+    assert kept.shape[0] == (~np.isin(sem[:, -1], synth.KITTI_FILTERS)).sum()
+
+
+def test_nuscenes_oracle_accumulator_matches_reference():
+    from pc_accumulation_lib_b200 import NuScenesOracleSemanticPointCloudAccumulator
+    g = load_golden('nusc_seq.npz')
+    scene = cases.nusc_seq_inputs()
+    semseg = synth.SceneSemseg()
+    for o in scene:
+        semseg.register(o)
+    acc = NuScenesOracleSemanticPointCloudAccumulator(
+        semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None,
+        synth.nusc_bev_params(pixel_size=int(g['P'])), ring_capacity_pts=400_000,
+        ring_max_frames=64)
+    for o in scene:
+        assert acc.integrate([o]) is None
+    np.testing.assert_array_equal(np.array(acc.poses), g['poses'])
+    np.testing.assert_array_equal(np.array(acc.seg_dists), g['seg_dists'])
+    assert list(g['dyn_instances']) == acc.dyn_instances
+    want = unpack_sem_pcs(g)
+    for a, b in zip(acc.sem_pcs, want):
+        np.testing.assert_array_equal(a, b)          # incl. retroactive dyn flags
+    bev = acc.generate_bev(int(g['present_idx']), 1, True)[0]
+    assert_bev_equal(bev, unpack_bev(g), exact=False)
+    assert len(bev['trajs_full']) > 1                 # ego + dynamic objects
+    assert acc.ego_global_xs[0] == scene[0]['ego_global_x']
+    # uv outside the image: the reference asserts in pts_feat_from_img
+    bad = dict(scene[0])
+    bad['pc'] = scene[0]['pc'].copy()
+    k = np.flatnonzero(bad['pc_cam_idx'] == 0)[0]
+    bad['pc'][k, 4] = 0.5
+    with pytest.raises(AssertionError):
+        acc.integrate([bad])
+    with pytest.raises(NotImplementedError):
+        NuScenesOracleSemanticPointCloudAccumulator(
+            semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, True, synth.nusc_bev_params())
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bev_direct.npz', {}),
+    ('bev_direct_p128.npz', dict(n=20000, seed=78, P=128, view=51.2)),
+])
+def test_sem_bev_generator_on_host_clouds(name, kw):
+    """BEVGenerator.generate(pcs, trajs, ...) handed numpy clouds, as the
+    reference's callers do."""
+    from pc_accumulation_lib_b200 import SemBEVGenerator
+    g = load_golden(name)
+    pcs, trajs, aug, gen = cases.bev_direct_inputs(**kw)
+    bg = SemBEVGenerator(gen['sem_idxs'], gen['view_size'], gen['pixel_size'], 0., 0., False,
+                         gen['int_scaler'], gen['int_sep_scaler'], gen['int_mid_threshold'],
+                         gen['height_filter'], gen['rgb_fill'])
+    bev = bg.generate(*cases.copy_pcs_trajs(pcs, trajs), **aug)
+    assert_bev_equal(bev, unpack_bev(g, 'bev_'), exact=False)
+    bev = bg.generate(*cases.copy_pcs_trajs(pcs, trajs))
+    assert_bev_equal(bev, unpack_bev(g, 'bevhead_'), exact=False)
+    assert bev['rgb_present'].shape == (3, gen['pixel_size'], gen['pixel_size'])
+    assert bev['road_full'].dtype == np.float16
+    # generate_bev() on pre-gridded clouds (reference: sem_bev.py:36-262)
+    want = unpack_bev(g, 'bev_')
+    P = gen['pixel_size']
+    grids = {}
+    for w in ('present', 'future', 'full'):
+        ij, z = g[f'grid_ij_{w}'], g[f'grid_z_{w}']
+        # rebuild the pre-processed cloud: grid xy, transformed z, untouched attributes
+        from oracle import oracle as orc
+        pre = orc.preprocess_pc(pcs[f'pc_{w}'], orc.rotation_matrix_3d(aug['rot_ang']),
+                                aug['trans_dx'], aug['trans_dy'],
+                                aug['zoom_scalar'] * gen['view_size'], P, gen['height_filter'])
+        np.testing.assert_array_equal(pre[:, :2].astype(np.int32), ij)
+        grids[w] = pre
+    bev2 = bg.generate_bev(grids['present'], grids['future'], grids['full'], want['trajs_present'],
+                           want['trajs_future'], want['trajs_full'])
+    assert_bev_equal(bev2, want, exact=False)
+
+
+def test_rgb_bev_generator():
+    from pc_accumulation_lib_b200 import RGBBEVGenerator
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    P = 32
+    def cloud(n):
+        pc = np.zeros((n, 7))
+        pc[:, 0:2] = rng.integers(0, P, (n, 2))
+        pc[:, 2] = rng.normal(0, 1, n)
+        pc[:, 4:7] = rng.integers(0, 256, (n, 3))
+        return pc
+    a, b = cloud(3000), cloud(1500)
+    bg = RGBBEVGenerator(40., P, rgb_fill=0)
+    out = bg.generate_bev(a, b, np.zeros((3, 3)), np.ones((2, 3)))
+    assert set(out) == {'rgb_present', 'rgb_future', 'poses_present', 'poses_future'}
+    for key, pc in (('rgb_present', a), ('rgb_future', b)):
+        cell = (P - 1 - pc[:, 1].astype(int)) * P + pc[:, 0].astype(int)
+        for ch in range(3):
+            med = orc._segment_median(cell, pc[:, 4 + ch], P * P)
+            med[np.isnan(med)] = 0
+            want = (med / 255.).reshape(P, P).astype(np.float16)
+            np.testing.assert_array_equal(out[key][ch], want)
+
+
+def test_missing_cuda_or_library_fails_loudly(monkeypatch):
+    from pc_accumulation_lib_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libpcacc.so')
+    with pytest.raises(ImportError):
+        _lib.load()
