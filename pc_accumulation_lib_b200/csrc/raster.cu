@@ -66,47 +66,63 @@ struct Eval {
     double z;
 };
 
-// one point, one variant: bev_generator.py:224-255,737-747 on (px,py,pz) that is
-// already in the accumulator's current frame
+// One point, one variant: bev_generator.py:224-255,737-747 on a point that is already in
+// the accumulator's current frame.  (px, py) are always known; pz is fetched through
+// `zload` only when it is needed: always if the rotation mixes z into x / y (never for
+// rotation_matrix_3d) and otherwise only for points that pass the x / y crop.
+// want_near: also report whether the point lies within GUARD_M of any decision boundary.
+template <typename ZLoad>
 __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, double px, double py,
-                                           double pz, bool want_near) {
+                                           ZLoad zload, bool want_near) {
     Eval e;
     e.keep = false;
     e.near = false;
     e.cell = -1;
+    e.z = 0.0;
+    const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
     // origin shift: one subtract per component (kitti360_sem_pc_accum.py:193)
-    double sx = __dsub_rn(px, bp.origin[0]);
-    double sy = __dsub_rn(py, bp.origin[1]);
-    double sz = __dsub_rn(pz, bp.origin[2]);
-    // rotation: FMA chain over k = 0..2 (strided 3x3 dgemm, bev_generator.py:227)
-    double q0 = __fma_rn(bp.R[2], sz, __fma_rn(bp.R[1], sy, __dmul_rn(bp.R[0], sx)));
-    double q1 = __fma_rn(bp.R[5], sz, __fma_rn(bp.R[4], sy, __dmul_rn(bp.R[3], sx)));
-    double q2 = __fma_rn(bp.R[8], sz, __fma_rn(bp.R[7], sy, __dmul_rn(bp.R[6], sx)));
+    const double sx = __dsub_rn(px, bp.origin[0]);
+    const double sy = __dsub_rn(py, bp.origin[1]);
+    double sz = 0.0;
+    if (!zfree) sz = __dsub_rn(zload(), bp.origin[2]);
+    // rotation: FMA chain over k = 0..2 (strided 3x3 dgemm, bev_generator.py:227);
+    // a zero coefficient contributes exactly nothing for finite z, so that link is skipped
+    double q0 = __fma_rn(bp.R[1], sy, __dmul_rn(bp.R[0], sx));
+    double q1 = __fma_rn(bp.R[4], sy, __dmul_rn(bp.R[3], sx));
+    if (!zfree) {
+        q0 = __fma_rn(bp.R[2], sz, q0);
+        q1 = __fma_rn(bp.R[5], sz, q1);
+    }
     q0 = __dadd_rn(q0, bp.trans_dx);
     q1 = __dadd_rn(q1, bp.trans_dy);
-    e.z = q2;
     const double hv = __dmul_rn(0.5, bp.view);
     bool in = (q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv);
-    bool hf_on = (bp.height_filter == bp.height_filter);
-    if (hf_on) in = in && (q2 < bp.height_filter);
-    double g0 = 0, g1 = 0;
-    const double dP = (double)P, hP = __dmul_rn(0.5, dP);
-    if (in || want_near) {
-        g0 = __dadd_rn(__dmul_rn(__ddiv_rn(q0, bp.view), dP), hP);
-        g1 = __dadd_rn(__dmul_rn(__ddiv_rn(q1, bp.view), dP), hP);
+    const bool cand = want_near ? ((fabs(q0) < hv + GUARD_M) && (fabs(q1) < hv + GUARD_M)) : in;
+    if (!cand) return e;
+    if (zfree) {
+        const double pz = zload();
+        // a non-finite z poisons x and y in the reference (0 * inf = NaN): the point is dropped
+        if (!(fabs(pz) <= 1.7976931348623157e308)) return e;
+        sz = __dsub_rn(pz, bp.origin[2]);
     }
+    const double q2 = __fma_rn(bp.R[8], sz, __fma_rn(bp.R[7], sy, __dmul_rn(bp.R[6], sx)));
+    e.z = q2;
+    const bool hf_on = (bp.height_filter == bp.height_filter);
+    if (hf_on) in = in && (q2 < bp.height_filter);
+    const double dP = (double)P, hP = __dmul_rn(0.5, dP);
+    const double g0 = __dadd_rn(__dmul_rn(__ddiv_rn(q0, bp.view), dP), hP);
+    const double g1 = __dadd_rn(__dmul_rn(__ddiv_rn(q1, bp.view), dP), hP);
     if (want_near) {
         const double eg = GUARD_M * dP / bp.view;
         bool n = (fabs(fabs(q0) - hv) < GUARD_M) || (fabs(fabs(q1) - hv) < GUARD_M);
         if (hf_on) n = n || (fabs(q2 - bp.height_filter) < GUARD_M);
         n = n || (fabs(g0 - rint(g0)) < eg) || (fabs(g1 - rint(g1)) < eg);
-        // only points that are, or could become, part of the view matter
-        e.near = n && (fabs(q0) < hv + GUARD_M) && (fabs(q1) < hv + GUARD_M);
+        e.near = n;
     }
     if (in) {
-        double fi = floor(g0), fj = floor(g1);
+        const double fi = floor(g0), fj = floor(g1);
         if (fi >= 0.0 && fi < dP && fj >= 0.0 && fj < dP) {
-            int i = (int)fi, j = (int)fj;
+            const int i = (int)fi, j = (int)fj;
             e.cell = (P - 1 - j) * P + i;  // row = P-1-j, col = i (bev_generator.py:453)
             e.keep = true;
         }
@@ -114,7 +130,7 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
     return e;
 }
 
-__global__ void __launch_bounds__(BIN_BLOCK)
+__global__ void __launch_bounds__(BIN_BLOCK, 2)
 k_bev_bin(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ double s_comp[12];
@@ -143,26 +159,35 @@ k_bev_bin(BinArgs a) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = a.P * a.P;
 
-    // load this thread's points once; they are reused by every variant
-    double sx[BIN_ITEMS], sy[BIN_ITEMS], sz[BIN_ITEMS];   // source-frame coordinates
-    double px[BIN_ITEMS], py[BIN_ITEMS], pz[BIN_ITEMS];   // current-frame coordinates
+    // This thread's points: two pairs of neighbours (16 B loads; frame offsets are
+    // multiples of 4 records, so the pairs are aligned).  x and y are always needed; z
+    // only up front when the frame is lazily re-based (the composed matrix mixes it in).
+    int64_t idx[BIN_ITEMS];
+    double px[BIN_ITEMS], py[BIN_ITEMS], pz[BIN_ITEMS];
     bool valid[BIN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < BIN_ITEMS; k++) {
-        int64_t i = tile0 + k * BIN_BLOCK + threadIdx.x;
-        valid[k] = i < cnt;
-        if (valid[k]) {
-            sx[k] = a.ring.x[off + i];
-            sy[k] = a.ring.y[off + i];
-            sz[k] = a.ring.z[off + i];
-        } else {
-            sx[k] = sy[k] = sz[k] = 0.0;
+    for (int h = 0; h < BIN_ITEMS / 2; h++) {
+        const int64_t i0 = tile0 + (int64_t)h * (2 * BIN_BLOCK) + 2 * threadIdx.x;
+        idx[2 * h] = i0;
+        idx[2 * h + 1] = i0 + 1;
+        valid[2 * h] = i0 < cnt;
+        valid[2 * h + 1] = i0 + 1 < cnt;
+        double2 X = make_double2(0, 0), Y = make_double2(0, 0), Z = make_double2(0, 0);
+        if (valid[2 * h]) {
+            X = *(const double2 *)(a.ring.x + off + i0);
+            Y = *(const double2 *)(a.ring.y + off + i0);
+            if (lazy) Z = *(const double2 *)(a.ring.z + off + i0);
         }
-        if (lazy) affine_chain(s_comp, 4, sx[k], sy[k], sz[k], px[k], py[k], pz[k]);
-        else {
-            px[k] = sx[k];
-            py[k] = sy[k];
-            pz[k] = sz[k];
+        px[2 * h] = X.x; px[2 * h + 1] = X.y;
+        py[2 * h] = Y.x; py[2 * h + 1] = Y.y;
+        pz[2 * h] = Z.x; pz[2 * h + 1] = Z.y;
+    }
+    if (lazy) {
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; k++) {
+            double nx, ny, nz;
+            affine_chain(s_comp, 4, px[k], py[k], pz[k], nx, ny, nz);
+            px[k] = nx; py[k] = ny; pz[k] = nz;
         }
     }
 
@@ -181,25 +206,30 @@ k_bev_bin(BinArgs a) {
             key[k] = 0;
             rank[k] = 0;
             rec[k] = make_uint4(0, 0, 0, 0);
-            int64_t i = tile0 + k * BIN_BLOCK + threadIdx.x;
             if (valid[k]) {
-                Eval e = eval_point(bp, a.P, px[k], py[k], pz[k], lazy);
-                if (lazy && e.near) {
-                    // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
-                    double ex = sx[k], ey = sy[k], ez = sz[k];
-                    for (int64_t ep = e0; ep < a.epoch_now; ep++) {
-                        const double *T = a.chain + (ep % a.max_frames) * 12;
-                        double nx, ny, nz;
-                        affine_chain(T, 4, ex, ey, ez, nx, ny, nz);
-                        ex = nx;
-                        ey = ny;
-                        ez = nz;
+                const int64_t gi = off + idx[k];
+                Eval e;
+                if (lazy) {
+                    const double zk = pz[k];
+                    e = eval_point(bp, a.P, px[k], py[k], [zk]() { return zk; }, true);
+                    if (e.near) {
+                        // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
+                        double ex = a.ring.x[gi], ey = a.ring.y[gi], ez = a.ring.z[gi];
+                        for (int64_t ep = e0; ep < a.epoch_now; ep++) {
+                            const double *T = a.chain + (ep % a.max_frames) * 12;
+                            double nx, ny, nz;
+                            affine_chain(T, 4, ex, ey, ez, nx, ny, nz);
+                            ex = nx; ey = ny; ez = nz;
+                        }
+                        e = eval_point(bp, a.P, ex, ey, [ez]() { return ez; }, false);
+                        atomicAdd(a.n_replay, 1ull);
                     }
-                    e = eval_point(bp, a.P, ex, ey, ez, false);
-                    atomicAdd(a.n_replay, 1ull);
+                } else {
+                    const double *zp = a.ring.z + gi;
+                    e = eval_point(bp, a.P, px[k], py[k], [zp]() { return *zp; }, false);
                 }
-                if (e.keep && a.ring.dyn[off + i] == 1) e.keep = false;  // static points only
-                if (a.dbg_cell && v == 0) a.dbg_cell[off + i] = e.keep ? e.cell : -1;
+                if (e.keep && a.ring.dyn[gi] == 1) e.keep = false;  // static points only
+                if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
                 if (e.keep) {
                     keep[k] = true;
                     key[k] = ((uint32_t)v * (uint32_t)PP + (uint32_t)e.cell) * 2u + win;
@@ -207,8 +237,8 @@ k_bev_bin(BinArgs a) {
                     unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
                     rec[k].x = (uint32_t)zb;
                     rec[k].y = (uint32_t)(zb >> 32);
-                    rec[k].z = a.ring.rgbs[off + i];
-                    rec[k].w = __float_as_uint(a.ring.inten[off + i]);
+                    rec[k].z = a.ring.rgbs[gi];
+                    rec[k].w = __float_as_uint(a.ring.inten[gi]);
                     my_cnt++;
                 }
             }
@@ -340,13 +370,6 @@ k_bev_scatter(const uint32_t *__restrict__ start, const uint32_t *__restrict__ t
 // ---------------------------------------------------------------------------
 // per-cell reduction + finalisation
 // ---------------------------------------------------------------------------
-struct CellStats {
-    uint32_t n[2], n_road[2], n_veh[2];
-    long long fx_hi[2], fx_lo[2];  // intensity sum of road points, 2^-40 fixed point, split at 2^32
-    double ext_z[2];               // min (or max) z
-    int med2[3][3];                // [window p/f/full][channel]: twice the median
-};
-
 #define FX_SCALE 1099511627776.0        /* 2^40 */
 #define FX_INV 9.094947017729282e-13    /* 2^-40 */
 
@@ -375,12 +398,60 @@ __device__ __forceinline__ int hist_kth(const uint32_t c[8], uint32_t excl, uint
     return __shfl_sync(0xffffffffu, bin, __ffs(m) - 1);
 }
 
+// Accumulates one record into the per-window statistics (everything except the medians).
+struct WinAcc {
+    uint32_t n_road[2], n_veh[2];
+    long long fx_hi[2], fx_lo[2];
+    double ext_z[2];
+};
+
+__device__ __forceinline__ void acc_record(WinAcc &a, const uint4 &r, int w, const pcacc_bev_params &bp,
+                                           double intensity_div, bool want_max) {
+    const double z = __longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x));
+    const int sem = (int)(r.z >> 24);
+    const bool road = sem == bp.road_cls;
+    const bool veh = (sem == bp.veh_cls[0]) || (sem == bp.veh_cls[1]) || (sem == bp.veh_cls[2]) ||
+                     (sem == bp.veh_cls[3]);
+    if (road) {
+        double iv = __ddiv_rn((double)__uint_as_float(r.w), intensity_div);
+        long long fx = __double2ll_rn(__dmul_rn(iv, FX_SCALE));
+        a.fx_hi[w] += fx >> 32;
+        a.fx_lo[w] += fx & 0xffffffffll;
+        a.n_road[w]++;
+    }
+    if (veh) a.n_veh[w]++;
+    a.ext_z[w] = want_max ? fmax(a.ext_z[w], z) : fmin(a.ext_z[w], z);
+}
+
+// 7 planes of one window from its statistics (bev_generator.py:396-415,457-480;
+// sem_bev.py:593-617,665-667)
+__device__ __forceinline__ void finalise_window(const pcacc_bev_params &bp, double n, double n_road,
+                                                double n_veh, double isum, double ez, const int med2[3],
+                                                double plane[7]) {
+    double a = __dadd_rn(n_road, 1.0), b = __dadd_rn(__dsub_rn(n, n_road), 1.0);
+    plane[0] = __ddiv_rn(a, __dadd_rn(a, b));
+    double c = __dadd_rn(n_veh, 1.0), d = __dadd_rn(__dsub_rn(n, n_veh), 1.0);
+    plane[5] = __ddiv_rn(c, __dadd_rn(c, d));
+    double I = __ddiv_rn(isum, __dadd_rn(n_road, 1.0));
+    double t = __dmul_rn(bp.int_sep_scaler, __dsub_rn(I, bp.int_mid_threshold));
+    double sg = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-t)));
+    double val = __dmul_rn(bp.int_scaler, sg);
+    plane[1] = val > 1.0 ? 1.0 : val;
+#pragma unroll
+    for (int k = 0; k < 3; k++) plane[2 + k] = __ddiv_rn(__dmul_rn((double)med2[k], 0.5), 255.0);
+    plane[6] = ez;
+}
+
+#define SMALL_T 16      /* cells with <= SMALL_T points are reduced by their own lane */
+#define SMALL_STRIDE 17 /* odd stride: lanes reading the same j hit distinct banks */
+
 template <bool F64OUT>
 __global__ void __launch_bounds__(RED_WARPS * 32)
 k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
              const pcacc_bev_params *__restrict__ params, int n_var, int P, double intensity_div,
              __half *__restrict__ out16, double *__restrict__ out64) {
     __shared__ __align__(16) uint32_t s_hist[RED_WARPS][2][3][256];
+    __shared__ uint32_t s_small[RED_WARPS][32 * SMALL_STRIDE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
     const int64_t n_cells = (int64_t)n_var * PP;
@@ -389,31 +460,87 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     if (cell0 >= n_cells) return;
     const int var = (int)(cell0 / PP);
     const int cell_in = (int)(cell0 - (int64_t)var * PP) + (int)lane;
-    const pcacc_bev_params bp = params[var];
+    const pcacc_bev_params &bp = params[var];
     uint32_t(*hist)[3][256] = s_hist[warp];
+    const bool want_max = bp.elevation_max != 0;
 
     // segment bounds of my cell: [s0, s1) present, [s1, s2) future
     const int64_t gc = cell0 + lane;
-    uint2 s01 = ((const uint2 *)start)[gc];
+    const uint2 s01 = ((const uint2 *)start)[gc];
     uint32_t s2 = __shfl_down_sync(0xffffffffu, s01.x, 1);
     if (lane == 31) s2 = start[2 * gc + 2];
-    const uint32_t my_np = s01.y - s01.x, my_nf = s2 - s01.y;
+    const uint32_t my_np = s01.y - s01.x, my_nf = s2 - s01.y, my_nt = my_np + my_nf;
 
-    CellStats st;
-    st.n[0] = my_np;
-    st.n[1] = my_nf;
+    WinAcc st;
 #pragma unroll
     for (int w = 0; w < 2; w++) {
         st.n_road[w] = st.n_veh[w] = 0;
         st.fx_hi[w] = st.fx_lo[w] = 0;
-        st.ext_z[w] = 0.0;
+        st.ext_z[w] = want_max ? -INFINITY : INFINITY;
     }
+    int med2[3][3];
 #pragma unroll
     for (int w = 0; w < 3; w++)
-        for (int c = 0; c < 3; c++) st.med2[w][c] = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) med2[w][c] = 0;
 
-    const bool want_max = bp.elevation_max != 0;
-    unsigned todo = __ballot_sync(0xffffffffu, (my_np + my_nf) > 0);
+    // ---- small cells: each lane reduces its own cell ---------------------------------
+    if (my_nt > 0 && my_nt <= SMALL_T) {
+        uint32_t *mine = s_small[warp] + lane * SMALL_STRIDE;
+        for (uint32_t i = 0; i < my_nt; i++) {
+            const uint4 r = sorted[s01.x + i];
+            mine[i] = r.z & 0x00ffffffu;
+            acc_record(st, r, i >= my_np ? 1 : 0, bp, intensity_div, want_max);
+        }
+        // rank of every colour byte inside its window and inside the full cell; ties
+        // broken by position, so ranks are a permutation and rank == k picks the
+        // k-th order statistic.  r, g, b are processed together, one byte lane each.
+        const uint32_t kp_lo = my_np ? (my_np - 1) / 2 * 0x010101u : 0xffffffffu;
+        const uint32_t kp_hi = my_np ? my_np / 2 * 0x010101u : 0xffffffffu;
+        const uint32_t kf_lo = my_nf ? (my_nf - 1) / 2 * 0x010101u : 0xffffffffu;
+        const uint32_t kf_hi = my_nf ? my_nf / 2 * 0x010101u : 0xffffffffu;
+        const uint32_t ka_lo = (my_nt - 1) / 2 * 0x010101u, ka_hi = my_nt / 2 * 0x010101u;
+        uint32_t lo_p = 0, hi_p = 0, lo_f = 0, hi_f = 0, lo_a = 0, hi_a = 0;
+        for (uint32_t i = 0; i < my_nt; i++) {
+            const uint32_t vi = mine[i];
+            const bool wi = i >= my_np;
+            uint32_t rank_w = 0, rank_a = 0;
+            for (uint32_t j = 0; j < my_nt; j++) {
+                const uint32_t vj = mine[j];
+                uint32_t m = __vcmpltu4(vj, vi);
+                if (j < i) m |= __vcmpeq4(vj, vi);
+                m &= 0x00010101u;
+                rank_a += m;
+                if ((j >= my_np) == wi) rank_w += m;
+            }
+            uint32_t m;
+            m = __vcmpeq4(rank_a, ka_lo) & 0x00ffffffu;
+            lo_a = (vi & m) | (lo_a & ~m);
+            m = __vcmpeq4(rank_a, ka_hi) & 0x00ffffffu;
+            hi_a = (vi & m) | (hi_a & ~m);
+            if (wi) {
+                m = __vcmpeq4(rank_w, kf_lo) & 0x00ffffffu;
+                lo_f = (vi & m) | (lo_f & ~m);
+                m = __vcmpeq4(rank_w, kf_hi) & 0x00ffffffu;
+                hi_f = (vi & m) | (hi_f & ~m);
+            } else {
+                m = __vcmpeq4(rank_w, kp_lo) & 0x00ffffffu;
+                lo_p = (vi & m) | (lo_p & ~m);
+                m = __vcmpeq4(rank_w, kp_hi) & 0x00ffffffu;
+                hi_p = (vi & m) | (hi_p & ~m);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            med2[0][c] = (int)((lo_p >> (8 * c)) & 255u) + (int)((hi_p >> (8 * c)) & 255u);
+            med2[1][c] = (int)((lo_f >> (8 * c)) & 255u) + (int)((hi_f >> (8 * c)) & 255u);
+            med2[2][c] = (int)((lo_a >> (8 * c)) & 255u) + (int)((hi_a >> (8 * c)) & 255u);
+        }
+    }
+    __syncwarp();
+
+    // ---- large cells: the whole warp reduces one cell at a time with histograms ---------
+    unsigned todo = __ballot_sync(0xffffffffu, my_nt > SMALL_T);
     while (todo) {
         const int owner = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -421,57 +548,42 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
         const uint32_t np = __shfl_sync(0xffffffffu, my_np, owner);
         const uint32_t nf = __shfl_sync(0xffffffffu, my_nf, owner);
         const uint32_t nt = np + nf;
-
-        // clear the six histograms (1536 words)
         {
             uint4 *h4 = (uint4 *)&hist[0][0][0];
 #pragma unroll
             for (int k = 0; k < 12; k++) h4[lane + 32 * k] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
-
-        uint32_t a_road[2] = {0, 0}, a_veh[2] = {0, 0};
-        long long a_hi[2] = {0, 0}, a_lo[2] = {0, 0};
-        double a_z[2];
-        a_z[0] = a_z[1] = want_max ? -INFINITY : INFINITY;
+        WinAcc a;
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            a.n_road[w] = a.n_veh[w] = 0;
+            a.fx_hi[w] = a.fx_lo[w] = 0;
+            a.ext_z[w] = want_max ? -INFINITY : INFINITY;
+        }
         for (uint32_t i = lane; i < nt; i += 32) {
             const uint4 r = sorted[b0 + i];
             const int w = i >= np ? 1 : 0;
-            const double z =
-                __longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x));
             const uint32_t c = r.z;
-            const int sem = (int)(c >> 24);
             atomicAdd(&hist[w][0][c & 255u], 1u);
             atomicAdd(&hist[w][1][(c >> 8) & 255u], 1u);
             atomicAdd(&hist[w][2][(c >> 16) & 255u], 1u);
-            const bool road = sem == bp.road_cls;
-            const bool veh = (sem == bp.veh_cls[0]) || (sem == bp.veh_cls[1]) ||
-                             (sem == bp.veh_cls[2]) || (sem == bp.veh_cls[3]);
-            if (road) {
-                double iv = __ddiv_rn((double)__uint_as_float(r.w), intensity_div);
-                long long fx = __double2ll_rn(__dmul_rn(iv, FX_SCALE));
-                a_hi[w] += fx >> 32;
-                a_lo[w] += fx & 0xffffffffll;
-                a_road[w]++;
-            }
-            if (veh) a_veh[w]++;
-            a_z[w] = want_max ? fmax(a_z[w], z) : fmin(a_z[w], z);
+            acc_record(a, r, w, bp, intensity_div, want_max);
         }
 #pragma unroll
         for (int w = 0; w < 2; w++) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                a_road[w] += __shfl_xor_sync(0xffffffffu, a_road[w], o);
-                a_veh[w] += __shfl_xor_sync(0xffffffffu, a_veh[w], o);
-                a_hi[w] += __shfl_xor_sync(0xffffffffu, a_hi[w], o);
-                a_lo[w] += __shfl_xor_sync(0xffffffffu, a_lo[w], o);
-                double oz = __shfl_xor_sync(0xffffffffu, a_z[w], o);
-                a_z[w] = want_max ? fmax(a_z[w], oz) : fmin(a_z[w], oz);
+                a.n_road[w] += __shfl_xor_sync(0xffffffffu, a.n_road[w], o);
+                a.n_veh[w] += __shfl_xor_sync(0xffffffffu, a.n_veh[w], o);
+                a.fx_hi[w] += __shfl_xor_sync(0xffffffffu, a.fx_hi[w], o);
+                a.fx_lo[w] += __shfl_xor_sync(0xffffffffu, a.fx_lo[w], o);
+                double oz = __shfl_xor_sync(0xffffffffu, a.ext_z[w], o);
+                a.ext_z[w] = want_max ? fmax(a.ext_z[w], oz) : fmin(a.ext_z[w], oz);
             }
         }
         __syncwarp();
-
-        int med2[3][3];
+        int m2[3][3];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             uint32_t cp[8], cf[8];
@@ -490,84 +602,75 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
 #pragma unroll
                 for (int j = 0; j < 8; j++) c[j] = (w == 0) ? cp[j] : (w == 1) ? cf[j] : cp[j] + cf[j];
                 const uint32_t nw = (w == 0) ? np : (w == 1) ? nf : nt;
-                uint32_t s = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += c[j];
-                uint32_t incl = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= (unsigned)o) incl += t;
-                }
-                int m2 = 0;
+                int v = 0;
                 if (nw > 0) {  // warp-uniform
+                    uint32_t s = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) s += c[j];
+                    uint32_t incl = s;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (unsigned)o) incl += t;
+                    }
                     int lo = hist_kth(c, incl - s, incl, (nw - 1) / 2, lane);
                     int hi = (nw & 1u) ? lo : hist_kth(c, incl - s, incl, nw / 2, lane);
-                    m2 = lo + hi;
+                    v = lo + hi;
                 }
-                med2[w][ch] = m2;
+                m2[w][ch] = v;
             }
         }
         if ((int)lane == owner) {
-#pragma unroll
-            for (int w = 0; w < 2; w++) {
-                st.n_road[w] = a_road[w];
-                st.n_veh[w] = a_veh[w];
-                st.fx_hi[w] = a_hi[w];
-                st.fx_lo[w] = a_lo[w];
-                st.ext_z[w] = a_z[w];
-            }
+            st = a;
 #pragma unroll
             for (int w = 0; w < 3; w++)
-                for (int c = 0; c < 3; c++) st.med2[w][c] = med2[w][c];
+#pragma unroll
+                for (int c = 0; c < 3; c++) med2[w][c] = m2[w][c];
         }
         __syncwarp();
     }
 
-    // ---- finalise my cell: 3 windows x 7 planes ----------------------------
+    // ---- finalise my cell: 3 windows x 7 planes ------------------------------------------
+    // values of a window without any point: computed once per warp, not per cell
+    double empty[7];
+    {
+        double e1 = 0.0;
+        if (lane == 0) {
+            const int zero3[3] = {0, 0, 0};
+            double pl[7];
+            finalise_window(bp, 0.0, 0.0, 0.0, 0.0, 0.0, zero3, pl);
+            e1 = pl[1];
+        }
+        e1 = __shfl_sync(0xffffffffu, e1, 0);
+        empty[0] = 0.5;
+        empty[1] = e1;
+        empty[2] = empty[3] = empty[4] = __ddiv_rn(bp.rgb_fill, 255.0);
+        empty[5] = 0.5;
+        empty[6] = 0.0;
+    }
 #pragma unroll
     for (int w = 0; w < 3; w++) {
-        double n, n_road, n_veh, isum, ez;
-        bool empty;
-        if (w < 2) {
-            n = (double)st.n[w];
-            n_road = (double)st.n_road[w];
-            n_veh = (double)st.n_veh[w];
-            isum = fx_to_double(st.fx_hi[w], st.fx_lo[w]);
-            empty = st.n[w] == 0;
-            ez = empty ? 0.0 : st.ext_z[w];
-        } else {
-            n = (double)(st.n[0] + st.n[1]);
-            n_road = (double)(st.n_road[0] + st.n_road[1]);
-            n_veh = (double)(st.n_veh[0] + st.n_veh[1]);
-            isum = fx_to_double(st.fx_hi[0] + st.fx_hi[1], st.fx_lo[0] + st.fx_lo[1]);
-            empty = (st.n[0] + st.n[1]) == 0;
-            if (st.n[0] == 0) ez = st.n[1] == 0 ? 0.0 : st.ext_z[1];
-            else if (st.n[1] == 0) ez = st.ext_z[0];
-            else ez = want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]);
-        }
         double plane[7];
-        // Dirichlet expectation, uniform prior (bev_generator.py:457-480)
-        {
-            double a = __dadd_rn(n_road, 1.0), b = __dadd_rn(__dsub_rn(n, n_road), 1.0);
-            plane[0] = __ddiv_rn(a, __dadd_rn(a, b));
-            double c = __dadd_rn(n_veh, 1.0), d = __dadd_rn(__dsub_rn(n, n_veh), 1.0);
-            plane[5] = __ddiv_rn(c, __dadd_rn(c, d));
-        }
-        // intensity mean over (count+1) then road_marking_transform (sem_bev.py:593-617)
-        {
-            double I = __ddiv_rn(isum, __dadd_rn(n_road, 1.0));
-            double t = __dmul_rn(bp.int_sep_scaler, __dsub_rn(I, bp.int_mid_threshold));
-            double sg = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-t)));
-            double val = __dmul_rn(bp.int_scaler, sg);
-            plane[1] = val > 1.0 ? 1.0 : val;
-        }
+        const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
+        if (nw == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double med = empty ? bp.rgb_fill : __dmul_rn((double)st.med2[w][c], 0.5);
-            plane[2 + c] = __ddiv_rn(med, 255.0);
+            for (int p = 0; p < 7; p++) plane[p] = empty[p];
+        } else {
+            double n_road, n_veh, isum, ez;
+            if (w < 2) {
+                n_road = (double)st.n_road[w];
+                n_veh = (double)st.n_veh[w];
+                isum = fx_to_double(st.fx_hi[w], st.fx_lo[w]);
+                ez = st.ext_z[w];
+            } else {
+                n_road = (double)(st.n_road[0] + st.n_road[1]);
+                n_veh = (double)(st.n_veh[0] + st.n_veh[1]);
+                isum = fx_to_double(st.fx_hi[0] + st.fx_hi[1], st.fx_lo[0] + st.fx_lo[1]);
+                // the unused side still holds +-inf, the identity of min / max
+                ez = want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]);
+            }
+            finalise_window(bp, (double)nw, n_road, n_veh, isum, ez, med2[w], plane);
         }
-        plane[6] = ez;
         const int64_t o = (((int64_t)var * 3 + w) * 7) * PP + cell_in;
 #pragma unroll
         for (int p = 0; p < 7; p++) {

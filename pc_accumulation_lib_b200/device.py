@@ -98,6 +98,7 @@ class DeviceCloud:
         self.h = h
         self.stage = Stager(self.device)
         self._keep = []      # device tensors that in-flight kernels still read
+        self._mark_f, self._mark_i = [], []   # queued dynamic-flag updates
 
     def close(self):
         if getattr(self, 'h', None) is not None and self.h:
@@ -135,11 +136,13 @@ class DeviceCloud:
 
     # -- lifetime --------------------------------------------------------------
     def reset(self):
+        self._mark_f, self._mark_i = [], []
         self._check(self.lib.pcacc_reset(self.h, _stream()))
 
     def sync(self) -> int:
         """Waits for the stream, refreshes the frame table, returns and clears
         the data-error flags."""
+        self.flush_marks()
         fl = C.c_uint32(0)
         self._check(self.lib.pcacc_sync(self.h, C.byref(fl), _stream()))
         self._keep.clear()
@@ -250,17 +253,30 @@ class DeviceCloud:
         self._check(self.lib.pcacc_evict(self.h, int(n_frames)))
 
     def mark_dynamic(self, frame_ids, inst_idx):
-        fi = np.ascontiguousarray(np.asarray(frame_ids, dtype=np.int64))
-        ii = np.ascontiguousarray(np.asarray(inst_idx, dtype=np.int32))
-        assert fi.size == ii.size
-        if fi.size == 0:
+        """dyn = 1 on the points of frame_ids[k] whose inst == inst_idx[k].  The
+        flags are only read by rasterise / export, so the pairs are queued on the
+        host and written by ONE launch right before the next reader."""
+        assert len(frame_ids) == len(inst_idx)
+        self._mark_f.extend(int(f) for f in frame_ids)
+        self._mark_i.extend(int(i) for i in inst_idx)
+
+    def flush_marks(self):
+        if not self._mark_f:
             return
+        first, n_live = self.live_frames()
+        pairs = [(f, i) for f, i in zip(self._mark_f, self._mark_i) if f >= first]
+        self._mark_f, self._mark_i = [], []
+        if not pairs:
+            return
+        fi = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int64))
+        ii = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int32))
         self._check(self.lib.pcacc_mark_dynamic(self.h, fi.ctypes.data_as(C.c_void_p),
                                                 ii.ctypes.data_as(C.c_void_p), int(fi.size),
                                                 _stream()))
 
     # -- export ----------------------------------------------------------------------
     def export_frame(self, fid: int, to_host=True):
+        self.flush_marks()
         n = self.frame_count(fid)
         out = torch.empty((n, 10), dtype=torch.float64, device=self.device)
         self._check(self.lib.pcacc_export_frame(self.h, int(fid), _ptr(out), _stream()))
@@ -309,6 +325,7 @@ class DeviceCloud:
     def rasterise(self, params, P: int, want_f64=False, want_cells=False, out=None):
         """params: list of BevParams. Returns (planes f16 (V,3,7,P,P) device
         tensor, planes f64 or None, per-ring-position cell index or None)."""
+        self.flush_marks()
         V = len(params)
         arr = (BevParams * V)(*params)
         if out is None:
