@@ -128,6 +128,20 @@ int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const int64_t *cam_
                             const int32_t *filters, int n_filters,
                             int64_t *frame_id, void *stream);
 
+/* The same for n_sweeps observations in ONE launch (offline dataset generation:
+ * all sweeps of a scene are on the device already).  Arrays of n_sweeps host
+ * entries; rgb_maps / sem_maps hold n_sweeps * n_cams device pointers
+ * (sweep-major); T_ego_world holds n_sweeps (4,4) matrices.  Every sweep becomes
+ * its own frame (ids first_frame_id .. +n_sweeps-1), placed at fixed upper-bound
+ * offsets so no sweep waits for another sweep's kept count. */
+int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const double *const *pc_dev,
+                                  const int64_t *const *cam_idx_dev, const int64_t *n,
+                                  const uint8_t *const *rgb_maps, const void *const *sem_maps,
+                                  int n_cams, int sem_dtype, int img_h, int img_w,
+                                  const double *T_ego_world, double intensity_div,
+                                  const int32_t *filters, int n_filters,
+                                  int64_t *first_frame_id, void *stream);
+
 /* Append an already-built (n,10) float64 cloud [x,y,z,i,r,g,b,sem,inst,dyn]
  * as one frame (used by BEVGenerator.generate(pcs, ...) when it is handed host
  * clouds, bev_generator/bev_generator.py:63-125).  Rows are stored unchanged. */

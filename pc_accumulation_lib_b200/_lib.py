@@ -64,6 +64,8 @@ SIGNATURES = {
     'pcacc_integrate_records': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32,
                                        _i32, _i32, _i32, _vp, _dbl, _vp, _i32,
                                        C.POINTER(_i64), _vp]),
+    'pcacc_integrate_records_batch': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
+                                             _i32, _vp, _dbl, _vp, _i32, C.POINTER(_i64), _vp]),
     'pcacc_integrate_cloud': (_i32, [_vp, _vp, _i64, C.POINTER(_i64), _vp]),
     'pcacc_rebase': (_i32, [_vp, _vp, _i32, _vp]),
     'pcacc_evict': (_i32, [_vp, _i32]),

@@ -22,6 +22,7 @@ struct FrameSlots {
     int64_t base_override;  // >= 0: use this ring offset instead of frame_off[slot]
     int64_t epoch;
     int64_t capacity;
+    int write_next;  // 0 inside a batch (the next frame has its own fixed base)
 };
 
 struct Filters {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void finish_frame(const FrameSlots &fs, int64_t base,
     fs.frame_cnt[fs.slot] = (int64_t)total;
     fs.frame_epoch[fs.slot] = fs.epoch;
     int64_t nxt = base + (((int64_t)total + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
-    fs.frame_off[fs.next_slot] = nxt;
+    if (fs.write_next) fs.frame_off[fs.next_slot] = nxt;
     for (int k = 0; k < 12; k++) fs.comp[k] = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
 }
 
@@ -333,6 +334,93 @@ k_integrate_records(const double *__restrict__ pc, const long long *__restrict__
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
+
+// ---------------------------------------------------------------------------
+// batched nuScenes integrate: every sweep of a scene in ONE launch
+// (blockIdx.y = sweep).  Each sweep is still its own frame with its own
+// order-preserving compaction; frames sit at fixed upper-bound offsets so no
+// sweep waits for another sweep's count.
+// ---------------------------------------------------------------------------
+struct SweepDesc {
+    const double *pc;
+    const long long *cam;
+    int64_t n;
+    CamMaps maps;
+    TMat T;
+    FrameSlots fs;
+    uint32_t n_tiles;
+    uint32_t state_off;   // first tile-state word of this sweep
+};
+
+template <int DT>
+__global__ void __launch_bounds__(IBLOCK)
+k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int img_w, Filters filt,
+                          RingDev ring, unsigned long long *__restrict__ state,
+                          uint32_t *__restrict__ tickets, uint32_t epoch,
+                          uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    const SweepDesc &sw = sweeps[blockIdx.y];
+    if (blockIdx.x >= sw.n_tiles) return;
+    uint32_t tile = lb_take_ticket(tickets + blockIdx.y, sw.n_tiles, &s_tile);
+    const int64_t base = sw.fs.base_override;
+    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    double x = 0, y = 0, z = 0, inten = 0, inst_f = 0;
+    uint32_t packed = 0;
+    if (i < sw.n) {
+        long long cam = sw.cam[i];
+        if (cam >= 0 && cam < sw.maps.n) {
+            const double *row = sw.pc + i * 7;
+            double uf = row[4], vf = row[5];
+            bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
+                          (vf < (double)img_h - 1.0);
+            if (!inside) {
+                atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
+            } else {
+                int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
+                int cls = load_class<DT>(sw.maps.sem[cam], pix, 1);
+                keep = (cls >= 0) && !class_filtered(filt, cls);
+                if (keep) {
+                    if (cls > 255) {
+                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                        cls &= 255;
+                    }
+                    const uint8_t *c = sw.maps.rgb[cam] + pix * 3;
+                    packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
+                             ((uint32_t)cls << 24);
+                    x = row[0];
+                    y = row[1];
+                    z = row[2];
+                    inten = row[3];
+                    inst_f = row[6];
+                }
+            }
+        }
+    }
+    uint32_t tile_end;
+    uint32_t rank = compact_rank<IBLOCK>(keep, state + sw.state_off, epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        int64_t o = base + rank;
+        if (o < sw.fs.capacity) {
+            double wx, wy, wz;
+            affine_chain(sw.T.m, 4, x, y, z, wx, wy, wz);
+            ring.x[o] = wx;
+            ring.y[o] = wy;
+            ring.z[o] = wz;
+            float fi = (float)inten;
+            if ((double)fi != inten) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
+            ring.inten[o] = fi;
+            ring.rgbs[o] = packed;
+            int32_t ii = sat_i32(inst_f);
+            if ((double)ii != inst_f) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+            ring.inst[o] = ii;
+            ring.dyn[o] = 0;
+        }
+    }
+    if (tile == sw.n_tiles - 1 && threadIdx.x == 0) finish_frame(sw.fs, base, tile_end);
+}
+
 // ---------------------------------------------------------------------------
 // import of a ready-made (n,10) float64 cloud
 // ---------------------------------------------------------------------------
@@ -515,7 +603,8 @@ static int make_lookback(pcacc_t h, int64_t n_tiles, LookBack *lb) {
 
 // Reserve a frame slot for up to n_in records. Decides the ring offset policy
 // on the host from upper bounds; syncs the table only when it has to.
-static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs, int64_t *frame_id) {
+static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs, int64_t *frame_id,
+                       bool fixed_slot = false) {
     if (n_in < 0) return pcacc_fail(h, PCACC_ERR_ARG, "negative point count");
     if (n_in > h->capacity)
         return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame of %lld points exceeds ring capacity %lld",
@@ -558,6 +647,8 @@ static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs,
             if (!any_after) h->wrapped = false;
             override_base = nxt;
             ub = nxt;
+        } else if (fixed_slot) {
+            override_base = ub;  // place at the upper bound: no dependence on earlier counts
         }
     }
     f.n_in = n_in;
@@ -575,6 +666,7 @@ static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs,
     fs->base_override = override_base;
     fs->epoch = h->rebase_epoch;
     fs->capacity = h->capacity;
+    fs->write_next = 1;
     h->next_id = id + 1;
     if (frame_id) *frame_id = id;
     return PCACC_OK;
@@ -745,6 +837,84 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
 #undef LAUNCH_IR
     pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+
+extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const double *const *pc_dev,
+                                             const int64_t *const *cam_idx_dev, const int64_t *n,
+                                             const uint8_t *const *rgb_maps,
+                                             const void *const *sem_maps, int n_cams, int sem_dtype,
+                                             int img_h, int img_w, const double *T_ego_world,
+                                             double intensity_div, const int32_t *filters,
+                                             int n_filters, int64_t *first_frame_id, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n_sweeps <= 0 || n_sweeps > 65535 || n_cams < 0 || n_cams > PCACC_MAX_CAMS || !pc_dev ||
+        !cam_idx_dev || !n || !T_ego_world)
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad integrate_records_batch arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    Filters filt;
+    int rc = fill_filters(h, filters, n_filters, &filt);
+    if (rc) return rc;
+    rc = set_inten_div(h, intensity_div);
+    if (rc) return rc;
+    if ((int)(h->next_id - h->first_id) + n_sweeps >= h->max_frames - 1)
+        return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame table too small for %d more frames", n_sweeps);
+    std::vector<SweepDesc> desc((size_t)n_sweeps);
+    int64_t total_tiles = 0, max_tiles = 1;
+    for (int k = 0; k < n_sweeps; k++) {
+        int64_t tiles = (n[k] + IBLOCK - 1) / IBLOCK;
+        if (tiles == 0) tiles = 1;
+        SweepDesc &d = desc[(size_t)k];
+        d.pc = pc_dev[k];
+        d.cam = (const long long *)cam_idx_dev[k];
+        d.n = n[k];
+        d.maps.n = n_cams;
+        for (int c = 0; c < PCACC_MAX_CAMS; c++) {
+            d.maps.rgb[c] = c < n_cams ? rgb_maps[(size_t)k * n_cams + c] : nullptr;
+            d.maps.sem[c] = c < n_cams ? sem_maps[(size_t)k * n_cams + c] : nullptr;
+        }
+        memcpy(d.T.m, T_ego_world + (size_t)k * 16, sizeof(d.T.m));
+        d.n_tiles = (uint32_t)tiles;
+        d.state_off = (uint32_t)total_tiles;
+        total_tiles += tiles;
+        if (tiles > max_tiles) max_tiles = tiles;
+        int64_t fid = -1;
+        rc = begin_frame(h, n[k], st, &d.fs, &fid, /*fixed_slot=*/true);
+        if (rc) return rc;
+        if (d.fs.base_override < 0)
+            return pcacc_fail(h, PCACC_ERR_STATE, "internal: batch frame without a fixed base");
+        d.fs.write_next = (k == n_sweeps - 1) ? 1 : 0;
+        if (k == 0 && first_frame_id) *first_frame_id = fid;
+    }
+    rc = pcacc_ensure_tiles(h, total_tiles);
+    if (rc) return rc;
+    // per-sweep tickets live behind the descriptors in the arena; zeroed by the upload
+    size_t desc_bytes = desc.size() * sizeof(SweepDesc);
+    std::vector<char> blob(desc_bytes + (size_t)n_sweeps * 4, 0);
+    memcpy(blob.data(), desc.data(), desc_bytes);
+    void *dev = nullptr;
+    rc = pcacc_arena_put(h, blob.data(), blob.size(), &dev, st);
+    if (rc) return rc;
+    const SweepDesc *d_desc = (const SweepDesc *)dev;
+    uint32_t *d_tickets = (uint32_t *)((char *)dev + desc_bytes);
+    uint32_t epoch = pcacc_next_epoch(h);
+    dim3 grid((unsigned)max_tiles, (unsigned)n_sweeps);
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
+#define LAUNCH_IRB(DT)                                                                           \
+    k_integrate_records_batch<DT><<<grid, IBLOCK, 0, st>>>(d_desc, img_h, img_w, filt, h->ring,  \
+                                                           h->d_tile_state, d_tickets, epoch,    \
+                                                           h->d_flags)
+    switch (sem_dtype) {
+        case PCACC_SEM_U8: LAUNCH_IRB(PCACC_SEM_U8); break;
+        case PCACC_SEM_I32: LAUNCH_IRB(PCACC_SEM_I32); break;
+        case PCACC_SEM_I64: LAUNCH_IRB(PCACC_SEM_I64); break;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
+    }
+#undef LAUNCH_IRB
+    PCACC_CUDA(h, cudaGetLastError());
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     return PCACC_OK;
 }
 

@@ -49,6 +49,7 @@ struct BinArgs {
     int64_t epoch_now;
     const pcacc_bev_params *params;  // device, n_var entries
     int n_var;
+    int v_per_block;       // variants handled by one block (blockIdx.z selects the group)
     int P;
     uint32_t *counts;      // n_var * 2*P*P (+1)
     uint32_t *tmp_key, *tmp_rank;
@@ -146,11 +147,13 @@ k_bev_bin(BinArgs a) {
     const int64_t e0 = a.frame_epoch[slot];
     const bool lazy = e0 < a.epoch_now;
 
-    // stage variant parameters and the frame's composed matrix
+    // stage this block's variant parameters and the frame's composed matrix
+    const int v_begin = (int)blockIdx.z * a.v_per_block;
+    const int v_end = min(a.n_var, v_begin + a.v_per_block);
     {
-        const uint32_t *src = (const uint32_t *)a.params;
+        const uint32_t *src = (const uint32_t *)(a.params + v_begin);
         uint32_t *dst = (uint32_t *)s_par;
-        const int words = a.n_var * (int)(sizeof(pcacc_bev_params) / 4);
+        const int words = (v_end - v_begin) * (int)(sizeof(pcacc_bev_params) / 4);
         for (int k = threadIdx.x; k < words; k += BIN_BLOCK) dst[k] = src[k];
         if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
     }
@@ -191,8 +194,8 @@ k_bev_bin(BinArgs a) {
         }
     }
 
-    for (int v = 0; v < a.n_var; v++) {
-        const pcacc_bev_params &bp = s_par[v];
+    for (int v = v_begin; v < v_end; v++) {
+        const pcacc_bev_params &bp = s_par[v - v_begin];
         const bool in_range = fid >= bp.frame_begin && fid < bp.frame_end;  // block-uniform
         if (!in_range) continue;
         const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
@@ -803,11 +806,20 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.dbg_cell = (v0 == 0) ? dbg_cell_dev : nullptr;
             a.flags = h->d_flags;
             int64_t nf = fhi - flo;
+            // spread the variants over blockIdx.z until the grid fills the chip
+            int64_t useful = 0;
+            for (int64_t f = flo; f < fhi; f++) useful += (ub[(size_t)(f - flo)] + BIN_TILE - 1) / BIN_TILE;
+            int groups = (int)(148 * 6 / (useful > 0 ? useful : 1));
+            if (groups < 1) groups = 1;
+            if (groups > nv) groups = nv;
+            a.v_per_block = (nv + groups - 1) / groups;
+            groups = (nv + a.v_per_block - 1) / a.v_per_block;
             for (int64_t f0 = 0; f0 < nf; f0 += 65535) {
                 int64_t ny = nf - f0 < 65535 ? nf - f0 : 65535;
                 BinArgs b = a;
                 b.frame_lo = flo + f0;
-                dim3 grid((unsigned)((max_cnt + BIN_TILE - 1) / BIN_TILE), (unsigned)ny);
+                dim3 grid((unsigned)((max_cnt + BIN_TILE - 1) / BIN_TILE), (unsigned)ny,
+                          (unsigned)groups);
                 size_t pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
                 k_bev_bin<<<grid, BIN_BLOCK, 0, st>>>(b);
                 PCACC_CUDA(h, cudaGetLastError());

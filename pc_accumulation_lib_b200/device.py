@@ -233,6 +233,31 @@ class DeviceCloud:
         self._keep += [pcd, cam] + rgb_d + sem_d
         return int(fid.value)
 
+    def integrate_records_batch(self, sweeps, filters, intensity_div=255.) -> int:
+        """sweeps: list of dicts with DEVICE tensors pc (n,7) f64, cam (n,) i64,
+        rgb [ (H,W,3) u8 ], sem [ (H,W) u8|i32|i64 ] and host T (4,4).  One launch
+        for the whole list; returns the first frame id."""
+        n_s = len(sweeps)
+        n_cams = len(sweeps[0]['rgb'])
+        sem_dt = _TORCH_SEM[sweeps[0]['sem'][0].dtype] if n_cams else _lib.SEM_U8
+        h, w = ((int(sweeps[0]['rgb'][0].shape[0]), int(sweeps[0]['rgb'][0].shape[1]))
+                if n_cams else (1, 1))
+        pcp = (C.c_void_p * n_s)(*[s['pc'].data_ptr() for s in sweeps])
+        cmp_ = (C.c_void_p * n_s)(*[s['cam'].data_ptr() for s in sweeps])
+        nn = (C.c_int64 * n_s)(*[int(s['pc'].shape[0]) for s in sweeps])
+        m = max(n_s * n_cams, 1)
+        rp = (C.c_void_p * m)(*[r.data_ptr() for s in sweeps for r in s['rgb']])
+        sp = (C.c_void_p * m)(*[r.data_ptr() for s in sweeps for r in s['sem']])
+        T = np.ascontiguousarray(np.stack([np.asarray(s['T'], dtype=np.float64).reshape(4, 4)
+                                           for s in sweeps]))
+        f, fp, nf = self._filters(filters)
+        fid = C.c_int64(-1)
+        self._check(self.lib.pcacc_integrate_records_batch(
+            self.h, n_s, C.cast(pcp, C.c_void_p), C.cast(cmp_, C.c_void_p), C.cast(nn, C.c_void_p),
+            C.cast(rp, C.c_void_p), C.cast(sp, C.c_void_p), n_cams, sem_dt, h, w,
+            T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf, C.byref(fid), _stream()))
+        return int(fid.value)
+
     def integrate_cloud(self, rec) -> int:
         r = self.stage.put('cloud', rec if isinstance(rec, torch.Tensor)
                            else np.asarray(rec, dtype=np.float64))
