@@ -235,9 +235,10 @@ int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
 #define PCACC_K_BIN 3       /* k_bev_bin */
 #define PCACC_K_SCAN 4      /* k_scan */
 #define PCACC_K_SCATTER 5   /* k_bev_scatter */
-#define PCACC_K_REDUCE 6    /* k_bev_reduce */
+#define PCACC_K_REDUCE 6    /* k_bev_consts + k_bev_reduce (empty and small cells) */
 #define PCACC_K_EXPORT 7    /* k_export_frame */
-#define PCACC_N_KERNELS 8
+#define PCACC_K_REDUCE_BIG 8 /* k_bev_reduce_big (queued large cells) */
+#define PCACC_N_KERNELS 9
 
 /* enable=1: every kernel launch of this handle is bracketed by CUDA events on
  * its launch stream. */

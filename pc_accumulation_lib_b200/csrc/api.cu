@@ -159,6 +159,7 @@ static void free_all(pcacc_t h) {
     cudaFree(h->d_arena);
     cudaFree(h->d_ws);
     cudaFree(h->d_rstats);
+    cudaFree(h->d_rgb_lut);
     for (auto &e : h->prof_events) cudaEventDestroy(e);
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_arena) cudaFreeHost(h->h_arena);
@@ -228,6 +229,7 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
     TRY(cudaMallocHost(&h->h_arena, h->arena_size));
 #undef TRY
     int rc = pcacc_ensure_tiles(h, 4096);
+    if (!rc) rc = pcacc_init_tables(h);
     if (rc) {
         free_all(h);
         delete h;

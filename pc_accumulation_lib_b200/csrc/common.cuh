@@ -198,6 +198,7 @@ struct pcacc_s {
     void *d_ws;
     size_t ws_size;
     int64_t *d_rstats;  // [1] binned [2] replays of the last rasterise
+    double *d_rgb_lut;   // (m2 * 0.5) / 255. for m2 = 0..510
     int64_t last_visit_ub;
     double inten_div;    // stored intensity / inten_div = reference intensity; 0 = not set yet
     uint32_t pending_flags;
@@ -217,6 +218,7 @@ struct pcacc_s {
 size_t pcacc_prof_begin(pcacc_t h, int kernel, cudaStream_t st);
 void pcacc_prof_end(pcacc_t h, int kernel, size_t ev0, cudaStream_t st);
 int pcacc_prof_flush(pcacc_t h);
+int pcacc_init_tables(pcacc_t h);
 
 int pcacc_fail(pcacc_t h, int status, const char *fmt, ...);
 int pcacc_cuda_check(pcacc_t h, cudaError_t e, const char *what);

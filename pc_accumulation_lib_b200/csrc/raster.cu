@@ -49,7 +49,7 @@ struct BinArgs {
     int64_t epoch_now;
     const pcacc_bev_params *params;  // device, n_var entries
     int n_var;
-    int v_per_block;       // variants handled by one block (blockIdx.z selects the group)
+    int n_frames;          // frames covered by this launch (<= BIN_MAXF), first = frame_lo
     int P;
     uint32_t *counts;      // n_var * 2*P*P (+1)
     uint32_t *tmp_key, *tmp_rank;
@@ -131,36 +131,89 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
     return e;
 }
 
+#define BIN_MAXF 2048 /* frames per launch */
+
+// Persistent blocks: the (frame, tile, variant-group) work list is derived on the
+// device from the frame table, so the launch never depends on counts the host has
+// not fetched yet.
 __global__ void __launch_bounds__(BIN_BLOCK, 2)
 k_bev_bin(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
+    __shared__ uint32_t s_tiles[BIN_MAXF + 1];
     __shared__ double s_comp[12];
     __shared__ uint32_t s_warp[BIN_BLOCK / 32];
     __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int PP = a.P * a.P;
 
-    const int64_t fid = a.frame_lo + blockIdx.y;
+    // stage all variant parameters; build the exclusive prefix of tiles per frame
+    {
+        const uint32_t *src = (const uint32_t *)a.params;
+        uint32_t *dst = (uint32_t *)s_par;
+        const int words = a.n_var * (int)(sizeof(pcacc_bev_params) / 4);
+        for (int k = threadIdx.x; k < words; k += BIN_BLOCK) dst[k] = src[k];
+        constexpr int PER = BIN_MAXF / BIN_BLOCK;
+        uint32_t loc[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int f = (int)threadIdx.x * PER + k;
+            uint32_t t = 0;
+            if (f < a.n_frames) {
+                const int64_t c = a.frame_cnt[(int)((a.frame_lo + f) % a.max_frames)];
+                t = (uint32_t)((c + BIN_TILE - 1) / BIN_TILE);
+            }
+            loc[k] = sum;
+            sum += t;
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < BIN_BLOCK / 32; w++)
+            if (w < (int)warp) wbase += s_warp[w];
+        const uint32_t excl = wbase + incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int f = (int)threadIdx.x * PER + k;
+            if (f <= a.n_frames) s_tiles[f] = excl + loc[k];
+        }
+        __syncthreads();
+    }
+    const uint32_t total_tiles = s_tiles[a.n_frames];
+    if (total_tiles == 0) return;
+    // spread the variants over several work items until the chip is filled
+    int groups = (int)((2u * gridDim.x + total_tiles - 1) / total_tiles);
+    groups = max(1, min(groups, a.n_var));
+    const int vpb = (a.n_var + groups - 1) / groups;
+    groups = (a.n_var + vpb - 1) / vpb;
+    const uint32_t n_items = total_tiles * (uint32_t)groups;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t tile_lin = item % total_tiles;
+    const int v_begin = (int)(item / total_tiles) * vpb;
+    const int v_end = min(a.n_var, v_begin + vpb);
+    int fl = 0, fh = a.n_frames;   // largest f with s_tiles[f] <= tile_lin
+    while (fh - fl > 1) {
+        const int m = (fl + fh) >> 1;
+        if (s_tiles[m] <= tile_lin) fl = m; else fh = m;
+    }
+    const int64_t fid = a.frame_lo + fl;
     const int slot = (int)(fid % a.max_frames);
     const int64_t cnt = a.frame_cnt[slot];
-    const int64_t tile0 = (int64_t)blockIdx.x * BIN_TILE;
-    if (tile0 >= cnt) return;
+    const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
     const int64_t off = a.frame_off[slot];
     const int64_t e0 = a.frame_epoch[slot];
     const bool lazy = e0 < a.epoch_now;
-
-    // stage this block's variant parameters and the frame's composed matrix
-    const int v_begin = (int)blockIdx.z * a.v_per_block;
-    const int v_end = min(a.n_var, v_begin + a.v_per_block);
-    {
-        const uint32_t *src = (const uint32_t *)(a.params + v_begin);
-        uint32_t *dst = (uint32_t *)s_par;
-        const int words = (v_end - v_begin) * (int)(sizeof(pcacc_bev_params) / 4);
-        for (int k = threadIdx.x; k < words; k += BIN_BLOCK) dst[k] = src[k];
-        if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
-    }
+    __syncthreads();   // previous item is done with s_comp / s_warp / s_base
+    if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
     __syncthreads();
-
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int PP = a.P * a.P;
 
     // This thread's points: two pairs of neighbours (16 B loads; frame offsets are
     // multiples of 4 records, so the pairs are aligned).  x and y are always needed; z
@@ -195,20 +248,20 @@ k_bev_bin(BinArgs a) {
     }
 
     for (int v = v_begin; v < v_end; v++) {
-        const pcacc_bev_params &bp = s_par[v - v_begin];
+        const pcacc_bev_params &bp = s_par[v];
         const bool in_range = fid >= bp.frame_begin && fid < bp.frame_end;  // block-uniform
         if (!in_range) continue;
         const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
         bool keep[BIN_ITEMS];
         uint32_t key[BIN_ITEMS], rank[BIN_ITEMS];
-        uint4 rec[BIN_ITEMS];
+        double zrec[BIN_ITEMS];
         uint32_t my_cnt = 0;
 #pragma unroll
         for (int k = 0; k < BIN_ITEMS; k++) {
             keep[k] = false;
             key[k] = 0;
             rank[k] = 0;
-            rec[k] = make_uint4(0, 0, 0, 0);
+            zrec[k] = 0.0;
             if (valid[k]) {
                 const int64_t gi = off + idx[k];
                 Eval e;
@@ -237,11 +290,7 @@ k_bev_bin(BinArgs a) {
                     keep[k] = true;
                     key[k] = ((uint32_t)v * (uint32_t)PP + (uint32_t)e.cell) * 2u + win;
                     rank[k] = atomicAdd(&a.counts[key[k]], 1u);
-                    unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
-                    rec[k].x = (uint32_t)zb;
-                    rec[k].y = (uint32_t)(zb >> 32);
-                    rec[k].z = a.ring.rgbs[gi];
-                    rec[k].w = __float_as_uint(a.ring.inten[gi]);
+                    zrec[k] = e.z;
                     my_cnt++;
                 }
             }
@@ -269,14 +318,18 @@ k_bev_bin(BinArgs a) {
         for (int k = 0; k < BIN_ITEMS; k++) {
             if (keep[k]) {
                 if ((int64_t)pos < a.cap) {
+                    const int64_t gi = off + idx[k];
+                    const unsigned long long zb = (unsigned long long)__double_as_longlong(zrec[k]);
                     a.tmp_key[pos] = key[k];
                     a.tmp_rank[pos] = rank[k];
-                    a.tmp_rec[pos] = rec[k];
+                    a.tmp_rec[pos] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), a.ring.rgbs[gi],
+                                                __float_as_uint(a.ring.inten[gi]));
                 }
                 pos++;
             }
         }
     }
+    }   // work items
 }
 
 // ---------------------------------------------------------------------------
@@ -401,59 +454,136 @@ __device__ __forceinline__ int hist_kth(const uint32_t c[8], uint32_t excl, uint
     return __shfl_sync(0xffffffffu, bin, __ffs(m) - 1);
 }
 
-// Accumulates one record into the per-window statistics (everything except the medians).
+// Per-window statistics of one cell (everything except the medians).
 struct WinAcc {
     uint32_t n_road[2], n_veh[2];
-    long long fx_hi[2], fx_lo[2];
+    long long fx_hi[2], fx_lo[2];   // sum of raw road intensities, 2^-40 fixed point split at 2^32
     double ext_z[2];
 };
 
-__device__ __forceinline__ void acc_record(WinAcc &a, const uint4 &r, int w, const pcacc_bev_params &bp,
-                                           double intensity_div, bool want_max) {
+__device__ __forceinline__ void acc_init(WinAcc &a, bool want_max) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        a.n_road[w] = a.n_veh[w] = 0;
+        a.fx_hi[w] = a.fx_lo[w] = 0;
+        a.ext_z[w] = want_max ? -INFINITY : INFINITY;
+    }
+}
+
+__device__ __forceinline__ void acc_record(WinAcc &a, const uint4 &r, int w, int road_cls, int v0,
+                                           int v1, int v2, int v3, bool want_max) {
     const double z = __longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x));
     const int sem = (int)(r.z >> 24);
-    const bool road = sem == bp.road_cls;
-    const bool veh = (sem == bp.veh_cls[0]) || (sem == bp.veh_cls[1]) || (sem == bp.veh_cls[2]) ||
-                     (sem == bp.veh_cls[3]);
-    if (road) {
-        double iv = __ddiv_rn((double)__uint_as_float(r.w), intensity_div);
-        long long fx = __double2ll_rn(__dmul_rn(iv, FX_SCALE));
+    if (sem == road_cls) {
+        // raw float32 intensity: exact in 2^-40 fixed point for |v| >= 2^-17
+        long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
         a.fx_hi[w] += fx >> 32;
         a.fx_lo[w] += fx & 0xffffffffll;
         a.n_road[w]++;
     }
-    if (veh) a.n_veh[w]++;
+    if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) a.n_veh[w]++;
     a.ext_z[w] = want_max ? fmax(a.ext_z[w], z) : fmin(a.ext_z[w], z);
 }
 
-// 7 planes of one window from its statistics (bev_generator.py:396-415,457-480;
-// sem_bev.py:593-617,665-667)
-__device__ __forceinline__ void finalise_window(const pcacc_bev_params &bp, double n, double n_road,
-                                                double n_veh, double isum, double ez, const int med2[3],
-                                                double plane[7]) {
-    double a = __dadd_rn(n_road, 1.0), b = __dadd_rn(__dsub_rn(n, n_road), 1.0);
-    plane[0] = __ddiv_rn(a, __dadd_rn(a, b));
-    double c = __dadd_rn(n_veh, 1.0), d = __dadd_rn(__dsub_rn(n, n_veh), 1.0);
-    plane[5] = __ddiv_rn(c, __dadd_rn(c, d));
-    double I = __ddiv_rn(isum, __dadd_rn(n_road, 1.0));
+// per-variant constants, computed once per rasterise call by k_bev_consts
+struct BevConsts {
+    double empty[7];   // planes of a window without any point
+    double pad;
+};
+
+// (m2 * 0.5) / 255. for m2 = twice the median, 0..510: filled once per handle
+#define RGB_LUT_N 511
+
+// road and dynamic planes of one window: Dirichlet expectation with a uniform prior,
+// (c+1) / ((c+1) + ((n-c)+1)) (bev_generator.py:457-480); the denominator is n+2 exactly
+__device__ __forceinline__ double dirichlet(uint32_t c, uint32_t n) {
+    return __ddiv_rn((double)(c + 1u), (double)(n + 2u));
+}
+
+// intensity plane: mean over (count+1) then road_marking_transform (sem_bev.py:593-617)
+__device__ __forceinline__ double intensity_plane(const pcacc_bev_params &bp, double isum, uint32_t n_road) {
+    double I = __ddiv_rn(isum, (double)(n_road + 1u));
     double t = __dmul_rn(bp.int_sep_scaler, __dsub_rn(I, bp.int_mid_threshold));
     double sg = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-t)));
     double val = __dmul_rn(bp.int_scaler, sg);
-    plane[1] = val > 1.0 ? 1.0 : val;
+    return val > 1.0 ? 1.0 : val;
+}
+
+__global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_var,
+                             BevConsts *__restrict__ consts) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_var) return;
+    const pcacc_bev_params &bp = params[v];
+    BevConsts c;
+    c.empty[0] = dirichlet(0, 0);
+    c.empty[1] = intensity_plane(bp, 0.0, 0);
+    c.empty[2] = c.empty[3] = c.empty[4] = __ddiv_rn(bp.rgb_fill, 255.0);
+    c.empty[5] = dirichlet(0, 0);
+    c.empty[6] = 0.0;
+    c.pad = 0.0;
+    consts[v] = c;
+}
+
+__global__ void k_rgb_lut(double *__restrict__ lut) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < RGB_LUT_N) lut[m] = __ddiv_rn(__dmul_rn((double)m, 0.5), 255.0);
+}
+
+// window statistics -> 7 planes
+__device__ __forceinline__ void window_planes(const pcacc_bev_params &bp, const BevConsts &cst,
+                                              const double *__restrict__ lut, uint32_t n,
+                                              uint32_t n_road, uint32_t n_veh, long long fx_hi,
+                                              long long fx_lo, double ez, const int med2[3],
+                                              double intensity_div, double plane[7]) {
+    plane[0] = dirichlet(n_road, n);
+    plane[5] = dirichlet(n_veh, n);
+    if (n_road == 0) {
+        plane[1] = cst.empty[1];   // sum 0 over count 0: the same arithmetic as an empty window
+    } else {
+        // sum(raw) / div instead of sum(raw / div): one rounding instead of n
+        double isum = __ddiv_rn(fx_to_double(fx_hi, fx_lo), intensity_div);
+        plane[1] = intensity_plane(bp, isum, n_road);
+    }
 #pragma unroll
-    for (int k = 0; k < 3; k++) plane[2 + k] = __ddiv_rn(__dmul_rn((double)med2[k], 0.5), 255.0);
+    for (int k = 0; k < 3; k++) plane[2 + k] = lut[med2[k]];
     plane[6] = ez;
 }
 
-#define SMALL_T 16      /* cells with <= SMALL_T points are reduced by their own lane */
+template <bool F64OUT>
+__device__ __forceinline__ void store_planes(__half *__restrict__ out16, double *__restrict__ out64,
+                                             int64_t o, int PP, const double plane[7]) {
+#pragma unroll
+    for (int p = 0; p < 7; p++) {
+        out16[o + (int64_t)p * PP] = __double2half(plane[p]);
+        if (F64OUT) out64[o + (int64_t)p * PP] = plane[p];
+    }
+}
+
+#define SMALL_T 15      /* cells with <= SMALL_T points are reduced by their own lane */
 #define SMALL_STRIDE 17 /* odd stride: lanes reading the same j hit distinct banks */
 
+// r, g, b in three 10-bit fields (bit 9 of each field is a guard bit): one subtraction
+// compares all three channels at once.
+#define F_ONE 0x00100401u    /* 1 in every field */
+#define F_GUARD 0x20080200u  /* bit 9 of every field */
+__device__ __forceinline__ uint32_t f_pack(uint32_t rgbs) {
+    return (rgbs & 255u) | ((rgbs & 0xff00u) << 2) | ((rgbs & 0xff0000u) << 4);
+}
+// bit 0 of field c = (a_c >= b_c); ag = a | F_GUARD
+__device__ __forceinline__ uint32_t f_ge(uint32_t ag, uint32_t b) { return ((ag - b) & F_GUARD) >> 9; }
+
+// ---------------------------------------------------------------------------
+// pass A: one warp per 32 consecutive cells.  Empty cells take the per-variant
+// constants, cells with <= SMALL_T points are reduced by their own lane, larger
+// cells are queued for pass B.
+// ---------------------------------------------------------------------------
 template <bool F64OUT>
 __global__ void __launch_bounds__(RED_WARPS * 32)
 k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
-             const pcacc_bev_params *__restrict__ params, int n_var, int P, double intensity_div,
+             const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
+             const double *__restrict__ lut, int n_var, int P, double intensity_div,
+             uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_count,
              __half *__restrict__ out16, double *__restrict__ out64) {
-    __shared__ __align__(16) uint32_t s_hist[RED_WARPS][2][3][256];
     __shared__ uint32_t s_small[RED_WARPS][32 * SMALL_STRIDE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
@@ -464,7 +594,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     const int var = (int)(cell0 / PP);
     const int cell_in = (int)(cell0 - (int64_t)var * PP) + (int)lane;
     const pcacc_bev_params &bp = params[var];
-    uint32_t(*hist)[3][256] = s_hist[warp];
+    const BevConsts &cst = consts[var];
     const bool want_max = bp.elevation_max != 0;
 
     // segment bounds of my cell: [s0, s1) present, [s1, s2) future
@@ -473,84 +603,154 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     uint32_t s2 = __shfl_down_sync(0xffffffffu, s01.x, 1);
     if (lane == 31) s2 = start[2 * gc + 2];
     const uint32_t my_np = s01.y - s01.x, my_nf = s2 - s01.y, my_nt = my_np + my_nf;
+    const int64_t o0 = ((int64_t)var * 3 * 7) * PP + cell_in;
+
+    // all 32 cells empty: nothing to read
+    if (__ballot_sync(0xffffffffu, my_nt != 0) == 0) {
+#pragma unroll
+        for (int w = 0; w < 3; w++) store_planes<F64OUT>(out16, out64, o0 + (int64_t)w * 7 * PP, PP, cst.empty);
+        return;
+    }
+
+    // queue the large cells for pass B
+    {
+        const bool big = my_nt > SMALL_T;
+        const unsigned bm = __ballot_sync(0xffffffffu, big);
+        if (bm) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(big_count, (uint32_t)__popc(bm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)gc;
+        }
+    }
 
     WinAcc st;
-#pragma unroll
-    for (int w = 0; w < 2; w++) {
-        st.n_road[w] = st.n_veh[w] = 0;
-        st.fx_hi[w] = st.fx_lo[w] = 0;
-        st.ext_z[w] = want_max ? -INFINITY : INFINITY;
-    }
+    acc_init(st, want_max);
     int med2[3][3];
 #pragma unroll
     for (int w = 0; w < 3; w++)
 #pragma unroll
         for (int c = 0; c < 3; c++) med2[w][c] = 0;
 
-    // ---- small cells: each lane reduces its own cell ---------------------------------
     if (my_nt > 0 && my_nt <= SMALL_T) {
+        const int road_cls = bp.road_cls, v0 = bp.veh_cls[0], v1 = bp.veh_cls[1], v2 = bp.veh_cls[2],
+                  v3 = bp.veh_cls[3];
         uint32_t *mine = s_small[warp] + lane * SMALL_STRIDE;
         for (uint32_t i = 0; i < my_nt; i++) {
             const uint4 r = sorted[s01.x + i];
-            mine[i] = r.z & 0x00ffffffu;
-            acc_record(st, r, i >= my_np ? 1 : 0, bp, intensity_div, want_max);
+            mine[i] = f_pack(r.z);
+            acc_record(st, r, i >= my_np ? 1 : 0, road_cls, v0, v1, v2, v3, want_max);
         }
-        // rank of every colour byte inside its window and inside the full cell; ties
-        // broken by position, so ranks are a permutation and rank == k picks the
-        // k-th order statistic.  r, g, b are processed together, one byte lane each.
-        const uint32_t kp_lo = my_np ? (my_np - 1) / 2 * 0x010101u : 0xffffffffu;
-        const uint32_t kp_hi = my_np ? my_np / 2 * 0x010101u : 0xffffffffu;
-        const uint32_t kf_lo = my_nf ? (my_nf - 1) / 2 * 0x010101u : 0xffffffffu;
-        const uint32_t kf_hi = my_nf ? my_nf / 2 * 0x010101u : 0xffffffffu;
-        const uint32_t ka_lo = (my_nt - 1) / 2 * 0x010101u, ka_hi = my_nt / 2 * 0x010101u;
+        // Order statistics without sorting: element i occupies the ranks [L_i, E_i) of its
+        // set, L_i = #{v_j < v_i}, E_i = #{v_j <= v_i}; it is the k-th smallest iff
+        // L_i <= k < E_i.  Counted separately over the present and the future part so that
+        // the window's own ranks and the full cell's ranks come out of the same pass.
+        const uint32_t kp_lo = (my_np ? (my_np - 1) / 2 : 31u) * F_ONE, kp_hi = (my_np ? my_np / 2 : 31u) * F_ONE;
+        const uint32_t kf_lo = (my_nf ? (my_nf - 1) / 2 : 31u) * F_ONE, kf_hi = (my_nf ? my_nf / 2 : 31u) * F_ONE;
+        const uint32_t ka_lo = (my_nt - 1) / 2 * F_ONE, ka_hi = my_nt / 2 * F_ONE;
         uint32_t lo_p = 0, hi_p = 0, lo_f = 0, hi_f = 0, lo_a = 0, hi_a = 0;
         for (uint32_t i = 0; i < my_nt; i++) {
-            const uint32_t vi = mine[i];
-            const bool wi = i >= my_np;
-            uint32_t rank_w = 0, rank_a = 0;
-            for (uint32_t j = 0; j < my_nt; j++) {
+            const uint32_t vi = mine[i], vig = vi | F_GUARD;
+            uint32_t e1 = 0, g1 = 0, e2 = 0, g2 = 0;   // #{v_j <= v_i}, #{v_j >= v_i} per part
+            for (uint32_t j = 0; j < my_np; j++) {
                 const uint32_t vj = mine[j];
-                uint32_t m = __vcmpltu4(vj, vi);
-                if (j < i) m |= __vcmpeq4(vj, vi);
-                m &= 0x00010101u;
-                rank_a += m;
-                if ((j >= my_np) == wi) rank_w += m;
+                e1 += f_ge(vig, vj);
+                g1 += f_ge(vj | F_GUARD, vi);
             }
-            uint32_t m;
-            m = __vcmpeq4(rank_a, ka_lo) & 0x00ffffffu;
-            lo_a = (vi & m) | (lo_a & ~m);
-            m = __vcmpeq4(rank_a, ka_hi) & 0x00ffffffu;
-            hi_a = (vi & m) | (hi_a & ~m);
-            if (wi) {
-                m = __vcmpeq4(rank_w, kf_lo) & 0x00ffffffu;
-                lo_f = (vi & m) | (lo_f & ~m);
-                m = __vcmpeq4(rank_w, kf_hi) & 0x00ffffffu;
-                hi_f = (vi & m) | (hi_f & ~m);
-            } else {
-                m = __vcmpeq4(rank_w, kp_lo) & 0x00ffffffu;
-                lo_p = (vi & m) | (lo_p & ~m);
-                m = __vcmpeq4(rank_w, kp_hi) & 0x00ffffffu;
-                hi_p = (vi & m) | (hi_p & ~m);
+            for (uint32_t j = my_np; j < my_nt; j++) {
+                const uint32_t vj = mine[j];
+                e2 += f_ge(vig, vj);
+                g2 += f_ge(vj | F_GUARD, vi);
+            }
+            const bool wi = i >= my_np;
+            // own window
+            {
+                const uint32_t E = wi ? e2 : e1, L = (wi ? my_nf : my_np) * F_ONE - (wi ? g2 : g1);
+                const uint32_t klo = wi ? kf_lo : kp_lo, khi = wi ? kf_hi : kp_hi;
+                // L <= k  and  E >= k+1, field-wise
+                uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
+                uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
+                if (wi) {
+                    lo_f = (vi & m) | (lo_f & ~m);
+                    hi_f = (vi & h) | (hi_f & ~h);
+                } else {
+                    lo_p = (vi & m) | (lo_p & ~m);
+                    hi_p = (vi & h) | (hi_p & ~h);
+                }
+            }
+            // full cell
+            {
+                const uint32_t E = e1 + e2, L = my_nt * F_ONE - (g1 + g2);
+                uint32_t m = (f_ge(ka_lo | F_GUARD, L) & f_ge(E | F_GUARD, ka_lo + F_ONE)) * 0x3ffu;
+                uint32_t h = (f_ge(ka_hi | F_GUARD, L) & f_ge(E | F_GUARD, ka_hi + F_ONE)) * 0x3ffu;
+                lo_a = (vi & m) | (lo_a & ~m);
+                hi_a = (vi & h) | (hi_a & ~h);
             }
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            med2[0][c] = (int)((lo_p >> (8 * c)) & 255u) + (int)((hi_p >> (8 * c)) & 255u);
-            med2[1][c] = (int)((lo_f >> (8 * c)) & 255u) + (int)((hi_f >> (8 * c)) & 255u);
-            med2[2][c] = (int)((lo_a >> (8 * c)) & 255u) + (int)((hi_a >> (8 * c)) & 255u);
+            med2[0][c] = (int)((lo_p >> (10 * c)) & 255u) + (int)((hi_p >> (10 * c)) & 255u);
+            med2[1][c] = (int)((lo_f >> (10 * c)) & 255u) + (int)((hi_f >> (10 * c)) & 255u);
+            med2[2][c] = (int)((lo_a >> (10 * c)) & 255u) + (int)((hi_a >> (10 * c)) & 255u);
         }
     }
-    __syncwarp();
 
-    // ---- large cells: the whole warp reduces one cell at a time with histograms ---------
-    unsigned todo = __ballot_sync(0xffffffffu, my_nt > SMALL_T);
-    while (todo) {
-        const int owner = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t b0 = __shfl_sync(0xffffffffu, s01.x, owner);
-        const uint32_t np = __shfl_sync(0xffffffffu, my_np, owner);
-        const uint32_t nf = __shfl_sync(0xffffffffu, my_nf, owner);
-        const uint32_t nt = np + nf;
+    // finalise: 3 windows x 7 planes (large cells are written by pass B)
+    if (my_nt <= SMALL_T) {
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
+            const int64_t o = o0 + (int64_t)w * 7 * PP;
+            if (nw == 0) {
+                store_planes<F64OUT>(out16, out64, o, PP, cst.empty);
+            } else {
+                double plane[7];
+                if (w < 2)
+                    window_planes(bp, cst, lut, nw, st.n_road[w], st.n_veh[w], st.fx_hi[w], st.fx_lo[w],
+                                  st.ext_z[w], med2[w], intensity_div, plane);
+                else  // the unused side still holds +-inf, the identity of min / max
+                    window_planes(bp, cst, lut, nw, st.n_road[0] + st.n_road[1],
+                                  st.n_veh[0] + st.n_veh[1], st.fx_hi[0] + st.fx_hi[1],
+                                  st.fx_lo[0] + st.fx_lo[1],
+                                  want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]),
+                                  med2[w], intensity_div, plane);
+                store_planes<F64OUT>(out16, out64, o, PP, plane);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass B: one warp per queued large cell (dynamic queue), 256-bin shared-memory
+// histograms per window and channel.
+// ---------------------------------------------------------------------------
+template <bool F64OUT>
+__global__ void __launch_bounds__(RED_WARPS * 32)
+k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
+                 const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
+                 const double *__restrict__ lut, int P, double intensity_div,
+                 const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
+                 uint32_t *__restrict__ next, __half *__restrict__ out16, double *__restrict__ out64) {
+    __shared__ __align__(16) uint32_t s_hist[RED_WARPS][2][3][256];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t(*hist)[3][256] = s_hist[warp];
+    const int PP = P * P;
+    const uint32_t n_big = *big_count;
+    while (true) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(next, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= n_big) break;
+        const uint32_t gc = big_list[q];
+        const int var = (int)(gc / (uint32_t)PP);
+        const int cell_in = (int)(gc - (uint32_t)var * (uint32_t)PP);
+        const pcacc_bev_params &bp = params[var];
+        const bool want_max = bp.elevation_max != 0;
+        const int road_cls = bp.road_cls, v0 = bp.veh_cls[0], v1 = bp.veh_cls[1], v2 = bp.veh_cls[2],
+                  v3 = bp.veh_cls[3];
+        const uint32_t b0 = start[2 * (int64_t)gc], b1 = start[2 * (int64_t)gc + 1],
+                       b2 = start[2 * (int64_t)gc + 2];
+        const uint32_t np = b1 - b0, nf = b2 - b1, nt = np + nf;
         {
             uint4 *h4 = (uint4 *)&hist[0][0][0];
 #pragma unroll
@@ -558,12 +758,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
         }
         __syncwarp();
         WinAcc a;
-#pragma unroll
-        for (int w = 0; w < 2; w++) {
-            a.n_road[w] = a.n_veh[w] = 0;
-            a.fx_hi[w] = a.fx_lo[w] = 0;
-            a.ext_z[w] = want_max ? -INFINITY : INFINITY;
-        }
+        acc_init(a, want_max);
         for (uint32_t i = lane; i < nt; i += 32) {
             const uint4 r = sorted[b0 + i];
             const int w = i >= np ? 1 : 0;
@@ -571,7 +766,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             atomicAdd(&hist[w][0][c & 255u], 1u);
             atomicAdd(&hist[w][1][(c >> 8) & 255u], 1u);
             atomicAdd(&hist[w][2][(c >> 16) & 255u], 1u);
-            acc_record(a, r, w, bp, intensity_div, want_max);
+            acc_record(a, r, w, road_cls, v0, v1, v2, v3, want_max);
         }
 #pragma unroll
         for (int w = 0; w < 2; w++) {
@@ -623,63 +818,36 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
                 m2[w][ch] = v;
             }
         }
-        if ((int)lane == owner) {
-            st = a;
+        __syncwarp();
+        // lanes 0..2 finalise one window each
+        if (lane < 3) {
+            const int w = (int)lane;
+            const BevConsts &cst = consts[var];
+            const uint32_t nw = (w == 0) ? np : (w == 1) ? nf : nt;
+            const int64_t o = (((int64_t)var * 3 + w) * 7) * PP + cell_in;
+            if (nw == 0) {
+                store_planes<F64OUT>(out16, out64, o, PP, cst.empty);
+            } else {
+                double plane[7];
+                int md[3];
 #pragma unroll
-            for (int w = 0; w < 3; w++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) med2[w][c] = m2[w][c];
+                for (int c = 0; c < 3; c++) md[c] = (w == 0) ? m2[0][c] : (w == 1) ? m2[1][c] : m2[2][c];
+                if (w < 2) {
+                    const int ww = w & 1;
+                    window_planes(bp, cst, lut, nw, ww ? a.n_road[1] : a.n_road[0],
+                                  ww ? a.n_veh[1] : a.n_veh[0], ww ? a.fx_hi[1] : a.fx_hi[0],
+                                  ww ? a.fx_lo[1] : a.fx_lo[0], ww ? a.ext_z[1] : a.ext_z[0], md,
+                                  intensity_div, plane);
+                } else {
+                    window_planes(bp, cst, lut, nw, a.n_road[0] + a.n_road[1], a.n_veh[0] + a.n_veh[1],
+                                  a.fx_hi[0] + a.fx_hi[1], a.fx_lo[0] + a.fx_lo[1],
+                                  want_max ? fmax(a.ext_z[0], a.ext_z[1]) : fmin(a.ext_z[0], a.ext_z[1]),
+                                  md, intensity_div, plane);
+                }
+                store_planes<F64OUT>(out16, out64, o, PP, plane);
+            }
         }
         __syncwarp();
-    }
-
-    // ---- finalise my cell: 3 windows x 7 planes ------------------------------------------
-    // values of a window without any point: computed once per warp, not per cell
-    double empty[7];
-    {
-        double e1 = 0.0;
-        if (lane == 0) {
-            const int zero3[3] = {0, 0, 0};
-            double pl[7];
-            finalise_window(bp, 0.0, 0.0, 0.0, 0.0, 0.0, zero3, pl);
-            e1 = pl[1];
-        }
-        e1 = __shfl_sync(0xffffffffu, e1, 0);
-        empty[0] = 0.5;
-        empty[1] = e1;
-        empty[2] = empty[3] = empty[4] = __ddiv_rn(bp.rgb_fill, 255.0);
-        empty[5] = 0.5;
-        empty[6] = 0.0;
-    }
-#pragma unroll
-    for (int w = 0; w < 3; w++) {
-        double plane[7];
-        const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
-        if (nw == 0) {
-#pragma unroll
-            for (int p = 0; p < 7; p++) plane[p] = empty[p];
-        } else {
-            double n_road, n_veh, isum, ez;
-            if (w < 2) {
-                n_road = (double)st.n_road[w];
-                n_veh = (double)st.n_veh[w];
-                isum = fx_to_double(st.fx_hi[w], st.fx_lo[w]);
-                ez = st.ext_z[w];
-            } else {
-                n_road = (double)(st.n_road[0] + st.n_road[1]);
-                n_veh = (double)(st.n_veh[0] + st.n_veh[1]);
-                isum = fx_to_double(st.fx_hi[0] + st.fx_hi[1], st.fx_lo[0] + st.fx_lo[1]);
-                // the unused side still holds +-inf, the identity of min / max
-                ez = want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]);
-            }
-            finalise_window(bp, (double)nw, n_road, n_veh, isum, ez, med2[w], plane);
-        }
-        const int64_t o = (((int64_t)var * 3 + w) * 7) * PP + cell_in;
-#pragma unroll
-        for (int p = 0; p < 7; p++) {
-            out16[o + (int64_t)p * PP] = __double2half(plane[p]);
-            if (F64OUT) out64[o + (int64_t)p * PP] = plane[p];
-        }
     }
 }
 
@@ -709,6 +877,14 @@ static int ensure_ws(pcacc_t h, size_t bytes) {
                           cudaGetErrorString(e));
     }
     h->ws_size = want;
+    return PCACC_OK;
+}
+
+int pcacc_init_tables(pcacc_t h) {
+    PCACC_CUDA(h, cudaMalloc(&h->d_rgb_lut, RGB_LUT_N * sizeof(double)));
+    k_rgb_lut<<<(RGB_LUT_N + 127) / 128, 128>>>(h->d_rgb_lut);
+    PCACC_CUDA(h, cudaGetLastError());
+    PCACC_CUDA(h, cudaDeviceSynchronize());
     return PCACC_OK;
 }
 
@@ -758,20 +934,27 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         if (cap > 0xfffffff0ll)
             return pcacc_fail(h, PCACC_ERR_CAPACITY, "more than 2^32 point visits in one batch");
         const int64_t n_keys = (int64_t)nv * PP * 2 + 1;
-        // workspace layout
+        // workspace layout: [counters | append/replay/big-queue counters] are zeroed per call
         size_t o_counts = 0;
-        size_t o_cnt2 = align_up(o_counts + (size_t)n_keys * 4, 256);  // two u64 counters
-        size_t o_key = align_up(o_cnt2 + 16, 256);
+        size_t o_cnt2 = align_up(o_counts + (size_t)n_keys * 4, 256);  // 4 x u64 counters
+        size_t o_key = align_up(o_cnt2 + 32, 256);
         size_t o_rank = align_up(o_key + (size_t)cap * 4, 256);
         size_t o_rec = align_up(o_rank + (size_t)cap * 4, 256);
         size_t o_sorted = align_up(o_rec + (size_t)cap * 16, 256);
-        size_t total = align_up(o_sorted + (size_t)cap * 16, 256);
+        size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
+        size_t o_big = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
+        // a cell is "large" only above SMALL_T points, so the queue never exceeds cap / (SMALL_T+1)
+        int64_t big_cap = cap / (SMALL_T + 1) + 1;
+        if (big_cap > (int64_t)nv * PP) big_cap = (int64_t)nv * PP;
+        size_t total = align_up(o_big + (size_t)big_cap * 4, 256);
         int rc = ensure_ws(h, total);
         if (rc) return rc;
         char *ws = (char *)h->d_ws;
         uint32_t *counts = (uint32_t *)(ws + o_counts);
         unsigned long long *ctr = (unsigned long long *)(ws + o_cnt2);
-        // counters + append/replay counters are contiguous up to o_key: one memset
+        uint32_t *big_count = (uint32_t *)(ctr + 2), *big_next = (uint32_t *)(ctr + 3);
+        BevConsts *d_consts = (BevConsts *)(ws + o_consts);
+        uint32_t *big_list = (uint32_t *)(ws + o_big);
         PCACC_CUDA(h, cudaMemsetAsync(ws, 0, o_key, st));
 
         void *d_params = nullptr;
@@ -806,22 +989,12 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.dbg_cell = (v0 == 0) ? dbg_cell_dev : nullptr;
             a.flags = h->d_flags;
             int64_t nf = fhi - flo;
-            // spread the variants over blockIdx.z until the grid fills the chip
-            int64_t useful = 0;
-            for (int64_t f = flo; f < fhi; f++) useful += (ub[(size_t)(f - flo)] + BIN_TILE - 1) / BIN_TILE;
-            int groups = (int)(148 * 6 / (useful > 0 ? useful : 1));
-            if (groups < 1) groups = 1;
-            if (groups > nv) groups = nv;
-            a.v_per_block = (nv + groups - 1) / groups;
-            groups = (nv + a.v_per_block - 1) / a.v_per_block;
-            for (int64_t f0 = 0; f0 < nf; f0 += 65535) {
-                int64_t ny = nf - f0 < 65535 ? nf - f0 : 65535;
+            for (int64_t f0 = 0; f0 < nf; f0 += BIN_MAXF) {
                 BinArgs b = a;
                 b.frame_lo = flo + f0;
-                dim3 grid((unsigned)((max_cnt + BIN_TILE - 1) / BIN_TILE), (unsigned)ny,
-                          (unsigned)groups);
+                b.n_frames = (int)(nf - f0 < BIN_MAXF ? nf - f0 : BIN_MAXF);
                 size_t pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
-                k_bev_bin<<<grid, BIN_BLOCK, 0, st>>>(b);
+                k_bev_bin<<<148 * 2, BIN_BLOCK, 0, st>>>(b);
                 PCACC_CUDA(h, cudaGetLastError());
                 pcacc_prof_end(h, PCACC_K_BIN, pe, st);
             }
@@ -847,20 +1020,40 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
-        // reduce + finalise (also correct on all-zero counters: every cell empty)
+        // per-variant constants, then reduce + finalise (also correct on all-zero
+        // counters: every cell empty)
+        h->launches[PCACC_K_REDUCE]++;
+        k_bev_consts<<<(nv + 31) / 32, 32, 0, st>>>((const pcacc_bev_params *)d_params, nv, d_consts);
+        PCACC_CUDA(h, cudaGetLastError());
         int64_t warps = (int64_t)nv * PP / 32;
         int64_t blocks = (warps + RED_WARPS - 1) / RED_WARPS;
         size_t pr = pcacc_prof_begin(h, PCACC_K_REDUCE, st);
         if (want_f64)
             k_bev_reduce<true><<<(unsigned)blocks, RED_WARPS * 32, 0, st>>>(
-                counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, nv, P,
-                h->inten_div, o16, o64);
+                counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
+                h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, o64);
         else
             k_bev_reduce<false><<<(unsigned)blocks, RED_WARPS * 32, 0, st>>>(
-                counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, nv, P,
-                h->inten_div, o16, nullptr);
+                counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
+                h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, nullptr);
         PCACC_CUDA(h, cudaGetLastError());
         pcacc_prof_end(h, PCACC_K_REDUCE, pr, st);
+        if (cap > SMALL_T) {
+            int64_t bb = (big_cap + RED_WARPS - 1) / RED_WARPS;
+            if (bb > 148 * 8) bb = 148 * 8;
+            pr = pcacc_prof_begin(h, PCACC_K_REDUCE_BIG, st);
+            if (want_f64)
+                k_bev_reduce_big<true><<<(unsigned)bb, RED_WARPS * 32, 0, st>>>(
+                    counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params,
+                    d_consts, h->d_rgb_lut, P, h->inten_div, big_list, big_count, big_next, o16, o64);
+            else
+                k_bev_reduce_big<false><<<(unsigned)bb, RED_WARPS * 32, 0, st>>>(
+                    counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params,
+                    d_consts, h->d_rgb_lut, P, h->inten_div, big_list, big_count, big_next, o16,
+                    nullptr);
+            PCACC_CUDA(h, cudaGetLastError());
+            pcacc_prof_end(h, PCACC_K_REDUCE_BIG, pr, st);
+        }
         // keep the counters of the last group for pcacc_raster_stats
         PCACC_CUDA(h, cudaMemcpyAsync(h->d_rstats + 1, ctr, 16, cudaMemcpyDeviceToDevice, st));
         h->last_visit_ub = cap;

@@ -249,7 +249,7 @@ def test_nusc_batched_integrate_equals_per_sweep(dev):
     frames as one pcacc_integrate_records call per sweep."""
     g = load_golden('nusc_seq.npz')
     scene = cases.nusc_seq_inputs()
-    cloud = dev.DeviceCloud(capacity_pts=sum(o['pc'].shape[0] for o in scene) + 256, max_frames=64)
+    cloud = dev.DeviceCloud(capacity_pts=2 * sum(o['pc'].shape[0] for o in scene), max_frames=64)
     T_gw = np.linalg.inv(scene[0]['ego_at_lidar_ts'])
     sweeps = [dict(pc=torch.from_numpy(o['pc']).cuda(), cam=torch.from_numpy(o['pc_cam_idx']).cuda(),
                    rgb=[torch.from_numpy(np.ascontiguousarray(i)).cuda() for i in o['images']],
