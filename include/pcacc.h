@@ -232,13 +232,14 @@ int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
 #define PCACC_K_INTEGRATE 0 /* k_integrate_frustum / _gt / _records / _cloud, k_gen_semantic_pc, k_project */
 #define PCACC_K_REBASE 1    /* k_rebase_lazy, k_materialise */
 #define PCACC_K_MARK 2      /* k_mark_dynamic */
-#define PCACC_K_BIN 3       /* k_bev_bin */
+#define PCACC_K_BIN 3       /* k_bev_bin (exact per-candidate work) */
 #define PCACC_K_SCAN 4      /* k_scan */
 #define PCACC_K_SCATTER 5   /* k_bev_scatter */
 #define PCACC_K_REDUCE 6    /* k_bev_consts + k_bev_reduce (empty and small cells) */
 #define PCACC_K_EXPORT 7    /* k_export_frame */
 #define PCACC_K_REDUCE_BIG 8 /* k_bev_reduce_big (queued large cells) */
-#define PCACC_N_KERNELS 9
+#define PCACC_K_CLASSIFY 9  /* k_bev_classify (streaming crop test over the ring) */
+#define PCACC_N_KERNELS 10
 
 /* enable=1: every kernel launch of this handle is bracketed by CUDA events on
  * its launch stream. */

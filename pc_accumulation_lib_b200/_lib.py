@@ -80,10 +80,10 @@ SIGNATURES = {
     'pcacc_frame_offset': (_i32, [_vp, _i64, C.POINTER(_i64)]),
     'pcacc_raster_stats': (_i32, [_vp, C.POINTER(_i64 * 3), _vp]),
     'pcacc_profile': (_i32, [_vp, _i32]),
-    'pcacc_profile_read': (_i32, [_vp, C.POINTER(_dbl * 9), C.POINTER(_i64 * 9)]),
+    'pcacc_profile_read': (_i32, [_vp, C.POINTER(_dbl * 10), C.POINTER(_i64 * 10)]),
 }
 KERNEL_CLASSES = ('integrate', 'rebase', 'mark_dynamic', 'bev_bin', 'scan', 'bev_scatter',
-                  'bev_reduce', 'export', 'bev_reduce_big')
+                  'bev_reduce', 'export', 'bev_reduce_big', 'bev_classify')
 
 _lib = None
 

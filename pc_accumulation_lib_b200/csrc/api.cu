@@ -166,7 +166,7 @@ static void free_all(pcacc_t h) {
 }
 
 extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pcacc_t *out) {
-    if (!out || capacity_pts <= 0 || max_frames < 4 || capacity_pts > 0x7fffffff00ll)
+    if (!out || capacity_pts <= 0 || max_frames < 4 || capacity_pts > 0xffffff00ll)
         return pcacc_fail(nullptr, PCACC_ERR_ARG, "pcacc_create: capacity_pts > 0 and max_frames >= 4 required");
     *out = nullptr;
     int n_dev = 0;

@@ -45,18 +45,20 @@ struct BinArgs {
     const int64_t *frame_off, *frame_cnt, *frame_epoch;
     const double *comp, *chain;
     int max_frames;
-    int64_t frame_lo;      // absolute id of blockIdx.y == 0
+    int64_t frame_lo;      // absolute id of the first frame of this launch
     int64_t epoch_now;
     const pcacc_bev_params *params;  // device, n_var entries
     int n_var;
     int n_frames;          // frames covered by this launch (<= BIN_MAXF), first = frame_lo
     int P;
     uint32_t *counts;      // n_var * 2*P*P (+1)
+    uint32_t *cand_gi;     // candidate list: ring position ...
+    uint32_t *cand_meta;   // ... and variant | frame-in-launch << 8
     uint32_t *tmp_key, *tmp_rank;
     uint4 *tmp_rec;
-    unsigned long long *n_append;  // device counter
+    unsigned long long *n_append;  // device counter (candidates)
     unsigned long long *n_replay;
-    int64_t cap;           // capacity of the tmp arrays
+    int64_t cap;           // capacity of the candidate / tmp arrays
     int32_t *dbg_cell;     // optional
     uint32_t *flags;
 };
@@ -67,47 +69,49 @@ struct Eval {
     double z;
 };
 
-// One point, one variant: bev_generator.py:224-255,737-747 on a point that is already in
-// the accumulator's current frame.  (px, py) are always known; pz is fetched through
-// `zload` only when it is needed: always if the rotation mixes z into x / y (never for
-// rotation_matrix_3d) and otherwise only for points that pass the x / y crop.
-// want_near: also report whether the point lies within GUARD_M of any decision boundary.
-template <typename ZLoad>
+#define KEY_INVALID 0xffffffffu
+
+// x / y part of bev_generator.py:224-231 for one point of the accumulator's current
+// frame: origin shift (one subtract per component, kitti360_sem_pc_accum.py:193), rotation
+// as an FMA chain over k = 0..2 (strided 3x3 dgemm), translation.  A zero coefficient
+// contributes exactly nothing for finite z, so that link of the chain is skipped (zfree).
+__device__ __forceinline__ void bev_xy(const pcacc_bev_params &bp, bool zfree, double px, double py,
+                                       double pz, double &q0, double &q1) {
+    const double sx = __dsub_rn(px, bp.origin[0]);
+    const double sy = __dsub_rn(py, bp.origin[1]);
+    q0 = __fma_rn(bp.R[1], sy, __dmul_rn(bp.R[0], sx));
+    q1 = __fma_rn(bp.R[4], sy, __dmul_rn(bp.R[3], sx));
+    if (!zfree) {
+        const double sz = __dsub_rn(pz, bp.origin[2]);
+        q0 = __fma_rn(bp.R[2], sz, q0);
+        q1 = __fma_rn(bp.R[5], sz, q1);
+    }
+    q0 = __dadd_rn(q0, bp.trans_dx);
+    q1 = __dadd_rn(q1, bp.trans_dy);
+}
+
+// The whole of bev_generator.py:224-255,737-747 for one point: crop (strict), height
+// filter, pos2grid (div, mul, add separately rounded), row = P-1-j, col = i.
+// want_near: also report whether any decision lies within GUARD_M of its boundary.
 __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, double px, double py,
-                                           ZLoad zload, bool want_near) {
+                                           double pz, bool want_near) {
     Eval e;
     e.keep = false;
     e.near = false;
     e.cell = -1;
     e.z = 0.0;
     const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
-    // origin shift: one subtract per component (kitti360_sem_pc_accum.py:193)
+    // a non-finite z poisons x and y in the reference (0 * inf = NaN): the point is dropped
+    if (zfree && !(fabs(pz) <= 1.7976931348623157e308)) return e;
+    double q0, q1;
+    bev_xy(bp, zfree, px, py, pz, q0, q1);
     const double sx = __dsub_rn(px, bp.origin[0]);
     const double sy = __dsub_rn(py, bp.origin[1]);
-    double sz = 0.0;
-    if (!zfree) sz = __dsub_rn(zload(), bp.origin[2]);
-    // rotation: FMA chain over k = 0..2 (strided 3x3 dgemm, bev_generator.py:227);
-    // a zero coefficient contributes exactly nothing for finite z, so that link is skipped
-    double q0 = __fma_rn(bp.R[1], sy, __dmul_rn(bp.R[0], sx));
-    double q1 = __fma_rn(bp.R[4], sy, __dmul_rn(bp.R[3], sx));
-    if (!zfree) {
-        q0 = __fma_rn(bp.R[2], sz, q0);
-        q1 = __fma_rn(bp.R[5], sz, q1);
-    }
-    q0 = __dadd_rn(q0, bp.trans_dx);
-    q1 = __dadd_rn(q1, bp.trans_dy);
-    const double hv = __dmul_rn(0.5, bp.view);
-    bool in = (q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv);
-    const bool cand = want_near ? ((fabs(q0) < hv + GUARD_M) && (fabs(q1) < hv + GUARD_M)) : in;
-    if (!cand) return e;
-    if (zfree) {
-        const double pz = zload();
-        // a non-finite z poisons x and y in the reference (0 * inf = NaN): the point is dropped
-        if (!(fabs(pz) <= 1.7976931348623157e308)) return e;
-        sz = __dsub_rn(pz, bp.origin[2]);
-    }
+    const double sz = __dsub_rn(pz, bp.origin[2]);
     const double q2 = __fma_rn(bp.R[8], sz, __fma_rn(bp.R[7], sy, __dmul_rn(bp.R[6], sx)));
     e.z = q2;
+    const double hv = __dmul_rn(0.5, bp.view);
+    bool in = (q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv);
     const bool hf_on = (bp.height_filter == bp.height_filter);
     if (hf_on) in = in && (q2 < bp.height_filter);
     const double dP = (double)P, hP = __dmul_rn(0.5, dP);
@@ -133,18 +137,22 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
 
 #define BIN_MAXF 2048 /* frames per launch */
 
-// Persistent blocks: the (frame, tile, variant-group) work list is derived on the
-// device from the frame table, so the launch never depends on counts the host has
-// not fetched yet.
-__global__ void __launch_bounds__(BIN_BLOCK, 2)
-k_bev_bin(BinArgs a) {
+// ---------------------------------------------------------------------------
+// pass 1a — k_bev_classify: pure streaming.  Persistent blocks walk a (frame, tile,
+// variant-group) work list that is derived on the device from the frame table (the
+// launch never depends on counts the host has not fetched); each thread loads x, y
+// (z only when it is needed) of 4 points, applies the lazy matrix, and tests the x / y
+// crop of every variant.  Candidates are appended (block-aggregated: one global atomic
+// per tile and variant) as (ring position, variant | frame).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_BLOCK, 4)
+k_bev_classify(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ uint32_t s_tiles[BIN_MAXF + 1];
     __shared__ double s_comp[12];
     __shared__ uint32_t s_warp[BIN_BLOCK / 32];
     __shared__ unsigned long long s_base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int PP = a.P * a.P;
 
     // stage all variant parameters; build the exclusive prefix of tiles per frame
     {
@@ -196,140 +204,164 @@ k_bev_bin(BinArgs a) {
     const uint32_t n_items = total_tiles * (uint32_t)groups;
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const uint32_t tile_lin = item % total_tiles;
-    const int v_begin = (int)(item / total_tiles) * vpb;
-    const int v_end = min(a.n_var, v_begin + vpb);
-    int fl = 0, fh = a.n_frames;   // largest f with s_tiles[f] <= tile_lin
-    while (fh - fl > 1) {
-        const int m = (fl + fh) >> 1;
-        if (s_tiles[m] <= tile_lin) fl = m; else fh = m;
-    }
-    const int64_t fid = a.frame_lo + fl;
-    const int slot = (int)(fid % a.max_frames);
-    const int64_t cnt = a.frame_cnt[slot];
-    const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
-    const int64_t off = a.frame_off[slot];
-    const int64_t e0 = a.frame_epoch[slot];
-    const bool lazy = e0 < a.epoch_now;
-    __syncthreads();   // previous item is done with s_comp / s_warp / s_base
-    if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
-    __syncthreads();
-
-    // This thread's points: two pairs of neighbours (16 B loads; frame offsets are
-    // multiples of 4 records, so the pairs are aligned).  x and y are always needed; z
-    // only up front when the frame is lazily re-based (the composed matrix mixes it in).
-    int64_t idx[BIN_ITEMS];
-    double px[BIN_ITEMS], py[BIN_ITEMS], pz[BIN_ITEMS];
-    bool valid[BIN_ITEMS];
-#pragma unroll
-    for (int h = 0; h < BIN_ITEMS / 2; h++) {
-        const int64_t i0 = tile0 + (int64_t)h * (2 * BIN_BLOCK) + 2 * threadIdx.x;
-        idx[2 * h] = i0;
-        idx[2 * h + 1] = i0 + 1;
-        valid[2 * h] = i0 < cnt;
-        valid[2 * h + 1] = i0 + 1 < cnt;
-        double2 X = make_double2(0, 0), Y = make_double2(0, 0), Z = make_double2(0, 0);
-        if (valid[2 * h]) {
-            X = *(const double2 *)(a.ring.x + off + i0);
-            Y = *(const double2 *)(a.ring.y + off + i0);
-            if (lazy) Z = *(const double2 *)(a.ring.z + off + i0);
+        const uint32_t tile_lin = item % total_tiles;
+        const int v_begin = (int)(item / total_tiles) * vpb;
+        const int v_end = min(a.n_var, v_begin + vpb);
+        int fl = 0, fh = a.n_frames;  // largest f with s_tiles[f] <= tile_lin
+        while (fh - fl > 1) {
+            const int m = (fl + fh) >> 1;
+            if (s_tiles[m] <= tile_lin) fl = m; else fh = m;
         }
-        px[2 * h] = X.x; px[2 * h + 1] = X.y;
-        py[2 * h] = Y.x; py[2 * h + 1] = Y.y;
-        pz[2 * h] = Z.x; pz[2 * h + 1] = Z.y;
-    }
-    if (lazy) {
-#pragma unroll
-        for (int k = 0; k < BIN_ITEMS; k++) {
-            double nx, ny, nz;
-            affine_chain(s_comp, 4, px[k], py[k], pz[k], nx, ny, nz);
-            px[k] = nx; py[k] = ny; pz[k] = nz;
-        }
-    }
+        const int64_t fid = a.frame_lo + fl;
+        const int slot = (int)(fid % a.max_frames);
+        const int64_t cnt = a.frame_cnt[slot];
+        const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
+        const int64_t off = a.frame_off[slot];
+        const bool lazy = a.frame_epoch[slot] < a.epoch_now;
+        bool need_z = lazy;
+        for (int v = v_begin; v < v_end; v++)
+            need_z = need_z || (s_par[v].R[2] != 0.0) || (s_par[v].R[5] != 0.0);
+        __syncthreads();  // the previous item is done with s_comp / s_warp / s_base
+        if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
+        __syncthreads();
 
-    for (int v = v_begin; v < v_end; v++) {
-        const pcacc_bev_params &bp = s_par[v];
-        const bool in_range = fid >= bp.frame_begin && fid < bp.frame_end;  // block-uniform
-        if (!in_range) continue;
-        const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
-        bool keep[BIN_ITEMS];
-        uint32_t key[BIN_ITEMS], rank[BIN_ITEMS];
-        double zrec[BIN_ITEMS];
-        uint32_t my_cnt = 0;
+        // 4 points per thread: two pairs of neighbours (16 B loads; frame offsets are
+        // multiples of 4 records, so the pairs are aligned)
+        double px[BIN_ITEMS], py[BIN_ITEMS], pz[BIN_ITEMS];
+        unsigned vmask = 0;
 #pragma unroll
-        for (int k = 0; k < BIN_ITEMS; k++) {
-            keep[k] = false;
-            key[k] = 0;
-            rank[k] = 0;
-            zrec[k] = 0.0;
-            if (valid[k]) {
-                const int64_t gi = off + idx[k];
-                Eval e;
-                if (lazy) {
-                    const double zk = pz[k];
-                    e = eval_point(bp, a.P, px[k], py[k], [zk]() { return zk; }, true);
-                    if (e.near) {
-                        // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
-                        double ex = a.ring.x[gi], ey = a.ring.y[gi], ez = a.ring.z[gi];
-                        for (int64_t ep = e0; ep < a.epoch_now; ep++) {
-                            const double *T = a.chain + (ep % a.max_frames) * 12;
-                            double nx, ny, nz;
-                            affine_chain(T, 4, ex, ey, ez, nx, ny, nz);
-                            ex = nx; ey = ny; ez = nz;
+        for (int h = 0; h < BIN_ITEMS / 2; h++) {
+            const int64_t i0 = tile0 + (int64_t)h * (2 * BIN_BLOCK) + 2 * threadIdx.x;
+            double2 X = make_double2(0, 0), Y = make_double2(0, 0), Z = make_double2(0, 0);
+            if (i0 < cnt) {
+                vmask |= 1u << (2 * h);
+                if (i0 + 1 < cnt) vmask |= 2u << (2 * h);
+                X = *(const double2 *)(a.ring.x + off + i0);
+                Y = *(const double2 *)(a.ring.y + off + i0);
+                if (need_z) Z = *(const double2 *)(a.ring.z + off + i0);
+            }
+            px[2 * h] = X.x; px[2 * h + 1] = X.y;
+            py[2 * h] = Y.x; py[2 * h + 1] = Y.y;
+            pz[2 * h] = Z.x; pz[2 * h + 1] = Z.y;
+        }
+        if (lazy) {
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS; k++) {
+                double nx, ny, nz;
+                affine_chain(s_comp, 4, px[k], py[k], pz[k], nx, ny, nz);
+                px[k] = nx; py[k] = ny; pz[k] = nz;
+            }
+        }
+
+        for (int v = v_begin; v < v_end; v++) {
+            const pcacc_bev_params &bp = s_par[v];
+            if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;  // block-uniform
+            const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
+            const double hv = __dmul_rn(0.5, bp.view);
+            const double lim = hv + GUARD_M;
+            unsigned cmask = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS; k++) {
+                double q0, q1;
+                bev_xy(bp, zfree, px[k], py[k], pz[k], q0, q1);
+                // lazily re-based frames keep a guard band; NaN fails both forms
+                const bool c = lazy ? ((fabs(q0) < lim) && (fabs(q1) < lim))
+                                    : ((q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv));
+                if (c) cmask |= 1u << k;
+            }
+            cmask &= vmask;
+            const uint32_t my_cnt = __popc(cmask);
+            uint32_t incl = my_cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned)o) incl += t;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, btotal = 0;
+#pragma unroll
+            for (int w = 0; w < BIN_BLOCK / 32; w++) {
+                const uint32_t c = s_warp[w];
+                if (w < (int)warp) wbase += c;
+                btotal += c;
+            }
+            if (threadIdx.x == 0)
+                s_base = btotal ? atomicAdd(a.n_append, (unsigned long long)btotal) : 0ull;
+            __syncthreads();
+            if (cmask) {
+                unsigned long long pos = s_base + wbase + (incl - my_cnt);
+                const uint32_t meta = (uint32_t)v | ((uint32_t)fl << 8);
+#pragma unroll
+                for (int k = 0; k < BIN_ITEMS; k++) {
+                    if ((cmask >> k) & 1u) {
+                        if ((int64_t)pos < a.cap) {
+                            a.cand_gi[pos] = (uint32_t)(off + tile0 + (int64_t)(k >> 1) * (2 * BIN_BLOCK) +
+                                                        2 * threadIdx.x + (k & 1));
+                            a.cand_meta[pos] = meta;
                         }
-                        e = eval_point(bp, a.P, ex, ey, [ez]() { return ez; }, false);
-                        atomicAdd(a.n_replay, 1ull);
+                        pos++;
                     }
-                } else {
-                    const double *zp = a.ring.z + gi;
-                    e = eval_point(bp, a.P, px[k], py[k], [zp]() { return *zp; }, false);
                 }
-                if (e.keep && a.ring.dyn[gi] == 1) e.keep = false;  // static points only
-                if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
-                if (e.keep) {
-                    keep[k] = true;
-                    key[k] = ((uint32_t)v * (uint32_t)PP + (uint32_t)e.cell) * 2u + win;
-                    rank[k] = atomicAdd(&a.counts[key[k]], 1u);
-                    zrec[k] = e.z;
-                    my_cnt++;
-                }
-            }
-        }
-        // block-aggregated append: one global atomic per block and variant
-        uint32_t incl = my_cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t wbase = 0, btotal = 0;
-#pragma unroll
-        for (int w = 0; w < BIN_BLOCK / 32; w++) {
-            uint32_t c = s_warp[w];
-            if (w < (int)warp) wbase += c;
-            btotal += c;
-        }
-        if (threadIdx.x == 0) s_base = btotal ? atomicAdd(a.n_append, (unsigned long long)btotal) : 0ull;
-        __syncthreads();
-        unsigned long long pos = s_base + wbase + (incl - my_cnt);
-#pragma unroll
-        for (int k = 0; k < BIN_ITEMS; k++) {
-            if (keep[k]) {
-                if ((int64_t)pos < a.cap) {
-                    const int64_t gi = off + idx[k];
-                    const unsigned long long zb = (unsigned long long)__double_as_longlong(zrec[k]);
-                    a.tmp_key[pos] = key[k];
-                    a.tmp_rank[pos] = rank[k];
-                    a.tmp_rec[pos] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), a.ring.rgbs[gi],
-                                                __float_as_uint(a.ring.inten[gi]));
-                }
-                pos++;
             }
         }
     }
-    }   // work items
+}
+
+// ---------------------------------------------------------------------------
+// pass 1b — k_bev_bin: one thread per candidate, no block synchronisation: exact
+// per-point work (lazy matrix + guard band / chain replay, height filter, pos2grid,
+// static filter), the cell counter (its old value is the rank in the cell segment) and
+// the 16 B record.  A candidate rejected here leaves a hole (KEY_INVALID).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bev_bin(BinArgs a) {
+    unsigned long long n = *a.n_append;
+    if (n > (unsigned long long)a.cap) n = (unsigned long long)a.cap;
+    const int PP = a.P * a.P;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < n;
+         c += (unsigned long long)gridDim.x * 256) {
+        const int64_t gi = (int64_t)a.cand_gi[c];
+        const uint32_t meta = a.cand_meta[c];
+        const int v = (int)(meta & 255u);
+        const int64_t fid = a.frame_lo + (int64_t)(meta >> 8);
+        const int slot = (int)(fid % a.max_frames);
+        const pcacc_bev_params &bp = a.params[v];
+        const int64_t e0 = a.frame_epoch[slot];
+        double x = a.ring.x[gi], y = a.ring.y[gi], z = a.ring.z[gi];
+        Eval e;
+        if (e0 < a.epoch_now) {
+            double cx, cy, cz;
+            affine_chain(a.comp + (int64_t)slot * 12, 4, x, y, z, cx, cy, cz);
+            e = eval_point(bp, a.P, cx, cy, cz, true);
+            if (e.near) {
+                // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
+                for (int64_t ep = e0; ep < a.epoch_now; ep++) {
+                    const double *T = a.chain + (ep % a.max_frames) * 12;
+                    double nx, ny, nz;
+                    affine_chain(T, 4, x, y, z, nx, ny, nz);
+                    x = nx; y = ny; z = nz;
+                }
+                e = eval_point(bp, a.P, x, y, z, false);
+                atomicAdd(a.n_replay, 1ull);
+            }
+        } else {
+            e = eval_point(bp, a.P, x, y, z, false);
+        }
+        if (e.keep && a.ring.dyn[gi] == 1) e.keep = false;  // static points only
+        if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
+        if (e.keep) {
+            const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
+            const uint32_t key = ((uint32_t)v * (uint32_t)PP + (uint32_t)e.cell) * 2u + win;
+            const unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
+            a.tmp_key[c] = key;
+            a.tmp_rank[c] = atomicAdd(&a.counts[key], 1u);
+            a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), a.ring.rgbs[gi],
+                                      __float_as_uint(a.ring.inten[gi]));
+        } else {
+            a.tmp_key[c] = KEY_INVALID;  // hole: rejected by the exact test
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -418,8 +450,9 @@ k_bev_scatter(const uint32_t *__restrict__ start, const uint32_t *__restrict__ t
     if (n > (unsigned long long)cap) n = (unsigned long long)cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * 256) {
-        uint32_t pos = start[tmp_key[i]] + tmp_rank[i];
-        sorted[pos] = tmp_rec[i];
+        const uint32_t key = tmp_key[i];
+        if (key == KEY_INVALID) continue;
+        sorted[start[key] + tmp_rank[i]] = tmp_rec[i];
     }
 }
 
@@ -939,6 +972,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         size_t o_cnt2 = align_up(o_counts + (size_t)n_keys * 4, 256);  // 4 x u64 counters
         size_t o_key = align_up(o_cnt2 + 32, 256);
         size_t o_rank = align_up(o_key + (size_t)cap * 4, 256);
+        // the candidate list (8 B) is dead once k_bev_bin has run: it shares the space of `sorted`
         size_t o_rec = align_up(o_rank + (size_t)cap * 4, 256);
         size_t o_sorted = align_up(o_rec + (size_t)cap * 16, 256);
         size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
@@ -980,6 +1014,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.n_var = nv;
             a.P = P;
             a.counts = counts;
+            a.cand_gi = (uint32_t *)(ws + o_sorted);
+            a.cand_meta = (uint32_t *)(ws + o_sorted + (size_t)cap * 4);
             a.tmp_key = (uint32_t *)(ws + o_key);
             a.tmp_rank = (uint32_t *)(ws + o_rank);
             a.tmp_rec = (uint4 *)(ws + o_rec);
@@ -989,15 +1025,18 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.dbg_cell = (v0 == 0) ? dbg_cell_dev : nullptr;
             a.flags = h->d_flags;
             int64_t nf = fhi - flo;
-            for (int64_t f0 = 0; f0 < nf; f0 += BIN_MAXF) {
-                BinArgs b = a;
-                b.frame_lo = flo + f0;
-                b.n_frames = (int)(nf - f0 < BIN_MAXF ? nf - f0 : BIN_MAXF);
-                size_t pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
-                k_bev_bin<<<148 * 2, BIN_BLOCK, 0, st>>>(b);
-                PCACC_CUDA(h, cudaGetLastError());
-                pcacc_prof_end(h, PCACC_K_BIN, pe, st);
-            }
+            if (nf > BIN_MAXF)
+                return pcacc_fail(h, PCACC_ERR_ARG, "more than %d frames in one rasterise call", BIN_MAXF);
+            a.frame_lo = flo;
+            a.n_frames = (int)nf;
+            size_t pe = pcacc_prof_begin(h, PCACC_K_CLASSIFY, st);
+            k_bev_classify<<<148 * 4, BIN_BLOCK, 0, st>>>(a);
+            PCACC_CUDA(h, cudaGetLastError());
+            pcacc_prof_end(h, PCACC_K_CLASSIFY, pe, st);
+            pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
+            k_bev_bin<<<148 * 8, 256, 0, st>>>(a);
+            PCACC_CUDA(h, cudaGetLastError());
+            pcacc_prof_end(h, PCACC_K_BIN, pe, st);
             // scan
             int64_t tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
             rc = pcacc_ensure_tiles(h, tiles);
@@ -1007,7 +1046,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             lb.ticket = h->d_ticket;
             lb.epoch = pcacc_next_epoch(h);
             lb.n_tiles = (uint32_t)tiles;
-            size_t pe = pcacc_prof_begin(h, PCACC_K_SCAN, st);
+            pe = pcacc_prof_begin(h, PCACC_K_SCAN, st);
             k_scan<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(counts, n_keys, lb);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_SCAN, pe, st);

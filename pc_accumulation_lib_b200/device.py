@@ -368,7 +368,7 @@ class DeviceCloud:
 
     def profile_read(self):
         """{kernel class: (device ms from CUDA events, launches)} since the last read."""
-        ms, n = (C.c_double * 9)(), (C.c_int64 * 9)()
+        ms, n = (C.c_double * 10)(), (C.c_int64 * 10)()
         self._check(self.lib.pcacc_profile_read(self.h, C.byref(ms), C.byref(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
 
