@@ -152,6 +152,8 @@ static void free_all(pcacc_t h) {
     cudaFree(h->d_frame_cnt);
     cudaFree(h->d_frame_epoch);
     cudaFree(h->d_comp);
+    cudaFree(h->d_cull);
+    cudaFree(h->d_aabb);
     cudaFree(h->d_chain);
     cudaFree(h->d_flags);
     cudaFree(h->d_tile_state);
@@ -213,6 +215,14 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
     TRY(cudaMalloc(&h->d_frame_epoch, (size_t)max_frames * 8));
     TRY(cudaMalloc(&h->d_comp, (size_t)max_frames * 12 * 8));
     TRY(cudaMalloc(&h->d_chain, (size_t)max_frames * 12 * 8));
+    TRY(cudaMalloc(&h->d_cull, (size_t)max_frames * 12 * 8));
+    TRY(cudaMalloc(&h->d_aabb, (size_t)max_frames * 6 * 8));
+    TRY(cudaMemset(h->d_cull, 0, (size_t)max_frames * 12 * 8));
+    {   // every box starts empty: min = +max code, max = 0
+        std::vector<unsigned long long> init((size_t)max_frames * 6);
+        for (size_t k = 0; k < init.size(); k++) init[k] = (k % 6) < 3 ? ~0ull : 0ull;
+        TRY(cudaMemcpy(h->d_aabb, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
     TRY(cudaMalloc(&h->d_flags, 4));
     TRY(cudaMalloc(&h->d_ticket, 4));
     TRY(cudaMalloc(&h->d_rstats, 4 * 8));

@@ -147,6 +147,60 @@ __device__ __forceinline__ uint32_t compact_rank(bool keep, unsigned long long *
 }
 
 // ---------------------------------------------------------------------------
+// per-frame bounding boxes (frame culling in the rasteriser)
+// ---------------------------------------------------------------------------
+// order-preserving map double -> uint64, so atomicMin / atomicMax work on doubles
+__device__ __forceinline__ unsigned long long ord_encode(double d) {
+    long long b = __double_as_longlong(d);
+    return b >= 0 ? ((unsigned long long)b ^ 0x8000000000000000ull) : ~(unsigned long long)b;
+}
+__device__ __forceinline__ double ord_decode(unsigned long long u) {
+    long long b = (u & 0x8000000000000000ull) ? (long long)(u ^ 0x8000000000000000ull) : (long long)~u;
+    return __longlong_as_double(b);
+}
+#define AABB_EMPTY_MIN 0xffffffffffffffffull
+#define AABB_EMPTY_MAX 0ull
+
+// Block-wide min / max of the kept points' stored coordinates -> 6 atomics per block.
+// Must be called by every thread of the block. NaN coordinates are ignored (fmin / fmax).
+template <int BLOCK>
+__device__ __forceinline__ void aabb_update(unsigned long long *aabb, bool keep, double x, double y,
+                                            double z) {
+    __shared__ double s_bb[BLOCK / 32][6];
+    double v[6];
+    v[0] = keep ? x : INFINITY;
+    v[1] = keep ? y : INFINITY;
+    v[2] = keep ? z : INFINITY;
+    v[3] = keep ? x : -INFINITY;
+    v[4] = keep ? y : -INFINITY;
+    v[5] = keep ? z : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = fmin(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+            v[3 + k] = fmax(v[3 + k], __shfl_xor_sync(0xffffffffu, v[3 + k], o));
+        }
+    }
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) s_bb[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        double r = s_bb[0][k];
+        for (int w = 1; w < BLOCK / 32; w++) r = k < 3 ? fmin(r, s_bb[w][k]) : fmax(r, s_bb[w][k]);
+        if (k < 3) {
+            if (r != INFINITY) atomicMin(&aabb[k], ord_encode(r));
+        } else {
+            if (r != -INFINITY) atomicMax(&aabb[k], ord_encode(r));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------
 struct FrameHost {
@@ -176,6 +230,8 @@ struct pcacc_s {
     int64_t *d_frame_cnt;
     int64_t *d_frame_epoch;
     double *d_comp;    // max_frames x 12: composed lazy matrix of each frame
+    double *d_cull;    // max_frames x 12: every transform since insertion (never reset): frame culling
+    unsigned long long *d_aabb;  // max_frames x 6: order-encoded min xyz / max xyz at insertion
     double *d_chain;   // max_frames x 12: re-base transforms, slot = epoch % max_frames
     uint32_t *d_flags;
     unsigned long long *d_tile_state;

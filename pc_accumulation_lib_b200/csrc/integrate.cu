@@ -18,10 +18,14 @@
 struct FrameSlots {
     int64_t *frame_off, *frame_cnt, *frame_epoch;
     double *comp;  // this frame's composed matrix (12 doubles), reset to identity
+    double *cull;  // this frame's total transform since insertion (12 doubles), reset to identity
+    unsigned long long *aabb;       // this frame's bounding box (already initialised to empty)
+    unsigned long long *aabb_next;  // the next slot's box: emptied by the tile that ends this frame
     int slot, next_slot;
     int64_t base_override;  // >= 0: use this ring offset instead of frame_off[slot]
     int64_t epoch;
     int64_t capacity;
+    int64_t slot_id;  // absolute frame id
     int write_next;  // 0 inside a batch (the next frame has its own fixed base)
 };
 
@@ -50,8 +54,15 @@ __device__ __forceinline__ void finish_frame(const FrameSlots &fs, int64_t base,
     fs.frame_cnt[fs.slot] = (int64_t)total;
     fs.frame_epoch[fs.slot] = fs.epoch;
     int64_t nxt = base + (((int64_t)total + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
-    if (fs.write_next) fs.frame_off[fs.next_slot] = nxt;
-    for (int k = 0; k < 12; k++) fs.comp[k] = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
+    if (fs.write_next) {
+        fs.frame_off[fs.next_slot] = nxt;
+        for (int k = 0; k < 6; k++) fs.aabb_next[k] = k < 3 ? AABB_EMPTY_MIN : AABB_EMPTY_MAX;
+    }
+    for (int k = 0; k < 12; k++) {
+        const double id = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
+        fs.comp[k] = id;
+        fs.cull[k] = id;
+    }
 }
 
 __device__ __forceinline__ int64_t frame_base(const FrameSlots &fs) {
@@ -214,6 +225,7 @@ k_integrate_frustum(const float4 *__restrict__ pts, int64_t n, PMat P,
             ring.dyn[o] = 0;
         }
     }
+    aabb_update<IBLOCK>(fs.aabb, keep, (double)p.x, (double)p.y, (double)p.z);
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
@@ -252,6 +264,7 @@ k_integrate_gt(const float4 *__restrict__ pts, int64_t n, const int16_t *__restr
             ring.dyn[o] = 0;
         }
     }
+    aabb_update<IBLOCK>(fs.aabb, keep, (double)p.x, (double)p.y, (double)p.z);
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
@@ -313,11 +326,11 @@ k_integrate_records(const double *__restrict__ pc, const long long *__restrict__
     }
     uint32_t tile_end;
     uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    double wx = 0, wy = 0, wz = 0;
     if (keep) {
         int64_t o = base + rank;
+        affine_chain(T.m, 4, x, y, z, wx, wy, wz);
         if (o < fs.capacity) {
-            double wx, wy, wz;
-            affine_chain(T.m, 4, x, y, z, wx, wy, wz);
             ring.x[o] = wx;
             ring.y[o] = wy;
             ring.z[o] = wz;
@@ -331,6 +344,7 @@ k_integrate_records(const double *__restrict__ pc, const long long *__restrict__
             ring.dyn[o] = 0;
         }
     }
+    aabb_update<IBLOCK>(fs.aabb, keep, wx, wy, wz);
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
@@ -351,6 +365,16 @@ struct SweepDesc {
     uint32_t n_tiles;
     uint32_t state_off;   // first tile-state word of this sweep
 };
+
+// empties the bounding boxes of frames first_id+1 .. first_id+n-1 (the first one was emptied
+// by the frame before it, or at creation)
+__global__ void k_aabb_empty(unsigned long long *__restrict__ aabb, int64_t first_id, int n,
+                             int max_frames) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n - 1) * 6) return;
+    int slot = (int)((first_id + 1 + t / 6) % max_frames);
+    aabb[(int64_t)slot * 6 + t % 6] = (t % 6) < 3 ? AABB_EMPTY_MIN : AABB_EMPTY_MAX;
+}
 
 template <int DT>
 __global__ void __launch_bounds__(IBLOCK)
@@ -400,11 +424,11 @@ k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int i
     }
     uint32_t tile_end;
     uint32_t rank = compact_rank<IBLOCK>(keep, state + sw.state_off, epoch, tile, s_warp, &tile_end);
+    double wx = 0, wy = 0, wz = 0;
     if (keep) {
         int64_t o = base + rank;
+        affine_chain(sw.T.m, 4, x, y, z, wx, wy, wz);
         if (o < sw.fs.capacity) {
-            double wx, wy, wz;
-            affine_chain(sw.T.m, 4, x, y, z, wx, wy, wz);
             ring.x[o] = wx;
             ring.y[o] = wy;
             ring.z[o] = wz;
@@ -418,6 +442,7 @@ k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int i
             ring.dyn[o] = 0;
         }
     }
+    aabb_update<IBLOCK>(sw.fs.aabb, keep, wx, wy, wz);
     if (tile == sw.n_tiles - 1 && threadIdx.x == 0) finish_frame(sw.fs, base, tile_end);
 }
 
@@ -429,6 +454,11 @@ k_integrate_cloud(const double *__restrict__ rec, int64_t n, RingDev ring, Frame
                   uint32_t *__restrict__ flags) {
     const int64_t base = frame_base(fs);
     int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    {
+        const bool have = i < n;
+        aabb_update<IBLOCK>(fs.aabb, have, have ? rec[i * 10] : 0.0, have ? rec[i * 10 + 1] : 0.0,
+                            have ? rec[i * 10 + 2] : 0.0);
+    }
     if (i < n) {
         const double *r = rec + i * 10;
         int64_t o = base + i;
@@ -468,12 +498,15 @@ k_integrate_cloud(const double *__restrict__ rec, int64_t n, RingDev ring, Frame
 // re-basing
 // ---------------------------------------------------------------------------
 // lazy: chain[epoch] = T; comp[f] = T @ comp[f] for every live frame
-__global__ void k_rebase_lazy(double *__restrict__ chain_slot, double *__restrict__ comp, TMat T,
-                              int first_slot, int n_live, int max_frames) {
+__global__ void k_rebase_lazy(double *__restrict__ chain_slot, double *__restrict__ comp,
+                              double *__restrict__ cull, TMat T, int first_slot, int n_live,
+                              int max_frames) {
     int t = threadIdx.x + blockIdx.x * blockDim.x;
     if (t < 12) chain_slot[t] = T.m[(t / 4) * 4 + (t % 4)];
-    if (t < n_live) {
-        double *c = comp + (int64_t)((first_slot + t) % max_frames) * 12;
+    // both per-frame matrices take the new link: `comp` (pending, reset when materialised)
+    // and `cull` (everything since insertion)
+    if (t < 2 * n_live) {
+        double *c = (t < n_live ? comp : cull) + (int64_t)((first_slot + (t % n_live)) % max_frames) * 12;
         double o[12];
         // 3x4 affine composition: rows of T times [c; 0 0 0 1]
         for (int r = 0; r < 3; r++) {
@@ -661,12 +694,16 @@ static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs,
     fs->frame_cnt = h->d_frame_cnt;
     fs->frame_epoch = h->d_frame_epoch;
     fs->comp = h->d_comp + (int64_t)slot * 12;
+    fs->cull = h->d_cull + (int64_t)slot * 12;
+    fs->aabb = h->d_aabb + (int64_t)slot * 6;
+    fs->aabb_next = h->d_aabb + (int64_t)((id + 1) % h->max_frames) * 6;
     fs->slot = slot;
     fs->next_slot = (int)((id + 1) % h->max_frames);
     fs->base_override = override_base;
     fs->epoch = h->rebase_epoch;
     fs->capacity = h->capacity;
     fs->write_next = 1;
+    fs->slot_id = id;
     h->next_id = id + 1;
     if (frame_id) *frame_id = id;
     return PCACC_OK;
@@ -900,6 +937,11 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
     const SweepDesc *d_desc = (const SweepDesc *)dev;
     uint32_t *d_tickets = (uint32_t *)((char *)dev + desc_bytes);
     uint32_t epoch = pcacc_next_epoch(h);
+    if (n_sweeps > 1) {
+        k_aabb_empty<<<((n_sweeps - 1) * 6 + 127) / 128, 128, 0, st>>>(h->d_aabb, desc[0].fs.slot_id,
+                                                                     n_sweeps, h->max_frames);
+        PCACC_CUDA(h, cudaGetLastError());
+    }
     dim3 grid((unsigned)max_tiles, (unsigned)n_sweeps);
     size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_IRB(DT)                                                                           \
@@ -988,10 +1030,10 @@ extern "C" int pcacc_rebase(pcacc_t h, const double *T_new_prev, int eager, void
     memcpy(T.m, T_new_prev, sizeof(T.m));
     int first_slot = (int)(h->first_id % h->max_frames);
     double *slot = h->d_chain + (h->rebase_epoch % h->max_frames) * 12;
-    int threads = n_live < 12 ? 12 : n_live;
+    int threads = 2 * n_live < 12 ? 12 : 2 * n_live;
     size_t pe = pcacc_prof_begin(h, PCACC_K_REBASE, st);
-    k_rebase_lazy<<<(threads + 127) / 128, 128, 0, st>>>(slot, h->d_comp, T, first_slot, n_live,
-                                                         h->max_frames);
+    k_rebase_lazy<<<(threads + 127) / 128, 128, 0, st>>>(slot, h->d_comp, h->d_cull, T, first_slot,
+                                                         n_live, h->max_frames);
     PCACC_CUDA(h, cudaGetLastError());
     pcacc_prof_end(h, PCACC_K_REBASE, pe, st);
     h->rebase_epoch += 1;

@@ -44,6 +44,8 @@ struct BinArgs {
     RingDev ring;
     const int64_t *frame_off, *frame_cnt, *frame_epoch;
     const double *comp, *chain;
+    const double *cull;              // total transform of each frame since insertion
+    const unsigned long long *aabb;  // order-encoded source-frame bounding boxes
     int max_frames;
     int64_t frame_lo;      // absolute id of the first frame of this launch
     int64_t epoch_now;
@@ -52,6 +54,7 @@ struct BinArgs {
     int n_frames;          // frames covered by this launch (<= BIN_MAXF), first = frame_lo
     int P;
     uint32_t *counts;      // n_var * 2*P*P (+1)
+    uint32_t *frame_tiles; // per frame of the launch: tiles to visit (k_bev_cull)
     uint32_t *cand_gi;     // candidate list: ring position ...
     uint32_t *cand_meta;   // ... and variant | frame-in-launch << 8
     uint32_t *tmp_key, *tmp_rank;
@@ -137,6 +140,66 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
 
 #define BIN_MAXF 2048 /* frames per launch */
 
+// Frame culling: can any point of the frame fall into the view of any variant?  The 8
+// corners of the frame's bounding box (source frame, recorded at integrate time) go
+// through the frame's total transform and the variant's shift / rotation; the image of
+// the box is inside the bounding box of the transformed corners.  Conservative (margin
+// far above fp64 rounding and above the lazy-vs-sequential chain difference); NaN / inf
+// boxes are never culled.
+__device__ __forceinline__ bool frame_may_touch_view(const BinArgs &a, int slot, int64_t fid) {
+    const unsigned long long *bb = a.aabb + (int64_t)slot * 6;
+    double lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = ord_decode(bb[k]);
+        hi[k] = ord_decode(bb[3 + k]);
+    }
+    if (!(lo[0] <= hi[0])) return true;  // empty / not tracked: let the points decide
+    const double *M = a.cull + (int64_t)slot * 12;
+    double cx[8], cy[8], cz[8];
+    double amax = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const double x = (c & 1) ? hi[0] : lo[0], y = (c & 2) ? hi[1] : lo[1], z = (c & 4) ? hi[2] : lo[2];
+        cx[c] = M[0] * x + M[1] * y + M[2] * z + M[3];
+        cy[c] = M[4] * x + M[5] * y + M[6] * z + M[7];
+        cz[c] = M[8] * x + M[9] * y + M[10] * z + M[11];
+        amax = fmax(amax, fmax(fabs(cx[c]), fmax(fabs(cy[c]), fabs(cz[c]))));
+    }
+    const double margin = 1e-5 + 1e-9 * amax;
+    for (int v = 0; v < a.n_var; v++) {
+        const pcacc_bev_params &bp = a.params[v];
+        if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;
+        double q0lo = INFINITY, q0hi = -INFINITY, q1lo = INFINITY, q1hi = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const double sx = cx[c] - bp.origin[0], sy = cy[c] - bp.origin[1], sz = cz[c] - bp.origin[2];
+            const double q0 = bp.R[0] * sx + bp.R[1] * sy + bp.R[2] * sz + bp.trans_dx;
+            const double q1 = bp.R[3] * sx + bp.R[4] * sy + bp.R[5] * sz + bp.trans_dy;
+            q0lo = fmin(q0lo, q0);
+            q0hi = fmax(q0hi, q0);
+            q1lo = fmin(q1lo, q1);
+            q1hi = fmax(q1hi, q1);
+        }
+        const double lim = 0.5 * bp.view + margin;
+        const bool outside = (q0lo > lim) || (q0hi < -lim) || (q1lo > lim) || (q1hi < -lim);
+        if (!outside) return true;   // also taken when anything is NaN
+    }
+    return false;
+}
+
+// one thread per frame: number of 1024-point tiles to visit (0 when the frame is empty or
+// provably outside every variant's view)
+__global__ void k_bev_cull(BinArgs a) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n_frames) return;
+    const int slot = (int)((a.frame_lo + f) % a.max_frames);
+    const int64_t c = a.frame_cnt[slot];
+    uint32_t t = (uint32_t)((c + BIN_TILE - 1) / BIN_TILE);
+    if (t && !frame_may_touch_view(a, slot, a.frame_lo + f)) t = 0;
+    a.frame_tiles[f] = t;
+}
+
 // ---------------------------------------------------------------------------
 // pass 1a — k_bev_classify: pure streaming.  Persistent blocks walk a (frame, tile,
 // variant-group) work list that is derived on the device from the frame table (the
@@ -166,11 +229,7 @@ k_bev_classify(BinArgs a) {
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const int f = (int)threadIdx.x * PER + k;
-            uint32_t t = 0;
-            if (f < a.n_frames) {
-                const int64_t c = a.frame_cnt[(int)((a.frame_lo + f) % a.max_frames)];
-                t = (uint32_t)((c + BIN_TILE - 1) / BIN_TILE);
-            }
+            const uint32_t t = f < a.n_frames ? a.frame_tiles[f] : 0u;  // 0 = empty or culled
             loc[k] = sum;
             sum += t;
         }
@@ -319,16 +378,28 @@ k_bev_bin(BinArgs a) {
     unsigned long long n = *a.n_append;
     if (n > (unsigned long long)a.cap) n = (unsigned long long)a.cap;
     const int PP = a.P * a.P;
-    for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < n;
-         c += (unsigned long long)gridDim.x * 256) {
-        const int64_t gi = (int64_t)a.cand_gi[c];
-        const uint32_t meta = a.cand_meta[c];
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n) return;
+    uint32_t gi32 = a.cand_gi[c], meta = a.cand_meta[c];
+    while (true) {
+        const int64_t gi = (int64_t)gi32;
+        // every field of the point in one round trip (rejections below are rare)
+        double x = a.ring.x[gi], y = a.ring.y[gi], z = a.ring.z[gi];
+        const uint32_t rgbs = a.ring.rgbs[gi];
+        const float inten = a.ring.inten[gi];
+        const uint8_t dyn = a.ring.dyn[gi];
         const int v = (int)(meta & 255u);
         const int64_t fid = a.frame_lo + (int64_t)(meta >> 8);
+        // next candidate's entry is fetched while this one is processed
+        const unsigned long long cn = c + stride;
+        if (cn < n) {
+            gi32 = a.cand_gi[cn];
+            meta = a.cand_meta[cn];
+        }
         const int slot = (int)(fid % a.max_frames);
         const pcacc_bev_params &bp = a.params[v];
         const int64_t e0 = a.frame_epoch[slot];
-        double x = a.ring.x[gi], y = a.ring.y[gi], z = a.ring.z[gi];
         Eval e;
         if (e0 < a.epoch_now) {
             double cx, cy, cz;
@@ -348,19 +419,20 @@ k_bev_bin(BinArgs a) {
         } else {
             e = eval_point(bp, a.P, x, y, z, false);
         }
-        if (e.keep && a.ring.dyn[gi] == 1) e.keep = false;  // static points only
+        if (dyn == 1) e.keep = false;  // static points only (sem_bev.py:54-58)
         if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
         if (e.keep) {
             const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
             const uint32_t key = ((uint32_t)v * (uint32_t)PP + (uint32_t)e.cell) * 2u + win;
             const unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
             a.tmp_key[c] = key;
+            a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), rgbs, __float_as_uint(inten));
             a.tmp_rank[c] = atomicAdd(&a.counts[key], 1u);
-            a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), a.ring.rgbs[gi],
-                                      __float_as_uint(a.ring.inten[gi]));
         } else {
             a.tmp_key[c] = KEY_INVALID;  // hole: rejected by the exact test
         }
+        if (cn >= n) break;
+        c = cn;
     }
 }
 
@@ -792,14 +864,26 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
         __syncwarp();
         WinAcc a;
         acc_init(a, want_max);
-        for (uint32_t i = lane; i < nt; i += 32) {
-            const uint4 r = sorted[b0 + i];
-            const int w = i >= np ? 1 : 0;
-            const uint32_t c = r.z;
-            atomicAdd(&hist[w][0][c & 255u], 1u);
-            atomicAdd(&hist[w][1][(c >> 8) & 255u], 1u);
-            atomicAdd(&hist[w][2][(c >> 16) & 255u], 1u);
-            acc_record(a, r, w, road_cls, v0, v1, v2, v3, want_max);
+        for (uint32_t i0 = 0; i0 < nt; i0 += 128) {
+            // four independent 16 B loads in flight per lane
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32 * u + lane;
+                r[u] = i < nt ? sorted[b0 + i] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32 * u + lane;
+                if (i < nt) {
+                    const int w = i >= np ? 1 : 0;
+                    const uint32_t c = r[u].z;
+                    atomicAdd(&hist[w][0][c & 255u], 1u);
+                    atomicAdd(&hist[w][1][(c >> 8) & 255u], 1u);
+                    atomicAdd(&hist[w][2][(c >> 16) & 255u], 1u);
+                    acc_record(a, r[u], w, road_cls, v0, v1, v2, v3, want_max);
+                }
+            }
         }
 #pragma unroll
         for (int w = 0; w < 2; w++) {
@@ -976,7 +1060,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         size_t o_rec = align_up(o_rank + (size_t)cap * 4, 256);
         size_t o_sorted = align_up(o_rec + (size_t)cap * 16, 256);
         size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
-        size_t o_big = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
+        size_t o_ftiles = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
+        size_t o_big = align_up(o_ftiles + (size_t)BIN_MAXF * 4, 256);
         // a cell is "large" only above SMALL_T points, so the queue never exceeds cap / (SMALL_T+1)
         int64_t big_cap = cap / (SMALL_T + 1) + 1;
         if (big_cap > (int64_t)nv * PP) big_cap = (int64_t)nv * PP;
@@ -1007,6 +1092,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.frame_epoch = h->d_frame_epoch;
             a.comp = h->d_comp;
             a.chain = h->d_chain;
+            a.cull = h->d_cull;
+            a.aabb = h->d_aabb;
             a.max_frames = h->max_frames;
             a.frame_lo = flo;
             a.epoch_now = h->rebase_epoch;
@@ -1014,6 +1101,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.n_var = nv;
             a.P = P;
             a.counts = counts;
+            a.frame_tiles = (uint32_t *)(ws + o_ftiles);
             a.cand_gi = (uint32_t *)(ws + o_sorted);
             a.cand_meta = (uint32_t *)(ws + o_sorted + (size_t)cap * 4);
             a.tmp_key = (uint32_t *)(ws + o_key);
@@ -1030,6 +1118,9 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.frame_lo = flo;
             a.n_frames = (int)nf;
             size_t pe = pcacc_prof_begin(h, PCACC_K_CLASSIFY, st);
+            k_bev_cull<<<(a.n_frames + 127) / 128, 128, 0, st>>>(a);
+            PCACC_CUDA(h, cudaGetLastError());
+            h->launches[PCACC_K_CLASSIFY]++;
             k_bev_classify<<<148 * 4, BIN_BLOCK, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_CLASSIFY, pe, st);

@@ -201,6 +201,43 @@ def test_kitti_sequence(dev, name, kw, gt, eager):
     cloud.close()
 
 
+@pytest.mark.parametrize('eager', [False, True])
+def test_long_trajectory_frame_culling(dev, eager):
+    """40 frames, 15 m apart: most frames lie outside the 80 m view and are culled by
+    their bounding boxes; the result must not change."""
+    P, n_frames = 64, 40
+    rng = np.random.default_rng(17)
+    frames = []
+    for f in range(n_frames):
+        seed = synth.seed_for(3, 500 + f)
+        pc = synth.kitti_lidar(seed, 8, 200)
+        yaw = rng.uniform(-0.05, 0.05)
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]
+        T[:3, 3] = [15.0 + rng.uniform(-1, 1), rng.uniform(-0.5, 0.5), 0.]
+        frames.append(dict(pc=pc, T=np.linalg.inv(T), rgb=None, cls=None,
+                           sem_gt=synth.kitti_sem_gt(seed, pc.shape[0])))
+    acc, cloud = _run_kitti(dev, frames, True, P, 1e9, eager)
+    first, n_live = cloud.live_frames()
+    for p_idx in (3, 20, 38):
+        origin = np.array(acc.poses[p_idx])
+        rot = orc.heading_rot_ang(np.array(acc.poses[:p_idx]) - origin)
+        bp = bev_params_from(dev, acc.gen_params, first, first + p_idx, first + n_live, origin, rot)
+        o16, o64, cells = cloud.rasterise([bp], P, want_f64=True, want_cells=True)
+        cloud.sync()
+        ref = acc.generate_bev(p_idx, return_f64=True)
+        dbg = ref.pop('_debug')
+        compare_planes(o16[0].cpu().numpy(), o64[0].cpu().numpy(),
+                       {w: dbg[f'planes_f64_{w}'] for w in ('present', 'future', 'full')},
+                       exact=(0, 2, 3, 4, 5, 6) if eager else (0, 2, 3, 4, 5))
+        fids = list(range(first, first + n_live))
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[:p_idx], P), dbg['cells_present'])
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[p_idx:], P), dbg['cells_future'])
+        st = cloud.raster_stats()
+        assert 0 < st['binned'] < 0.5 * cloud.resident_points()
+    cloud.close()
+
+
 def test_nusc_sequence(dev):
     g = load_golden('nusc_seq.npz')
     scene = cases.nusc_seq_inputs()
