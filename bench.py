@@ -297,6 +297,7 @@ def run_ours(args, rank, world, local_rank, dist):
     }
     # stages made of two kernels are timed as one stage: reduce = small-cell pass + queued
     # large-cell pass; bin = streaming crop test + exact per-candidate pass
+    prof_raw = dict(prof)
     prof['bev_reduce'] = (prof['bev_reduce'][0] + prof.pop('bev_reduce_big')[0], prof['bev_reduce'][1])
     prof['bev_bin'] = (prof['bev_bin'][0] + prof.pop('bev_classify')[0], prof['bev_bin'][1])
     dom = max(prof, key=lambda k: prof[k][0])
@@ -314,8 +315,8 @@ def run_ours(args, rank, world, local_rank, dist):
                 'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' (burst copy)',
                 'launch_us': dom_ms / max(dom_n, 1) * 1e3,
                 'share_of_step': dom_ms / ms_total,
-                'kernel_ms': {k: round(v[0], 3) for k, v in prof.items() if v[1]},
-                'kernel_launches': {k: v[1] for k, v in prof.items() if v[1]}}
+                'kernel_ms': {k: round(v[0], 3) for k, v in prof_raw.items() if v[1]},
+                'kernel_launches': {k: v[1] for k, v in prof_raw.items() if v[1]}}
     b_step = S * (alg['integrate'] + alg['bev_bin'] + alg['bev_reduce'])
     path_ach = b_step * args.steps / (ms_total * 1e-3) / 1e9
     roofline_path = {'achieved': path_ach, 'peak': peak, 'unit': 'GB/s', 'frac': path_ach / peak,

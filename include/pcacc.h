@@ -51,6 +51,7 @@ typedef enum {
 #define PCACC_SEM_U8 0
 #define PCACC_SEM_I32 1
 #define PCACC_SEM_I64 2
+#define PCACC_SEM_I16 4
 #define PCACC_SEM_F32_PROB 3 /* (H,W,K) float32 class probabilities: class = first argmax over K */
 
 const char *pcacc_strerror(int status);

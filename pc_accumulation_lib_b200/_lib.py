@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'libpcacc.so')
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_STATE = -1, -2, -3, -4, -5
 FLAG_UV_OUT_OF_IMAGE, FLAG_INTENSITY_F32, FLAG_ATTR_RANGE, FLAG_CELL_OVERFLOW = 1, 2, 4, 8
-SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB = 0, 1, 2, 3
+SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB, SEM_I16 = 0, 1, 2, 3, 4
 BEV_PLANES, BEV_WINDOWS = 7, 3
 ABI_VERSION = 1
 

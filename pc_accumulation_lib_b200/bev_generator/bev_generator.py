@@ -126,20 +126,31 @@ class BEVGenerator(ABC):
         return xm, ym, iters
 
     def crop_trajectory(self, traj, aug_view_size, thresh=1e-4):
+        """Edges of the polyline against the open view box: a vertex is kept if it starts
+        an edge and lies inside; an edge that crosses the boundary contributes its
+        bisection point.  (The last in-view vertex is never emitted — as in the reference.)
+        The inside test is vectorised; only crossing edges run the scalar bisection."""
         half = 0.5 * aug_view_size
         bbox = [-half, -half, half, half]
-        kept = []
-        for a, b in zip(traj[:-1], traj[1:]):
-            ax, ay = list(a[:2])
-            bx, by = list(b[:2])
-            a_in = self.point_in_box(ax, ay, *bbox)
-            b_in = self.point_in_box(bx, by, *bbox)
-            if a_in:
-                kept.append([ax, ay, a[2]])
-            if a_in != b_in:
-                ix, iy, _ = self.cal_intersec_pnt(ax, ay, bx, by, bbox, thresh)
-                kept.append([ix, iy, a[2]])
-        return np.array(kept) if kept else np.zeros((0, 3))
+        n = traj.shape[0]
+        if n < 2:
+            return np.zeros((0, 3))
+        x, y = traj[:, 0], traj[:, 1]
+        inside = (-half < x) & (x < half) & (-half < y) & (y < half)
+        a_in, b_in = inside[:-1], inside[1:]
+        cross = a_in != b_in
+        per_edge = a_in.astype(np.int64) + cross
+        total = int(per_edge.sum())
+        if total == 0:
+            return np.zeros((0, 3))
+        out = np.empty((total, 3))
+        first = np.cumsum(per_edge) - per_edge          # output row of each edge's first entry
+        ka = np.flatnonzero(a_in)
+        out[first[ka]] = traj[ka, :3]
+        for k in np.flatnonzero(cross):
+            ix, iy, _ = self.cal_intersec_pnt(x[k], y[k], x[k + 1], y[k + 1], bbox, thresh)
+            out[first[k] + int(a_in[k])] = (ix, iy, traj[k, 2])
+        return out
 
     def geometric_transform(self, pc_mat, rot_ang, trans_dx, trans_dy, aug_view_size,
                             is_traj=False):

@@ -146,6 +146,43 @@ __device__ __forceinline__ uint32_t compact_rank(bool keep, unsigned long long *
     return s_warp[warp] + in_warp;
 }
 
+// The same for ITEMS flags per thread, where item k of thread t is element k*BLOCK + t of
+// the tile (ITEMS * BLOCK/32 <= 32).
+template <int BLOCK, int ITEMS>
+__device__ __forceinline__ void compact_rank_multi(const bool (&keep)[ITEMS], unsigned long long *state,
+                                                   uint32_t epoch, uint32_t tile,
+                                                   uint32_t *s_cnt /*ITEMS*BLOCK/32+1*/,
+                                                   uint32_t (&rank)[ITEMS], uint32_t *tile_end) {
+    constexpr int NW = BLOCK / 32;
+    static_assert(ITEMS * NW <= 32, "one warp scans all sub-row counts");
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t in_warp[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, keep[k]);
+        in_warp[k] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[k * NW + warp] = __popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t c = (lane < ITEMS * NW) ? s_cnt[lane] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t base = lb_exclusive_prefix(state, epoch, tile, total);
+        if (lane < ITEMS * NW) s_cnt[lane] = base + incl - c;
+        if (lane == 0) s_cnt[ITEMS * NW] = base + total;
+    }
+    __syncthreads();
+    *tile_end = s_cnt[ITEMS * NW];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) rank[k] = s_cnt[k * NW + warp] + in_warp[k];
+}
+
 // ---------------------------------------------------------------------------
 // per-frame bounding boxes (frame culling in the rasteriser)
 // ---------------------------------------------------------------------------
@@ -163,10 +200,13 @@ __device__ __forceinline__ double ord_decode(unsigned long long u) {
 
 // Block-wide min / max of the kept points' stored coordinates -> 6 atomics per block.
 // Must be called by every thread of the block. NaN coordinates are ignored (fmin / fmax).
+// v = this thread's (min x, min y, min z, max x, max y, max z); +-inf when it kept nothing.
+template <int BLOCK>
+__device__ __forceinline__ void aabb_update_v(unsigned long long *aabb, double (&v)[6]);
+
 template <int BLOCK>
 __device__ __forceinline__ void aabb_update(unsigned long long *aabb, bool keep, double x, double y,
                                             double z) {
-    __shared__ double s_bb[BLOCK / 32][6];
     double v[6];
     v[0] = keep ? x : INFINITY;
     v[1] = keep ? y : INFINITY;
@@ -174,6 +214,12 @@ __device__ __forceinline__ void aabb_update(unsigned long long *aabb, bool keep,
     v[3] = keep ? x : -INFINITY;
     v[4] = keep ? y : -INFINITY;
     v[5] = keep ? z : -INFINITY;
+    aabb_update_v<BLOCK>(aabb, v);
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void aabb_update_v(unsigned long long *aabb, double (&v)[6]) {
+    __shared__ double s_bb[BLOCK / 32][6];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll

@@ -73,6 +73,7 @@ template <int DT>
 __device__ __forceinline__ int load_class(const void *map, int64_t pix, int K) {
     if (DT == PCACC_SEM_U8) return (int)((const uint8_t *)map)[pix];
     if (DT == PCACC_SEM_I32) return ((const int32_t *)map)[pix];
+    if (DT == PCACC_SEM_I16) return (int)((const int16_t *)map)[pix];
     if (DT == PCACC_SEM_I64) {
         long long v = ((const long long *)map)[pix];
         return (v < -2147483647ll || v > 2147483647ll) ? -2147483647 : (int)v;
@@ -169,6 +170,7 @@ k_gen_semantic_pc(const float4 *__restrict__ pts, int64_t n, PMat P, const void 
             if (DT == PCACC_SEM_U8) f = (double)((const uint8_t *)map)[pix + k];
             else if (DT == PCACC_SEM_I32) f = (double)((const int32_t *)map)[pix + k];
             else if (DT == PCACC_SEM_I64) f = (double)((const long long *)map)[pix + k];
+            else if (DT == PCACC_SEM_I16) f = (double)((const int16_t *)map)[pix + k];
             else f = (double)((const float *)map)[pix + k];
             o[4 + k] = f;
         }
@@ -280,74 +282,101 @@ struct TMat {
     double m[16];
 };
 
+#define REC_ITEMS 4                       /* points per thread in the records kernels */
+#define REC_TILE (IBLOCK * REC_ITEMS)
+
+// One tile (1024 consecutive points) of the nuScenes record path.  Item k of thread t is
+// point tile*1024 + k*256 + t.  Only the two pixel coordinates are read for every point;
+// xyz / intensity / instance of the (few) kept points are fetched after the gather.
+template <int DT>
+__device__ __forceinline__ void records_tile(const double *__restrict__ pc,
+                                             const long long *__restrict__ cam_idx, int64_t n,
+                                             const CamMaps &maps, int img_h, int img_w,
+                                             const double *__restrict__ T, const Filters &filt,
+                                             const RingDev &ring, const FrameSlots &fs,
+                                             unsigned long long *state, uint32_t epoch, uint32_t tile,
+                                             uint32_t n_tiles, int64_t base,
+                                             uint32_t *__restrict__ flags, uint32_t *s_cnt) {
+    bool keep[REC_ITEMS];
+    uint32_t packed[REC_ITEMS];
+    long long cam[REC_ITEMS];
+#pragma unroll
+    for (int k = 0; k < REC_ITEMS; k++) {
+        const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+        cam[k] = i < n ? cam_idx[i] : -1;
+        keep[k] = false;
+        packed[k] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < REC_ITEMS; k++) {
+        if (cam[k] >= 0 && cam[k] < maps.n) {
+            const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+            const double uf = pc[i * 7 + 4], vf = pc[i * 7 + 5];
+            // pts_feat_from_img bounds assertion, datasets/nuscenes_utils.py:190-195
+            const bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
+                                (vf < (double)img_h - 1.0);
+            if (!inside) {
+                atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
+            } else {
+                const int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
+                int cls = load_class<DT>(maps.sem[cam[k]], pix, 1);
+                keep[k] = (cls >= 0) && !class_filtered(filt, cls);
+                if (keep[k]) {
+                    if (cls > 255) {
+                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                        cls &= 255;
+                    }
+                    const uint8_t *c = maps.rgb[cam[k]] + pix * 3;
+                    packed[k] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
+                                ((uint32_t)cls << 24);
+                }
+            }
+        }
+    }
+    uint32_t rank[REC_ITEMS], tile_end;
+    compact_rank_multi<IBLOCK, REC_ITEMS>(keep, state, epoch, tile, s_cnt, rank, &tile_end);
+    double bb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int k = 0; k < REC_ITEMS; k++) {
+        if (keep[k]) {
+            const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+            const double *row = pc + i * 7;
+            double wx, wy, wz;
+            affine_chain(T, 4, row[0], row[1], row[2], wx, wy, wz);
+            bb[0] = fmin(bb[0], wx); bb[1] = fmin(bb[1], wy); bb[2] = fmin(bb[2], wz);
+            bb[3] = fmax(bb[3], wx); bb[4] = fmax(bb[4], wy); bb[5] = fmax(bb[5], wz);
+            const int64_t o = base + rank[k];
+            if (o < fs.capacity) {
+                ring.x[o] = wx;
+                ring.y[o] = wy;
+                ring.z[o] = wz;
+                const double inten = row[3], inst_f = row[6];
+                const float fi = (float)inten;
+                if ((double)fi != inten) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
+                ring.inten[o] = fi;
+                ring.rgbs[o] = packed[k];
+                const int32_t ii = sat_i32(inst_f);
+                if ((double)ii != inst_f) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                ring.inst[o] = ii;
+                ring.dyn[o] = 0;
+            }
+        }
+    }
+    aabb_update_v<IBLOCK>(fs.aabb, bb);
+    if (tile == n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
+}
+
 template <int DT>
 __global__ void __launch_bounds__(IBLOCK)
 k_integrate_records(const double *__restrict__ pc, const long long *__restrict__ cam_idx, int64_t n,
                     CamMaps maps, int img_h, int img_w, TMat T, Filters filt, RingDev ring,
                     FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[REC_ITEMS * IBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
-    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
-    const int64_t base = frame_base(fs);
-    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
-    bool keep = false;
-    double x = 0, y = 0, z = 0, inten = 0, inst_f = 0;
-    uint32_t packed = 0;
-    if (i < n) {
-        long long cam = cam_idx[i];
-        if (cam >= 0 && cam < maps.n) {
-            const double *row = pc + i * 7;
-            double uf = row[4], vf = row[5];
-            // pts_feat_from_img bounds assertion, datasets/nuscenes_utils.py:190-195
-            bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
-                          (vf < (double)img_h - 1.0);
-            if (!inside) {
-                atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
-            } else {
-                int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
-                int cls = load_class<DT>(maps.sem[cam], pix, 1);
-                keep = (cls >= 0) && !class_filtered(filt, cls);
-                if (keep) {
-                    if (cls > 255) {
-                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-                        cls &= 255;
-                    }
-                    const uint8_t *c = maps.rgb[cam] + pix * 3;
-                    packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
-                             ((uint32_t)cls << 24);
-                    x = row[0];
-                    y = row[1];
-                    z = row[2];
-                    inten = row[3];
-                    inst_f = row[6];
-                }
-            }
-        }
-    }
-    uint32_t tile_end;
-    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
-    double wx = 0, wy = 0, wz = 0;
-    if (keep) {
-        int64_t o = base + rank;
-        affine_chain(T.m, 4, x, y, z, wx, wy, wz);
-        if (o < fs.capacity) {
-            ring.x[o] = wx;
-            ring.y[o] = wy;
-            ring.z[o] = wz;
-            float fi = (float)inten;
-            if ((double)fi != inten) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
-            ring.inten[o] = fi;
-            ring.rgbs[o] = packed;
-            int32_t ii = sat_i32(inst_f);
-            if ((double)ii != inst_f) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-            ring.inst[o] = ii;
-            ring.dyn[o] = 0;
-        }
-    }
-    aabb_update<IBLOCK>(fs.aabb, keep, wx, wy, wz);
-    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
+    const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    records_tile<DT>(pc, cam_idx, n, maps, img_h, img_w, T.m, filt, ring, fs, lb.state, lb.epoch, tile,
+                     lb.n_tiles, frame_base(fs), flags, s_cnt);
 }
-
 
 // ---------------------------------------------------------------------------
 // batched nuScenes integrate: every sweep of a scene in ONE launch
@@ -382,68 +411,13 @@ k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int i
                           RingDev ring, unsigned long long *__restrict__ state,
                           uint32_t *__restrict__ tickets, uint32_t epoch,
                           uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[REC_ITEMS * IBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
     const SweepDesc &sw = sweeps[blockIdx.y];
     if (blockIdx.x >= sw.n_tiles) return;
-    uint32_t tile = lb_take_ticket(tickets + blockIdx.y, sw.n_tiles, &s_tile);
-    const int64_t base = sw.fs.base_override;
-    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
-    bool keep = false;
-    double x = 0, y = 0, z = 0, inten = 0, inst_f = 0;
-    uint32_t packed = 0;
-    if (i < sw.n) {
-        long long cam = sw.cam[i];
-        if (cam >= 0 && cam < sw.maps.n) {
-            const double *row = sw.pc + i * 7;
-            double uf = row[4], vf = row[5];
-            bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
-                          (vf < (double)img_h - 1.0);
-            if (!inside) {
-                atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
-            } else {
-                int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
-                int cls = load_class<DT>(sw.maps.sem[cam], pix, 1);
-                keep = (cls >= 0) && !class_filtered(filt, cls);
-                if (keep) {
-                    if (cls > 255) {
-                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-                        cls &= 255;
-                    }
-                    const uint8_t *c = sw.maps.rgb[cam] + pix * 3;
-                    packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
-                             ((uint32_t)cls << 24);
-                    x = row[0];
-                    y = row[1];
-                    z = row[2];
-                    inten = row[3];
-                    inst_f = row[6];
-                }
-            }
-        }
-    }
-    uint32_t tile_end;
-    uint32_t rank = compact_rank<IBLOCK>(keep, state + sw.state_off, epoch, tile, s_warp, &tile_end);
-    double wx = 0, wy = 0, wz = 0;
-    if (keep) {
-        int64_t o = base + rank;
-        affine_chain(sw.T.m, 4, x, y, z, wx, wy, wz);
-        if (o < sw.fs.capacity) {
-            ring.x[o] = wx;
-            ring.y[o] = wy;
-            ring.z[o] = wz;
-            float fi = (float)inten;
-            if ((double)fi != inten) atomicOr(flags, PCACC_FLAG_INTENSITY_F32);
-            ring.inten[o] = fi;
-            ring.rgbs[o] = packed;
-            int32_t ii = sat_i32(inst_f);
-            if ((double)ii != inst_f) atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-            ring.inst[o] = ii;
-            ring.dyn[o] = 0;
-        }
-    }
-    aabb_update<IBLOCK>(sw.fs.aabb, keep, wx, wy, wz);
-    if (tile == sw.n_tiles - 1 && threadIdx.x == 0) finish_frame(sw.fs, base, tile_end);
+    const uint32_t tile = lb_take_ticket(tickets + blockIdx.y, sw.n_tiles, &s_tile);
+    records_tile<DT>(sw.pc, sw.cam, sw.n, sw.maps, img_h, img_w, sw.T.m, filt, ring, sw.fs,
+                     state + sw.state_off, epoch, tile, sw.n_tiles, sw.fs.base_override, flags, s_cnt);
 }
 
 // ---------------------------------------------------------------------------
@@ -748,6 +722,7 @@ extern "C" int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n,
         case PCACC_SEM_U8: LAUNCH_GSP(PCACC_SEM_U8); break;
         case PCACC_SEM_I32: LAUNCH_GSP(PCACC_SEM_I32); break;
         case PCACC_SEM_I64: LAUNCH_GSP(PCACC_SEM_I64); break;
+        case PCACC_SEM_I16: LAUNCH_GSP(PCACC_SEM_I16); break;
         case PCACC_SEM_F32_PROB: LAUNCH_GSP(PCACC_SEM_F32_PROB); break;
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown map dtype %d", map_dtype);
     }
@@ -792,6 +767,7 @@ extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t 
         case PCACC_SEM_U8: LAUNCH_IF(PCACC_SEM_U8); break;
         case PCACC_SEM_I32: LAUNCH_IF(PCACC_SEM_I32); break;
         case PCACC_SEM_I64: LAUNCH_IF(PCACC_SEM_I64); break;
+        case PCACC_SEM_I16: LAUNCH_IF(PCACC_SEM_I16); break;
         case PCACC_SEM_F32_PROB: LAUNCH_IF(PCACC_SEM_F32_PROB); break;
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown sem dtype %d", sem_dtype);
     }
@@ -852,7 +828,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
     }
     TMat T;
     memcpy(T.m, T_ego_world, sizeof(T.m));
-    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    int64_t tiles = (n + REC_TILE - 1) / REC_TILE;
     if (tiles == 0) tiles = 1;
     LookBack lb;
     rc = make_lookback(h, tiles, &lb);
@@ -869,6 +845,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
         case PCACC_SEM_U8: LAUNCH_IR(PCACC_SEM_U8); break;
         case PCACC_SEM_I32: LAUNCH_IR(PCACC_SEM_I32); break;
         case PCACC_SEM_I64: LAUNCH_IR(PCACC_SEM_I64); break;
+        case PCACC_SEM_I16: LAUNCH_IR(PCACC_SEM_I16); break;
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
     }
 #undef LAUNCH_IR
@@ -901,7 +878,7 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
     std::vector<SweepDesc> desc((size_t)n_sweeps);
     int64_t total_tiles = 0, max_tiles = 1;
     for (int k = 0; k < n_sweeps; k++) {
-        int64_t tiles = (n[k] + IBLOCK - 1) / IBLOCK;
+        int64_t tiles = (n[k] + REC_TILE - 1) / REC_TILE;
         if (tiles == 0) tiles = 1;
         SweepDesc &d = desc[(size_t)k];
         d.pc = pc_dev[k];
@@ -952,6 +929,7 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
         case PCACC_SEM_U8: LAUNCH_IRB(PCACC_SEM_U8); break;
         case PCACC_SEM_I32: LAUNCH_IRB(PCACC_SEM_I32); break;
         case PCACC_SEM_I64: LAUNCH_IRB(PCACC_SEM_I64); break;
+        case PCACC_SEM_I16: LAUNCH_IRB(PCACC_SEM_I16); break;
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
     }
 #undef LAUNCH_IRB
@@ -1061,9 +1039,9 @@ extern "C" int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int
     void *dev = nullptr;
     int rc = pcacc_arena_put(h, buf.data(), buf.size() * sizeof(int32_t), &dev, st);
     if (rc) return rc;
-    int64_t bx = (max_n + IBLOCK - 1) / IBLOCK;
+    int64_t bx = (max_n + 4 * IBLOCK - 1) / (4 * IBLOCK);  // grid-stride: 4 rounds per thread
     if (bx < 1) bx = 1;
-    if (bx > 1024) bx = 1024;
+    if (bx > 64) bx = 64;
     for (int k0 = 0; k0 < n_pairs; k0 += 32768) {
         int ny = n_pairs - k0 < 32768 ? n_pairs - k0 : 32768;
         dim3 grid((unsigned)bx, (unsigned)ny);

@@ -27,8 +27,8 @@
 #define BIN_TILE (BIN_BLOCK * BIN_ITEMS)
 #define MAX_VGROUP 32
 
-#define SCAN_BLOCK 256
-#define SCAN_ITEMS 16
+#define SCAN_BLOCK 512
+#define SCAN_ITEMS 32
 #define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
 
 #define RED_WARPS 4
@@ -40,6 +40,14 @@
 
 static_assert(sizeof(pcacc_bev_params) == 208, "pcacc_bev_params layout is part of the ABI");
 
+// per-variant constants, computed once per rasterise call by k_bev_consts
+struct BevConsts {
+    double empty[7];    // planes of a window without any point
+    __half empty_h[4];  // the same as float16: road, intensity, rgb (r = g = b), elevation
+    double pv;          // P / view: grid_floor's estimate
+};
+__device__ __forceinline__ double bev_pv(const BevConsts *c, int v) { return c[v].pv; }
+
 struct BinArgs {
     RingDev ring;
     const int64_t *frame_off, *frame_cnt, *frame_epoch;
@@ -50,6 +58,7 @@ struct BinArgs {
     int64_t frame_lo;      // absolute id of the first frame of this launch
     int64_t epoch_now;
     const pcacc_bev_params *params;  // device, n_var entries
+    const BevConsts *consts;         // device, n_var entries
     int n_var;
     int n_frames;          // frames covered by this launch (<= BIN_MAXF), first = frame_lo
     int P;
@@ -74,6 +83,7 @@ struct Eval {
 
 #define KEY_INVALID 0xffffffffu
 
+
 // x / y part of bev_generator.py:224-231 for one point of the accumulator's current
 // frame: origin shift (one subtract per component, kitti360_sem_pc_accum.py:193), rotation
 // as an FMA chain over k = 0..2 (strided 3x3 dgemm), translation.  A zero coefficient
@@ -96,8 +106,20 @@ __device__ __forceinline__ void bev_xy(const pcacc_bev_params &bp, bool zfree, d
 // The whole of bev_generator.py:224-255,737-747 for one point: crop (strict), height
 // filter, pos2grid (div, mul, add separately rounded), row = P-1-j, col = i.
 // want_near: also report whether any decision lies within GUARD_M of its boundary.
-__device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, double px, double py,
-                                           double pz, bool want_near) {
+// floor of pos2grid's  q / V * P + 0.5 P  (div, mul, add separately rounded,
+// bev_generator.py:737-747).  The fused estimate q * (P/V) + 0.5 P differs from the
+// reference value by < 1e-12 for |g| <= 1e4, so its floor is the reference's floor unless
+// it lies within 1e-9 of an integer — only then is the exact sequence evaluated.
+__device__ __forceinline__ double grid_floor(double q, double view, double dP, double hP, double pv,
+                                             double &g_est) {
+    g_est = fma(q, pv, hP);
+    const double f = floor(g_est), t = g_est - f;
+    if (t > 1e-9 && t < 1.0 - 1e-9 && fabs(g_est) < 1e4) return f;
+    return floor(__dadd_rn(__dmul_rn(__ddiv_rn(q, view), dP), hP));
+}
+
+__device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, double pv, double px,
+                                           double py, double pz, bool want_near) {
     Eval e;
     e.keep = false;
     e.near = false;
@@ -118,8 +140,9 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
     const bool hf_on = (bp.height_filter == bp.height_filter);
     if (hf_on) in = in && (q2 < bp.height_filter);
     const double dP = (double)P, hP = __dmul_rn(0.5, dP);
-    const double g0 = __dadd_rn(__dmul_rn(__ddiv_rn(q0, bp.view), dP), hP);
-    const double g1 = __dadd_rn(__dmul_rn(__ddiv_rn(q1, bp.view), dP), hP);
+    double g0, g1;  // estimates; the floors below are exact
+    const double fi = grid_floor(q0, bp.view, dP, hP, pv, g0);
+    const double fj = grid_floor(q1, bp.view, dP, hP, pv, g1);
     if (want_near) {
         const double eg = GUARD_M * dP / bp.view;
         bool n = (fabs(fabs(q0) - hv) < GUARD_M) || (fabs(fabs(q1) - hv) < GUARD_M);
@@ -128,7 +151,6 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
         e.near = n;
     }
     if (in) {
-        const double fi = floor(g0), fj = floor(g1);
         if (fi >= 0.0 && fi < dP && fj >= 0.0 && fj < dP) {
             const int i = (int)fi, j = (int)fj;
             e.cell = (P - 1 - j) * P + i;  // row = P-1-j, col = i (bev_generator.py:453)
@@ -140,13 +162,23 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
 
 #define BIN_MAXF 2048 /* frames per launch */
 
-// Frame culling: can any point of the frame fall into the view of any variant?  The 8
+// Frame culling: can any point of the frame fall into the view of a variant?  The 8
 // corners of the frame's bounding box (source frame, recorded at integrate time) go
 // through the frame's total transform and the variant's shift / rotation; the image of
 // the box is inside the bounding box of the transformed corners.  Conservative (margin
 // far above fp64 rounding and above the lazy-vs-sequential chain difference); NaN / inf
-// boxes are never culled.
-__device__ __forceinline__ bool frame_may_touch_view(const BinArgs &a, int slot, int64_t fid) {
+// boxes are never culled.  One thread per (frame, variant); frame_tiles[] starts at 0.
+__global__ void k_bev_cull(BinArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_frames * a.n_var) return;
+    const int f = t / a.n_var, v = t - f * a.n_var;
+    const int64_t fid = a.frame_lo + f;
+    const int slot = (int)(fid % a.max_frames);
+    const pcacc_bev_params &bp = a.params[v];
+    if (!(fid >= bp.frame_begin && fid < bp.frame_end)) return;
+    const int64_t cnt = a.frame_cnt[slot];
+    const uint32_t tiles = (uint32_t)((cnt + BIN_TILE - 1) / BIN_TILE);
+    if (tiles == 0) return;
     const unsigned long long *bb = a.aabb + (int64_t)slot * 6;
     double lo[3], hi[3];
 #pragma unroll
@@ -154,26 +186,19 @@ __device__ __forceinline__ bool frame_may_touch_view(const BinArgs &a, int slot,
         lo[k] = ord_decode(bb[k]);
         hi[k] = ord_decode(bb[3 + k]);
     }
-    if (!(lo[0] <= hi[0])) return true;  // empty / not tracked: let the points decide
-    const double *M = a.cull + (int64_t)slot * 12;
-    double cx[8], cy[8], cz[8];
-    double amax = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const double x = (c & 1) ? hi[0] : lo[0], y = (c & 2) ? hi[1] : lo[1], z = (c & 4) ? hi[2] : lo[2];
-        cx[c] = M[0] * x + M[1] * y + M[2] * z + M[3];
-        cy[c] = M[4] * x + M[5] * y + M[6] * z + M[7];
-        cz[c] = M[8] * x + M[9] * y + M[10] * z + M[11];
-        amax = fmax(amax, fmax(fabs(cx[c]), fmax(fabs(cy[c]), fabs(cz[c]))));
-    }
-    const double margin = 1e-5 + 1e-9 * amax;
-    for (int v = 0; v < a.n_var; v++) {
-        const pcacc_bev_params &bp = a.params[v];
-        if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;
-        double q0lo = INFINITY, q0hi = -INFINITY, q1lo = INFINITY, q1hi = -INFINITY;
+    bool touch = true;
+    if (lo[0] <= hi[0]) {  // a tracked, non-empty box (otherwise let the points decide)
+        const double *M = a.cull + (int64_t)slot * 12;
+        double q0lo = INFINITY, q0hi = -INFINITY, q1lo = INFINITY, q1hi = -INFINITY, amax = 0.0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const double sx = cx[c] - bp.origin[0], sy = cy[c] - bp.origin[1], sz = cz[c] - bp.origin[2];
+            const double x = (c & 1) ? hi[0] : lo[0], y = (c & 2) ? hi[1] : lo[1],
+                         z = (c & 4) ? hi[2] : lo[2];
+            const double cx = M[0] * x + M[1] * y + M[2] * z + M[3];
+            const double cy = M[4] * x + M[5] * y + M[6] * z + M[7];
+            const double cz = M[8] * x + M[9] * y + M[10] * z + M[11];
+            amax = fmax(amax, fmax(fabs(cx), fmax(fabs(cy), fabs(cz))));
+            const double sx = cx - bp.origin[0], sy = cy - bp.origin[1], sz = cz - bp.origin[2];
             const double q0 = bp.R[0] * sx + bp.R[1] * sy + bp.R[2] * sz + bp.trans_dx;
             const double q1 = bp.R[3] * sx + bp.R[4] * sy + bp.R[5] * sz + bp.trans_dy;
             q0lo = fmin(q0lo, q0);
@@ -181,23 +206,11 @@ __device__ __forceinline__ bool frame_may_touch_view(const BinArgs &a, int slot,
             q1lo = fmin(q1lo, q1);
             q1hi = fmax(q1hi, q1);
         }
-        const double lim = 0.5 * bp.view + margin;
+        const double lim = 0.5 * bp.view + 1e-5 + 1e-9 * amax;
         const bool outside = (q0lo > lim) || (q0hi < -lim) || (q1lo > lim) || (q1hi < -lim);
-        if (!outside) return true;   // also taken when anything is NaN
+        touch = !outside;  // also true when anything is NaN
     }
-    return false;
-}
-
-// one thread per frame: number of 1024-point tiles to visit (0 when the frame is empty or
-// provably outside every variant's view)
-__global__ void k_bev_cull(BinArgs a) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.n_frames) return;
-    const int slot = (int)((a.frame_lo + f) % a.max_frames);
-    const int64_t c = a.frame_cnt[slot];
-    uint32_t t = (uint32_t)((c + BIN_TILE - 1) / BIN_TILE);
-    if (t && !frame_may_touch_view(a, slot, a.frame_lo + f)) t = 0;
-    a.frame_tiles[f] = t;
+    if (touch) atomicMax(&a.frame_tiles[f], tiles);
 }
 
 // ---------------------------------------------------------------------------
@@ -213,6 +226,7 @@ k_bev_classify(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ uint32_t s_tiles[BIN_MAXF + 1];
     __shared__ double s_comp[12];
+    __shared__ double s_A[MAX_VGROUP][8];   // lazy frames: x / y rows of variant ∘ frame matrix
     __shared__ uint32_t s_warp[BIN_BLOCK / 32];
     __shared__ unsigned long long s_base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -280,8 +294,22 @@ k_bev_classify(BinArgs a) {
         bool need_z = lazy;
         for (int v = v_begin; v < v_end; v++)
             need_z = need_z || (s_par[v].R[2] != 0.0) || (s_par[v].R[5] != 0.0);
-        __syncthreads();  // the previous item is done with s_comp / s_warp / s_base
+        __syncthreads();  // the previous item is done with s_comp / s_A / s_warp / s_base
         if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
+        __syncthreads();
+        if (lazy && threadIdx.x < 8 * (v_end - v_begin)) {
+            // Candidate test of a lazily re-based frame: one 2x4 affine map per variant,
+            // q = R (M p - origin) + trans.  Not the reference's rounding sequence — it does not
+            // have to be: candidates keep a guard band of GUARD_M (>> any fp64 discrepancy) and
+            // k_bev_bin decides each of them with the exact arithmetic.
+            const int v = v_begin + (int)threadIdx.x / 8, r = ((int)threadIdx.x >> 2) & 1, c = (int)threadIdx.x & 3;
+            const pcacc_bev_params &bp = s_par[v];
+            double acc = bp.R[3 * r] * s_comp[c] + bp.R[3 * r + 1] * s_comp[4 + c] + bp.R[3 * r + 2] * s_comp[8 + c];
+            if (c == 3)
+                acc += (r ? bp.trans_dy : bp.trans_dx) -
+                       (bp.R[3 * r] * bp.origin[0] + bp.R[3 * r + 1] * bp.origin[1] + bp.R[3 * r + 2] * bp.origin[2]);
+            s_A[v][4 * r + c] = acc;
+        }
         __syncthreads();
 
         // 4 points per thread: two pairs of neighbours (16 B loads; frame offsets are
@@ -303,30 +331,28 @@ k_bev_classify(BinArgs a) {
             py[2 * h] = Y.x; py[2 * h + 1] = Y.y;
             pz[2 * h] = Z.x; pz[2 * h + 1] = Z.y;
         }
-        if (lazy) {
-#pragma unroll
-            for (int k = 0; k < BIN_ITEMS; k++) {
-                double nx, ny, nz;
-                affine_chain(s_comp, 4, px[k], py[k], pz[k], nx, ny, nz);
-                px[k] = nx; py[k] = ny; pz[k] = nz;
-            }
-        }
-
         for (int v = v_begin; v < v_end; v++) {
             const pcacc_bev_params &bp = s_par[v];
             if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;  // block-uniform
-            const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
             const double hv = __dmul_rn(0.5, bp.view);
-            const double lim = hv + GUARD_M;
             unsigned cmask = 0;
+            if (lazy) {
+                const double *A = s_A[v];
+                const double lim = hv + GUARD_M;
 #pragma unroll
-            for (int k = 0; k < BIN_ITEMS; k++) {
-                double q0, q1;
-                bev_xy(bp, zfree, px[k], py[k], pz[k], q0, q1);
-                // lazily re-based frames keep a guard band; NaN fails both forms
-                const bool c = lazy ? ((fabs(q0) < lim) && (fabs(q1) < lim))
-                                    : ((q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv));
-                if (c) cmask |= 1u << k;
+                for (int k = 0; k < BIN_ITEMS; k++) {
+                    const double q0 = fma(A[0], px[k], fma(A[1], py[k], fma(A[2], pz[k], A[3])));
+                    const double q1 = fma(A[4], px[k], fma(A[5], py[k], fma(A[6], pz[k], A[7])));
+                    if ((fabs(q0) < lim) && (fabs(q1) < lim)) cmask |= 1u << k;  // NaN fails
+                }
+            } else {
+                const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
+#pragma unroll
+                for (int k = 0; k < BIN_ITEMS; k++) {
+                    double q0, q1;
+                    bev_xy(bp, zfree, px[k], py[k], pz[k], q0, q1);  // exact: the final crop test
+                    if ((q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv)) cmask |= 1u << k;
+                }
             }
             cmask &= vmask;
             const uint32_t my_cnt = __popc(cmask);
@@ -399,12 +425,13 @@ k_bev_bin(BinArgs a) {
         }
         const int slot = (int)(fid % a.max_frames);
         const pcacc_bev_params &bp = a.params[v];
+        const double pv = bev_pv(a.consts, v);
         const int64_t e0 = a.frame_epoch[slot];
         Eval e;
         if (e0 < a.epoch_now) {
             double cx, cy, cz;
             affine_chain(a.comp + (int64_t)slot * 12, 4, x, y, z, cx, cy, cz);
-            e = eval_point(bp, a.P, cx, cy, cz, true);
+            e = eval_point(bp, a.P, pv, cx, cy, cz, true);
             if (e.near) {
                 // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
                 for (int64_t ep = e0; ep < a.epoch_now; ep++) {
@@ -413,11 +440,11 @@ k_bev_bin(BinArgs a) {
                     affine_chain(T, 4, x, y, z, nx, ny, nz);
                     x = nx; y = ny; z = nz;
                 }
-                e = eval_point(bp, a.P, x, y, z, false);
+                e = eval_point(bp, a.P, pv, x, y, z, false);
                 atomicAdd(a.n_replay, 1ull);
             }
         } else {
-            e = eval_point(bp, a.P, x, y, z, false);
+            e = eval_point(bp, a.P, pv, x, y, z, false);
         }
         if (dyn == 1) e.keep = false;  // static points only (sem_bev.py:54-58)
         if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
@@ -590,14 +617,12 @@ __device__ __forceinline__ void acc_record(WinAcc &a, const uint4 &r, int w, int
     a.ext_z[w] = want_max ? fmax(a.ext_z[w], z) : fmin(a.ext_z[w], z);
 }
 
-// per-variant constants, computed once per rasterise call by k_bev_consts
-struct BevConsts {
-    double empty[7];   // planes of a window without any point
-    double pad;
-};
 
 // (m2 * 0.5) / 255. for m2 = twice the median, 0..510: filled once per handle
 #define RGB_LUT_N 511
+// followed by the Dirichlet expectation (c+1)/(n+2) for the small cells, n, c = 0..15
+#define DIR_LUT_OFF 512
+#define LUT_TOTAL (DIR_LUT_OFF + 256)
 
 // road and dynamic planes of one window: Dirichlet expectation with a uniform prior,
 // (c+1) / ((c+1) + ((n-c)+1)) (bev_generator.py:457-480); the denominator is n+2 exactly
@@ -614,7 +639,7 @@ __device__ __forceinline__ double intensity_plane(const pcacc_bev_params &bp, do
     return val > 1.0 ? 1.0 : val;
 }
 
-__global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_var,
+__global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_var, int P,
                              BevConsts *__restrict__ consts) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_var) return;
@@ -625,23 +650,38 @@ __global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_
     c.empty[2] = c.empty[3] = c.empty[4] = __ddiv_rn(bp.rgb_fill, 255.0);
     c.empty[5] = dirichlet(0, 0);
     c.empty[6] = 0.0;
-    c.pad = 0.0;
+    c.empty_h[0] = __double2half(c.empty[0]);
+    c.empty_h[1] = __double2half(c.empty[1]);
+    c.empty_h[2] = __double2half(c.empty[2]);
+    c.empty_h[3] = __double2half(c.empty[6]);
+    c.pv = (double)P / bp.view;
     consts[v] = c;
 }
 
 __global__ void k_rgb_lut(double *__restrict__ lut) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < RGB_LUT_N) lut[m] = __ddiv_rn(__dmul_rn((double)m, 0.5), 255.0);
+    else if (m == RGB_LUT_N) lut[m] = 0.0;
+    else if (m < LUT_TOTAL) {
+        const uint32_t n = (uint32_t)(m - DIR_LUT_OFF) >> 4, c = (uint32_t)(m - DIR_LUT_OFF) & 15u;
+        lut[m] = dirichlet(c, n);
+    }
 }
 
-// window statistics -> 7 planes
+// window statistics -> 7 planes.  SMALL: n <= 15, the Dirichlet quotient comes from the table
+template <bool SMALL>
 __device__ __forceinline__ void window_planes(const pcacc_bev_params &bp, const BevConsts &cst,
                                               const double *__restrict__ lut, uint32_t n,
                                               uint32_t n_road, uint32_t n_veh, long long fx_hi,
                                               long long fx_lo, double ez, const int med2[3],
                                               double intensity_div, double plane[7]) {
-    plane[0] = dirichlet(n_road, n);
-    plane[5] = dirichlet(n_veh, n);
+    if (SMALL) {
+        plane[0] = lut[DIR_LUT_OFF + n * 16 + n_road];
+        plane[5] = lut[DIR_LUT_OFF + n * 16 + n_veh];
+    } else {
+        plane[0] = dirichlet(n_road, n);
+        plane[5] = dirichlet(n_veh, n);
+    }
     if (n_road == 0) {
         plane[1] = cst.empty[1];   // sum 0 over count 0: the same arithmetic as an empty window
     } else {
@@ -652,6 +692,22 @@ __device__ __forceinline__ void window_planes(const pcacc_bev_params &bp, const 
 #pragma unroll
     for (int k = 0; k < 3; k++) plane[2 + k] = lut[med2[k]];
     plane[6] = ez;
+}
+
+template <bool F64OUT>
+__device__ __forceinline__ void store_empty(__half *__restrict__ out16, double *__restrict__ out64,
+                                            int64_t o, int PP, const BevConsts &cst) {
+    out16[o] = cst.empty_h[0];
+    out16[o + (int64_t)PP] = cst.empty_h[1];
+    out16[o + 2 * (int64_t)PP] = cst.empty_h[2];
+    out16[o + 3 * (int64_t)PP] = cst.empty_h[2];
+    out16[o + 4 * (int64_t)PP] = cst.empty_h[2];
+    out16[o + 5 * (int64_t)PP] = cst.empty_h[0];
+    out16[o + 6 * (int64_t)PP] = cst.empty_h[3];
+    if (F64OUT) {
+#pragma unroll
+        for (int p = 0; p < 7; p++) out64[o + (int64_t)p * PP] = cst.empty[p];
+    }
 }
 
 template <bool F64OUT>
@@ -713,7 +769,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     // all 32 cells empty: nothing to read
     if (__ballot_sync(0xffffffffu, my_nt != 0) == 0) {
 #pragma unroll
-        for (int w = 0; w < 3; w++) store_planes<F64OUT>(out16, out64, o0 + (int64_t)w * 7 * PP, PP, cst.empty);
+        for (int w = 0; w < 3; w++) store_empty<F64OUT>(out16, out64, o0 + (int64_t)w * 7 * PP, PP, cst);
         return;
     }
 
@@ -807,14 +863,14 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
             const int64_t o = o0 + (int64_t)w * 7 * PP;
             if (nw == 0) {
-                store_planes<F64OUT>(out16, out64, o, PP, cst.empty);
+                store_empty<F64OUT>(out16, out64, o, PP, cst);
             } else {
                 double plane[7];
                 if (w < 2)
-                    window_planes(bp, cst, lut, nw, st.n_road[w], st.n_veh[w], st.fx_hi[w], st.fx_lo[w],
+                    window_planes<true>(bp, cst, lut, nw, st.n_road[w], st.n_veh[w], st.fx_hi[w], st.fx_lo[w],
                                   st.ext_z[w], med2[w], intensity_div, plane);
                 else  // the unused side still holds +-inf, the identity of min / max
-                    window_planes(bp, cst, lut, nw, st.n_road[0] + st.n_road[1],
+                    window_planes<true>(bp, cst, lut, nw, st.n_road[0] + st.n_road[1],
                                   st.n_veh[0] + st.n_veh[1], st.fx_hi[0] + st.fx_hi[1],
                                   st.fx_lo[0] + st.fx_lo[1],
                                   want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]),
@@ -829,6 +885,30 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
 // pass B: one warp per queued large cell (dynamic queue), 256-bin shared-memory
 // histograms per window and channel.
 // ---------------------------------------------------------------------------
+// warp-wide reductions on the REDUX unit (one instruction per 32-bit word)
+__device__ __forceinline__ long long warp_sum_i64(long long x) {
+    // three 21-bit limbs: the 32 partial limbs sum without overflow
+    const unsigned l0 = (unsigned)(x & 0x1fffff), l1 = (unsigned)((x >> 21) & 0x1fffff);
+    const int l2 = (int)(x >> 42);
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1);
+    const int s2 = __reduce_add_sync(0xffffffffu, l2);
+    return (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
+}
+__device__ __forceinline__ double warp_min_f64(double v) {
+    const unsigned long long u = ord_encode(v);
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ord_decode(((unsigned long long)mh << 32) | ml);
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+    const unsigned long long u = ord_encode(v);
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ord_decode(((unsigned long long)mh << 32) | ml);
+}
+
 template <bool F64OUT>
 __global__ void __launch_bounds__(RED_WARPS * 32)
 k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
@@ -887,15 +967,11 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
         }
 #pragma unroll
         for (int w = 0; w < 2; w++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a.n_road[w] += __shfl_xor_sync(0xffffffffu, a.n_road[w], o);
-                a.n_veh[w] += __shfl_xor_sync(0xffffffffu, a.n_veh[w], o);
-                a.fx_hi[w] += __shfl_xor_sync(0xffffffffu, a.fx_hi[w], o);
-                a.fx_lo[w] += __shfl_xor_sync(0xffffffffu, a.fx_lo[w], o);
-                double oz = __shfl_xor_sync(0xffffffffu, a.ext_z[w], o);
-                a.ext_z[w] = want_max ? fmax(a.ext_z[w], oz) : fmin(a.ext_z[w], oz);
-            }
+            a.n_road[w] = __reduce_add_sync(0xffffffffu, a.n_road[w]);
+            a.n_veh[w] = __reduce_add_sync(0xffffffffu, a.n_veh[w]);
+            a.fx_hi[w] = warp_sum_i64(a.fx_hi[w]);
+            a.fx_lo[w] = warp_sum_i64(a.fx_lo[w]);
+            a.ext_z[w] = want_max ? warp_max_f64(a.ext_z[w]) : warp_min_f64(a.ext_z[w]);
         }
         __syncwarp();
         int m2[3][3];
@@ -943,7 +1019,7 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
             const uint32_t nw = (w == 0) ? np : (w == 1) ? nf : nt;
             const int64_t o = (((int64_t)var * 3 + w) * 7) * PP + cell_in;
             if (nw == 0) {
-                store_planes<F64OUT>(out16, out64, o, PP, cst.empty);
+                store_empty<F64OUT>(out16, out64, o, PP, cst);
             } else {
                 double plane[7];
                 int md[3];
@@ -951,12 +1027,12 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
                 for (int c = 0; c < 3; c++) md[c] = (w == 0) ? m2[0][c] : (w == 1) ? m2[1][c] : m2[2][c];
                 if (w < 2) {
                     const int ww = w & 1;
-                    window_planes(bp, cst, lut, nw, ww ? a.n_road[1] : a.n_road[0],
+                    window_planes<false>(bp, cst, lut, nw, ww ? a.n_road[1] : a.n_road[0],
                                   ww ? a.n_veh[1] : a.n_veh[0], ww ? a.fx_hi[1] : a.fx_hi[0],
                                   ww ? a.fx_lo[1] : a.fx_lo[0], ww ? a.ext_z[1] : a.ext_z[0], md,
                                   intensity_div, plane);
                 } else {
-                    window_planes(bp, cst, lut, nw, a.n_road[0] + a.n_road[1], a.n_veh[0] + a.n_veh[1],
+                    window_planes<false>(bp, cst, lut, nw, a.n_road[0] + a.n_road[1], a.n_veh[0] + a.n_veh[1],
                                   a.fx_hi[0] + a.fx_hi[1], a.fx_lo[0] + a.fx_lo[1],
                                   want_max ? fmax(a.ext_z[0], a.ext_z[1]) : fmin(a.ext_z[0], a.ext_z[1]),
                                   md, intensity_div, plane);
@@ -998,8 +1074,8 @@ static int ensure_ws(pcacc_t h, size_t bytes) {
 }
 
 int pcacc_init_tables(pcacc_t h) {
-    PCACC_CUDA(h, cudaMalloc(&h->d_rgb_lut, RGB_LUT_N * sizeof(double)));
-    k_rgb_lut<<<(RGB_LUT_N + 127) / 128, 128>>>(h->d_rgb_lut);
+    PCACC_CUDA(h, cudaMalloc(&h->d_rgb_lut, LUT_TOTAL * sizeof(double)));
+    k_rgb_lut<<<(LUT_TOTAL + 127) / 128, 128>>>(h->d_rgb_lut);
     PCACC_CUDA(h, cudaGetLastError());
     PCACC_CUDA(h, cudaDeviceSynchronize());
     return PCACC_OK;
@@ -1054,14 +1130,14 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         // workspace layout: [counters | append/replay/big-queue counters] are zeroed per call
         size_t o_counts = 0;
         size_t o_cnt2 = align_up(o_counts + (size_t)n_keys * 4, 256);  // 4 x u64 counters
-        size_t o_key = align_up(o_cnt2 + 32, 256);
+        size_t o_ftiles = align_up(o_cnt2 + 32, 256);                  // per-frame tile counts
+        size_t o_key = align_up(o_ftiles + (size_t)BIN_MAXF * 4, 256);
         size_t o_rank = align_up(o_key + (size_t)cap * 4, 256);
         // the candidate list (8 B) is dead once k_bev_bin has run: it shares the space of `sorted`
         size_t o_rec = align_up(o_rank + (size_t)cap * 4, 256);
         size_t o_sorted = align_up(o_rec + (size_t)cap * 16, 256);
         size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
-        size_t o_ftiles = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
-        size_t o_big = align_up(o_ftiles + (size_t)BIN_MAXF * 4, 256);
+        size_t o_big = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
         // a cell is "large" only above SMALL_T points, so the queue never exceeds cap / (SMALL_T+1)
         int64_t big_cap = cap / (SMALL_T + 1) + 1;
         if (big_cap > (int64_t)nv * PP) big_cap = (int64_t)nv * PP;
@@ -1079,6 +1155,11 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         void *d_params = nullptr;
         rc = pcacc_arena_put(h, params + v0, (size_t)nv * sizeof(pcacc_bev_params), &d_params, st);
         if (rc) return rc;
+
+        // per-variant constants (empty-window planes, P/view)
+        h->launches[PCACC_K_REDUCE]++;
+        k_bev_consts<<<(nv + 31) / 32, 32, 0, st>>>((const pcacc_bev_params *)d_params, nv, P, d_consts);
+        PCACC_CUDA(h, cudaGetLastError());
 
         const bool want_f64 = out_f64_dev != nullptr;
         __half *o16 = (__half *)out_f16_dev + (int64_t)v0 * 21 * PP;
@@ -1098,6 +1179,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.frame_lo = flo;
             a.epoch_now = h->rebase_epoch;
             a.params = (const pcacc_bev_params *)d_params;
+            a.consts = d_consts;
             a.n_var = nv;
             a.P = P;
             a.counts = counts;
@@ -1118,7 +1200,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.frame_lo = flo;
             a.n_frames = (int)nf;
             size_t pe = pcacc_prof_begin(h, PCACC_K_CLASSIFY, st);
-            k_bev_cull<<<(a.n_frames + 127) / 128, 128, 0, st>>>(a);
+            k_bev_cull<<<(a.n_frames * nv + 127) / 128, 128, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             h->launches[PCACC_K_CLASSIFY]++;
             k_bev_classify<<<148 * 4, BIN_BLOCK, 0, st>>>(a);
@@ -1150,11 +1232,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
-        // per-variant constants, then reduce + finalise (also correct on all-zero
-        // counters: every cell empty)
-        h->launches[PCACC_K_REDUCE]++;
-        k_bev_consts<<<(nv + 31) / 32, 32, 0, st>>>((const pcacc_bev_params *)d_params, nv, d_consts);
-        PCACC_CUDA(h, cudaGetLastError());
+        // reduce + finalise (also correct on all-zero counters: every cell empty)
         int64_t warps = (int64_t)nv * PP / 32;
         int64_t blocks = (warps + RED_WARPS - 1) / RED_WARPS;
         size_t pr = pcacc_prof_begin(h, PCACC_K_REDUCE, st);

@@ -15,9 +15,16 @@ from . import _lib
 from ._lib import BevParams, PcaccError, check
 
 _SEM_DTYPES = {np.dtype(np.uint8): _lib.SEM_U8, np.dtype(np.int32): _lib.SEM_I32,
-               np.dtype(np.int64): _lib.SEM_I64}
+               np.dtype(np.int64): _lib.SEM_I64, np.dtype(np.int16): _lib.SEM_I16}
 _TORCH_SEM = {torch.uint8: _lib.SEM_U8, torch.int32: _lib.SEM_I32,
-              torch.int64: _lib.SEM_I64}
+              torch.int64: _lib.SEM_I64, torch.int16: _lib.SEM_I16}
+
+
+def _narrow_class_map(sem: np.ndarray) -> torch.Tensor:
+    """Host class maps arrive as int64 (the ONNX argmax): 8 B/pixel over PCIe for values
+    that fit a byte.  Clamp to [-1, 256] and send int16: negatives stay 'invalid', anything
+    above 255 still trips the kernel's class-range flag."""
+    return torch.clamp(torch.from_numpy(np.ascontiguousarray(sem)), -1, 256).to(torch.int16)
 
 
 def require_cuda():
@@ -130,8 +137,10 @@ class DeviceCloud:
         sem = np.asarray(sem)
         if sem.dtype == np.float32 and sem.ndim == 3:
             return self.stage.put(key, sem), _lib.SEM_F32_PROB, int(sem.shape[-1])
+        if sem.dtype in (np.int64, np.int32):
+            return self.stage.put(key, _narrow_class_map(sem)), _lib.SEM_I16, 1
         if sem.dtype not in _SEM_DTYPES:
-            sem = sem.astype(np.int64)
+            return self.stage.put(key, _narrow_class_map(sem.astype(np.int64))), _lib.SEM_I16, 1
         return self.stage.put(key, sem), _SEM_DTYPES[sem.dtype], 1
 
     # -- lifetime --------------------------------------------------------------
