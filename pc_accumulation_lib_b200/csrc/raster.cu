@@ -144,7 +144,7 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
     const double fi = grid_floor(q0, bp.view, dP, hP, pv, g0);
     const double fj = grid_floor(q1, bp.view, dP, hP, pv, g1);
     if (want_near) {
-        const double eg = GUARD_M * dP / bp.view;
+        const double eg = GUARD_M * pv;
         bool n = (fabs(fabs(q0) - hv) < GUARD_M) || (fabs(fabs(q1) - hv) < GUARD_M);
         if (hf_on) n = n || (fabs(q2 - bp.height_filter) < GUARD_M);
         n = n || (fabs(g0 - rint(g0)) < eg) || (fabs(g1 - rint(g1)) < eg);
@@ -399,8 +399,18 @@ k_bev_classify(BinArgs a) {
 // static filter), the cell counter (its old value is the rank in the cell segment) and
 // the 16 B record.  A candidate rejected here leaves a hole (KEY_INVALID).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_bev_bin(BinArgs a) {
+    __shared__ pcacc_bev_params s_par[MAX_VGROUP];
+    __shared__ double s_pv[MAX_VGROUP];
+    {
+        const uint32_t *src = (const uint32_t *)a.params;
+        uint32_t *dst = (uint32_t *)s_par;
+        const int words = a.n_var * (int)(sizeof(pcacc_bev_params) / 4);
+        for (int k = threadIdx.x; k < words; k += 256) dst[k] = src[k];
+        if ((int)threadIdx.x < a.n_var) s_pv[threadIdx.x] = bev_pv(a.consts, threadIdx.x);
+        __syncthreads();
+    }
     unsigned long long n = *a.n_append;
     if (n > (unsigned long long)a.cap) n = (unsigned long long)a.cap;
     const int PP = a.P * a.P;
@@ -424,8 +434,8 @@ k_bev_bin(BinArgs a) {
             meta = a.cand_meta[cn];
         }
         const int slot = (int)(fid % a.max_frames);
-        const pcacc_bev_params &bp = a.params[v];
-        const double pv = bev_pv(a.consts, v);
+        const pcacc_bev_params &bp = s_par[v];
+        const double pv = s_pv[v];
         const int64_t e0 = a.frame_epoch[slot];
         Eval e;
         if (e0 < a.epoch_now) {

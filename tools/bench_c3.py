@@ -57,6 +57,8 @@ bps = [dev.make_bev_params(first, first + p, first + n_live, origin, R, 0.1 * v,
                            synth.SEM_IDXS) for v in range(a.variants)]
 out = torch.empty((a.variants, 3, 7, a.P, a.P), dtype=torch.float16, device='cuda')
 n_res = cloud.resident_points()
+cloud.profile(True)
+cloud.profile_read()
 for it in range(a.iters):
     e0 = ev()
     cloud.rasterise(bps, a.P, out=out)
@@ -65,3 +67,6 @@ for it in range(a.iters):
     ms = e0.elapsed_time(e1)
     alg = (33 * n_res + 42 * a.P * a.P) * a.variants
     print(f'rasterise {n_res} pts x{a.variants}: {ms:.3f} ms  alg {alg/ms/1e6:.1f} GB/s', cloud.raster_stats())
+
+prof = cloud.profile_read()
+print({k: round(v[0] / a.iters * 1e3, 1) for k, v in prof.items() if v[1]})
