@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from pc_accumulation_lib_b200 import synth  # noqa: E402
+from pc_accumulation_lib_b200 import parallel, synth  # noqa: E402
 
 N_SWEEPS = 40
 PRESENT_IDXS = [6, 10, 14, 18, 22, 26, 30, 34]
@@ -59,8 +59,10 @@ def bev_setup():
     return bp
 
 
-def make_scenes(rank, n):
-    return [synth.nusc_scene(synth.seed_for(4, 100 * rank + k), N_SWEEPS) for k in range(n)]
+def make_scenes(rank, n, world=1):
+    """The first n scenes of this rank's shard of the global scene list (scene id -> seed)."""
+    ids = parallel.shard_units(n * world, rank, world)
+    return [synth.nusc_scene(synth.seed_for(4, sid), N_SWEEPS) for sid in ids]
 
 
 # ---------------------------------------------------------------------------
@@ -154,7 +156,7 @@ def run_ours(args, rank, world, local_rank, dist):
     dev = torch.device('cuda', local_rank)
     pk, pk_kind = peaks()
 
-    scenes = make_scenes(rank, N_DISTINCT)
+    scenes = make_scenes(rank, N_DISTINCT, world)
     n_in_scene = sum(o['pc'].shape[0] for o in scenes[0])
     S = args.scenes_per_step
     bevs_per_scene = len(PRESENT_IDXS) * BEVS_PER_PRESENT
@@ -277,13 +279,14 @@ def run_ours(args, rank, world, local_rank, dist):
     clk = clocks.stop()
     prof = cloud.profile_read()
     cloud.profile(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    # the only collective of the run: summary statistics (sum of work, max of time)
     pts_step_rank = S * n_in_scene
-    value = world * pts_step_rank * args.steps / (ms_max * 1e-3)
-    bevs_per_s = world * S * bevs_per_scene * args.steps / (ms_max * 1e-3)
+    tot = parallel.reduce_stats(dist, {'points': pts_step_rank * args.steps,
+                                       'bevs': S * bevs_per_scene * args.steps,
+                                       'ms_max': ms_total}, device=dev)
+    ms_max = tot['ms_max']
+    value = tot['points'] / (ms_max * 1e-3)
+    bevs_per_s = tot['bevs'] / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (CUDA events inside the timed region) ------
     n_res = float(np.mean([n_keep[s % N_DISTINCT] for s in range(S)]))
