@@ -228,6 +228,16 @@ int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset);
  * [0] points visited, [1] points binned (in view, static), [2] exact-chain replays */
 int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
 
+/* ---- host helper: trajectory crop ------------------------------------------
+ * BEVGenerator.crop_trajectory + cal_intersec_pnt, bev_generator/bev_generator.py:257-371:
+ * polyline traj (n,3) against the open box (-view/2, view/2)^2.  A vertex that starts an
+ * edge and lies inside is kept; an edge that crosses the boundary adds its midpoint-
+ * bisection point (refined until the replaced end moved by <= thresh).  Pure host code
+ * (a few dozen points per BEV; the Python loop was the end-to-end bottleneck).
+ * out: at least 2*n rows of 3 doubles; *n_out rows are written. */
+int pcacc_crop_trajectory(const double *traj, int n, double view, double thresh, double *out,
+                          int *n_out);
+
 /* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
  * Kernel classes of this library. */
 #define PCACC_K_INTEGRATE 0 /* k_integrate_frustum / _gt / _records / _cloud, k_gen_semantic_pc, k_project */

@@ -17,12 +17,14 @@ Point clouds reach `generate()` in one of two forms:
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import time
 from abc import ABC, abstractmethod
 
 import numpy as np
 
+from .. import _lib
 from ..device import DeviceCloud, make_bev_params
 
 WINDOWS = ('present', 'future', 'full')
@@ -129,28 +131,17 @@ class BEVGenerator(ABC):
         """Edges of the polyline against the open view box: a vertex is kept if it starts
         an edge and lies inside; an edge that crosses the boundary contributes its
         bisection point.  (The last in-view vertex is never emitted — as in the reference.)
-        The inside test is vectorised; only crossing edges run the scalar bisection."""
-        half = 0.5 * aug_view_size
-        bbox = [-half, -half, half, half]
+        Runs in libpcacc's host helper `pcacc_crop_trajectory` (same double arithmetic)."""
+        traj = np.ascontiguousarray(traj[:, :3], dtype=np.float64)
         n = traj.shape[0]
         if n < 2:
             return np.zeros((0, 3))
-        x, y = traj[:, 0], traj[:, 1]
-        inside = (-half < x) & (x < half) & (-half < y) & (y < half)
-        a_in, b_in = inside[:-1], inside[1:]
-        cross = a_in != b_in
-        per_edge = a_in.astype(np.int64) + cross
-        total = int(per_edge.sum())
-        if total == 0:
-            return np.zeros((0, 3))
-        out = np.empty((total, 3))
-        first = np.cumsum(per_edge) - per_edge          # output row of each edge's first entry
-        ka = np.flatnonzero(a_in)
-        out[first[ka]] = traj[ka, :3]
-        for k in np.flatnonzero(cross):
-            ix, iy, _ = self.cal_intersec_pnt(x[k], y[k], x[k + 1], y[k + 1], bbox, thresh)
-            out[first[k] + int(a_in[k])] = (ix, iy, traj[k, 2])
-        return out
+        out = np.empty((2 * n, 3))
+        m = C.c_int(0)
+        _lib.check(_lib.load().pcacc_crop_trajectory(
+            traj.ctypes.data_as(C.c_void_p), n, float(aug_view_size), float(thresh),
+            out.ctypes.data_as(C.c_void_p), C.byref(m)))
+        return out[:m.value].copy() if m.value else np.zeros((0, 3))
 
     def geometric_transform(self, pc_mat, rot_ang, trans_dx, trans_dy, aug_view_size,
                             is_traj=False):
@@ -242,7 +233,7 @@ class BEVGenerator(ABC):
                 if same:        # full = present ++ future: one pass does all three
                     planes, _, _ = cloud.rasterise(
                         params(cloud, pp.frame_begin, pp.frame_end, pf.frame_end, pp.origin), P)
-                    return planes.cpu().numpy(), True
+                    return cloud.planes_to_host(planes), True
                 # general case: each window rasterised as a 'present' window
                 outs = []
                 for w in (pp, pf, pa):
@@ -253,7 +244,7 @@ class BEVGenerator(ABC):
                 return torch.stack(outs, dim=1).cpu().numpy(), True
             planes, _, _ = cloud.rasterise(
                 params(cloud, pp.frame_begin, pp.frame_end, pp.frame_end, pp.origin), P)
-            return planes.cpu().numpy(), False
+            return cloud.planes_to_host(planes), False
 
         # host arrays: upload into a scratch ring as frames
         clouds = [np.asarray(pp, dtype=np.float64)]
