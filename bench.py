@@ -43,6 +43,7 @@ BEVS_PER_PRESENT = 4
 P = 256
 N_DISTINCT = 4            # distinct synthetic scenes per rank (replicated on the device)
 METRIC = 'lidar_points_fused_and_rasterised_per_s'
+OUT = sys.stdout
 
 
 def peaks():
@@ -381,7 +382,8 @@ def run_ours(args, rank, world, local_rank, dist):
             line['cpu_baseline'] = cpu
         if extra:
             line['extra'] = extra
-        print(json.dumps(line))
+        OUT.write(json.dumps(line) + '\n')
+        OUT.flush()
 
 
 def c3_extra(torch, DeviceCloud, pk):
@@ -459,9 +461,21 @@ def c3_extra(torch, DeviceCloud, pk):
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ---------------------------------------------------------------------------
-def cpu_scene(scene, n_sweeps, present_idxs, rng):
-    """One bounded sample of the workload on the CPU port (oracle/oracle.py):
-    returns (points integrated, BEVs, seconds)."""
+_CPU_ACC = None
+
+
+def _cpu_bev(job):
+    p, aug = job
+    _CPU_ACC.generate_bev(p, **aug)
+    return 1
+
+
+def cpu_scene(scene, n_sweeps, present_idxs, rng, workers=1):
+    """One bounded sample of the workload on the CPU port (oracle/oracle.py): returns
+    (points integrated, BEVs, seconds).  integrate() is sequential by nature; the BEVs of
+    the scene are independent and are spread over `workers` forked processes — the
+    reference's own parallelism (Pool(bev_num), kitti360_sem_pc_accum.py:236-241)."""
+    global _CPU_ACC
     from oracle import oracle as orc
     bp = bev_setup()
     gp = dict(sem_idxs=synth.SEM_IDXS, view_size=bp['view_size'], pixel_size=P,
@@ -474,26 +488,38 @@ def cpu_scene(scene, n_sweeps, present_idxs, rng):
     for o in scene[:n_sweeps]:
         acc.integrate(o, o['_semseg'])
         pts += o['pc'].shape[0]
-    n_b = 0
+    jobs = []
     for p in present_idxs:
         for _ in range(BEVS_PER_PRESENT):
             rot = 2 * np.pi * rng.random_sample()
             r, a = 5.0 * rng.random_sample(), 2 * np.pi * rng.random_sample()
             z = 1 + min(max(rng.normal(0, 0.1), -0.1), 0.1)
-            acc.generate_bev(p, rot_ang=rot, trans_dx=r * np.cos(a), trans_dy=r * np.sin(a),
-                             zoom_scalar=z, do_warping=True)
-            n_b += 1
+            jobs.append((p, dict(rot_ang=rot, trans_dx=r * np.cos(a), trans_dy=r * np.sin(a),
+                                 zoom_scalar=z, do_warping=True)))
+    _CPU_ACC = acc
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(workers) as pool:
+            n_b = sum(pool.map(_cpu_bev, jobs))
+    else:
+        n_b = sum(_cpu_bev(j) for j in jobs)
+    _CPU_ACC = None
     return pts, n_b, time.perf_counter() - t0
+
+
+def cpu_workers():
+    return max(1, min(os.cpu_count() or 1, len(PRESENT_IDXS) * BEVS_PER_PRESENT))
 
 
 def cpu_baseline_sample(scene):
     rng = np.random.RandomState(5)
-    pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng)
-    return {'value': pts / dt, 'unit': 'points/s', 'cores': 1, 'kind': 'port',
+    w = cpu_workers()
+    pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng, w)
+    return {'value': pts / dt, 'unit': 'points/s', 'cores': w, 'kind': 'port',
             'bevs_per_s': n_b / dt, 'seconds': dt,
             'sample': f'1 scene: {N_SWEEPS} sweeps ({pts} pts) + {n_b} BEVs through oracle/oracle.py '
-                      '(vectorised numpy + C FMA-chain restatement of the reference, 1 thread; the '
-                      'literal reference is ~100x slower per BEV, BASELINE.md)',
+                      '(vectorised numpy + C FMA-chain restatement of the reference; integrate serial, BEVs '
+                      f'over {w} forked workers; the literal reference is ~100x slower per BEV, BASELINE.md)',
             'host_cpus': os.cpu_count()}
 
 
@@ -502,17 +528,18 @@ def run_reference(args, rank, world):
         return
     scene = make_scenes(0, 1)[0]
     rng = np.random.RandomState(5)
+    w = cpu_workers()
     for _ in range(min(args.warmup, 1)):
-        cpu_scene(scene, 8, PRESENT_IDXS[:1], rng)
+        cpu_scene(scene, 8, PRESENT_IDXS[:1], rng, w)
     tot_pts, tot_b, tot_t = 0, 0, 0.0
     for _ in range(args.steps):
-        pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng)
+        pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng, w)
         tot_pts, tot_b, tot_t = tot_pts + pts, tot_b + n_b, tot_t + dt
     v = tot_pts / tot_t
     sample = (f'each step = 1 scene: {N_SWEEPS} sweeps + {len(PRESENT_IDXS) * BEVS_PER_PRESENT} BEVs '
-              'on the CPU port of the reference algorithm (oracle/oracle.py); the reference itself is '
+              f'on the CPU port of the reference algorithm (oracle/oracle.py), BEVs over {w} forked workers; the reference itself is '
               'pure Python and /root/reference is not present on the GPU box')
-    print(json.dumps({
+    OUT.write(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'points/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': tot_t / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
@@ -521,14 +548,26 @@ def run_reference(args, rank, world):
                                'configs[3]: 40 sweeps x 34688 pts, CAM_FRONT 1600x900, '
                                '32 BEVs/scene (8 present idx x 4 aug), 256x256, present/future/full',
                    'scenes_per_step': 1},
-        'cpu_baseline': {'value': v, 'unit': 'points/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+        'cpu_baseline': {'value': v, 'unit': 'points/s', 'cores': w, 'kind': 'port', 'sample': sample,
                          'host_cpus': os.cpu_count()},
         'e2e': {'value': v, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    }) + '\n')
+    OUT.flush()
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE
+    JSON line on stdout.  Everything else is routed to stderr; the JSON goes to the saved fd."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, 'w')
 
 
 def main():
+    global OUT
+    OUT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -547,6 +586,9 @@ def main():
         run_reference(args, rank, world)
         return
     import torch
+    # torchrun pins OMP_NUM_THREADS=1; the host-side staging copies of the e2e path are
+    # parallel memcpys, so give every rank its share of the cores back
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the product has no CPU path '
                          '(use --impl reference for the host baseline)')
