@@ -1,11 +1,12 @@
 // raster.cu — BEV rasterisation of the resident ring (K7-K12 of SURVEY.md §2.1).
 //
-//   k_bev_bin      shift / lazy re-base / rotate / translate / crop / height /
-//                  static filter / pos2grid -> cell key; per-(cell,window)
-//                  counting (the returned count is the point's rank in its
-//                  segment) and block-aggregated append of a 16 B record
-//   k_scan         single-pass chained exclusive scan of the counters
-//   k_bev_scatter  counting-sort placement: sorted[start[key] + rank] = record
+//   k_bev_cull     per (frame, variant): can the frame's bounding box touch the view?
+//   k_bev_classify streaming pass over the ring: lazy re-base matrix, shift / rotate /
+//                  translate, x / y crop -> block-aggregated candidate list
+//   k_bev_bin      per candidate: exact re-base (guard band / chain replay), height and
+//                  static filters, pos2grid -> cell key, cell counter (RED), 16 B record
+//   k_scan         single-pass chained inclusive scan of the counters
+//   k_bev_scatter  counting-sort placement: sorted[--cursor[key]] = record
 //   k_bev_reduce   per-cell reductions (counts, fixed-point intensity sum,
 //                  min/max z, 256-bin histogram medians) for present / future /
 //                  full, Dirichlet + sigmoid finalisation, float16 planes
@@ -48,6 +49,16 @@ struct BevConsts {
 };
 __device__ __forceinline__ double bev_pv(const BevConsts *c, int v) { return c[v].pv; }
 
+// per (frame of the launch, variant): the x / y part of  R (M p - origin) + trans  folded
+// into one 2x4 affine map of the STORED coordinates (M = the frame's pending lazy matrix,
+// identity when there is none).  Not the reference's rounding sequence: it only selects
+// candidates (k_bev_classify, with a guard band) and feeds the float32 screening of
+// k_bev_bin; every decision that matters is re-taken in exact arithmetic.
+struct FrameVar {
+    double A[8];
+    float Af[8];
+};
+
 struct BinArgs {
     RingDev ring;
     const int64_t *frame_off, *frame_cnt, *frame_epoch;
@@ -64,9 +75,10 @@ struct BinArgs {
     int P;
     uint32_t *counts;      // n_var * 2*P*P (+1)
     uint32_t *frame_tiles; // per frame of the launch: tiles to visit (k_bev_cull)
+    FrameVar *fvar;        // n_frames x n_var (k_bev_cull)
     uint32_t *cand_gi;     // candidate list: ring position ...
     uint32_t *cand_meta;   // ... and variant | frame-in-launch << 8
-    uint32_t *tmp_key, *tmp_rank;
+    uint32_t *tmp_key;
     uint4 *tmp_rec;
     unsigned long long *n_append;  // device counter (candidates)
     unsigned long long *n_replay;
@@ -179,6 +191,24 @@ __global__ void k_bev_cull(BinArgs a) {
     const int64_t cnt = a.frame_cnt[slot];
     const uint32_t tiles = (uint32_t)((cnt + BIN_TILE - 1) / BIN_TILE);
     if (tiles == 0) return;
+    {
+        const double *Mp = a.comp + (int64_t)slot * 12;  // identity unless lazily re-based
+        FrameVar fv;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double acc = bp.R[3 * r] * Mp[c] + bp.R[3 * r + 1] * Mp[4 + c] + bp.R[3 * r + 2] * Mp[8 + c];
+                if (c == 3)
+                    acc += (r ? bp.trans_dy : bp.trans_dx) -
+                           (bp.R[3 * r] * bp.origin[0] + bp.R[3 * r + 1] * bp.origin[1] +
+                            bp.R[3 * r + 2] * bp.origin[2]);
+                fv.A[4 * r + c] = acc;
+                fv.Af[4 * r + c] = (float)acc;
+            }
+        }
+        a.fvar[(int64_t)f * a.n_var + v] = fv;
+    }
     const unsigned long long *bb = a.aabb + (int64_t)slot * 6;
     double lo[3], hi[3];
 #pragma unroll
@@ -225,8 +255,6 @@ __global__ void __launch_bounds__(BIN_BLOCK, 4)
 k_bev_classify(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ uint32_t s_tiles[BIN_MAXF + 1];
-    __shared__ double s_comp[12];
-    __shared__ double s_A[MAX_VGROUP][8];   // lazy frames: x / y rows of variant ∘ frame matrix
     __shared__ uint32_t s_warp[BIN_BLOCK / 32];
     __shared__ unsigned long long s_base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -290,27 +318,15 @@ k_bev_classify(BinArgs a) {
         const int64_t cnt = a.frame_cnt[slot];
         const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
         const int64_t off = a.frame_off[slot];
-        const bool lazy = a.frame_epoch[slot] < a.epoch_now;
-        bool need_z = lazy;
-        for (int v = v_begin; v < v_end; v++)
-            need_z = need_z || (s_par[v].R[2] != 0.0) || (s_par[v].R[5] != 0.0);
-        __syncthreads();  // the previous item is done with s_comp / s_A / s_warp / s_base
-        if (threadIdx.x < 12) s_comp[threadIdx.x] = a.comp[(int64_t)slot * 12 + threadIdx.x];
-        __syncthreads();
-        if (lazy && threadIdx.x < 8 * (v_end - v_begin)) {
-            // Candidate test of a lazily re-based frame: one 2x4 affine map per variant,
-            // q = R (M p - origin) + trans.  Not the reference's rounding sequence — it does not
-            // have to be: candidates keep a guard band of GUARD_M (>> any fp64 discrepancy) and
-            // k_bev_bin decides each of them with the exact arithmetic.
-            const int v = v_begin + (int)threadIdx.x / 8, r = ((int)threadIdx.x >> 2) & 1, c = (int)threadIdx.x & 3;
+        const FrameVar *fv = a.fvar + (int64_t)fl * a.n_var;
+        // z is only streamed when some variant's map mixes it into x / y (a lazily re-based
+        // frame, or a rotation that is not about the z axis)
+        bool need_z = false;
+        for (int v = v_begin; v < v_end; v++) {
             const pcacc_bev_params &bp = s_par[v];
-            double acc = bp.R[3 * r] * s_comp[c] + bp.R[3 * r + 1] * s_comp[4 + c] + bp.R[3 * r + 2] * s_comp[8 + c];
-            if (c == 3)
-                acc += (r ? bp.trans_dy : bp.trans_dx) -
-                       (bp.R[3 * r] * bp.origin[0] + bp.R[3 * r + 1] * bp.origin[1] + bp.R[3 * r + 2] * bp.origin[2]);
-            s_A[v][4 * r + c] = acc;
+            if (fid >= bp.frame_begin && fid < bp.frame_end)
+                need_z = need_z || (fv[v].A[2] != 0.0) || (fv[v].A[6] != 0.0);
         }
-        __syncthreads();
 
         // 4 points per thread: two pairs of neighbours (16 B loads; frame offsets are
         // multiples of 4 records, so the pairs are aligned)
@@ -331,28 +347,21 @@ k_bev_classify(BinArgs a) {
             py[2 * h] = Y.x; py[2 * h + 1] = Y.y;
             pz[2 * h] = Z.x; pz[2 * h + 1] = Z.y;
         }
+
         for (int v = v_begin; v < v_end; v++) {
             const pcacc_bev_params &bp = s_par[v];
             if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;  // block-uniform
-            const double hv = __dmul_rn(0.5, bp.view);
+            // candidate = within the view plus a guard band; k_bev_bin takes the real decision
+            const double lim = __dmul_rn(0.5, bp.view) + GUARD_M;
+            double A[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) A[k] = fv[v].A[k];
             unsigned cmask = 0;
-            if (lazy) {
-                const double *A = s_A[v];
-                const double lim = hv + GUARD_M;
 #pragma unroll
-                for (int k = 0; k < BIN_ITEMS; k++) {
-                    const double q0 = fma(A[0], px[k], fma(A[1], py[k], fma(A[2], pz[k], A[3])));
-                    const double q1 = fma(A[4], px[k], fma(A[5], py[k], fma(A[6], pz[k], A[7])));
-                    if ((fabs(q0) < lim) && (fabs(q1) < lim)) cmask |= 1u << k;  // NaN fails
-                }
-            } else {
-                const bool zfree = (bp.R[2] == 0.0) && (bp.R[5] == 0.0);
-#pragma unroll
-                for (int k = 0; k < BIN_ITEMS; k++) {
-                    double q0, q1;
-                    bev_xy(bp, zfree, px[k], py[k], pz[k], q0, q1);  // exact: the final crop test
-                    if ((q0 > -hv) && (q0 < hv) && (q1 > -hv) && (q1 < hv)) cmask |= 1u << k;
-                }
+            for (int k = 0; k < BIN_ITEMS; k++) {
+                const double q0 = fma(A[0], px[k], fma(A[1], py[k], fma(A[2], pz[k], A[3])));
+                const double q1 = fma(A[4], px[k], fma(A[5], py[k], fma(A[6], pz[k], A[7])));
+                if ((fabs(q0) < lim) && (fabs(q1) < lim)) cmask |= 1u << k;  // NaN fails
             }
             cmask &= vmask;
             const uint32_t my_cnt = __popc(cmask);
@@ -399,6 +408,31 @@ k_bev_classify(BinArgs a) {
 // static filter), the cell counter (its old value is the rank in the cell segment) and
 // the 16 B record.  A candidate rejected here leaves a hole (KEY_INVALID).
 // ---------------------------------------------------------------------------
+// Exact evaluation of one candidate: lazy matrix + guard band, exact chain replay when a
+// decision is within GUARD_M of its boundary (update_sem_pcs, sem_pc_accum.py:167-183).
+__device__ __forceinline__ Eval exact_candidate(const BinArgs &a, const pcacc_bev_params &bp, double pv,
+                                             int slot, int64_t e0, double x, double y, double z) {
+    Eval e;
+    if (e0 < a.epoch_now) {
+        double cx, cy, cz;
+        affine_chain(a.comp + (int64_t)slot * 12, 4, x, y, z, cx, cy, cz);
+        e = eval_point(bp, a.P, pv, cx, cy, cz, true);
+        if (e.near) {
+            for (int64_t ep = e0; ep < a.epoch_now; ep++) {
+                const double *T = a.chain + (ep % a.max_frames) * 12;
+                double nx, ny, nz;
+                affine_chain(T, 4, x, y, z, nx, ny, nz);
+                x = nx; y = ny; z = nz;
+            }
+            e = eval_point(bp, a.P, pv, x, y, z, false);
+            atomicAdd(a.n_replay, 1ull);
+        }
+    } else {
+        e = eval_point(bp, a.P, pv, x, y, z, false);
+    }
+    return e;
+}
+
 __global__ void __launch_bounds__(256, 4)
 k_bev_bin(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
@@ -415,48 +449,83 @@ k_bev_bin(BinArgs a) {
     if (n > (unsigned long long)a.cap) n = (unsigned long long)a.cap;
     const int PP = a.P * a.P;
     const unsigned long long stride = (unsigned long long)gridDim.x * 256;
-    unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
-    if (c >= n) return;
-    uint32_t gi32 = a.cand_gi[c], meta = a.cand_meta[c];
-    while (true) {
+
+    // exact evaluation of one candidate whose point data is already in registers
+    auto process = [&](unsigned long long c, uint32_t gi32, uint32_t meta, double x, double y, double z,
+                       uint32_t rgbs, float inten, uint32_t dyn) {
         const int64_t gi = (int64_t)gi32;
-        // every field of the point in one round trip (rejections below are rare)
-        double x = a.ring.x[gi], y = a.ring.y[gi], z = a.ring.z[gi];
-        const uint32_t rgbs = a.ring.rgbs[gi];
-        const float inten = a.ring.inten[gi];
-        const uint8_t dyn = a.ring.dyn[gi];
         const int v = (int)(meta & 255u);
         const int64_t fid = a.frame_lo + (int64_t)(meta >> 8);
-        // next candidate's entry is fetched while this one is processed
-        const unsigned long long cn = c + stride;
-        if (cn < n) {
-            gi32 = a.cand_gi[cn];
-            meta = a.cand_meta[cn];
-        }
         const int slot = (int)(fid % a.max_frames);
         const pcacc_bev_params &bp = s_par[v];
         const double pv = s_pv[v];
         const int64_t e0 = a.frame_epoch[slot];
         Eval e;
-        if (e0 < a.epoch_now) {
-            double cx, cy, cz;
-            affine_chain(a.comp + (int64_t)slot * 12, 4, x, y, z, cx, cy, cz);
-            e = eval_point(bp, a.P, pv, cx, cy, cz, true);
-            if (e.near) {
-                // exact sequential re-base chain (update_sem_pcs, sem_pc_accum.py:167-183)
-                for (int64_t ep = e0; ep < a.epoch_now; ep++) {
-                    const double *T = a.chain + (ep % a.max_frames) * 12;
-                    double nx, ny, nz;
-                    affine_chain(T, 4, x, y, z, nx, ny, nz);
-                    x = nx; y = ny; z = nz;
-                }
-                e = eval_point(bp, a.P, pv, x, y, z, false);
-                atomicAdd(a.n_replay, 1ull);
+        // ---- float32 screening -------------------------------------------------------------
+        // The composed map of the stored coordinates, evaluated in float32 with a running
+        // bound of its own rounding error.  When the point is farther than that bound (plus
+        // 1e-5 m) from the crop boundary and from every cell boundary, the cell index is
+        // decided here and only z is computed in float64; everything else falls through to
+        // the exact path below.  err: 16 float ulps of the sum of the term magnitudes covers
+        // the roundings of A -> float, p -> float and the three FMAs.
+        if (bp.R[6] == 0.0 && bp.R[7] == 0.0 && bp.R[8] == 1.0) {
+            const FrameVar &fv = a.fvar[(int64_t)(meta >> 8) * a.n_var + v];
+            const float xf = (float)x, yf = (float)y, zf = (float)z;
+            const float q0 = fmaf(fv.Af[0], xf, fmaf(fv.Af[1], yf, fmaf(fv.Af[2], zf, fv.Af[3])));
+            const float q1 = fmaf(fv.Af[4], xf, fmaf(fv.Af[5], yf, fmaf(fv.Af[6], zf, fv.Af[7])));
+            const float m0 = 1e-5f + 9.6e-7f * (fabsf(fv.Af[0] * xf) + fabsf(fv.Af[1] * yf) +
+                                               fabsf(fv.Af[2] * zf) + fabsf(fv.Af[3]) + (float)bp.view);
+            const float m1 = 1e-5f + 9.6e-7f * (fabsf(fv.Af[4] * xf) + fabsf(fv.Af[5] * yf) +
+                                               fabsf(fv.Af[6] * zf) + fabsf(fv.Af[7]) + (float)bp.view);
+            const float hvf = 0.5f * (float)bp.view;
+            const float d0 = hvf - fabsf(q0), d1 = hvf - fabsf(q1);   // > 0 inside the view
+            if (d0 < -m0 || d1 < -m1) {
+                // certainly outside the view (the guard band let it through): not binned
+                if (a.dbg_cell && v == 0) a.dbg_cell[gi] = -1;
+                a.tmp_key[c] = KEY_INVALID;
+                return;
             }
-        } else {
-            e = eval_point(bp, a.P, pv, x, y, z, false);
+            if (d0 > m0 && d1 > m1) {
+                const float pvf = (float)pv, hPf = 0.5f * (float)a.P;
+                const float g0 = fmaf(q0, pvf, hPf), g1 = fmaf(q1, pvf, hPf);
+                const float f0 = floorf(g0), f1 = floorf(g1);
+                const float e0g = m0 * pvf + 4.8e-7f * (fabsf(g0) + hPf + 1.f), e1g = m1 * pvf + 4.8e-7f * (fabsf(g1) + hPf + 1.f);
+                const float t0 = g0 - f0, t1 = g1 - f1;
+                if (t0 > e0g && t0 < 1.f - e0g && t1 > e1g && t1 < 1.f - e1g && f0 >= 0.f &&
+                    f0 < (float)a.P && f1 >= 0.f && f1 < (float)a.P) {
+                    // z in the reference's arithmetic: third row of the lazy matrix, then the shift
+                    double cz = z;
+                    if (e0 < a.epoch_now) {
+                        const double *m2 = a.comp + (int64_t)slot * 12 + 8;
+                        cz = __fma_rn(m2[3], 1.0, __fma_rn(m2[2], z, __fma_rn(m2[1], y, __dmul_rn(m2[0], x))));
+                    }
+                    // + 0.0: the exact path's  fma(1, sz, +0)  turns -0.0 into +0.0
+                    const double q2 = __dadd_rn(__dsub_rn(cz, bp.origin[2]), 0.0);
+                    const bool hf_on = (bp.height_filter == bp.height_filter);
+                    // q2 == q2 rejects a non-finite z like the exact path does
+                    if (q2 == q2 && fabs(q2) <= 1.7976931348623157e308 &&
+                        (!hf_on || fabs(q2 - bp.height_filter) > 1e-5)) {
+                        const bool keep = (dyn != 1u) && (!hf_on || q2 < bp.height_filter);
+                        const int cell = (a.P - 1 - (int)f1) * a.P + (int)f0;
+                        if (a.dbg_cell && v == 0) a.dbg_cell[gi] = keep ? cell : -1;
+                        if (keep) {
+                            const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
+                            const uint32_t key = ((uint32_t)v * (uint32_t)PP + (uint32_t)cell) * 2u + win;
+                            const unsigned long long zb = (unsigned long long)__double_as_longlong(q2);
+                            a.tmp_key[c] = key;
+                            a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), rgbs, __float_as_uint(inten));
+                            atomicAdd(&a.counts[key], 1u);
+                        } else {
+                            a.tmp_key[c] = KEY_INVALID;
+                        }
+                        return;
+                    }
+                }
+            }
         }
-        if (dyn == 1) e.keep = false;  // static points only (sem_bev.py:54-58)
+        // ---- exact path (rare) -------------------------------------------------------------
+        e = exact_candidate(a, bp, pv, slot, e0, x, y, z);
+        if (dyn == 1u) e.keep = false;  // static points only (sem_bev.py:54-58)
         if (a.dbg_cell && v == 0) a.dbg_cell[gi] = e.keep ? e.cell : -1;
         if (e.keep) {
             const uint32_t win = fid >= bp.frame_split ? 1u : 0u;
@@ -464,17 +533,35 @@ k_bev_bin(BinArgs a) {
             const unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
             a.tmp_key[c] = key;
             a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), rgbs, __float_as_uint(inten));
-            a.tmp_rank[c] = atomicAdd(&a.counts[key], 1u);
+#ifndef EXP_NO_ATOMIC
+            atomicAdd(&a.counts[key], 1u);  // result unused: a fire-and-forget reduction
+#endif
         } else {
             a.tmp_key[c] = KEY_INVALID;  // hole: rejected by the exact test
         }
-        if (cn >= n) break;
-        c = cn;
+    };
+
+    // two candidates per iteration: both points' loads are in flight before either is used
+    for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < n; c += 2 * stride) {
+        const unsigned long long c2 = c + stride;
+        const bool two = c2 < n;
+        const uint32_t gA = a.cand_gi[c], mA = a.cand_meta[c];
+        const uint32_t gB = two ? a.cand_gi[c2] : gA, mB = two ? a.cand_meta[c2] : mA;
+        const double xA = a.ring.x[gA], yA = a.ring.y[gA], zA = a.ring.z[gA];
+        const uint32_t rA = a.ring.rgbs[gA];
+        const float iA = a.ring.inten[gA];
+        const uint32_t dA = a.ring.dyn[gA];
+        const double xB = a.ring.x[gB], yB = a.ring.y[gB], zB = a.ring.z[gB];
+        const uint32_t rB = a.ring.rgbs[gB];
+        const float iB = a.ring.inten[gB];
+        const uint32_t dB = a.ring.dyn[gB];
+        process(c, gA, mA, xA, yA, zA, rA, iA, dA);
+        if (two) process(c2, gB, mB, xB, yB, zB, rB, iB, dB);
     }
 }
 
 // ---------------------------------------------------------------------------
-// exclusive scan of n u32 counters, in place (chained single pass)
+// inclusive scan of n u32 counters, in place (chained single pass)
 // ---------------------------------------------------------------------------
 struct ScanLB {
     unsigned long long *state;
@@ -533,8 +620,8 @@ k_scan(uint32_t *__restrict__ data, int64_t n, ScanLB lb) {
     uint32_t o[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        o[k] = run;
         run += v[k];
+        o[k] = run;  // inclusive: the scatter counts each segment down to its start
     }
     if (base + SCAN_ITEMS <= n) {
         uint4 *p = (uint4 *)(data + base);
@@ -552,16 +639,20 @@ k_scan(uint32_t *__restrict__ data, int64_t n, ScanLB lb) {
 // scatter
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_bev_scatter(const uint32_t *__restrict__ start, const uint32_t *__restrict__ tmp_key,
-              const uint32_t *__restrict__ tmp_rank, const uint4 *__restrict__ tmp_rec,
-              const unsigned long long *__restrict__ n_append, int64_t cap, uint4 *__restrict__ sorted) {
+k_bev_scatter(uint32_t *__restrict__ cursor, const uint32_t *__restrict__ tmp_key,
+              const uint4 *__restrict__ tmp_rec, const unsigned long long *__restrict__ n_append,
+              int64_t cap, uint4 *__restrict__ sorted) {
+    // cursor[key] enters as the inclusive prefix (= end of the key's segment); every record
+    // takes the slot below it, so the array leaves as the segments' starts — which is what
+    // the reduction reads.  The order inside a segment is arbitrary (see the file header).
     unsigned long long n = *n_append;
     if (n > (unsigned long long)cap) n = (unsigned long long)cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * 256) {
         const uint32_t key = tmp_key[i];
         if (key == KEY_INVALID) continue;
-        sorted[start[key] + tmp_rank[i]] = tmp_rec[i];
+        const uint4 rec = tmp_rec[i];
+        sorted[atomicSub(&cursor[key], 1u) - 1u] = rec;
     }
 }
 
@@ -1142,12 +1233,12 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         size_t o_cnt2 = align_up(o_counts + (size_t)n_keys * 4, 256);  // 4 x u64 counters
         size_t o_ftiles = align_up(o_cnt2 + 32, 256);                  // per-frame tile counts
         size_t o_key = align_up(o_ftiles + (size_t)BIN_MAXF * 4, 256);
-        size_t o_rank = align_up(o_key + (size_t)cap * 4, 256);
         // the candidate list (8 B) is dead once k_bev_bin has run: it shares the space of `sorted`
-        size_t o_rec = align_up(o_rank + (size_t)cap * 4, 256);
+        size_t o_rec = align_up(o_key + (size_t)cap * 4, 256);
         size_t o_sorted = align_up(o_rec + (size_t)cap * 16, 256);
         size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
-        size_t o_big = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
+        size_t o_fvar = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
+        size_t o_big = align_up(o_fvar + (size_t)(fhi > flo ? fhi - flo : 0) * nv * sizeof(FrameVar), 256);
         // a cell is "large" only above SMALL_T points, so the queue never exceeds cap / (SMALL_T+1)
         int64_t big_cap = cap / (SMALL_T + 1) + 1;
         if (big_cap > (int64_t)nv * PP) big_cap = (int64_t)nv * PP;
@@ -1194,10 +1285,10 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.P = P;
             a.counts = counts;
             a.frame_tiles = (uint32_t *)(ws + o_ftiles);
+            a.fvar = (FrameVar *)(ws + o_fvar);
             a.cand_gi = (uint32_t *)(ws + o_sorted);
             a.cand_meta = (uint32_t *)(ws + o_sorted + (size_t)cap * 4);
             a.tmp_key = (uint32_t *)(ws + o_key);
-            a.tmp_rank = (uint32_t *)(ws + o_rank);
             a.tmp_rec = (uint4 *)(ws + o_rec);
             a.n_append = ctr;
             a.n_replay = ctr + 1;
@@ -1220,6 +1311,9 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             k_bev_bin<<<148 * 8, 256, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_BIN, pe, st);
+#ifdef EXP_BIN_ONLY
+            continue;  // experiment builds stop after the bin stage
+#endif
             // scan
             int64_t tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
             rc = pcacc_ensure_tiles(h, tiles);
@@ -1237,8 +1331,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             int64_t sb = (cap + 255) / 256;
             if (sb > 148 * 16) sb = 148 * 16;
             pe = pcacc_prof_begin(h, PCACC_K_SCATTER, st);
-            k_bev_scatter<<<(unsigned)sb, 256, 0, st>>>(counts, a.tmp_key, a.tmp_rank, a.tmp_rec, ctr,
-                                                        cap, (uint4 *)(ws + o_sorted));
+            k_bev_scatter<<<(unsigned)sb, 256, 0, st>>>(counts, a.tmp_key, a.tmp_rec, ctr, cap,
+                                                        (uint4 *)(ws + o_sorted));
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
