@@ -221,6 +221,15 @@ int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_variants, i
                     void *out_f16_dev, double *out_f64_dev, int32_t *dbg_cell_dev,
                     void *stream);
 
+/* Polynomial warp of finished planes — BEVGenerator.warp_dense_probmaps,
+ * bev_generator/bev_generator.py:482-525: out[b, p, jw, iw] = in[b, p, jmap[b][jw], imap[b][iw]].
+ * The warp is a pure gather, so applying it to the float16 planes equals casting the warped
+ * float64 maps (sem_bev.py:121-257).  imap / jmap: HOST arrays (n_bevs x P) of source indices,
+ * already clamped to [0, P-1] (the Python mirror computes them with the reference's
+ * rint(c1*k + c2*k^2)).  in / out: (n_bevs, n_planes, P, P) float16, distinct buffers. */
+int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f16_dev, int n_bevs, int n_planes,
+                      int P, const int32_t *imap, const int32_t *jmap, void *stream);
+
 /* ring position (record index) of a live frame's first point, for dbg_cell_dev */
 int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset);
 
@@ -247,7 +256,7 @@ int pcacc_crop_trajectory(const double *traj, int n, double view, double thresh,
 #define PCACC_K_SCAN 4      /* k_scan */
 #define PCACC_K_SCATTER 5   /* k_bev_scatter */
 #define PCACC_K_REDUCE 6    /* k_bev_consts + k_bev_reduce (empty and small cells) */
-#define PCACC_K_EXPORT 7    /* k_export_frame */
+#define PCACC_K_EXPORT 7    /* k_export_frame, k_warp_planes */
 #define PCACC_K_REDUCE_BIG 8 /* k_bev_reduce_big (queued large cells) */
 #define PCACC_K_CLASSIFY 9  /* k_bev_classify (streaming crop test over the ring) */
 #define PCACC_N_KERNELS 10

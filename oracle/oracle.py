@@ -366,8 +366,75 @@ def raster_window(pc_grid, P, sem_idxs, int_scaler, int_sep_scaler,
 PLANES = ('road', 'intensity', 'r', 'g', 'b', 'dynamic', 'elevation')
 
 
+# ---------------------------------------------------------------------------
+#  polynomial warp (bev_generator/bev_generator.py:482-698), SURVEY §8f rank 1
+# ---------------------------------------------------------------------------
+def cal_warp_params(idx_0, idx_1, idx_max):
+    """bev_generator.py:663-683."""
+    a_1 = (idx_1 - idx_0 ** 2 / idx_max) / (idx_0 * (1.0 - idx_0 / idx_max))
+    a_2 = (1.0 - a_1) / idx_max
+    return a_1, a_2
+
+
+def random_warp_params(np_rng, py_rng, mean_ratio, max_ratio, I, J):
+    """get_random_warp_params, bev_generator.py:621-661: two np.random.normal draws, then
+    two random.random() draws for the signs."""
+    max_val = max_ratio * (I / 2.0)
+    mean_val = mean_ratio * max_val
+    i_warp = np_rng.normal(mean_val, max_val)
+    j_warp = np_rng.normal(mean_val, max_val)
+    if abs(i_warp) > max_val:
+        i_warp = max_val
+    if abs(j_warp) > max_val:
+        j_warp = max_val
+    if py_rng.random() < 0.5:
+        i_warp = -i_warp
+    if py_rng.random() < 0.5:
+        j_warp = -j_warp
+    return int(I / 2) + i_warp, int(J / 2) + j_warp
+
+
+def warp_index_map(c_1, c_2, n):
+    """Source index of every warped index: clamp(rint(c_1 k + c_2 k^2)), bev_generator.py:508-520."""
+    k = np.arange(n)
+    src = np.rint(c_1 * k + c_2 * k ** 2).astype(np.int64)
+    return np.clip(src, 0, n - 1)
+
+
+def warp_dense(maps, a_1, a_2, b_1, b_2):
+    """warp_dense_probmaps, bev_generator.py:482-525: B[:, jw, iw] = A[:, j(jw), i(iw)]."""
+    n, I, J = maps.shape
+    imap = warp_index_map(a_1, a_2, I)
+    jmap = warp_index_map(b_1, b_2, J)
+    return maps[:, jmap[:, None], imap[None, :]]
+
+
+def warp_traj(traj, a_1, a_2, j_warp, P):
+    """warp_sparse_points + warp_point, bev_generator.py:527-590 (the j warp is reversed)."""
+    import math
+    b_1, b_2 = cal_warp_params(P - j_warp, int(P / 2), P - 1)
+    out = np.array(traj, dtype=float).reshape(-1, 3)
+
+    def one(v, c_1, c_2):
+        if math.isclose(c_2, 0.0, abs_tol=1e-6):
+            w = v
+        else:
+            with np.errstate(invalid='ignore'):
+                w = int(np.rint((-c_1 + np.sqrt(c_1 ** 2 + 4.0 * c_2 * v)) / (2 * c_2)))
+        if w < 0:
+            w = 0
+        elif w >= P:
+            w = P - 1
+        return w
+
+    for k in range(out.shape[0]):
+        out[k, 0] = one(out[k, 0], a_1, a_2)
+        out[k, 1] = one(out[k, 1], b_1, b_2)
+    return out
+
+
 def generate(pcs, trajs, gen_params, rot_ang=0., trans_dx=0., trans_dy=0.,
-             zoom_scalar=1., do_warping=False, return_f64=False):
+             zoom_scalar=1., do_warping=False, return_f64=False, warp_rngs=None):
     """BEVGenerator.generate + SemBEVGenerator.generate_bev
     (bev_generator/bev_generator.py:63-125, sem_bev.py:36-262), warp excluded.
 
@@ -386,6 +453,14 @@ def generate(pcs, trajs, gen_params, rot_ang=0., trans_dx=0., trans_dy=0.,
 
     bev = {}
     dbg = {}
+    warp = None
+    if gen_params.get('do_warp'):
+        # sem_bev.py:121-190: one set of warp parameters for all maps and trajectories
+        i_mid = int(P / 2)
+        i_warp, j_warp = random_warp_params(warp_rngs[0], warp_rngs[1], 0.15, 0.30, P, P)
+        a_1, a_2 = cal_warp_params(i_warp, i_mid, P - 1)
+        b_1, b_2 = cal_warp_params(j_warp, i_mid, P - 1)
+        warp = (a_1, a_2, b_1, b_2, j_warp)
     for w in ('present', 'future', 'full'):
         pc = pcs[f'pc_{w}']
         if pc is None:
@@ -399,6 +474,9 @@ def generate(pcs, trajs, gen_params, rot_ang=0., trans_dx=0., trans_dy=0.,
             gen_params['int_sep_scaler'], gen_params['int_mid_threshold'],
             gen_params.get('rgb_fill', 0), return_f64=True,
             elevation_mode=gen_params.get('elevation_mode', 'min'))
+        if warp is not None:
+            planes = warp_dense(planes, *warp[:4])
+            tr = [warp_traj(t, warp[0], warp[1], warp[4], P) for t in tr]
         h = planes.astype(np.float16)
         bev[f'road_{w}'] = h[0]
         bev[f'trajs_{w}'] = tr
@@ -415,7 +493,10 @@ def generate(pcs, trajs, gen_params, rot_ang=0., trans_dx=0., trans_dy=0.,
     if 'gt_lanes' in trajs:
         lanes = [transform_traj(t, R, trans_dx, trans_dy, view, P)
                  for t in trajs['gt_lanes']]
-        bev['gt_lanes'] = [l for l in lanes if l.shape[0] > 0]
+        lanes = [l for l in lanes if l.shape[0] > 0]
+        if warp is not None:
+            lanes = [warp_traj(t, warp[0], warp[1], warp[4], P) for t in lanes]
+        bev['gt_lanes'] = lanes
     if return_f64:
         bev['_debug'] = dbg
     return bev

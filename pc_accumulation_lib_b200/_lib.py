@@ -77,6 +77,7 @@ SIGNATURES = {
     'pcacc_export_frame': (_i32, [_vp, _i64, _vp, _vp]),
     'pcacc_rasterise': (_i32, [_vp, C.POINTER(BevParams), _i32, _i32, _vp, _vp,
                                _vp, _vp]),
+    'pcacc_warp_planes': (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     'pcacc_frame_offset': (_i32, [_vp, _i64, C.POINTER(_i64)]),
     'pcacc_raster_stats': (_i32, [_vp, C.POINTER(_i64 * 3), _vp]),
     'pcacc_crop_trajectory': (_i32, [_vp, _i32, _dbl, _dbl, _vp, C.POINTER(_i32)]),

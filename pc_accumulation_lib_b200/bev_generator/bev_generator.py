@@ -74,6 +74,7 @@ class BEVGenerator(ABC):
         # injectable RNG for generate_rand_aug (the reference seeds numpy's
         # global RNG from pid*time, bev_generator.py:168)
         self.rng = None
+        self.py_rng = None             # `random.Random` for the warp's sign draws
         self.elevation_max = False      # north-star variant; reference = per-cell min z
         self._scratch = None            # DeviceCloud for host-array inputs
 
@@ -210,9 +211,17 @@ class BEVGenerator(ABC):
         self._scratch.reset()
         return self._scratch
 
-    def _rasterise_windows(self, pcs, augs):
-        """pcs: the reference's dict. Returns (planes (V,3,7,P,P) numpy f16,
-        has_future)."""
+    def _rasterise_windows(self, pcs, augs, warps=None):
+        """Rasterise (and optionally warp) on the device, then copy the planes to the host."""
+        planes, has_future, cloud = self._rasterise_device(pcs, augs)
+        if warps is not None:
+            planes = cloud.warp_planes(planes.contiguous(), [w['imap'] for w in warps],
+                                       [w['jmap'] for w in warps])
+        return cloud.planes_to_host(planes.contiguous()), has_future
+
+    def _rasterise_device(self, pcs, augs):
+        """pcs: the reference's dict. Returns (planes (V,3,7,P,P) float16 device tensor,
+        has_future, the DeviceCloud that produced them)."""
         P = self.pixel_size
         pp, pf, pa = self.extract_pc_dict(pcs)
         has_future = pf is not None
@@ -233,7 +242,7 @@ class BEVGenerator(ABC):
                 if same:        # full = present ++ future: one pass does all three
                     planes, _, _ = cloud.rasterise(
                         params(cloud, pp.frame_begin, pp.frame_end, pf.frame_end, pp.origin), P)
-                    return cloud.planes_to_host(planes), True
+                    return planes, True, cloud
                 # general case: each window rasterised as a 'present' window
                 outs = []
                 for w in (pp, pf, pa):
@@ -241,10 +250,10 @@ class BEVGenerator(ABC):
                         params(w.cloud, w.frame_begin, w.frame_end, w.frame_end, w.origin), P)
                     outs.append(pl[:, 0])
                 import torch
-                return torch.stack(outs, dim=1).cpu().numpy(), True
+                return torch.stack(outs, dim=1), True, pp.cloud
             planes, _, _ = cloud.rasterise(
                 params(cloud, pp.frame_begin, pp.frame_end, pp.frame_end, pp.origin), P)
-            return cloud.planes_to_host(planes), False
+            return planes, False, cloud
 
         # host arrays: upload into a scratch ring as frames
         clouds = [np.asarray(pp, dtype=np.float64)]
@@ -258,11 +267,11 @@ class BEVGenerator(ABC):
             params(cloud, fids[0], fids[1] if has_future else fids[0] + 1,
                    fids[1] + 1 if has_future else fids[0] + 1, zero), P)
         if not has_future:
-            return pl.cpu().numpy(), False
+            return pl, False, cloud
         # pc_full is an input of its own in the reference API: rasterise it as well
         plf, _, _ = cloud.rasterise(params(cloud, fids[2], fids[2] + 1, fids[2] + 1, zero), P)
         pl[:, 2] = plf[:, 0]
-        return pl.cpu().numpy(), True
+        return pl, True, cloud
 
     @staticmethod
     def _pad10(c):
@@ -298,7 +307,11 @@ class BEVGenerator(ABC):
             if not a.get('do_warping', False):
                 a['rot_ang'] = self.heading_angle(ego_p)
             full.append(a)
-        planes, has_future = self._rasterise_windows(pcs, full)
+        warps = None
+        if self.do_warp:
+            # one polynomial warp per BEV, drawn like sem_bev.py:121-129
+            warps = [self.draw_warp() for _ in full]
+        planes, has_future = self._rasterise_windows(pcs, full, warps)
         bevs = []
         for v, a in enumerate(full):
             view = a['zoom_scalar'] * self.view_size
@@ -312,8 +325,102 @@ class BEVGenerator(ABC):
                 lanes = self.preprocess_trajs(self.extract_gt_lane_dicts(trajs), a['rot_ang'],
                                               a['trans_dx'], a['trans_dy'], view)
                 lanes = [ln for ln in lanes if ln.shape[0] > 0]
+            if warps is not None:
+                w = warps[v]
+                for k in tw:
+                    tw[k] = self.warp_trajs(tw[k], w['a_1'], w['a_2'], w['b_1'], w['b_2'], w['i_mid'],
+                                            w['j_mid'], w['i_warp'], w['j_warp'])
+                if lanes is not None:
+                    lanes = self.warp_trajs(lanes, w['a_1'], w['a_2'], w['b_1'], w['b_2'], w['i_mid'],
+                                            w['j_mid'], w['i_warp'], w['j_warp'])
             bevs.append(self._assemble(planes, v, tw, lanes, has_future))
         return bevs
+
+    # ------------------------------------------------------------------
+    # polynomial warp (bev_generator.py:482-698): parameters and trajectories on the
+    # host, the dense gather on the device (pcacc_warp_planes)
+    # ------------------------------------------------------------------
+    @staticmethod
+    def cal_warp_params(idx_0, idx_1, idx_max):
+        a_1 = (idx_1 - idx_0 ** 2 / idx_max) / (idx_0 * (1.0 - idx_0 / idx_max))
+        a_2 = (1.0 - a_1) / idx_max
+        return (a_1, a_2)
+
+    def get_random_warp_params(self, mean_ratio, max_ratio, I, J):
+        """Two normal draws, then two uniform draws for the signs.  `self.rng` /
+        `self.py_rng` replace the reference's global numpy / `random` state when set."""
+        import random as _random
+        np_rng = self.rng if self.rng is not None else np.random
+        py_rng = getattr(self, 'py_rng', None) or _random
+        max_val = max_ratio * (I / 2.0)
+        mean_val = mean_ratio * max_val
+        i_warp = np_rng.normal(mean_val, max_val)
+        j_warp = np_rng.normal(mean_val, max_val)
+        if abs(i_warp) > max_val:
+            i_warp = max_val
+        if abs(j_warp) > max_val:
+            j_warp = max_val
+        if py_rng.random() < 0.5:
+            i_warp = -i_warp
+        if py_rng.random() < 0.5:
+            j_warp = -j_warp
+        return (int(I / 2) + i_warp, int(J / 2) + j_warp)
+
+    @staticmethod
+    def warp_index_map(c_1, c_2, n):
+        """Source index of every warped index: clamp(rint(c_1 k + c_2 k^2), 0, n-1)."""
+        k = np.arange(n)
+        return np.clip(np.rint(c_1 * k + c_2 * k ** 2).astype(np.int64), 0, n - 1)
+
+    def draw_warp(self):
+        P = self.pixel_size
+        i_mid = j_mid = int(P / 2)
+        i_warp, j_warp = self.get_random_warp_params(0.15, 0.30, P, P)
+        a_1, a_2 = self.cal_warp_params(i_warp, i_mid, P - 1)
+        b_1, b_2 = self.cal_warp_params(j_warp, j_mid, P - 1)
+        return dict(a_1=a_1, a_2=a_2, b_1=b_1, b_2=b_2, i_mid=i_mid, j_mid=j_mid, i_warp=i_warp,
+                    j_warp=j_warp, imap=self.warp_index_map(a_1, a_2, P),
+                    jmap=self.warp_index_map(b_1, b_2, P))
+
+    def warp_dense_probmaps(self, probmaps, a_1, a_2, b_1, b_2):
+        """(n,h,w) maps -> warped maps, B[:, jw, iw] = A[:, j(jw), i(iw)].  A gather: done with
+        index tensors on the device for host arrays of any dtype; the rasteriser's own float16
+        planes go through pcacc_warp_planes instead."""
+        import torch
+        probmaps = np.asarray(probmaps)
+        n, I, J = probmaps.shape
+        imap = torch.from_numpy(self.warp_index_map(a_1, a_2, I)).cuda()
+        jmap = torch.from_numpy(self.warp_index_map(b_1, b_2, J)).cuda()
+        t = torch.from_numpy(np.ascontiguousarray(probmaps)).cuda()
+        return t[:, jmap[:, None], imap[None, :]].cpu().numpy()
+
+    @staticmethod
+    def warp_point(x, y, a_1, a_2, b_1, b_2, I, J):
+        import math
+
+        def inv(v, c_1, c_2, n):
+            if math.isclose(c_2, 0.0, abs_tol=1e-6):
+                w = v
+            else:
+                w = int(np.rint((-c_1 + np.sqrt(c_1 ** 2 + 4.0 * c_2 * v)) / (2 * c_2)))
+            return 0 if w < 0 else (n - 1 if w >= n else w)
+        return (inv(x, a_1, a_2, I), inv(y, b_1, b_2, J))
+
+    def warp_points(self, pnt_list, a_1, a_2, b_1, b_2, I, J):
+        return [self.warp_point(p[0], p[1], a_1, a_2, b_1, b_2, I, J) for p in pnt_list]
+
+    def warp_sparse_points(self, pnts, a_1, a_2, b_1, b_2, i_mid, j_mid, i_warp, j_warp):
+        # the j warp is applied reversed, as in the reference (bev_generator.py:530-533)
+        b_1_rev, b_2_rev = self.cal_warp_params(self.pixel_size - j_warp, j_mid, self.pixel_size - 1)
+        out = self.warp_points(list(zip(pnts[:, 0], pnts[:, 1])), a_1, a_2, b_1_rev, b_2_rev,
+                               self.pixel_size, self.pixel_size)
+        pnts[:, 0] = [i for i, _ in out]
+        pnts[:, 1] = [j for _, j in out]
+        return pnts
+
+    def warp_trajs(self, trajs, a_1, a_2, b_1, b_2, i_mid, j_mid, i_warp, j_warp):
+        return [self.warp_sparse_points(t, a_1, a_2, b_1, b_2, i_mid, j_mid, i_warp, j_warp)
+                for t in trajs]
 
     def generate(self, pcs: dict, trajs: dict, rot_ang: float = 0., trans_dx: float = 0.,
                  trans_dy: float = 0., zoom_scalar: float = 1., do_warping: bool = False):

@@ -29,9 +29,6 @@ class SemBEVGenerator(BEVGenerator):
         self.rgb_fill = rgb_fill
 
     def _assemble(self, planes, v, trajs_by_window, gt_lane_trajs, has_future):
-        if self.do_warp:
-            raise NotImplementedError(
-                'polynomial warp (bev_generator.py:482-698) is not on the B200 path yet')
         bev = {}
         for wi, w in enumerate(WINDOWS if has_future else WINDOWS[:1]):
             pl = planes[v, wi]

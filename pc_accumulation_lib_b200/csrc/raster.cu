@@ -1373,6 +1373,53 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
     return PCACC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// polynomial warp of finished planes (a separable gather)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_warp_planes(const __half *__restrict__ in, __half *__restrict__ out, const int32_t *__restrict__ imap,
+              const int32_t *__restrict__ jmap, int n_planes, int P, int64_t total) {
+    const int64_t PP = (int64_t)P * P;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int iw = (int)(t % P);
+        const int jw = (int)((t / P) % P);
+        const int64_t bp = t / PP;             // bev * n_planes + plane
+        const int b = (int)(bp / n_planes);
+        const int i = imap[(int64_t)b * P + iw], j = jmap[(int64_t)b * P + jw];
+        out[t] = in[bp * PP + (int64_t)j * P + i];
+    }
+}
+
+extern "C" int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f16_dev, int n_bevs,
+                                 int n_planes, int P, const int32_t *imap, const int32_t *jmap,
+                                 void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (!in_f16_dev || !out_f16_dev || in_f16_dev == out_f16_dev || n_bevs <= 0 || n_planes <= 0 ||
+        P <= 0 || !imap || !jmap)
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad warp_planes arguments");
+    for (int64_t k = 0; k < (int64_t)n_bevs * P; k++)
+        if (imap[k] < 0 || imap[k] >= P || jmap[k] < 0 || jmap[k] >= P)
+            return pcacc_fail(h, PCACC_ERR_ARG, "warp index outside [0, P)");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<int32_t> buf((size_t)2 * n_bevs * P);
+    memcpy(buf.data(), imap, (size_t)n_bevs * P * 4);
+    memcpy(buf.data() + (size_t)n_bevs * P, jmap, (size_t)n_bevs * P * 4);
+    void *dev = nullptr;
+    int rc = pcacc_arena_put(h, buf.data(), buf.size() * 4, &dev, st);
+    if (rc) return rc;
+    const int64_t total = (int64_t)n_bevs * n_planes * P * P;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    h->launches[PCACC_K_EXPORT]++;
+    k_warp_planes<<<(unsigned)blocks, 256, 0, st>>>((const __half *)in_f16_dev, (__half *)out_f16_dev,
+                                                    (const int32_t *)dev,
+                                                    (const int32_t *)dev + (size_t)n_bevs * P, n_planes,
+                                                    P, total);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
 extern "C" int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream) {
     if (!h || !stats) return PCACC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;

@@ -381,6 +381,19 @@ class DeviceCloud:
         self._check(self.lib.pcacc_profile_read(self.h, C.byref(ms), C.byref(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
 
+    def warp_planes(self, planes, imaps, jmaps):
+        """planes (V,3,7,P,P) float16 device tensor, imaps / jmaps (V,P) int source indices
+        -> warped planes (new tensor)."""
+        V, P = int(planes.shape[0]), int(planes.shape[-1])
+        n_planes = int(planes.numel() // (V * P * P))
+        im = np.ascontiguousarray(np.asarray(imaps, dtype=np.int32).reshape(V, P))
+        jm = np.ascontiguousarray(np.asarray(jmaps, dtype=np.int32).reshape(V, P))
+        out = torch.empty_like(planes)
+        self._check(self.lib.pcacc_warp_planes(self.h, _ptr(planes), _ptr(out), V, n_planes, P,
+                                               im.ctypes.data_as(C.c_void_p),
+                                               jm.ctypes.data_as(C.c_void_p), _stream()))
+        return out
+
     def planes_to_host(self, planes):
         """(V,3,7,P,P) float16 device tensor -> numpy, through a reusable pinned buffer."""
         n = planes.numel()

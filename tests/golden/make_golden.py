@@ -174,6 +174,27 @@ def gen_bev_direct(ref, name, **kw):
     save(name, out)
 
 
+def gen_bev_warp(ref, name, seeds=(11, 12, 13), **kw):
+    """do_warp=True: the reference draws the warp from the GLOBAL numpy and `random` RNGs
+    (bev_generator.py:621-661); both are seeded right before each call."""
+    import random
+    pcs, trajs, aug, gen = cases.bev_direct_inputs(**kw)
+    g = ref.SemBEVGenerator(gen['sem_idxs'], gen['view_size'], gen['pixel_size'], 0., 0., True,
+                            gen['int_scaler'], gen['int_sep_scaler'], gen['int_mid_threshold'],
+                            gen['height_filter'], gen['rgb_fill'])
+    out = {'input_sha256': np.array(cases.digest(
+        pcs['pc_present'], pcs['pc_future'], trajs['ego_traj_full'])),
+        'seeds': np.array(seeds, dtype=np.int64)}
+    for s in seeds:
+        p, t = cases.copy_pcs_trajs(pcs, trajs)
+        np.random.seed(s)
+        random.seed(s)
+        with quiet():
+            bev = g.generate(p, t, **aug)
+        pack_bev(bev, f'bev{s}_', out)
+    save(name, out)
+
+
 def main():
     ref = ref_loader.load()
     gen_kitti_project(ref)
@@ -188,6 +209,7 @@ def main():
     gen_bev_direct(ref, 'bev_direct.npz')
     gen_bev_direct(ref, 'bev_direct_p128.npz', n=20000, seed=78, P=128,
                    view=51.2)
+    gen_bev_warp(ref, 'bev_warp.npz')
 
 
 if __name__ == '__main__':

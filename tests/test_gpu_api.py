@@ -202,3 +202,28 @@ def test_missing_cuda_or_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libpcacc.so')
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_sem_bev_generator_polynomial_warp():
+    """do_warp=True: the warp parameters come from injected RNG streams
+    seeded like the reference's global ones; grids are gathered on the device, trajectories
+    warped on the host — both equal the reference's output."""
+    import random
+    from pc_accumulation_lib_b200 import SemBEVGenerator
+    g = load_golden('bev_warp.npz')
+    pcs, trajs, aug, gen = cases.bev_direct_inputs()
+    bg = SemBEVGenerator(gen['sem_idxs'], gen['view_size'], gen['pixel_size'], 0., 0., True,
+                         gen['int_scaler'], gen['int_sep_scaler'], gen['int_mid_threshold'],
+                         gen['height_filter'], gen['rgb_fill'])
+    for s in g['seeds']:
+        bg.rng, bg.py_rng = np.random.RandomState(int(s)), random.Random(int(s))
+        bev = bg.generate(*cases.copy_pcs_trajs(pcs, trajs), **aug)
+        assert_bev_equal(bev, unpack_bev(g, f'bev{int(s)}_'), exact=False)
+    # the stand-alone dense warp helper on a float64 stack
+    rng = np.random.default_rng(2)
+    maps = rng.random((5, 32, 32))
+    a_1, a_2 = bg.cal_warp_params(19.5, 16, 31)
+    b_1, b_2 = bg.cal_warp_params(12.25, 16, 31)
+    from oracle import oracle as orc
+    np.testing.assert_array_equal(bg.warp_dense_probmaps(maps, a_1, a_2, b_1, b_2),
+                                  orc.warp_dense(maps, a_1, a_2, b_1, b_2))

@@ -139,3 +139,19 @@ def test_bev_direct_golden(name, kw):
         np.testing.assert_array_equal(pcg[:, 2], g[f'grid_z_{w}'])
     bev = orc.generate(pcs, trajs, gen)
     assert_bev_equal(bev, unpack_bev(g, 'bevhead_'))
+
+
+def test_bev_warp_golden():
+    """Polynomial warp (do_warp=True): the oracle, fed the same RNG streams the reference
+    drew from (global numpy + `random`, seeded per case), reproduces the reference's warped
+    grids and trajectories."""
+    import random
+    g = load_golden('bev_warp.npz')
+    pcs, trajs, aug, gen = cases.bev_direct_inputs()
+    assert str(g['input_sha256']) == cases.digest(
+        pcs['pc_present'], pcs['pc_future'], trajs['ego_traj_full'])
+    gen = dict(gen, do_warp=True)
+    for s in g['seeds']:
+        rngs = (np.random.RandomState(int(s)), random.Random(int(s)))
+        bev = orc.generate(*cases.copy_pcs_trajs(pcs, trajs), gen, warp_rngs=rngs, **aug)
+        assert_bev_equal(bev, unpack_bev(g, f'bev{int(s)}_'))
