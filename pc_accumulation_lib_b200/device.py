@@ -246,6 +246,11 @@ class DeviceCloud:
         """sweeps: list of dicts with DEVICE tensors pc (n,7) f64, cam (n,) i64,
         rgb [ (H,W,3) u8 ], sem [ (H,W) u8|i32|i64 ] and host T (4,4).  One launch
         for the whole list; returns the first frame id."""
+        return self.integrate_prepared(self.prepare_records_batch(sweeps, filters, intensity_div))
+
+    def prepare_records_batch(self, sweeps, filters, intensity_div=255.):
+        """The argument block of integrate_records_batch, built once for inputs that stay
+        resident (offline dataset generation re-integrates the same device buffers)."""
         n_s = len(sweeps)
         n_cams = len(sweeps[0]['rgb'])
         sem_dt = _TORCH_SEM[sweeps[0]['sem'][0].dtype] if n_cams else _lib.SEM_U8
@@ -260,11 +265,15 @@ class DeviceCloud:
         T = np.ascontiguousarray(np.stack([np.asarray(s['T'], dtype=np.float64).reshape(4, 4)
                                            for s in sweeps]))
         f, fp, nf = self._filters(filters)
+        args = (n_s, C.cast(pcp, C.c_void_p), C.cast(cmp_, C.c_void_p), C.cast(nn, C.c_void_p),
+                C.cast(rp, C.c_void_p), C.cast(sp, C.c_void_p), n_cams, sem_dt, h, w,
+                T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf)
+        return {'args': args, 'keep': (sweeps, pcp, cmp_, nn, rp, sp, T, f)}
+
+    def integrate_prepared(self, prep) -> int:
         fid = C.c_int64(-1)
-        self._check(self.lib.pcacc_integrate_records_batch(
-            self.h, n_s, C.cast(pcp, C.c_void_p), C.cast(cmp_, C.c_void_p), C.cast(nn, C.c_void_p),
-            C.cast(rp, C.c_void_p), C.cast(sp, C.c_void_p), n_cams, sem_dt, h, w,
-            T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf, C.byref(fid), _stream()))
+        self._check(self.lib.pcacc_integrate_records_batch(self.h, *prep['args'], C.byref(fid),
+                                                           _stream()))
         return int(fid.value)
 
     def integrate_cloud(self, rec) -> int:
@@ -293,6 +302,13 @@ class DeviceCloud:
         assert len(frame_ids) == len(inst_idx)
         self._mark_f.extend(int(f) for f in frame_ids)
         self._mark_i.extend(int(i) for i in inst_idx)
+
+    def mark_dynamic_now(self, frame_ids: np.ndarray, inst_idx: np.ndarray):
+        """Unqueued variant for callers that already hold contiguous int64 / int32 arrays."""
+        if frame_ids.size:
+            self._check(self.lib.pcacc_mark_dynamic(self.h, frame_ids.ctypes.data_as(C.c_void_p),
+                                                    inst_idx.ctypes.data_as(C.c_void_p),
+                                                    int(frame_ids.size), _stream()))
 
     def flush_marks(self):
         if not self._mark_f:
@@ -361,7 +377,7 @@ class DeviceCloud:
         tensor, planes f64 or None, per-ring-position cell index or None)."""
         self.flush_marks()
         V = len(params)
-        arr = (BevParams * V)(*params)
+        arr = params if isinstance(params, C.Array) else (BevParams * V)(*params)
         if out is None:
             out = torch.empty((V, 3, 7, P, P), dtype=torch.float16, device=self.device)
         o64 = (torch.empty((V, 3, 7, P, P), dtype=torch.float64, device=self.device)
