@@ -70,52 +70,55 @@ def make_scenes(rank, n, world=1):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a
+    thread (the timed region can be shorter than one `nvidia-smi -lms` period)."""
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+               ('sw_power_cap', 0x4))
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.idx
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.idx])
+                except Exception:
+                    idx = self.idx
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception as e:      # pragma: no cover - depends on the box
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
-                 '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                                'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': float(np.max(mx)) if mx else None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz,
+                    'reasons': ['clock sampling unavailable: %s' % self.err]}
+        return {'sm_mhz': float(np.median(self.sm)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm)}
 
 
 # ---------------------------------------------------------------------------
@@ -171,6 +174,9 @@ def run_ours(args, rank, world, local_rank, dist):
     acc = NuScenesOracleSemanticPointCloudAccumulator(
         semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None, bev_setup(),
         ring_capacity_pts=n_in_scene + 4096, ring_max_frames=N_SWEEPS + 8, device=local_rank)
+    # data-error flags are checked at the next synchronising call (generate_bev) instead of
+    # after every sweep, so the staging of sweep k+1 overlaps the kernels of sweep k
+    acc.sync_each_integrate = False
 
     def new_scene_state():
         acc.cloud.reset()
@@ -373,7 +379,8 @@ def run_ours(args, rank, world, local_rank, dist):
     e2e = {'value': e2e_pts, 'unit': 'points/s', 'h2d_bytes_per_step': int(h2d),
            'd2h_bytes_per_step': int(d2h), 'bevs_per_s': n_b * world / dt,
            'scenes_per_step': e2e_scenes, 'steps': args.e2e_steps,
-           'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev, numpy in/out'}
+           'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev, numpy in/out '
+                  '(sync_each_integrate=False: error flags checked at generate_bev)'}
 
     # ---- CPU baseline + long-horizon extra (rank 0, N = 1) ---------------------------
     cpu = None

@@ -34,26 +34,40 @@ def require_cuda():
 
 
 class Stager:
-    """Reusable pinned-host + device buffer pairs for host->device inputs."""
+    """Host -> device staging of inputs through reusable pinned buffers (two per key, used
+    alternately, so the copy of the next observation can start while the kernels of the
+    previous one still read theirs).
+
+    `put(..., mapped=True)` stops at the pinned buffer and hands its address to the kernel:
+    pinned memory is device-accessible under unified addressing, and the integrate kernels
+    only sample a few thousand pixels of each camera map — reading those over PCIe beats
+    DMA-ing the whole image into HBM first."""
 
     def __init__(self, device):
         self.device = device
-        self._slots = {}     # key -> [pinned, device, event]
+        self._slots = {}     # key -> [[pinned, device, event], [pinned, device, event], turn]
+        self._touched = []
 
-    def _slot(self, key, nbytes):
-        sl = self._slots.get(key)
-        if sl is None or sl[0].numel() < nbytes:
+    def _slot(self, key, nbytes, need_dev):
+        ring = self._slots.get(key)
+        if ring is None:
+            ring = self._slots[key] = [None, None, 0]
+        turn = ring[2]
+        ring[2] = turn ^ 1
+        sl = ring[turn]
+        if sl is None or sl[0].numel() < nbytes or (need_dev and sl[1] is None):
             cap = max(nbytes, 1) * 5 // 4 + 64
-            sl = [torch.empty(cap, dtype=torch.uint8, pin_memory=True),
-                  torch.empty(cap, dtype=torch.uint8, device=self.device),
-                  torch.cuda.Event()]
-            sl[2].record()
-            self._slots[key] = sl
+            ev = torch.cuda.Event()
+            ev.record()
+            sl = ring[turn] = [torch.empty(cap, dtype=torch.uint8, pin_memory=True),
+                               torch.empty(cap, dtype=torch.uint8, device=self.device)
+                               if need_dev else None, ev]
         return sl
 
-    def put(self, key, arr):
-        """numpy array / CPU tensor -> device tensor of the same dtype and shape on the
-        current stream (CUDA tensors pass through)."""
+    def put(self, key, arr, mapped=False):
+        """numpy array / CPU tensor -> tensor of the same dtype and shape whose data_ptr() the
+        kernels may dereference: a device copy, or (mapped) the pinned host buffer itself.
+        CUDA tensors pass through."""
         if isinstance(arr, torch.Tensor):
             if arr.is_cuda:
                 return arr.contiguous()
@@ -61,13 +75,22 @@ class Stager:
         else:
             t = torch.from_numpy(np.ascontiguousarray(arr))
         nbytes = t.numel() * t.element_size()
-        pin, dev, ev = self._slot(key, nbytes)
+        sl = self._slot(key, nbytes, not mapped)
+        pin, dev, ev = sl
         if nbytes:
-            ev.synchronize()        # the previous async copy out of this pinned buffer is done
+            ev.synchronize()        # everything that read this buffer two puts ago is done
             pin[:nbytes].copy_(t.reshape(-1).view(torch.uint8))
-            dev[:nbytes].copy_(pin[:nbytes], non_blocking=True)
-            ev.record()
-        return dev[:nbytes].view(t.dtype).view(t.shape)
+            if not mapped:
+                dev[:nbytes].copy_(pin[:nbytes], non_blocking=True)
+            self._touched.append(sl)
+        src = pin if mapped else dev
+        return src[:nbytes].view(t.dtype).view(t.shape)
+
+    def fence(self):
+        """Call after enqueuing the kernels that consume the buffers put since the last fence."""
+        for sl in self._touched:
+            sl[2].record()
+        self._touched = []
 
 
 def _stream():
@@ -104,6 +127,8 @@ class DeviceCloud:
                                     C.byref(h)))
         self.h = h
         self.stage = Stager(self.device)
+        # camera maps handed over as host arrays are read in place from pinned memory
+        self.map_images = True
         self._keep = []      # device tensors that in-flight kernels still read
         self._mark_f, self._mark_i = [], []   # queued dynamic-flag updates
 
@@ -126,8 +151,12 @@ class DeviceCloud:
         f = np.ascontiguousarray(np.asarray(list(filters or []), dtype=np.int32))
         return f, f.ctypes.data_as(C.c_void_p), int(f.size)
 
-    def _sem_arg(self, sem, key):
-        """class map (H,W) of u8/i32/i64, or (H,W,K) float32 probabilities."""
+    def _sem_arg(self, sem, key, mapped=False):
+        """class map (H,W) of u8/i16/i32/i64, or (H,W,K) float32 probabilities."""
+        if mapped and not isinstance(sem, torch.Tensor):
+            sem = np.asarray(sem)
+            if sem.dtype in _SEM_DTYPES:     # read in place over PCIe: no narrowing needed
+                return self.stage.put(key, sem, mapped=True), _SEM_DTYPES[sem.dtype], 1
         if isinstance(sem, torch.Tensor):
             if sem.dtype == torch.float32:
                 return self.stage.put(key, sem), _lib.SEM_F32_PROB, int(sem.shape[-1])
@@ -181,8 +210,8 @@ class DeviceCloud:
                              if not isinstance(pc, torch.Tensor) else pc)
         assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
         rgb_d = self.stage.put('rgb', rgb if isinstance(rgb, torch.Tensor)
-                               else np.asarray(rgb, dtype=np.uint8))
-        sem_d, sem_dt, K = self._sem_arg(sem, 'sem')
+                               else np.asarray(rgb, dtype=np.uint8), mapped=self.map_images)
+        sem_d, sem_dt, K = self._sem_arg(sem, 'sem', mapped=self.map_images)
         h, w = int(rgb_d.shape[0]), int(rgb_d.shape[1])
         assert tuple(sem_d.shape[:2]) == (h, w), (sem_d.shape, rgb_d.shape)
         Pm = _hostd(P, 12)
@@ -191,7 +220,7 @@ class DeviceCloud:
         self._check(self.lib.pcacc_integrate_frustum(
             self.h, _ptr(pts), int(pts.shape[0]), Pm.ctypes.data_as(C.c_void_p), _ptr(rgb_d),
             _ptr(sem_d), sem_dt, K, h, w, float(max_depth), fp, nf, C.byref(fid), _stream()))
-        self._keep += [pts, rgb_d, sem_d]
+        self.stage.fence()
         return int(fid.value)
 
     def integrate_gt(self, pc, sem_gt, filters) -> int:
@@ -207,7 +236,7 @@ class DeviceCloud:
         fid = C.c_int64(-1)
         self._check(self.lib.pcacc_integrate_gt(self.h, _ptr(pts), int(pts.shape[0]), _ptr(sg),
                                                 fp, nf, C.byref(fid), _stream()))
-        self._keep += [pts, sg]
+        self.stage.fence()
         return int(fid.value)
 
     def integrate_records(self, pc, cam_idx, rgbs, sems, T_ego_world, filters,
@@ -222,8 +251,8 @@ class DeviceCloud:
         rgb_d, sem_d, sem_dt = [], [], None
         for k in range(n_cams):
             r = self.stage.put(f'rgb{k}', rgbs[k] if isinstance(rgbs[k], torch.Tensor)
-                               else np.asarray(rgbs[k], dtype=np.uint8))
-            s, dt, K = self._sem_arg(sems[k], f'sem{k}')
+                               else np.asarray(rgbs[k], dtype=np.uint8), mapped=self.map_images)
+            s, dt, K = self._sem_arg(sems[k], f'sem{k}', mapped=self.map_images)
             assert K == 1 and dt != _lib.SEM_F32_PROB
             assert sem_dt in (None, dt), 'all class maps must share one dtype'
             sem_dt = dt
@@ -239,7 +268,7 @@ class DeviceCloud:
             self.h, _ptr(pcd), _ptr(cam), int(pcd.shape[0]), C.cast(rp, C.c_void_p),
             C.cast(sp, C.c_void_p), n_cams, sem_dt if sem_dt is not None else _lib.SEM_U8, h, w,
             T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf, C.byref(fid), _stream()))
-        self._keep += [pcd, cam] + rgb_d + sem_d
+        self.stage.fence()
         return int(fid.value)
 
     def integrate_records_batch(self, sweeps, filters, intensity_div=255.) -> int:
@@ -283,7 +312,7 @@ class DeviceCloud:
         fid = C.c_int64(-1)
         self._check(self.lib.pcacc_integrate_cloud(self.h, _ptr(r), int(r.shape[0]),
                                                    C.byref(fid), _stream()))
-        self._keep.append(r)
+        self.stage.fence()
         return int(fid.value)
 
     # -- state updates -------------------------------------------------------------
@@ -344,6 +373,7 @@ class DeviceCloud:
         self._check(self.lib.pcacc_project(_ptr(pts), n, stride, Pm.ctypes.data_as(C.c_void_p),
                                            int(img_h), int(img_w), float(max_depth), _ptr(u),
                                            _ptr(v), _ptr(m), _stream()))
+        self.stage.fence()
         return u, v, m
 
     def gen_semantic_pc(self, pc, semantic_map, P):
@@ -369,6 +399,7 @@ class DeviceCloud:
         self._check(self.lib.pcacc_gen_semantic_pc(
             self.h, _ptr(pts), n, Pm.ctypes.data_as(C.c_void_p), _ptr(mp), dt, h, w, K, _ptr(out),
             _ptr(nk), _stream()))
+        self.stage.fence()
         return out[:int(nk.item())]
 
     # -- rasterise ------------------------------------------------------------------------

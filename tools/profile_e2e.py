@@ -17,6 +17,7 @@ def run():
     acc = NuScenesOracleSemanticPointCloudAccumulator(
         semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None, bench.bev_setup(),
         ring_capacity_pts=n_in + 4096, ring_max_frames=bench.N_SWEEPS + 8)
+    acc.sync_each_integrate = SYNC
     t0 = time.perf_counter()
     for o in scene:
         acc.integrate([o])
@@ -30,6 +31,8 @@ def run():
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1, n
 
+import os as _os
+SYNC = bool(int(_os.environ.get('E2E_SYNC', '0')))
 run()
 ti, tb, n = run()
 print(f'integrate 40 sweeps: {ti*1e3:.1f} ms ({ti/40*1e3:.2f} ms/sweep); {n} BEVs: {tb*1e3:.1f} ms ({tb/n*1e3:.2f} ms/BEV)')
