@@ -834,6 +834,18 @@ __device__ __forceinline__ uint32_t f_pack(uint32_t rgbs) {
 // bit 0 of field c = (a_c >= b_c); ag = a | F_GUARD
 __device__ __forceinline__ uint32_t f_ge(uint32_t ag, uint32_t b) { return ((ag - b) & F_GUARD) >> 9; }
 
+// per-warp shared-memory state of pass A
+struct SmallWarp {
+    uint32_t val[32 * SMALL_T];      // packed r,g,b of the small cells' points, back to back
+    uint32_t cs[33];                 // first compacted index of each cell (cs[32] = total)
+    uint32_t s0[32];                 // first record of each cell in `sorted`
+    uint32_t n_road[32][2], n_veh[32][2];
+    unsigned long long fx_hi[32][2], fx_lo[32][2], zc[32][2];
+    uint32_t med[32][6];             // lo/hi order statistics: present, future, full
+    uint8_t meta[32 * SMALL_T];      // cell | window << 5 of each point
+    uint8_t np[32], nt[32];
+};
+
 // ---------------------------------------------------------------------------
 // pass A: one warp per 32 consecutive cells.  Empty cells take the per-variant
 // constants, cells with <= SMALL_T points are reduced by their own lane, larger
@@ -846,7 +858,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
              const double *__restrict__ lut, int n_var, int P, double intensity_div,
              uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_count,
              __half *__restrict__ out16, double *__restrict__ out64) {
-    __shared__ uint32_t s_small[RED_WARPS][32 * SMALL_STRIDE];
+    __shared__ SmallWarp s_sw[RED_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
     const int64_t n_cells = (int64_t)n_var * PP;
@@ -886,76 +898,122 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
         }
     }
 
-    WinAcc st;
-    acc_init(st, want_max);
-    int med2[3][3];
+    // ---- small cells, point-parallel ---------------------------------------------------
+    // The points of the warp's small cells are laid out back to back (compacted index q)
+    // and spread over the lanes, so a lane's work is one point, not one cell: loads are
+    // coalesced and the rank loops of neighbouring lanes have (nearly) the same length.
+    const bool small = my_nt > 0 && my_nt <= SMALL_T;
+    uint32_t cs_incl = small ? my_nt : 0u;
 #pragma unroll
-    for (int w = 0; w < 3; w++)
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, cs_incl, o);
+        if (lane >= (unsigned)o) cs_incl += t;
+    }
+    const uint32_t T = __shfl_sync(0xffffffffu, cs_incl, 31);
+    SmallWarp &sw = s_sw[warp];
+    sw.cs[lane] = cs_incl - (small ? my_nt : 0u);
+    if (lane == 31) sw.cs[32] = T;
+    sw.s0[lane] = s01.x;
+    sw.np[lane] = (uint8_t)(small ? my_np : 0u);
+    sw.nt[lane] = (uint8_t)(small ? my_nt : 0u);
 #pragma unroll
-        for (int c = 0; c < 3; c++) med2[w][c] = 0;
+    for (int w = 0; w < 2; w++) {
+        sw.n_road[lane][w] = 0;
+        sw.n_veh[lane][w] = 0;
+        sw.fx_hi[lane][w] = 0;
+        sw.fx_lo[lane][w] = 0;
+        sw.zc[lane][w] = want_max ? 0ull : ~0ull;   // order-encoded -inf / +inf
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) sw.med[lane][k] = 0;
+    __syncwarp();
 
-    if (my_nt > 0 && my_nt <= SMALL_T) {
+    if (T) {
         const int road_cls = bp.road_cls, v0 = bp.veh_cls[0], v1 = bp.veh_cls[1], v2 = bp.veh_cls[2],
                   v3 = bp.veh_cls[3];
-        uint32_t *mine = s_small[warp] + lane * SMALL_STRIDE;
-        for (uint32_t i = 0; i < my_nt; i++) {
-            const uint4 r = sorted[s01.x + i];
-            mine[i] = f_pack(r.z);
-            acc_record(st, r, i >= my_np ? 1 : 0, road_cls, v0, v1, v2, v3, want_max);
+        // pass 1: one record per lane and round; statistics through shared-memory atomics
+        for (uint32_t q = lane; q < T; q += 32) {
+            int c = 0;   // the cell with cs[c] <= q < cs[c+1]
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (sw.cs[c + step] <= q) c += step;
+            const uint32_t li = q - sw.cs[c];
+            const int w = li >= sw.np[c] ? 1 : 0;
+            const uint4 r = sorted[sw.s0[c] + li];
+            sw.val[q] = f_pack(r.z);
+            sw.meta[q] = (uint8_t)(c | (w << 5));
+            const int sem = (int)(r.z >> 24);
+            if (sem == road_cls) {
+                const long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
+                atomicAdd(&sw.n_road[c][w], 1u);
+                atomicAdd(&sw.fx_hi[c][w], (unsigned long long)(fx >> 32));
+                atomicAdd(&sw.fx_lo[c][w], (unsigned long long)(fx & 0xffffffffll));
+            }
+            if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) atomicAdd(&sw.n_veh[c][w], 1u);
+            const unsigned long long zc =
+                ord_encode(__longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x)));
+            if (want_max) atomicMax(&sw.zc[c][w], zc); else atomicMin(&sw.zc[c][w], zc);
         }
-        // Order statistics without sorting: element i occupies the ranks [L_i, E_i) of its
-        // set, L_i = #{v_j < v_i}, E_i = #{v_j <= v_i}; it is the k-th smallest iff
-        // L_i <= k < E_i.  Counted separately over the present and the future part so that
-        // the window's own ranks and the full cell's ranks come out of the same pass.
-        const uint32_t kp_lo = (my_np ? (my_np - 1) / 2 : 31u) * F_ONE, kp_hi = (my_np ? my_np / 2 : 31u) * F_ONE;
-        const uint32_t kf_lo = (my_nf ? (my_nf - 1) / 2 : 31u) * F_ONE, kf_hi = (my_nf ? my_nf / 2 : 31u) * F_ONE;
-        const uint32_t ka_lo = (my_nt - 1) / 2 * F_ONE, ka_hi = my_nt / 2 * F_ONE;
-        uint32_t lo_p = 0, hi_p = 0, lo_f = 0, hi_f = 0, lo_a = 0, hi_a = 0;
-        for (uint32_t i = 0; i < my_nt; i++) {
-            const uint32_t vi = mine[i], vig = vi | F_GUARD;
-            uint32_t e1 = 0, g1 = 0, e2 = 0, g2 = 0;   // #{v_j <= v_i}, #{v_j >= v_i} per part
-            for (uint32_t j = 0; j < my_np; j++) {
-                const uint32_t vj = mine[j];
+        __syncwarp();
+        // pass 2: order statistics without sorting.  Point i occupies the ranks [L_i, E_i) of
+        // its set (L = #{v_j < v_i}, E = #{v_j <= v_i}); it is the k-th smallest iff
+        // L <= k < E.  Counted separately over the present and the future part of the cell,
+        // so the window's own ranks and the full cell's ranks come out of the same loop;
+        // r, g, b are compared together in three 10-bit fields.
+        for (uint32_t q = lane; q < T; q += 32) {
+            const int c = sw.meta[q] & 31, wi = sw.meta[q] >> 5;
+            const uint32_t base = sw.cs[c], np = sw.np[c], nt = sw.nt[c], nf = nt - np;
+            const uint32_t vi = sw.val[q], vig = vi | F_GUARD;
+            uint32_t e1 = 0, g1 = 0, e2 = 0, g2 = 0;
+            for (uint32_t j = 0; j < np; j++) {
+                const uint32_t vj = sw.val[base + j];
                 e1 += f_ge(vig, vj);
                 g1 += f_ge(vj | F_GUARD, vi);
             }
-            for (uint32_t j = my_np; j < my_nt; j++) {
-                const uint32_t vj = mine[j];
+            for (uint32_t j = np; j < nt; j++) {
+                const uint32_t vj = sw.val[base + j];
                 e2 += f_ge(vig, vj);
                 g2 += f_ge(vj | F_GUARD, vi);
             }
-            const bool wi = i >= my_np;
-            // own window
-            {
-                const uint32_t E = wi ? e2 : e1, L = (wi ? my_nf : my_np) * F_ONE - (wi ? g2 : g1);
-                const uint32_t klo = wi ? kf_lo : kp_lo, khi = wi ? kf_hi : kp_hi;
-                // L <= k  and  E >= k+1, field-wise
-                uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
-                uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
-                if (wi) {
-                    lo_f = (vi & m) | (lo_f & ~m);
-                    hi_f = (vi & h) | (hi_f & ~h);
-                } else {
-                    lo_p = (vi & m) | (lo_p & ~m);
-                    hi_p = (vi & h) | (hi_p & ~h);
-                }
+            {   // own window
+                const uint32_t nw = wi ? nf : np;
+                const uint32_t E = wi ? e2 : e1, L = nw * F_ONE - (wi ? g2 : g1);
+                const uint32_t klo = (nw - 1) / 2 * F_ONE, khi = nw / 2 * F_ONE;
+                const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
+                const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
+                if (m) atomicOr(&sw.med[c][2 * wi], vi & m);
+                if (h) atomicOr(&sw.med[c][2 * wi + 1], vi & h);
             }
-            // full cell
-            {
-                const uint32_t E = e1 + e2, L = my_nt * F_ONE - (g1 + g2);
-                uint32_t m = (f_ge(ka_lo | F_GUARD, L) & f_ge(E | F_GUARD, ka_lo + F_ONE)) * 0x3ffu;
-                uint32_t h = (f_ge(ka_hi | F_GUARD, L) & f_ge(E | F_GUARD, ka_hi + F_ONE)) * 0x3ffu;
-                lo_a = (vi & m) | (lo_a & ~m);
-                hi_a = (vi & h) | (hi_a & ~h);
+            {   // full cell
+                const uint32_t E = e1 + e2, L = nt * F_ONE - (g1 + g2);
+                const uint32_t klo = (nt - 1) / 2 * F_ONE, khi = nt / 2 * F_ONE;
+                const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
+                const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
+                if (m) atomicOr(&sw.med[c][4], vi & m);
+                if (h) atomicOr(&sw.med[c][5], vi & h);
             }
         }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            med2[0][c] = (int)((lo_p >> (10 * c)) & 255u) + (int)((hi_p >> (10 * c)) & 255u);
-            med2[1][c] = (int)((lo_f >> (10 * c)) & 255u) + (int)((hi_f >> (10 * c)) & 255u);
-            med2[2][c] = (int)((lo_a >> (10 * c)) & 255u) + (int)((hi_a >> (10 * c)) & 255u);
-        }
+        __syncwarp();
     }
+
+    // back to one cell per lane
+    WinAcc st;
+    int med2[3][3];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        st.n_road[w] = sw.n_road[lane][w];
+        st.n_veh[w] = sw.n_veh[lane][w];
+        st.fx_hi[w] = (long long)sw.fx_hi[lane][w];
+        st.fx_lo[w] = (long long)sw.fx_lo[lane][w];
+        // an empty window keeps the identity of min / max
+        st.ext_z[w] = (w == 0 ? my_np : my_nf) ? ord_decode(sw.zc[lane][w]) : (want_max ? -INFINITY : INFINITY);
+    }
+#pragma unroll
+    for (int w = 0; w < 3; w++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            med2[w][c] = (int)((sw.med[lane][2 * w] >> (10 * c)) & 255u) +
+                         (int)((sw.med[lane][2 * w + 1] >> (10 * c)) & 255u);
 
     // finalise: 3 windows x 7 planes (large cells are written by pass B)
     if (my_nt <= SMALL_T) {
