@@ -768,6 +768,11 @@ __global__ void k_rgb_lut(double *__restrict__ lut) {
         lut[m] = dirichlet(c, n);
     }
 }
+// the same table rounded to fp16 behind the doubles (the fp16-only output reads these)
+__global__ void k_rgb_lut16(double *__restrict__ lut) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < LUT_TOTAL) ((__half *)(lut + LUT_TOTAL))[m] = __double2half(lut[m]);
+}
 
 // window statistics -> 7 planes.  SMALL: n <= 15, the Dirichlet quotient comes from the table
 template <bool SMALL>
@@ -861,21 +866,20 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     __shared__ SmallWarp s_sw[RED_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
-    const int64_t n_cells = (int64_t)n_var * PP;
-    const int64_t gw = (int64_t)blockIdx.x * RED_WARPS + warp;
-    const int64_t cell0 = gw * 32;
-    if (cell0 >= n_cells) return;
-    const int var = (int)(cell0 / PP);
-    const int cell_in = (int)(cell0 - (int64_t)var * PP) + (int)lane;
+    // blockIdx.y = variant, blockIdx.x = 32*RED_WARPS consecutive cells of it (PP % 32 == 0)
+    const int var = (int)blockIdx.y;
+    const int cw = ((int)blockIdx.x * RED_WARPS + (int)warp) * 32;
+    if (cw >= PP) return;
+    const int cell_in = cw + (int)lane;
     const pcacc_bev_params &bp = params[var];
     const BevConsts &cst = consts[var];
     const bool want_max = bp.elevation_max != 0;
 
     // segment bounds of my cell: [s0, s1) present, [s1, s2) future
-    const int64_t gc = cell0 + lane;
+    const uint32_t gc = (uint32_t)var * (uint32_t)PP + (uint32_t)cell_in;
     const uint2 s01 = ((const uint2 *)start)[gc];
     uint32_t s2 = __shfl_down_sync(0xffffffffu, s01.x, 1);
-    if (lane == 31) s2 = start[2 * gc + 2];
+    if (lane == 31) s2 = start[2 * (size_t)gc + 2];
     const uint32_t my_np = s01.y - s01.x, my_nf = s2 - s01.y, my_nt = my_np + my_nf;
     const int64_t o0 = ((int64_t)var * 3 * 7) * PP + cell_in;
 
@@ -894,7 +898,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(big_count, (uint32_t)__popc(bm));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)gc;
+            if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = gc;
         }
     }
 
@@ -926,6 +930,10 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) sw.med[lane][k] = 0;
+    if (small) {   // tag my points with cell | window << 5
+        const uint32_t b = cs_incl - my_nt;
+        for (uint32_t j = 0; j < my_nt; j++) sw.meta[b + j] = (uint8_t)(lane | (j >= my_np ? 32u : 0u));
+    }
     __syncwarp();
 
     if (T) {
@@ -933,15 +941,10 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
                   v3 = bp.veh_cls[3];
         // pass 1: one record per lane and round; statistics through shared-memory atomics
         for (uint32_t q = lane; q < T; q += 32) {
-            int c = 0;   // the cell with cs[c] <= q < cs[c+1]
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (sw.cs[c + step] <= q) c += step;
+            const int c = sw.meta[q] & 31, w = sw.meta[q] >> 5;
             const uint32_t li = q - sw.cs[c];
-            const int w = li >= sw.np[c] ? 1 : 0;
             const uint4 r = sorted[sw.s0[c] + li];
             sw.val[q] = f_pack(r.z);
-            sw.meta[q] = (uint8_t)(c | (w << 5));
             const int sem = (int)(r.z >> 24);
             if (sem == road_cls) {
                 const long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
@@ -996,18 +999,20 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
         __syncwarp();
     }
 
-    // back to one cell per lane
-    WinAcc st;
-    int med2[3][3];
+    // back to one cell per lane (large cells are written by pass B)
+    const bool fin = my_nt <= SMALL_T;
+    uint32_t nr[2], nv[2];
+    long long hi[2], lo[2];
+    double ez[2];
 #pragma unroll
     for (int w = 0; w < 2; w++) {
-        st.n_road[w] = sw.n_road[lane][w];
-        st.n_veh[w] = sw.n_veh[lane][w];
-        st.fx_hi[w] = (long long)sw.fx_hi[lane][w];
-        st.fx_lo[w] = (long long)sw.fx_lo[lane][w];
-        // an empty window keeps the identity of min / max
-        st.ext_z[w] = (w == 0 ? my_np : my_nf) ? ord_decode(sw.zc[lane][w]) : (want_max ? -INFINITY : INFINITY);
+        nr[w] = sw.n_road[lane][w];
+        nv[w] = sw.n_veh[lane][w];
+        hi[w] = (long long)sw.fx_hi[lane][w];
+        lo[w] = (long long)sw.fx_lo[lane][w];
+        ez[w] = ord_decode(sw.zc[lane][w]);   // an empty window keeps the identity of min / max
     }
+    int med2[3][3];
 #pragma unroll
     for (int w = 0; w < 3; w++)
 #pragma unroll
@@ -1015,26 +1020,67 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             med2[w][c] = (int)((sw.med[lane][2 * w] >> (10 * c)) & 255u) +
                          (int)((sw.med[lane][2 * w + 1] >> (10 * c)) & 255u);
 
-    // finalise: 3 windows x 7 planes (large cells are written by pass B)
-    if (my_nt <= SMALL_T) {
+    // intensity planes: the (cell, window) pairs that hold road points are compacted over the
+    // warp, so the division / exp chain runs once per 32 pairs instead of once per window.
+    // 'full' needs its own evaluation only if both halves hold road points; otherwise its sum
+    // and count are those of the non-empty half (same operands, same result).
+    const bool need0 = fin && nr[0] != 0, need1 = fin && nr[1] != 0, need2 = need0 && need1;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1),
+                   m2 = __ballot_sync(0xffffffffu, need2);
+    const uint32_t b1 = (uint32_t)__popc(m0), b2 = b1 + (uint32_t)__popc(m1), tot = b2 + (uint32_t)__popc(m2);
+    const uint32_t k0 = (uint32_t)__popc(m0 & lt), k1 = b1 + (uint32_t)__popc(m1 & lt),
+                   k2 = b2 + (uint32_t)__popc(m2 & lt);
+    // the packed values are dead after pass 2: 96 x (hi, lo, n) fit exactly
+    long long *e_hi = (long long *)sw.val, *e_lo = e_hi + 96;
+    uint32_t *e_n = (uint32_t *)(e_lo + 96);
+    static_assert(sizeof(sw.val) >= 96 * (2 * sizeof(long long) + sizeof(uint32_t)), "evaluation slots");
+    if (need0) { e_hi[k0] = hi[0]; e_lo[k0] = lo[0]; e_n[k0] = nr[0]; }
+    if (need1) { e_hi[k1] = hi[1]; e_lo[k1] = lo[1]; e_n[k1] = nr[1]; }
+    if (need2) { e_hi[k2] = hi[0] + hi[1]; e_lo[k2] = lo[0] + lo[1]; e_n[k2] = nr[0] + nr[1]; }
+    __syncwarp();
+    for (uint32_t i = lane; i < tot; i += 32) {
+        // sum(raw) / div instead of sum(raw / div): one rounding instead of n
+        const double isum = __ddiv_rn(fx_to_double(e_hi[i], e_lo[i]), intensity_div);
+        const double val = intensity_plane(bp, isum, e_n[i]);
+        e_hi[i] = __double_as_longlong(val);
+    }
+    __syncwarp();
+    double I[3];
+    I[0] = need0 ? __longlong_as_double(e_hi[k0]) : cst.empty[1];   // no road points: sum 0 over count 0,
+    I[1] = need1 ? __longlong_as_double(e_hi[k1]) : cst.empty[1];   // the arithmetic of an empty window
+    I[2] = need2 ? __longlong_as_double(e_hi[k2]) : (need0 ? I[0] : I[1]);
+
+    // finalise: 3 windows x 7 planes, one store sequence for empty and non-empty windows
+    // (the Dirichlet table's entry n = c = 0 is the empty window's 1/2)
+    if (fin) {
+        const __half *lut16 = (const __half *)(lut + LUT_TOTAL);
+        __half *ob = out16 + o0;
 #pragma unroll
         for (int w = 0; w < 3; w++) {
             const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
-            const int64_t o = o0 + (int64_t)w * 7 * PP;
-            if (nw == 0) {
-                store_empty<F64OUT>(out16, out64, o, PP, cst);
-            } else {
+            const uint32_t nrw = (w < 2) ? nr[w & 1] : nr[0] + nr[1], nvw = (w < 2) ? nv[w & 1] : nv[0] + nv[1];
+            const double zz = (w < 2) ? ez[w & 1] : (want_max ? fmax(ez[0], ez[1]) : fmin(ez[0], ez[1]));
+            const bool ne = nw != 0;
+            const uint32_t di = DIR_LUT_OFF + nw * 16;
+            const size_t ow = (size_t)w * 7 * PP;
+            if (F64OUT) {
                 double plane[7];
-                if (w < 2)
-                    window_planes<true>(bp, cst, lut, nw, st.n_road[w], st.n_veh[w], st.fx_hi[w], st.fx_lo[w],
-                                  st.ext_z[w], med2[w], intensity_div, plane);
-                else  // the unused side still holds +-inf, the identity of min / max
-                    window_planes<true>(bp, cst, lut, nw, st.n_road[0] + st.n_road[1],
-                                  st.n_veh[0] + st.n_veh[1], st.fx_hi[0] + st.fx_hi[1],
-                                  st.fx_lo[0] + st.fx_lo[1],
-                                  want_max ? fmax(st.ext_z[0], st.ext_z[1]) : fmin(st.ext_z[0], st.ext_z[1]),
-                                  med2[w], intensity_div, plane);
-                store_planes<F64OUT>(out16, out64, o, PP, plane);
+                plane[0] = lut[di + nrw];
+                plane[1] = I[w];
+#pragma unroll
+                for (int k = 0; k < 3; k++) plane[2 + k] = ne ? lut[med2[w][k]] : cst.empty[2];
+                plane[5] = lut[di + nvw];
+                plane[6] = ne ? zz : cst.empty[6];
+                store_planes<true>(out16, out64, o0 + (int64_t)ow, PP, plane);
+            } else {
+                ob[ow] = lut16[di + nrw];
+                ob[ow + (size_t)PP] = __double2half(I[w]);
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    ob[ow + (size_t)(2 + k) * PP] = ne ? lut16[med2[w][k]] : cst.empty_h[2];
+                ob[ow + (size_t)5 * PP] = lut16[di + nvw];
+                ob[ow + (size_t)6 * PP] = ne ? __double2half(zz) : cst.empty_h[3];
             }
         }
     }
@@ -1233,8 +1279,9 @@ static int ensure_ws(pcacc_t h, size_t bytes) {
 }
 
 int pcacc_init_tables(pcacc_t h) {
-    PCACC_CUDA(h, cudaMalloc(&h->d_rgb_lut, LUT_TOTAL * sizeof(double)));
+    PCACC_CUDA(h, cudaMalloc(&h->d_rgb_lut, LUT_TOTAL * (sizeof(double) + sizeof(__half))));
     k_rgb_lut<<<(LUT_TOTAL + 127) / 128, 128>>>(h->d_rgb_lut);
+    k_rgb_lut16<<<(LUT_TOTAL + 127) / 128, 128>>>(h->d_rgb_lut);
     PCACC_CUDA(h, cudaGetLastError());
     PCACC_CUDA(h, cudaDeviceSynchronize());
     return PCACC_OK;
@@ -1395,15 +1442,14 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
         // reduce + finalise (also correct on all-zero counters: every cell empty)
-        int64_t warps = (int64_t)nv * PP / 32;
-        int64_t blocks = (warps + RED_WARPS - 1) / RED_WARPS;
+        const dim3 blocks((unsigned)((PP / 32 + RED_WARPS - 1) / RED_WARPS), (unsigned)nv);
         size_t pr = pcacc_prof_begin(h, PCACC_K_REDUCE, st);
         if (want_f64)
-            k_bev_reduce<true><<<(unsigned)blocks, RED_WARPS * 32, 0, st>>>(
+            k_bev_reduce<true><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, o64);
         else
-            k_bev_reduce<false><<<(unsigned)blocks, RED_WARPS * 32, 0, st>>>(
+            k_bev_reduce<false><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, nullptr);
         PCACC_CUDA(h, cudaGetLastError());
