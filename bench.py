@@ -317,6 +317,22 @@ def run_ours(args, rank, world, local_rank, dist):
         extended += 1
     clk = clocks.stop()
     clk['untimed_steps_added_for_sampling'] = extended
+    # the same kernels timed ALONE (one stream, untimed extra pass): inside the timed region
+    # the scenes of 4 streams overlap, so an event pair around one launch also spans the
+    # other streams' kernels it shared the SMs with
+    alone = {}
+    if n_str > 1:
+        torch.cuda.synchronize()
+        clouds[0].profile(True)
+        clouds[0].profile_read()
+        own = [s for s in range(S) if s % n_str == 0]
+        for _ in range(2):
+            for s in own:
+                scene_pass(s, clouds[0], outs[0])
+            torch.cuda.synchronize()
+            clouds[0]._keep.clear()
+        alone = clouds[0].profile_read()
+        clouds[0].profile(False)
     # the only collective of the run: summary statistics (sum of work, max of time)
     pts_step_rank = S * n_in_scene
     tot = parallel.reduce_stats(dist, {'points': pts_step_rank * args.steps,
@@ -359,11 +375,24 @@ def run_ours(args, rank, world, local_rank, dist):
                 'share_of_step': dom_ms / max(sum(v[0] for v in prof.values()), 1e-9),
                 'kernel_ms': {k: round(v[0], 3) for k, v in prof_raw.items() if v[1]},
                 'kernel_launches': {k: v[1] for k, v in prof_raw.items() if v[1]}}
+    if alone:
+        a = dict(alone)
+        a['bev_reduce'] = (a['bev_reduce'][0] + a.pop('bev_reduce_big')[0], a['bev_reduce'][1])
+        a['bev_bin'] = (a['bev_bin'][0] + a.pop('bev_classify')[0], a['bev_bin'][1])
+        if a.get(dom, (0, 0))[1]:
+            us = a[dom][0] / a[dom][1] * 1e3
+            roofline['alone'] = {'launch_us': us, 'achieved': alg.get(dom, 0.0) / (us * 1e-6) / 1e9,
+                                 'frac': alg.get(dom, 0.0) / (us * 1e-6) / 1e9 / peak,
+                                 'note': 'same launches on one stream after the timed region (no '
+                                         'overlap with other scenes); the timed-region figure above '
+                                         'spans kernels of 4 concurrent streams'}
     b_step = S * (alg['integrate'] + alg['bev_bin'] + alg['bev_reduce'])
     path_ach = b_step * args.steps / (ms_total * 1e-3) / 1e9
     roofline_path = {'achieved': path_ach, 'peak': peak, 'unit': 'GB/s', 'frac': path_ach / peak,
                      'bytes_per_step': b_step,
-                     'note': 'all algorithmic bytes of the step (integrate + rasterise) / step time'}
+                     'note': 'all algorithmic bytes of the step (integrate + rasterise) / step time; the '
+                             '32 BEVs of a scene re-read the same ~9 MB of resident points, which '
+                             'stay in the 126 MB L2, so this can exceed the HBM peak'}
     gpu_launches = int(sum(v[1] for v in prof.values()))
 
     # ---- e2e: public API, host buffers, copies inside the timed region ---------------

@@ -22,6 +22,7 @@
 #ifndef PCACC_H_
 #define PCACC_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -246,6 +247,20 @@ int pcacc_raster_stats(pcacc_t h, int64_t stats[3], void *stream);
  * out: at least 2*n rows of 3 doubles; *n_out rows are written. */
 int pcacc_crop_trajectory(const double *traj, int n, double view, double thresh, double *out,
                           int *n_out);
+
+/* ---- host helper: all trajectories of one generate call ---------------------
+ * BEVGenerator.preprocess_pc_and_trajs for the trajectory lists (bev_generator.py:127-160:
+ * geometric_transform 207-238 -> crop_trajectory 257-316 -> pos2grid 737-747), for n_var
+ * augmentation variants at once.  pts: the polylines back to back, (traj_off[n_traj], 3)
+ * doubles; polyline t = rows traj_off[t] .. traj_off[t+1].  variants: n_var x 12 doubles
+ * {R[9] row-major, trans_dx, trans_dy, view}.  Per variant and polyline: R @ p as numpy's
+ * float64 matmul computes it (FMA chain over k), += (dx, dy), crop against the open view
+ * box, x,y -> floor(q / view * P + 0.5 P).  Polylines of fewer than 2 points give 0 rows.
+ * out: n_var x 2*traj_off[n_traj] rows of 3 doubles; the rows of (v, t) start at row
+ * v*2*traj_off[n_traj] + 2*traj_off[t]; out_cnt[v*n_traj + t] rows are valid. */
+int pcacc_preprocess_trajectories(const double *pts, const int32_t *traj_off, int n_traj,
+                                  const double *variants, int n_var, int P, double thresh,
+                                  double *out, int32_t *out_cnt);
 
 /* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
  * Kernel classes of this library. */

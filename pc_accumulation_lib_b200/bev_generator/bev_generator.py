@@ -213,11 +213,17 @@ class BEVGenerator(ABC):
 
     def _rasterise_windows(self, pcs, augs, warps=None):
         """Rasterise (and optionally warp) on the device, then copy the planes to the host."""
+        pending, has_future, cloud = self._rasterise_windows_begin(pcs, augs, warps)
+        return cloud.planes_to_host_finish(pending), has_future
+
+    def _rasterise_windows_begin(self, pcs, augs, warps=None):
+        """Enqueue rasterise (+ warp) and the device -> host copy; returns (pending, has_future,
+        cloud) for `cloud.planes_to_host_finish(pending)`."""
         planes, has_future, cloud = self._rasterise_device(pcs, augs)
         if warps is not None:
             planes = cloud.warp_planes(planes.contiguous(), [w['imap'] for w in warps],
                                        [w['jmap'] for w in warps])
-        return cloud.planes_to_host(planes.contiguous()), has_future
+        return cloud.planes_to_host_begin(planes.contiguous()), has_future, cloud
 
     def _rasterise_device(self, pcs, augs):
         """pcs: the reference's dict. Returns (planes (V,3,7,P,P) float16 device tensor,
@@ -311,20 +317,20 @@ class BEVGenerator(ABC):
         if self.do_warp:
             # one polynomial warp per BEV, drawn like sem_bev.py:121-129
             warps = [self.draw_warp() for _ in full]
-        planes, has_future = self._rasterise_windows(pcs, full, warps)
+        # the device works (rasterise, warp, copy to pinned memory) while the host prepares
+        # the trajectories
+        pending, has_future, cloud = self._rasterise_windows_begin(pcs, full, warps)
+        groups = [[ego_p] + list(oth_p), [ego_f] + list(oth_f), [ego_a] + list(oth_a)]
+        if 'gt_lanes' in trajs:
+            groups.append(list(self.extract_gt_lane_dicts(trajs)))
+        done = self.preprocess_trajs_batch(groups, full)
+        planes = cloud.planes_to_host_finish(pending)
         bevs = []
         for v, a in enumerate(full):
-            view = a['zoom_scalar'] * self.view_size
-            tw = {}
-            for w, ego, oth in (('present', ego_p, oth_p), ('future', ego_f, oth_f),
-                                ('full', ego_a, oth_a)):
-                tw[w] = self.preprocess_trajs([ego] + list(oth), a['rot_ang'], a['trans_dx'],
-                                              a['trans_dy'], view)
+            tw = {'present': done[v][0], 'future': done[v][1], 'full': done[v][2]}
             lanes = None
             if 'gt_lanes' in trajs:
-                lanes = self.preprocess_trajs(self.extract_gt_lane_dicts(trajs), a['rot_ang'],
-                                              a['trans_dx'], a['trans_dy'], view)
-                lanes = [ln for ln in lanes if ln.shape[0] > 0]
+                lanes = [ln for ln in done[v][3] if ln.shape[0] > 0]
             if warps is not None:
                 w = warps[v]
                 for k in tw:
@@ -335,6 +341,46 @@ class BEVGenerator(ABC):
                                             w['j_mid'], w['i_warp'], w['j_warp'])
             bevs.append(self._assemble(planes, v, tw, lanes, has_future))
         return bevs
+
+    def preprocess_trajs_batch(self, groups, augs):
+        """preprocess_trajs for several lists of polylines and several augmentation variants in
+        one call of libpcacc's host helper `pcacc_preprocess_trajectories` (same double
+        arithmetic as geometric_transform -> crop_trajectory -> pos2grid).
+        Returns out[v][g] = list of (m,3) arrays."""
+        arrs = []
+        for g in groups:
+            for t in g:
+                t = np.asarray(t, dtype=np.float64)
+                arrs.append(t.reshape(-1, 3) if t.size else np.zeros((0, 3)))
+        n_traj, n_var = len(arrs), len(augs)
+        off = np.zeros(n_traj + 1, dtype=np.int32)
+        if n_traj:
+            np.cumsum([a.shape[0] for a in arrs], out=off[1:])
+        N = int(off[-1])
+        pts = np.ascontiguousarray(np.concatenate(arrs, axis=0)) if N else np.zeros((0, 3))
+        var = np.empty((n_var, 12), dtype=np.float64)
+        for v, a in enumerate(augs):
+            var[v, :9] = self.rotation_matrix_3d(a['rot_ang']).reshape(9)
+            var[v, 9], var[v, 10] = a['trans_dx'], a['trans_dy']
+            var[v, 11] = a['zoom_scalar'] * self.view_size
+        out = np.empty((n_var, 2 * N, 3), dtype=np.float64)
+        cnt = np.zeros((n_var, max(n_traj, 1)), dtype=np.int32)
+        _lib.check(_lib.load().pcacc_preprocess_trajectories(
+            pts.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), n_traj,
+            var.ctypes.data_as(C.c_void_p), n_var, int(self.pixel_size), 1e-4,
+            out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        res = []
+        for v in range(n_var):
+            per_group, t = [], 0
+            for g in groups:
+                lst = []
+                for _ in g:
+                    b = 2 * int(off[t])
+                    lst.append(out[v, b:b + int(cnt[v, t])])
+                    t += 1
+                per_group.append(lst)
+            res.append(per_group)
+        return res
 
     # ------------------------------------------------------------------
     # polynomial warp (bev_generator.py:482-698): parameters and trajectories on the

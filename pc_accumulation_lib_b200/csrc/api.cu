@@ -125,54 +125,6 @@ FrameHost *pcacc_frame(pcacc_t h, int64_t frame_id) {
     return &h->frames[(int)(frame_id % h->max_frames)];
 }
 
-// ---------------------------------------------------------------------------
-// host-side trajectory crop (same double arithmetic as the reference's Python)
-// ---------------------------------------------------------------------------
-static inline bool in_box(double x, double y, double h) { return (-h < x && x < h) && (-h < y && y < h); }
-
-extern "C" int pcacc_crop_trajectory(const double *traj, int n, double view, double thresh, double *out,
-                                     int *n_out) {
-    if (!traj || !out || !n_out || n < 0) return PCACC_ERR_ARG;
-    const double h = 0.5 * view;
-    int m = 0;
-    for (int k = 0; k + 1 < n; k++) {
-        double x0 = traj[3 * k], y0 = traj[3 * k + 1], x1 = traj[3 * k + 3], y1 = traj[3 * k + 4];
-        const double z0 = traj[3 * k + 2];
-        const bool a_in = in_box(x0, y0, h), b_in = in_box(x1, y1, h);
-        if (a_in) {
-            out[3 * m] = x0;
-            out[3 * m + 1] = y0;
-            out[3 * m + 2] = z0;
-            m++;
-        }
-        if (a_in != b_in) {
-            double xm = 0.0, ym = 0.0, moved = INFINITY;
-            while (moved > thresh) {
-                xm = 0.5 * (x0 + x1);
-                ym = 0.5 * (y0 + y1);
-                const bool first_in = in_box(x0, y0, h), mid_in = in_box(xm, ym, h);
-                if (mid_in == first_in) {   // midpoint on the side of end 0: replace end 0
-                    const double dx = xm - x0, dy = ym - y0;
-                    moved = sqrt(dx * dx + dy * dy);
-                    x0 = xm;
-                    y0 = ym;
-                } else {
-                    const double dx = xm - x1, dy = ym - y1;
-                    moved = sqrt(dx * dx + dy * dy);
-                    x1 = xm;
-                    y1 = ym;
-                }
-            }
-            out[3 * m] = xm;
-            out[3 * m + 1] = ym;
-            out[3 * m + 2] = z0;
-            m++;
-        }
-    }
-    *n_out = m;
-    return PCACC_OK;
-}
-
 extern "C" const char *pcacc_strerror(int status) {
     switch (status) {
         case PCACC_OK: return "ok";

@@ -45,8 +45,10 @@ class Stager:
 
     def __init__(self, device):
         self.device = device
-        self._slots = {}     # key -> [[pinned, device, event], [pinned, device, event], turn]
+        self._slots = {}     # key -> [[pinned, device, event, ...], [pinned, device, event, ...], turn]
         self._touched = []
+        self._events = [torch.cuda.Event() for _ in range(4)]
+        self._ev_turn = 0
 
     def _slot(self, key, nbytes, need_dev):
         ring = self._slots.get(key)
@@ -76,20 +78,36 @@ class Stager:
             t = torch.from_numpy(np.ascontiguousarray(arr))
         nbytes = t.numel() * t.element_size()
         sl = self._slot(key, nbytes, not mapped)
-        pin, dev, ev = sl
+        # typed views of the slot's buffers are cached: observations of one stream keep
+        # their shapes, and a dozen tensor-view calls per put cost more than the copy
+        sig = (t.dtype, tuple(t.shape), mapped)
+        if len(sl) < 5 or sl[3] != sig:
+            pin_v = sl[0][:nbytes].view(t.dtype).view(t.shape)
+            dev_v = None if mapped else sl[1][:nbytes].view(t.dtype).view(t.shape)
+            del sl[3:]
+            sl += [sig, pin_v, dev_v]
+        pin_v, dev_v = sl[4], sl[5]
         if nbytes:
-            ev.synchronize()        # everything that read this buffer two puts ago is done
-            pin[:nbytes].copy_(t.reshape(-1).view(torch.uint8))
+            sl[2].synchronize()     # everything that read this buffer two puts ago is done
+            pin_v.copy_(t)          # torch splits large host copies over its thread pool
             if not mapped:
-                dev[:nbytes].copy_(pin[:nbytes], non_blocking=True)
+                dev_v.copy_(pin_v, non_blocking=True)
             self._touched.append(sl)
-        src = pin if mapped else dev
-        return src[:nbytes].view(t.dtype).view(t.shape)
+        return pin_v if mapped else dev_v
 
     def fence(self):
-        """Call after enqueuing the kernels that consume the buffers put since the last fence."""
+        """Call after enqueuing the kernels that consume the buffers put since the last fence.
+        One event per fence (a ring of four: a slot is reused two fences later), recorded on
+        an explicitly looked-up stream — Event.record() without one costs a
+        torch.cuda.current_stream() call (~25 us) per slot."""
+        if not self._touched:
+            return
+        ring = self._events
+        ev = ring[self._ev_turn]
+        self._ev_turn = (self._ev_turn + 1) % len(ring)
+        ev.record(torch.cuda.current_stream(self.device))
         for sl in self._touched:
-            sl[2].record()
+            sl[2] = ev
         self._touched = []
 
 
@@ -443,14 +461,26 @@ class DeviceCloud:
 
     def planes_to_host(self, planes):
         """(V,3,7,P,P) float16 device tensor -> numpy, through a reusable pinned buffer."""
+        return self.planes_to_host_finish(self.planes_to_host_begin(planes))
+
+    def planes_to_host_begin(self, planes):
+        """Enqueue the device -> pinned copy; the caller may do host work before `_finish`."""
         n = planes.numel()
         buf = getattr(self, '_pin_out', None)
         if buf is None or buf.numel() < n:
             buf = self._pin_out = torch.empty(max(n, 1), dtype=torch.float16, pin_memory=True)
         view = buf[:n].view(planes.shape)
         view.copy_(planes, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return view.numpy().copy()
+        ev = torch.cuda.Event()
+        ev.record()
+        return view, ev, planes      # `planes` stays referenced until the copy is done
+
+    def planes_to_host_finish(self, pending):
+        view, ev, _ = pending
+        ev.synchronize()
+        out = np.empty(tuple(view.shape), dtype=np.float16)
+        torch.from_numpy(out).copy_(view)       # multi-threaded for large blocks, unlike ndarray.copy
+        return out
 
     def raster_stats(self):
         s = (C.c_int64 * 3)()

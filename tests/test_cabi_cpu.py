@@ -97,6 +97,17 @@ def test_host_trajectory_path_matches_reference(name, kw):
             for x, y in zip(got, want[f'trajs_{w}']):
                 np.testing.assert_array_equal(np.asarray(x).reshape(-1, 3),
                                               np.asarray(y).reshape(-1, 3))
+        # the batched helper (all windows, one call) gives the same rows
+        groups = [[trajs[f'ego_traj_{w}']] + list(trajs[f'other_trajs_{w}'])
+                  for w in ('present', 'future', 'full')]
+        aug_v = dict(rot_ang=rot, trans_dx=dx, trans_dy=dy, zoom_scalar=view / gen['view_size'])
+        assert aug_v['zoom_scalar'] * gen['view_size'] == view
+        got_b = bg.preprocess_trajs_batch(groups, [aug_v, aug_v])
+        for v in range(2):
+            for gi, w in enumerate(('present', 'future', 'full')):
+                assert len(got_b[v][gi]) == len(want[f'trajs_{w}'])
+                for x, y in zip(got_b[v][gi], want[f'trajs_{w}']):
+                    np.testing.assert_array_equal(x, np.asarray(y).reshape(-1, 3))
 
 
 def test_rand_aug_is_injectable_and_ordered_like_the_reference():
