@@ -193,7 +193,7 @@ int pcacc_export_frame(pcacc_t h, int64_t frame_id, double *out_dev, void *strea
  *   SemBEVGenerator.generate_bev's grids (bev_generator/sem_bev.py:54-118,
  *     196-257): partition_semantic_pc, gen_sem_probmap, gen_intensity_map,
  *     road_marking_transform, get_elevation_map, get_rgb_maps, astype(float16).
- * Trajectories stay on the host (Python mirror). */
+ * Trajectories stay on the host (pcacc_preprocess_trajectories). */
 typedef struct {
     int64_t frame_begin;   /* absolute ids: present = [frame_begin, frame_split) */
     int64_t frame_split;   /*               future  = [frame_split, frame_end)   */
