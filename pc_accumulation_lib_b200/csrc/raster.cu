@@ -36,6 +36,9 @@
 // from a handful of stores (32 empty cells) to thousands of instructions and a block's slot
 // is held until its slowest warp is done (measured: 2 -> 78 us, 4 -> 84 us, 8 -> 100 us)
 #define RED_WARPS 2
+// pass B: a warp per queued cell with 6 KB of histograms; 4 warps per block share the
+// dynamic queue's ticket traffic (2 -> 142 us, 4 -> 104 us on the long-horizon window)
+#define REDB_WARPS 4
 
 // guard band (metres) inside which a lazily re-based point is re-evaluated with
 // the exact sequential chain; composed-vs-sequential error is < 1e-11 m for
@@ -1118,13 +1121,13 @@ __device__ __forceinline__ double warp_max_f64(double v) {
 }
 
 template <bool F64OUT>
-__global__ void __launch_bounds__(RED_WARPS * 32)
+__global__ void __launch_bounds__(REDB_WARPS * 32)
 k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
                  const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
                  const double *__restrict__ lut, int P, double intensity_div,
                  const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
                  uint32_t *__restrict__ next, __half *__restrict__ out16, double *__restrict__ out64) {
-    __shared__ __align__(16) uint32_t s_hist[RED_WARPS][2][3][256];
+    __shared__ __align__(16) uint32_t s_hist[REDB_WARPS][2][3][256];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t(*hist)[3][256] = s_hist[warp];
     const int PP = P * P;
@@ -1458,15 +1461,15 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         PCACC_CUDA(h, cudaGetLastError());
         pcacc_prof_end(h, PCACC_K_REDUCE, pr, st);
         if (cap > SMALL_T) {
-            int64_t bb = (big_cap + RED_WARPS - 1) / RED_WARPS;
+            int64_t bb = (big_cap + REDB_WARPS - 1) / REDB_WARPS;
             if (bb > 148 * 8) bb = 148 * 8;
             pr = pcacc_prof_begin(h, PCACC_K_REDUCE_BIG, st);
             if (want_f64)
-                k_bev_reduce_big<true><<<(unsigned)bb, RED_WARPS * 32, 0, st>>>(
+                k_bev_reduce_big<true><<<(unsigned)bb, REDB_WARPS * 32, 0, st>>>(
                     counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params,
                     d_consts, h->d_rgb_lut, P, h->inten_div, big_list, big_count, big_next, o16, o64);
             else
-                k_bev_reduce_big<false><<<(unsigned)bb, RED_WARPS * 32, 0, st>>>(
+                k_bev_reduce_big<false><<<(unsigned)bb, REDB_WARPS * 32, 0, st>>>(
                     counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params,
                     d_consts, h->d_rgb_lut, P, h->inten_div, big_list, big_count, big_next, o16,
                     nullptr);

@@ -70,3 +70,10 @@ for it in range(a.iters):
 
 prof = cloud.profile_read()
 print({k: round(v[0] / a.iters * 1e3, 1) for k, v in prof.items() if v[1]})
+# for `ncu --profile-from-start off`: one more rasterise between cudaProfilerStart/Stop
+cloud.profile(False)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+cloud.rasterise(bps, a.P, out=out)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
