@@ -282,11 +282,15 @@ struct TMat {
     double m[16];
 };
 
-#define REC_ITEMS 4                       /* points per thread in the records kernels */
-#define REC_TILE (IBLOCK * REC_ITEMS)
+// Records kernels: 128 threads x 8 points.  A scene's 40 sweeps x 34 tiles are 1360 blocks;
+// with 256-thread blocks only 8 fit an SM (1184 slots on 148 SMs) and the last 176 blocks
+// ran as a second, nearly empty wave.
+#define RBLOCK 128
+#define REC_ITEMS 8                       /* points per thread in the records kernels */
+#define REC_TILE (RBLOCK * REC_ITEMS)
 
 // One tile (1024 consecutive points) of the nuScenes record path.  Item k of thread t is
-// point tile*1024 + k*256 + t.  Only the two pixel coordinates are read for every point;
+// point tile*1024 + k*128 + t.  Only the two pixel coordinates are read for every point;
 // xyz / intensity / instance of the (few) kept points are fetched after the gather.
 template <int DT>
 __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
@@ -302,7 +306,7 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
     long long cam[REC_ITEMS];
 #pragma unroll
     for (int k = 0; k < REC_ITEMS; k++) {
-        const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+        const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
         cam[k] = i < n ? cam_idx[i] : -1;
         keep[k] = false;
         packed[k] = 0;
@@ -310,7 +314,7 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
 #pragma unroll
     for (int k = 0; k < REC_ITEMS; k++) {
         if (cam[k] >= 0 && cam[k] < maps.n) {
-            const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+            const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
             const double uf = pc[i * 7 + 4], vf = pc[i * 7 + 5];
             // pts_feat_from_img bounds assertion, datasets/nuscenes_utils.py:190-195
             const bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
@@ -334,12 +338,12 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
         }
     }
     uint32_t rank[REC_ITEMS], tile_end;
-    compact_rank_multi<IBLOCK, REC_ITEMS>(keep, state, epoch, tile, s_cnt, rank, &tile_end);
+    compact_rank_multi<RBLOCK, REC_ITEMS>(keep, state, epoch, tile, s_cnt, rank, &tile_end);
     double bb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int k = 0; k < REC_ITEMS; k++) {
         if (keep[k]) {
-            const int64_t i = (int64_t)tile * REC_TILE + k * IBLOCK + threadIdx.x;
+            const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
             const double *row = pc + i * 7;
             double wx, wy, wz;
             affine_chain(T, 4, row[0], row[1], row[2], wx, wy, wz);
@@ -362,16 +366,16 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
             }
         }
     }
-    aabb_update_v<IBLOCK>(fs.aabb, bb);
+    aabb_update_v<RBLOCK>(fs.aabb, bb);
     if (tile == n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
 template <int DT>
-__global__ void __launch_bounds__(IBLOCK)
+__global__ void __launch_bounds__(RBLOCK)
 k_integrate_records(const double *__restrict__ pc, const long long *__restrict__ cam_idx, int64_t n,
                     CamMaps maps, int img_h, int img_w, TMat T, Filters filt, RingDev ring,
                     FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_cnt[REC_ITEMS * IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[REC_ITEMS * RBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
     const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
     records_tile<DT>(pc, cam_idx, n, maps, img_h, img_w, T.m, filt, ring, fs, lb.state, lb.epoch, tile,
@@ -406,12 +410,12 @@ __global__ void k_aabb_empty(unsigned long long *__restrict__ aabb, int64_t firs
 }
 
 template <int DT>
-__global__ void __launch_bounds__(IBLOCK)
+__global__ void __launch_bounds__(RBLOCK)
 k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int img_w, Filters filt,
                           RingDev ring, unsigned long long *__restrict__ state,
                           uint32_t *__restrict__ tickets, uint32_t epoch,
                           uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_cnt[REC_ITEMS * IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[REC_ITEMS * RBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
     const SweepDesc &sw = sweeps[blockIdx.y];
     if (blockIdx.x >= sw.n_tiles) return;
@@ -838,7 +842,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
     if (rc) return rc;
     size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_IR(DT)                                                                           \
-    k_integrate_records<DT><<<(unsigned)tiles, IBLOCK, 0, st>>>(                                \
+    k_integrate_records<DT><<<(unsigned)tiles, RBLOCK, 0, st>>>(                                \
         pc_dev, (const long long *)cam_idx_dev, n, maps, img_h, img_w, T, filt, h->ring, fs, lb, \
         h->d_flags)
     switch (sem_dtype) {
@@ -922,7 +926,7 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
     dim3 grid((unsigned)max_tiles, (unsigned)n_sweeps);
     size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
 #define LAUNCH_IRB(DT)                                                                           \
-    k_integrate_records_batch<DT><<<grid, IBLOCK, 0, st>>>(d_desc, img_h, img_w, filt, h->ring,  \
+    k_integrate_records_batch<DT><<<grid, RBLOCK, 0, st>>>(d_desc, img_h, img_w, filt, h->ring,  \
                                                            h->d_tile_state, d_tickets, epoch,    \
                                                            h->d_flags)
     switch (sem_dtype) {
