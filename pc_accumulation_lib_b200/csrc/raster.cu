@@ -577,36 +577,43 @@ struct ScanLB {
 
 __global__ void __launch_bounds__(SCAN_BLOCK)
 k_scan(uint32_t *__restrict__ data, int64_t n, ScanLB lb) {
+    // Warp w of the block owns 1024 consecutive counters; lane l holds the 16-byte pieces
+    // k*32 + l (k = 0..7) of them, so every load and store of a warp is one contiguous
+    // 512-byte run.  Order of the elements: (k, lane, component).
     __shared__ uint32_t s_warp[SCAN_BLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
     uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    if (base + SCAN_ITEMS <= n) {
-        const uint4 *p = (const uint4 *)(data + base);
+    constexpr int NK = SCAN_ITEMS / 4;
+    const int64_t wbase = (int64_t)tile * SCAN_TILE + (int64_t)warp * (32 * SCAN_ITEMS);
+    uint4 v[NK];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
-            uint4 q = p[k];
-            v[4 * k] = q.x;
-            v[4 * k + 1] = q.y;
-            v[4 * k + 2] = q.z;
-            v[4 * k + 3] = q.w;
+    for (int k = 0; k < NK; k++) {
+        const int64_t e = wbase + ((int64_t)k * 32 + lane) * 4;
+        if (e + 4 <= n) {
+            v[k] = *(const uint4 *)(data + e);
+        } else {
+            v[k].x = e < n ? data[e] : 0u;
+            v[k].y = e + 1 < n ? data[e + 1] : 0u;
+            v[k].z = e + 2 < n ? data[e + 2] : 0u;
+            v[k].w = 0u;
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? data[base + k] : 0u;
     }
-    uint32_t tsum = 0;
+    // exclusive offset of every piece inside the warp's run
+    uint32_t off[NK], carry = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) tsum += v[k];
-    uint32_t incl = tsum;
+    for (int k = 0; k < NK; k++) {
+        const uint32_t sum = v[k].x + v[k].y + v[k].z + v[k].w;
+        uint32_t incl = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        off[k] = carry + incl - sum;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_warp[warp] = carry;   // the warp's total
     __syncthreads();
     if (warp == 0) {
         constexpr int NW = SCAN_BLOCK / 32;
@@ -622,22 +629,23 @@ k_scan(uint32_t *__restrict__ data, int64_t n, ScanLB lb) {
         if (lane < NW) s_warp[lane] = ex + wi - c;
     }
     __syncthreads();
-    uint32_t run = s_warp[warp] + incl - tsum;
-    uint32_t o[SCAN_ITEMS];
+    const uint32_t wex = s_warp[warp];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        run += v[k];
-        o[k] = run;  // inclusive: the scatter counts each segment down to its start
-    }
-    if (base + SCAN_ITEMS <= n) {
-        uint4 *p = (uint4 *)(data + base);
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; k++)
-            p[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++)
-            if (base + k < n) data[base + k] = o[k];
+    for (int k = 0; k < NK; k++) {
+        // inclusive: the scatter counts each segment down to its start
+        uint4 o;
+        o.x = wex + off[k] + v[k].x;
+        o.y = o.x + v[k].y;
+        o.z = o.y + v[k].z;
+        o.w = o.z + v[k].w;
+        const int64_t e = wbase + ((int64_t)k * 32 + lane) * 4;
+        if (e + 4 <= n) {
+            *(uint4 *)(data + e) = o;
+        } else {
+            if (e < n) data[e] = o.x;
+            if (e + 1 < n) data[e + 1] = o.y;
+            if (e + 2 < n) data[e + 2] = o.z;
+        }
     }
 }
 
