@@ -1,0 +1,168 @@
+"""Parity at BASELINE.json's full sizes.
+
+* configs[1] (nuScenes-shaped scene, 40 sweeps x 34,688 points, CAM_FRONT 1600x900) is small
+  enough for the oracle: direct comparison, same bars as tests/test_gpu_core.py.
+* configs[2] (KITTI-360-shaped long horizon, 200 frames x 120,000 points = 24 M resident)
+  is checked through size-independent properties: determinism, conservation of points,
+  an independent per-cell count (torch.bincount over the debug cell indices) against the
+  road / vehicle probability planes, window consistency (full = present when the split is
+  moved to the end), and equivariance under an exact 90 degree rotation.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import oracle as orc                                  # noqa: E402
+from pc_accumulation_lib_b200 import synth                        # noqa: E402
+from tests.test_gpu_core import (bev_params_from, compare_planes, gen_params,  # noqa: E402
+                                 window_cells)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from pc_accumulation_lib_b200 import device
+    return device
+
+
+def test_full_size_nuscenes_scene_matches_oracle(dev):
+    """configs[1] at full size: records of every sweep, cell indices and planes of two BEVs."""
+    P = 256
+    scene = synth.nusc_scene(synth.seed_for(4, 0), 40)
+    assert scene[0]['pc'].shape[0] == 34688 and scene[0]['images'][0].shape[:2] == (900, 1600)
+    gp = gen_params(synth.nusc_bev_params(pixel_size=P))
+    acc = orc.NuscOracle(synth.NUSC_FILTERS, gp)
+    cloud = dev.DeviceCloud(capacity_pts=sum(o['pc'].shape[0] for o in scene) + 4096, max_frames=48)
+    T_gw = np.linalg.inv(scene[0]['ego_at_lidar_ts'])
+    fids = []
+    for o in scene:
+        fids.append(cloud.integrate_records(o['pc'], o['pc_cam_idx'], o['images'], o['_semseg'],
+                                            T_gw @ o['ego_at_lidar_ts'], synth.NUSC_FILTERS, 255.))
+        acc.integrate(o, o['_semseg'])
+    pairs_f, pairs_i = [], []
+    for ts, s in enumerate(acc.sem_pcs):
+        for idx in np.unique(s[s[:, 9] == 1, 8]):
+            pairs_f.append(fids[ts])
+            pairs_i.append(int(idx))
+    assert pairs_f
+    cloud.mark_dynamic(pairs_f, pairs_i)
+    assert cloud.sync() == 0
+    for k in (0, 17, 39):
+        np.testing.assert_array_equal(cloud.export_frame(fids[k]), acc.sem_pcs[k], err_msg=f'frame {k}')
+    assert cloud.resident_points() == sum(s.shape[0] for s in acc.sem_pcs)
+    for p_idx in (9, 30):
+        origin = np.array(acc.poses[p_idx])
+        rot = orc.heading_rot_ang(np.array(acc.poses[:p_idx]) - origin)
+        bp = bev_params_from(dev, gp, fids[0], fids[p_idx], fids[-1] + 1, origin, rot)
+        o16, o64, cells = cloud.rasterise([bp], P, want_f64=True, want_cells=True)
+        cloud.sync()
+        ref = acc.generate_bev(p_idx, return_f64=True)
+        dbg = ref.pop('_debug')
+        compare_planes(o16[0].cpu().numpy(), o64[0].cpu().numpy(),
+                       {w: dbg[f'planes_f64_{w}'] for w in ('present', 'future', 'full')})
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[:p_idx], P), dbg['cells_present'])
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[p_idx:], P), dbg['cells_future'])
+    cloud.close()
+
+
+def _long_horizon(dev, F, eager=False):
+    n_distinct = 8
+    pcs = [synth.kitti_lidar(synth.seed_for(3, f)) for f in range(n_distinct)]
+    N = pcs[0].shape[0]
+    sgs = [synth.kitti_sem_gt(synth.seed_for(3, f), N)[:, 0].copy() for f in range(n_distinct)]
+    pcs_d = [torch.from_numpy(p).cuda() for p in pcs]
+    sgs_d = [torch.from_numpy(s).cuda() for s in sgs]
+    Ts = [synth.kitti_step_transform(synth.seed_for(3, f)) for f in range(F)]
+    cloud = dev.DeviceCloud(F * N + 1024, F + 8)
+    poses = []
+    for f in range(F):
+        if f:
+            cloud.rebase(Ts[f], eager=eager)
+            poses = [list(np.matmul(Ts[f], np.array([p + [1]]).T)[:, 0][:-1]) for p in poses]
+        cloud.integrate_gt(pcs_d[f % n_distinct], sgs_d[f % n_distinct], synth.KITTI_FILTERS)
+        poses.append([0., 0., 0.])
+    assert cloud.sync() & ~2 == 0
+    return cloud, poses, sgs_d, N
+
+
+def test_full_size_long_horizon_properties(dev):
+    """configs[2]: 200 frames x 120,000 points (24 M resident), one 256x256 BEV at frame 100."""
+    P, F = 256, 200
+    cloud, poses, sgs_d, N = _long_horizon(dev, F)
+    assert cloud.resident_points() == F * N          # kitti_sem_gt draws unfiltered classes only
+    first, n_live = cloud.live_frames()
+    assert n_live == F
+    p = F // 2
+    origin = np.array(poses[p])
+    d = np.array(poses[p - 1]) - np.array(poses[p - 2])
+    rot = np.pi - (0.5 * np.pi + np.arctan2(d[1], d[0]))
+    R = orc.rotation_matrix_3d(rot)
+    sem = synth.SEM_IDXS
+
+    def params(fb, fs, fe, Rm, dx=0., dy=0.):
+        return dev.make_bev_params(fb, fs, fe, origin, Rm, dx, dy, 80., None, 20., 20., .5, 0, sem)
+
+    bp = params(first, first + p, first + F, R, 1.25, -0.5)
+    o16, _, cells = cloud.rasterise([bp], P, want_cells=True)
+    cloud.sync()
+    st = cloud.raster_stats()
+    a = o16.clone()
+
+    # 1. determinism: same bits on a second pass
+    b, _, _ = cloud.rasterise([bp], P)
+    cloud.sync()
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+    # 2. conservation: every visited point is either binned into a valid cell or dropped
+    assert st['visited'] <= F * N and 0 < st['binned'] < st['visited']
+    valid = cells >= 0
+    assert int(valid.sum().item()) == st['binned']
+    assert int(cells.max().item()) < P * P
+
+    # 3. independent per-cell counts -> Dirichlet planes, per window (ring order = input order:
+    #    the use_gt_sem path keeps every point)
+    n_distinct = len(sgs_d)
+    veh = torch.tensor([sem['car'], sem['truck'], sem['bus'], sem['motorcycle']], device='cuda')
+    cnt = {w: [torch.zeros(P * P, dtype=torch.int64, device='cuda') for _ in range(3)]
+           for w in ('present', 'future')}
+    for f in range(F):
+        off = cloud.frame_offset(first + f)
+        c = cells[off:off + N].long()
+        s = sgs_d[f % n_distinct].long()
+        ok = c >= 0
+        w = 'present' if f < p else 'future'
+        cnt[w][0] += torch.bincount(c[ok], minlength=P * P)
+        cnt[w][1] += torch.bincount(c[ok & (s == sem['road'])], minlength=P * P)
+        cnt[w][2] += torch.bincount(c[ok & torch.isin(s, veh)], minlength=P * P)
+    cnt['full'] = [cnt['present'][k] + cnt['future'][k] for k in range(3)]
+    assert int(cnt['full'][0].sum().item()) == st['binned']
+    for wi, w in enumerate(('present', 'future', 'full')):
+        n_all, n_road, n_veh = (t.double() for t in cnt[w])
+        want_road = ((n_road + 1.) / (n_all + 2.)).to(torch.float16).view(P, P)
+        want_veh = ((n_veh + 1.) / (n_all + 2.)).to(torch.float16).view(P, P)
+        assert torch.equal(a[0, wi, 0].view(torch.int16), want_road.view(torch.int16)), w
+        assert torch.equal(a[0, wi, 5].view(torch.int16), want_veh.view(torch.int16)), w
+        # unobserved cells carry the fill values: rgb 0, elevation 0
+        empty = (cnt[w][0] == 0).view(P, P)
+        assert bool(empty.any().item())
+        assert float(a[0, wi, 2:5][:, empty].abs().max().item()) == 0.0
+        assert float(a[0, wi, 6][empty].abs().max().item()) == 0.0
+
+    # 4. window consistency: with the split at the end, 'present' is the old 'full'
+    c_all, _, _ = cloud.rasterise([params(first, first + F, first + F, R, 1.25, -0.5)], P)
+    cloud.sync()
+    assert torch.equal(c_all[0, 0].view(torch.int16), a[0, 2].view(torch.int16))
+    assert torch.equal(c_all[0, 2].view(torch.int16), a[0, 2].view(torch.int16))
+
+    # 5. equivariance under an exact quarter turn: q' = (-q_y, q_x) bit for bit (negation and
+    #    row swaps are exact), so every plane turns with np.rot90
+    R90 = np.stack([-R[1], R[0], R[2]])
+    r90, _, _ = cloud.rasterise([params(first, first + p, first + F, R90, 0.5, 1.25)], P)
+    cloud.sync()
+    want = torch.rot90(a[0], 1, dims=(-2, -1))
+    same = (r90[0].view(torch.int16) == want.contiguous().view(torch.int16))
+    # a coordinate exactly on a cell boundary would break the symmetry of floor(); none expected
+    assert bool(same.all().item()), int((~same).sum().item())
+    cloud.close()
