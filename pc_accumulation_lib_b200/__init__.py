@@ -7,7 +7,7 @@ is not built or no CUDA device is present — there is no CPU path.
 """
 __all__ = ['Kitti360SemanticPointCloudAccumulator', 'NuScenesOracleSemanticPointCloudAccumulator',
            'SemanticPointCloudAccumulator', 'SemBEVGenerator', 'RGBBEVGenerator', 'BEVGenerator',
-           'DeviceCloud']
+           'DeviceCloud', 'AsyncBevWriter']
 
 
 def __getattr__(name):
@@ -23,6 +23,9 @@ def __getattr__(name):
     if name in ('SemBEVGenerator', 'RGBBEVGenerator', 'BEVGenerator'):
         from . import bev_generator as m
         return getattr(m, name)
+    if name == 'AsyncBevWriter':
+        from .sem_pc_accum import AsyncBevWriter as c
+        return c
     if name == 'DeviceCloud':
         from .device import DeviceCloud as c
         return c

@@ -123,3 +123,38 @@ def test_rand_aug_is_injectable_and_ordered_like_the_reference():
     z = min(max(r.normal(0, 0.1), -0.1), 0.1)
     assert a['rot_ang'] == rot and a['trans_dx'] == tr * np.cos(ta)
     assert a['trans_dy'] == tr * np.sin(ta) and a['zoom_scalar'] == 1 + z
+
+
+def test_async_writer_files_are_the_reference_format(tmp_path):
+    """sem_pc_accum.py:280-308: a .gz holding pickle.dumps(bev); the threaded writer must
+    produce what the synchronous one does (read here the way read_compressed_pickle does)."""
+    import gzip
+    import pickle
+    from pc_accumulation_lib_b200.sem_pc_accum import SemanticPointCloudAccumulator as Acc
+    rng = np.random.RandomState(5)
+    bevs = []
+    for k in range(12):
+        bev = {f'{n}_{w}': rng.rand(64, 64).astype(np.float16)
+               for n in ('road', 'intensity', 'dynamic', 'elevation') for w in ('present', 'future', 'full')}
+        bev.update({f'rgb_{w}': rng.rand(3, 64, 64).astype(np.float16) for w in ('present', 'future', 'full')})
+        bev.update({f'trajs_{w}': [rng.rand(5, 3)] for w in ('present', 'future', 'full')})
+        bevs.append(bev)
+    with Acc.async_writer(n_threads=4, max_pending=3) as wr:
+        for k, bev in enumerate(bevs):
+            wr.submit(bev, f'bev_{k:03d}.pkl', str(tmp_path))
+    assert wr.n_written == len(bevs) and wr.bytes_written > 0
+    for k, bev in enumerate(bevs):
+        Acc.write_compressed_pickle(bev, f'sync_{k:03d}.pkl', str(tmp_path))
+        with gzip.open(tmp_path / f'bev_{k:03d}.pkl.gz', 'rb') as f:
+            a = f.read()
+        with gzip.open(tmp_path / f'sync_{k:03d}.pkl.gz', 'rb') as f:
+            b = f.read()
+        assert a == b == pickle.dumps(bev)
+        got = Acc.read_compressed_pickle(str(tmp_path / f'bev_{k:03d}.pkl.gz'))
+        assert sorted(got) == sorted(bev)
+        np.testing.assert_array_equal(got['rgb_full'], bev['rgb_full'])
+    # an unwritable directory surfaces as IOError at close (the reference prints and goes on)
+    wr = Acc.async_writer(2)
+    wr.submit(bevs[0], 'x', str(tmp_path / 'missing_dir'))
+    with pytest.raises(IOError):
+        wr.close()
