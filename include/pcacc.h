@@ -262,6 +262,38 @@ int pcacc_preprocess_trajectories(const double *pts, const int32_t *traj_off, in
                                   const double *variants, int n_var, int P, double thresh,
                                   double *out, int32_t *out_cnt);
 
+/* ---- the dataloader's input side ----------------------
+ * What produces the (N,7) rows and pc_cam_idx that pcacc_integrate_records consumes.
+ *
+ * pcacc_assign_boxes — the box loop of inst_centric_get_sweeps, datasets/nuscenes_utils.py:
+ * 412-470, with find_points_in_box :317-329 and apply_tf :233-243: for every box in order,
+ * box_points = ([xyz 1] @ inv(target_from_box).T)[:, :3] (float64 FMA chain),
+ * inside = all(|box_points / dxdydz| < 0.5 + tolerance); a later box overwrites an earlier
+ * one.  The 4x4 inverses are computed by the caller (numpy LA.inv, as the reference does) and
+ * passed as box_from_target (host, n_boxes x 16, row-major); dxdydz: host n_boxes x 3.
+ * pts: device, (n, stride) float32 (pts_f32 != 0) or float64, x y z in the first three columns.
+ * out_box: device (n,) int32 = index of the LAST box that contains the point, -1 if none.
+ * out_count: device (n_boxes,) int32 = points inside each box (the loop skips boxes with none,
+ * which decides the instance numbering on the host). */
+int pcacc_assign_boxes(pcacc_t h, const void *pts_dev, int pts_f32, int64_t n, int64_t stride,
+                       const double *box_from_target, const double *dxdydz, int n_boxes,
+                       double tolerance, int32_t *out_box_dev, int32_t *out_count_dev, void *stream);
+
+/* pcacc_project_cameras — obs_dataloaders/nuscenes_obs_dataloader.py:176-198:
+ * pc_in_glob = homo_transform(glob_from_ego, pc_in_ego); for every camera j in order:
+ * pc_in_cam = homo_transform(inv(cam.glob_from_self), pc_in_glob); NuScenesCamera.project_pts3d
+ * (datasets/nuscenes_utils.py:112-136: valid = z > depth_thres; uv = (viewpad(K) [p 1])[:2] /
+ * (...)[2], nuscenes-devkit view_points with normalize=True; inside = 1 < uv < img_wh - 1);
+ * pc_uv[inside] = uv, pc_cam_idx[inside] = j (a later camera overwrites an earlier one).
+ * pc_ego: device (n, stride) float64.  Host arrays: glob_from_ego 16 doubles; cam_from_glob
+ * n_cams x 16 (the inverses, computed by the caller); cam_K n_cams x 9; img_wh n_cams x 2
+ * (width, height as doubles).  out_uv: device (n,2) float64, zeros where no camera sees the
+ * point; out_cam_idx: device (n,) int64, -1 there.  At most PCACC_MAX_CAMS cameras. */
+int pcacc_project_cameras(pcacc_t h, const double *pc_ego_dev, int64_t n, int64_t stride,
+                          const double *glob_from_ego, const double *cam_from_glob,
+                          const double *cam_K, const double *img_wh, int n_cams, double depth_thres,
+                          double *out_uv_dev, int64_t *out_cam_idx_dev, void *stream);
+
 /* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
  * Kernel classes of this library. */
 #define PCACC_K_INTEGRATE 0 /* k_integrate_frustum / _gt / _records / _cloud, k_gen_semantic_pc, k_project */

@@ -187,6 +187,85 @@ def nusc_obs2sem(pc, pc_cam_idx, rgbs, class_maps, T_ego_world, filters):
 
 
 # ---------------------------------------------------------------------------
+#  the dataloader's input side (multi-camera projection,
+#  box -> point instance assignment)
+# ---------------------------------------------------------------------------
+def apply_tf(tf, points):
+    """datasets/nuscenes_utils.py:233-243: ([xyz 1] @ tf.T)[:, :3]; float32 points are
+    promoted to float64 by the product.  Same FMA chain as homo_transform [measured]."""
+    assert points.shape[1] >= 3 and tf.shape == (4, 4)
+    if points.shape[0] == 1:
+        xyz1 = np.pad(points[:, :3], pad_width=[(0, 0), (0, 1)], constant_values=1.0)
+        return (xyz1 @ tf.T)[:, :3]
+    return affine(tf, points[:, :3])
+
+
+def find_points_in_box(points, target_from_box, dxdydz, tolerance):
+    """datasets/nuscenes_utils.py:317-329."""
+    box_points = apply_tf(np.linalg.inv(target_from_box), points[:, :3])
+    return np.all(np.abs(box_points / np.asarray(dxdydz, dtype=float)) < (0.5 + tolerance), axis=1)
+
+
+def assign_boxes(points, target_from_boxes, sizes, tolerance):
+    """The box loop of inst_centric_get_sweeps (datasets/nuscenes_utils.py:412-470) reduced
+    to what it does to the points: boxes are visited in order and every point inside takes
+    the box's index, later boxes overwriting earlier ones.  Returns (box index per point, -1
+    if none; number of points inside each box — the loop skips boxes with none)."""
+    box = -np.ones(points.shape[0], dtype=np.int32)
+    cnt = np.zeros(len(target_from_boxes), dtype=np.int32)
+    for b, (tfb, size) in enumerate(zip(target_from_boxes, sizes)):
+        m = find_points_in_box(points, tfb, size, tolerance)
+        cnt[b] = int(m.sum())
+        box[m] = b
+    return box, cnt
+
+
+def view_points(points, view, normalize):
+    """nuscenes-devkit (version unpinned by the reference, README.md:29)
+    nuscenes/utils/geometry_utils.py `view_points`, restated from its published source:
+    pad `view` into a 4x4 identity, multiply the homogeneous points, keep three rows and,
+    when `normalize`, divide every row by the third."""
+    assert view.shape[0] <= 4 and view.shape[1] <= 4 and points.shape[0] == 3
+    n = points.shape[1]
+    if n == 1:
+        viewpad = np.eye(4)
+        viewpad[:view.shape[0], :view.shape[1]] = view
+        pts = np.dot(viewpad, np.concatenate((points, np.ones((1, n)))))[:3, :]
+    else:
+        viewpad = np.eye(4)
+        viewpad[:view.shape[0], :view.shape[1]] = view
+        pts = affine(viewpad, np.ascontiguousarray(points.T)).T
+    if normalize:
+        pts = pts / pts[2:3, :].repeat(3, 0).reshape(3, n)
+    return pts
+
+
+def project_pts3d(pc, cam_K, img_wh, depth_thres=1e-3):
+    """NuScenesCamera.project_pts3d, datasets/nuscenes_utils.py:112-136."""
+    mask_valid = pc[:, 2] > depth_thres
+    out = np.zeros((pc.shape[0], 2), dtype=float) - 10
+    uv = view_points(np.ascontiguousarray(pc[mask_valid].T), cam_K, normalize=True)
+    out[mask_valid] = uv[:2, :].T
+    mask_in_img = (out > 1) & (out < np.asarray(img_wh, dtype=float) - 1)
+    return out, np.all(mask_in_img, axis=1) & mask_valid
+
+
+def project_to_cameras(pc_in_ego, glob_from_ego, cams, depth_thres=1e-3):
+    """obs_dataloaders/nuscenes_obs_dataloader.py:176-198: every camera in turn, a later
+    camera overwriting an earlier one.  cams: list of dicts glob_from_self (4,4), cam_K
+    (3,3), img_wh (2,).  Returns (pc_uv (N,2) float64, pc_cam_idx (N,) int)."""
+    pc_in_glob = homo_transform(glob_from_ego, pc_in_ego)
+    pc_uv = np.zeros((pc_in_ego.shape[0], 2), dtype=float)
+    pc_cam_idx = -np.ones(pc_in_ego.shape[0], dtype=int)
+    for j, cam in enumerate(cams):
+        pc_in_cam = homo_transform(np.linalg.inv(cam['glob_from_self']), pc_in_glob)
+        uv, mask = project_pts3d(pc_in_cam, cam['cam_K'], cam['img_wh'], depth_thres)
+        pc_uv[mask] = uv[mask]
+        pc_cam_idx[mask] = j
+    return pc_uv, pc_cam_idx
+
+
+# ---------------------------------------------------------------------------
 #  a14-a20: the BEV generator
 # ---------------------------------------------------------------------------
 def rotation_matrix_3d(ang):

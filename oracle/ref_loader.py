@@ -94,6 +94,7 @@ def load():
         BEVGenerator=ref_bevgen.BEVGenerator,
         homo_transform=ref_nusc_utils.homo_transform,
         pts_feat_from_img=ref_nusc_utils.pts_feat_from_img,
+        nusc_utils=ref_nusc_utils,
         base_module=ref_sem_pc_accum,
     )
     # keep the stubs for `datasets`/`utils` registered: the reference modules

@@ -82,6 +82,8 @@ SIGNATURES = {
     'pcacc_raster_stats': (_i32, [_vp, C.POINTER(_i64 * 3), _vp]),
     'pcacc_crop_trajectory': (_i32, [_vp, _i32, _dbl, _dbl, _vp, C.POINTER(_i32)]),
     'pcacc_preprocess_trajectories': (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _dbl, _vp, _vp]),
+    'pcacc_assign_boxes': (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    'pcacc_project_cameras': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_profile': (_i32, [_vp, _i32]),
     'pcacc_profile_read': (_i32, [_vp, C.POINTER(_dbl * 10), C.POINTER(_i64 * 10)]),
 }

@@ -1,0 +1,84 @@
+"""Mirror of the parts of the reference's datasets/nuscenes_utils.py (and of the projection
+loop of obs_dataloaders/nuscenes_obs_dataloader.py:176-198) that produce the inputs of
+`NuScenesOracleSemanticPointCloudAccumulator.integrate`: the (N,7) rows `[x, y, z, intensity,
+u, v, inst]` and `pc_cam_idx`.  Same function names and argument meaning; the per-point work
+runs in libpcacc (`pcacc_assign_boxes`, `pcacc_project_cameras`), the 4x4 inverses and the
+small bookkeeping stay in numpy exactly as the reference has them.
+
+`pts_feat_from_img(..., 'bilinear')` is not mirrored: the reference's bilinear branch
+multiplies (N,) weights with (N,C) features and only broadcasts for C == N
+(datasets/nuscenes_utils.py:206-208); the accumulator uses 'nearest', which is part of
+`pcacc_integrate_records`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..device import DeviceCloud
+
+_cloud = None
+
+
+def _dev() -> DeviceCloud:
+    """A small handle that only provides the parameter arena / stream plumbing."""
+    global _cloud
+    if _cloud is None:
+        _cloud = DeviceCloud(capacity_pts=1024, max_frames=4)
+    return _cloud
+
+
+def homo_transform(tf, points):
+    """datasets/nuscenes_utils.py:46-60 (host; a handful of poses per observation)."""
+    assert tf.shape == (4, 4), f"{tf.shape} is not (4, 4)"
+    assert points.shape == (points.shape[0], 3), f"{points.shape} is not (N, 3)"
+    _pts = np.concatenate([points, np.ones((points.shape[0], 1))], axis=1)
+    _pts = tf @ _pts.T
+    return _pts[:3, :].T
+
+
+def apply_tf(tf, points, in_place=False):
+    """datasets/nuscenes_utils.py:233-243 (host)."""
+    assert points.shape[1] >= 3, f"expect points.shape[1] >= 3, get {points.shape[1]}"
+    assert tf.shape == (4, 4), f"expect tf.shape == 4, get {tf.shape}"
+    xyz1 = np.pad(points[:, :3], pad_width=[(0, 0), (0, 1)], constant_values=1.0)
+    if in_place:
+        points[:, :3] = (xyz1 @ tf.T)[:, :3]
+    else:
+        return (xyz1 @ tf.T)[:, :3]
+
+
+def find_points_in_box(points, target_from_box, dxdydz, tolerance):
+    """datasets/nuscenes_utils.py:317-329 -> (N,) bool."""
+    box, _ = _dev().assign_boxes(points, [target_from_box], [dxdydz], tolerance)
+    return (box >= 0).cpu().numpy()
+
+
+def assign_points_to_boxes(points, target_from_boxes, sizes, tolerance):
+    """All boxes of a sweep in one launch: the effect of the loop at
+    datasets/nuscenes_utils.py:412-470 on the points.  -> (index of the last box containing
+    each point, -1 if none; points inside each box).  The caller skips boxes whose count is
+    zero and maps box -> instance / class index as the reference does."""
+    box, cnt = _dev().assign_boxes(points, target_from_boxes, sizes, tolerance)
+    return box.cpu().numpy(), cnt.cpu().numpy()
+
+
+def project_pts3d(pc, cam_K, img_wh, depth_thres=1e-3):
+    """NuScenesCamera.project_pts3d, datasets/nuscenes_utils.py:112-136, for points already in
+    the camera frame -> (uv (N,2) with -10 rows for invalid points, mask_in_img (N,) bool)."""
+    cam = dict(glob_from_self=np.eye(4), cam_K=cam_K, img_wh=img_wh)
+    pc = np.ascontiguousarray(pc, dtype=np.float64)
+    uv, idx = _dev().project_cameras(pc, np.eye(4), [cam], depth_thres)
+    mask = (idx >= 0).cpu().numpy()
+    # the device reports uv only for points inside the image; the reference also returns the
+    # off-image projections of valid points, which its only caller discards
+    # (nuscenes_obs_dataloader.py:191-196)
+    out = np.zeros((pc.shape[0], 2)) - 10.
+    out[mask] = uv.cpu().numpy()[mask]
+    return out, mask
+
+
+def project_to_cameras(pc_in_ego, glob_from_ego, cams, depth_thres=1e-3):
+    """obs_dataloaders/nuscenes_obs_dataloader.py:176-198 -> (pc_uv (N,2) float64,
+    pc_cam_idx (N,) int64); cams: list of dicts glob_from_self (4,4), cam_K (3,3), img_wh."""
+    uv, idx = _dev().project_cameras(pc_in_ego, glob_from_ego, cams, depth_thres)
+    return uv.cpu().numpy(), idx.cpu().numpy()

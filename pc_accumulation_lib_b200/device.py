@@ -482,6 +482,55 @@ class DeviceCloud:
         torch.from_numpy(out).copy_(view)       # multi-threaded for large blocks, unlike ndarray.copy
         return out
 
+    # -- the dataloader's input side -----------------------
+    def assign_boxes(self, points, target_from_boxes, sizes, tolerance):
+        """Box loop of inst_centric_get_sweeps (datasets/nuscenes_utils.py:412-470).
+        points: (n, >=3) float32/float64 numpy array or CUDA tensor; target_from_boxes: list of
+        (4,4); sizes: list of dxdydz.  -> (box index per point int32 CUDA tensor, -1 = none;
+        points inside each box int32 CUDA tensor)."""
+        pts = self.stage.put('box_pts', points)
+        if pts.dtype not in (torch.float32, torch.float64):
+            pts = pts.double()
+        pts = pts.contiguous()
+        n, stride = int(pts.shape[0]), int(pts.shape[1])
+        nb = len(target_from_boxes)
+        inv = np.ascontiguousarray(np.stack([np.linalg.inv(np.asarray(T, dtype=np.float64))
+                                             for T in target_from_boxes])) if nb else np.zeros((0, 4, 4))
+        sz = np.ascontiguousarray(np.asarray(sizes, dtype=np.float64).reshape(nb, 3)) if nb else np.zeros((0, 3))
+        box = torch.empty(n, dtype=torch.int32, device=self.device)
+        cnt = torch.empty(nb, dtype=torch.int32, device=self.device)
+        self._check(self.lib.pcacc_assign_boxes(
+            self.h, _ptr(pts), int(pts.dtype == torch.float32), n, stride,
+            inv.ctypes.data_as(C.c_void_p), sz.ctypes.data_as(C.c_void_p), nb, float(tolerance),
+            _ptr(box), _ptr(cnt), _stream()))
+        self.stage.fence()
+        return box, cnt
+
+    def project_cameras(self, pc_in_ego, glob_from_ego, cams, depth_thres=1e-3):
+        """nuscenes_obs_dataloader.py:176-198.  pc_in_ego (n,3) float64; cams: list of dicts
+        glob_from_self (4,4), cam_K (3,3), img_wh (2,).  -> (pc_uv (n,2) float64, pc_cam_idx
+        (n,) int64) CUDA tensors."""
+        pts = self.stage.put('cam_pts', pc_in_ego if isinstance(pc_in_ego, torch.Tensor)
+                             else np.asarray(pc_in_ego, dtype=np.float64)).contiguous()
+        assert pts.dtype == torch.float64 and pts.dim() == 2 and pts.shape[1] >= 3
+        n, stride = int(pts.shape[0]), int(pts.shape[1])
+        nc = len(cams)
+        g = _hostd(glob_from_ego, 16)
+        inv = np.ascontiguousarray(np.stack([np.linalg.inv(np.asarray(c['glob_from_self'], dtype=np.float64))
+                                             for c in cams])) if nc else np.zeros((0, 4, 4))
+        K = np.ascontiguousarray(np.stack([np.asarray(c['cam_K'], dtype=np.float64).reshape(3, 3)
+                                           for c in cams])) if nc else np.zeros((0, 3, 3))
+        wh = np.ascontiguousarray(np.stack([np.asarray(c['img_wh'], dtype=np.float64).reshape(2)
+                                            for c in cams])) if nc else np.zeros((0, 2))
+        uv = torch.empty((n, 2), dtype=torch.float64, device=self.device)
+        cam = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._check(self.lib.pcacc_project_cameras(
+            self.h, _ptr(pts), n, stride, g.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p),
+            K.ctypes.data_as(C.c_void_p), wh.ctypes.data_as(C.c_void_p), nc, float(depth_thres),
+            _ptr(uv), _ptr(cam), _stream()))
+        self.stage.fence()
+        return uv, cam
+
     def raster_stats(self):
         s = (C.c_int64 * 3)()
         self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))

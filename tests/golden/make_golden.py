@@ -195,8 +195,61 @@ def gen_bev_warp(ref, name, seeds=(11, 12, 13), **kw):
     save(name, out)
 
 
+def gen_input_side(ref, name):
+    """datasets/nuscenes_utils.py run unmodified: find_points_in_box / apply_tf (box loop of
+    inst_centric_get_sweeps restated around them), homo_transform and
+    NuScenesCamera.project_pts3d (called unbound on a stand-in `self`; nuscenes-devkit's
+    view_points is absent here and is restated from its published source)."""
+    import types
+    nu = ref.nusc_utils
+    c = cases.input_side_inputs()
+
+    def view_points(points, view, normalize):          # nuscenes-devkit geometry_utils
+        assert view.shape[0] <= 4 and view.shape[1] <= 4 and points.shape[0] == 3
+        viewpad = np.eye(4)
+        viewpad[:view.shape[0], :view.shape[1]] = view
+        nbr_points = points.shape[1]
+        points = np.concatenate((points, np.ones((1, nbr_points))))
+        points = np.dot(viewpad, points)
+        points = points[:3, :]
+        if normalize:
+            points = points / points[2:3, :].repeat(3, 0).reshape(3, nbr_points)
+        return points
+
+    nu.view_points = view_points
+    out = {}
+    # box loop (:412-470): in order, later boxes overwrite
+    for tag, pts in (('f64', c['pc']), ('f32', c['pc_f32'])):
+        box = -np.ones(pts.shape[0], dtype=np.int32)
+        cnt = np.zeros(len(c['boxes']), dtype=np.int32)
+        for b, (T, size) in enumerate(zip(c['boxes'], c['sizes'])):
+            m = nu.find_points_in_box(pts, T, size, c['tolerance'])
+            cnt[b] = m.sum()
+            box[m] = b
+        out[f'box_{tag}'], out[f'cnt_{tag}'] = box, cnt
+    # multi-camera projection (nuscenes_obs_dataloader.py:176-198)
+    pc_in_glob = nu.homo_transform(c['glob_from_ego'], c['pc'])
+    pc_uv = np.zeros((c['pc'].shape[0], 2), dtype=float)
+    pc_cam_idx = -np.ones(c['pc'].shape[0], dtype=int)
+    for j, cam in enumerate(c['cams']):
+        pc_in_cam = nu.homo_transform(np.linalg.inv(cam['glob_from_self']), pc_in_glob)
+        fake = types.SimpleNamespace(cam_K=cam['cam_K'], img_wh=cam['img_wh'])
+        uv, mask = nu.NuScenesCamera.project_pts3d(fake, pc_in_cam)
+        pc_uv[mask] = uv[mask]
+        pc_cam_idx[mask] = j
+        out[f'uv_cam{j}'], out[f'mask_cam{j}'] = uv, mask
+    out['pc_uv'], out['pc_cam_idx'] = pc_uv, pc_cam_idx.astype(np.int64)
+    out['input_digest'] = np.frombuffer(cases.digest(c['pc'], c['glob_from_ego'],
+                                                     *[k['glob_from_self'] for k in c['cams']],
+                                                     *c['boxes'], *c['sizes']).encode(), dtype=np.uint8)
+    save(name, out)
+
+
 def main():
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'input_side':
+        gen_input_side(ref, 'input_side.npz')
+        return
     gen_kitti_project(ref)
     gen_kitti_seq(ref, 'kitti_seq.npz', use_gt_sem=False, P=64, horizon=14.0,
                   present_idx=3, n_frames=9)
@@ -210,6 +263,7 @@ def main():
     gen_bev_direct(ref, 'bev_direct_p128.npz', n=20000, seed=78, P=128,
                    view=51.2)
     gen_bev_warp(ref, 'bev_warp.npz')
+    gen_input_side(ref, 'input_side.npz')
 
 
 if __name__ == '__main__':

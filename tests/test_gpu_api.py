@@ -227,3 +227,36 @@ def test_sem_bev_generator_polynomial_warp():
     from oracle import oracle as orc
     np.testing.assert_array_equal(bg.warp_dense_probmaps(maps, a_1, a_2, b_1, b_2),
                                   orc.warp_dense(maps, a_1, a_2, b_1, b_2))
+
+
+def test_input_side_kernels_match_reference_golden():
+    """pcacc_assign_boxes / pcacc_project_cameras through the mirror of
+    datasets/nuscenes_utils.py, against the reference's own outputs (bit-exact)."""
+    from pc_accumulation_lib_b200.datasets import nuscenes_utils as nu
+    g = load_golden('input_side.npz')
+    c = cases.input_side_inputs()
+    for tag, pts in (('f64', c['pc']), ('f32', c['pc_f32'])):
+        box, cnt = nu.assign_points_to_boxes(pts, c['boxes'], c['sizes'], c['tolerance'])
+        np.testing.assert_array_equal(box, g[f'box_{tag}'])
+        np.testing.assert_array_equal(cnt, g[f'cnt_{tag}'])
+    b = 4
+    m = nu.find_points_in_box(c['pc'], c['boxes'][b], c['sizes'][b], c['tolerance'])
+    assert m.dtype == bool and int(m.sum()) == int(g['cnt_f64'][b])
+    uv, idx = nu.project_to_cameras(c['pc'], c['glob_from_ego'], c['cams'])
+    np.testing.assert_array_equal(idx, g['pc_cam_idx'])
+    np.testing.assert_array_equal(uv, g['pc_uv'])
+    # one camera, points already in its frame (NuScenesCamera.project_pts3d)
+    j = 3
+    pc_cam = nu.homo_transform(np.linalg.inv(c['cams'][j]['glob_from_self']),
+                               nu.homo_transform(c['glob_from_ego'], c['pc']))
+    uv1, mask1 = nu.project_pts3d(pc_cam, c['cams'][j]['cam_K'], c['cams'][j]['img_wh'])
+    np.testing.assert_array_equal(mask1, g[f'mask_cam{j}'])
+    np.testing.assert_array_equal(uv1[mask1], g[f'uv_cam{j}'][mask1])
+    # empty inputs and more boxes than one launch holds
+    box, cnt = nu.assign_points_to_boxes(np.zeros((0, 3)), c['boxes'], c['sizes'], 0.01)
+    assert box.shape == (0,) and not cnt.any()
+    many = c['boxes'] * 12
+    box, cnt = nu.assign_points_to_boxes(c['pc'], many, c['sizes'] * 12, c['tolerance'])
+    want = np.where(g['box_f64'] >= 0, g['box_f64'] + 11 * len(c['boxes']), -1)
+    np.testing.assert_array_equal(box, want)
+    np.testing.assert_array_equal(cnt, np.tile(g['cnt_f64'], 12))

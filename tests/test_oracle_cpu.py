@@ -155,3 +155,27 @@ def test_bev_warp_golden():
         rngs = (np.random.RandomState(int(s)), random.Random(int(s)))
         bev = orc.generate(*cases.copy_pcs_trajs(pcs, trajs), gen, warp_rngs=rngs, **aug)
         assert_bev_equal(bev, unpack_bev(g, f'bev{int(s)}_'))
+
+
+def test_input_side_matches_reference_golden():
+    """box -> point assignment and multi-camera projection, pinned to
+    datasets/nuscenes_utils.py run unmodified (tests/golden/make_golden.py gen_input_side)."""
+    g = load_golden('input_side.npz')
+    c = cases.input_side_inputs()
+    for tag, pts in (('f64', c['pc']), ('f32', c['pc_f32'])):
+        box, cnt = orc.assign_boxes(pts, c['boxes'], c['sizes'], c['tolerance'])
+        np.testing.assert_array_equal(box, g[f'box_{tag}'])
+        np.testing.assert_array_equal(cnt, g[f'cnt_{tag}'])
+    assert (g['cnt_f64'] == 0).any() and (g['box_f64'] >= 0).sum() > 100
+    pc_glob = orc.homo_transform(c['glob_from_ego'], c['pc'])
+    for j, cam in enumerate(c['cams']):
+        pc_cam = orc.homo_transform(np.linalg.inv(cam['glob_from_self']), pc_glob)
+        uv, mask = orc.project_pts3d(pc_cam, cam['cam_K'], cam['img_wh'])
+        np.testing.assert_array_equal(uv, g[f'uv_cam{j}'])
+        np.testing.assert_array_equal(mask, g[f'mask_cam{j}'])
+    uv, idx = orc.project_to_cameras(c['pc'], c['glob_from_ego'], c['cams'])
+    np.testing.assert_array_equal(uv, g['pc_uv'])
+    np.testing.assert_array_equal(idx, g['pc_cam_idx'])
+    # the seams are seen by two cameras: the later one must have won
+    seen = np.stack([g[f'mask_cam{j}'] for j in range(len(c['cams']))])
+    assert (seen.sum(axis=0) > 1).sum() > 100
