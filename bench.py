@@ -455,6 +455,7 @@ def run_ours(args, rank, world, local_rank, dist):
                 c.close()
             torch.cuda.empty_cache()
             extra['kitti360_long_horizon'] = c3_extra(torch, DeviceCloud, pk)
+            extra['input_side'] = input_side_extra(torch, DeviceCloud, pk)
 
     if rank == 0:
         line = {
@@ -557,6 +558,47 @@ def c3_extra(torch, DeviceCloud, pk):
     }
     cloud.close()
     return res
+
+
+def input_side_extra(torch, DeviceCloud, pk):
+    """the dataloader's multi-camera projection and box -> point
+    assignment for one nuScenes sample (10 sweeps x 34,688 points, 6 cameras, 64 boxes),
+    device-resident, next to the same functions of the CPU port on one core."""
+    from tests.golden import cases
+    c = cases.input_side_inputs(n=34688 * 10, n_boxes=64)
+    cloud = DeviceCloud(1024, 4)
+    pts = torch.from_numpy(c['pc']).cuda()
+    pts32 = torch.from_numpy(c['pc_f32']).cuda()
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_p = timed(lambda: cloud.project_cameras(pts, c['glob_from_ego'], c['cams']))
+    ms_b = timed(lambda: cloud.assign_boxes(pts32, c['boxes'], c['sizes'], c['tolerance']))
+    n = int(pts.shape[0])
+    from oracle import oracle as orc          # CPU port, timed as the baseline of this row only
+    t0 = time.perf_counter()
+    orc.project_to_cameras(c['pc'], c['glob_from_ego'], c['cams'])
+    t1 = time.perf_counter()
+    orc.assign_boxes(c['pc_f32'], c['boxes'], c['sizes'], c['tolerance'])
+    t2 = time.perf_counter()
+    cloud.close()
+    return {'points': n, 'cameras': len(c['cams']), 'boxes': len(c['boxes']),
+            'project_cameras_us': ms_p * 1e3, 'project_points_per_s': n / (ms_p * 1e-3),
+            'project_alg_GBps': 48.0 * n / (ms_p * 1e-3) / 1e9,     # 24 B in, 16 B uv + 8 B index out
+            'assign_boxes_us': ms_b * 1e3, 'assign_points_per_s': n / (ms_b * 1e-3),
+            'assign_alg_GBps': 16.0 * n / (ms_b * 1e-3) / 1e9,      # 12 B in (f32 xyz), 4 B out
+            'cpu_port_project_points_per_s': n / (t1 - t0), 'cpu_port_assign_points_per_s': n / (t2 - t1),
+            'note': 'includes the per-call host work (numpy inverses, parameter block upload)'}
 
 
 # ---------------------------------------------------------------------------
