@@ -745,9 +745,13 @@ __device__ __forceinline__ double dirichlet(uint32_t c, uint32_t n) {
     return __ddiv_rn((double)(c + 1u), (double)(n + 2u));
 }
 
-// intensity plane: mean over (count+1) then road_marking_transform (sem_bev.py:593-617)
-__device__ __forceinline__ double intensity_plane(const pcacc_bev_params &bp, double isum, uint32_t n_road) {
-    double I = __ddiv_rn(isum, (double)(n_road + 1u));
+// intensity plane: mean over (count+1) then road_marking_transform (sem_bev.py:593-617).
+// raw_sum = sum of the raw road intensities; the reference divides every intensity by
+// intensity_div (255 on nuScenes) before it sums: sum(raw) / (div * (n+1)) rounds once
+// instead of n+1 times (div * (n+1) is exact), DESIGN.md §6.
+__device__ __forceinline__ double intensity_plane(const pcacc_bev_params &bp, double raw_sum, uint32_t n_road,
+                                                  double intensity_div) {
+    double I = __ddiv_rn(raw_sum, __dmul_rn(intensity_div, (double)(n_road + 1u)));
     double t = __dmul_rn(bp.int_sep_scaler, __dsub_rn(I, bp.int_mid_threshold));
     double sg = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-t)));
     double val = __dmul_rn(bp.int_scaler, sg);
@@ -761,7 +765,7 @@ __global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_
     const pcacc_bev_params &bp = params[v];
     BevConsts c;
     c.empty[0] = dirichlet(0, 0);
-    c.empty[1] = intensity_plane(bp, 0.0, 0);
+    c.empty[1] = intensity_plane(bp, 0.0, 0, 1.0);
     c.empty[2] = c.empty[3] = c.empty[4] = __ddiv_rn(bp.rgb_fill, 255.0);
     c.empty[5] = dirichlet(0, 0);
     c.empty[6] = 0.0;
@@ -805,9 +809,7 @@ __device__ __forceinline__ void window_planes(const pcacc_bev_params &bp, const 
     if (n_road == 0) {
         plane[1] = cst.empty[1];   // sum 0 over count 0: the same arithmetic as an empty window
     } else {
-        // sum(raw) / div instead of sum(raw / div): one rounding instead of n
-        double isum = __ddiv_rn(fx_to_double(fx_hi, fx_lo), intensity_div);
-        plane[1] = intensity_plane(bp, isum, n_road);
+        plane[1] = intensity_plane(bp, fx_to_double(fx_hi, fx_lo), n_road, intensity_div);
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) plane[2 + k] = lut[med2[k]];
@@ -982,11 +984,13 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             const uint32_t base = sw.cs[c], np = sw.np[c], nt = sw.nt[c], nf = nt - np;
             const uint32_t vi = sw.val[q], vig = vi | F_GUARD;
             uint32_t e1 = 0, g1 = 0, e2 = 0, g2 = 0;
+#pragma unroll 2
             for (uint32_t j = 0; j < np; j++) {
                 const uint32_t vj = sw.val[base + j];
                 e1 += f_ge(vig, vj);
                 g1 += f_ge(vj | F_GUARD, vi);
             }
+#pragma unroll 2
             for (uint32_t j = np; j < nt; j++) {
                 const uint32_t vj = sw.val[base + j];
                 e2 += f_ge(vig, vj);
@@ -1028,11 +1032,12 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     }
     int med2[3][3];
 #pragma unroll
-    for (int w = 0; w < 3; w++)
+    for (int w = 0; w < 3; w++) {
+        // lo + hi per 10-bit field in one add (at most 510 per field)
+        const uint32_t sm = sw.med[lane][2 * w] + sw.med[lane][2 * w + 1];
 #pragma unroll
-        for (int c = 0; c < 3; c++)
-            med2[w][c] = (int)((sw.med[lane][2 * w] >> (10 * c)) & 255u) +
-                         (int)((sw.med[lane][2 * w + 1] >> (10 * c)) & 255u);
+        for (int c = 0; c < 3; c++) med2[w][c] = (int)((sm >> (10 * c)) & 1023u);
+    }
 
     // intensity planes: the (cell, window) pairs that hold road points are compacted over the
     // warp, so the division / exp chain runs once per 32 pairs instead of once per window.
@@ -1054,9 +1059,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     if (need2) { e_hi[k2] = hi[0] + hi[1]; e_lo[k2] = lo[0] + lo[1]; e_n[k2] = nr[0] + nr[1]; }
     __syncwarp();
     for (uint32_t i = lane; i < tot; i += 32) {
-        // sum(raw) / div instead of sum(raw / div): one rounding instead of n
-        const double isum = __ddiv_rn(fx_to_double(e_hi[i], e_lo[i]), intensity_div);
-        const double val = intensity_plane(bp, isum, e_n[i]);
+        const double val = intensity_plane(bp, fx_to_double(e_hi[i], e_lo[i]), e_n[i], intensity_div);
         e_hi[i] = __double_as_longlong(val);
     }
     __syncwarp();
