@@ -186,10 +186,13 @@ __device__ __forceinline__ Eval eval_point(const pcacc_bev_params &bp, int P, do
 // the box is inside the bounding box of the transformed corners.  Conservative (margin
 // far above fp64 rounding and above the lazy-vs-sequential chain difference); NaN / inf
 // boxes are never culled.  One thread per (frame, variant); frame_tiles[] starts at 0.
+__device__ void bev_write_consts(const pcacc_bev_params &bp, int P, BevConsts *__restrict__ out);
+
 __global__ void k_bev_cull(BinArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_frames * a.n_var) return;
     const int f = t / a.n_var, v = t - f * a.n_var;
+    if (f == 0) bev_write_consts(a.params[v], a.P, (BevConsts *)a.consts + v);
     const int64_t fid = a.frame_lo + f;
     const int slot = (int)(fid % a.max_frames);
     const pcacc_bev_params &bp = a.params[v];
@@ -758,11 +761,8 @@ __device__ __forceinline__ double intensity_plane(const pcacc_bev_params &bp, do
     return val > 1.0 ? 1.0 : val;
 }
 
-__global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_var, int P,
-                             BevConsts *__restrict__ consts) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_var) return;
-    const pcacc_bev_params &bp = params[v];
+// per-variant constants (empty-window planes, P/view)
+__device__ void bev_write_consts(const pcacc_bev_params &bp, int P, BevConsts *__restrict__ out) {
     BevConsts c;
     c.empty[0] = dirichlet(0, 0);
     c.empty[1] = intensity_plane(bp, 0.0, 0, 1.0);
@@ -774,7 +774,15 @@ __global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_
     c.empty_h[2] = __double2half(c.empty[2]);
     c.empty_h[3] = __double2half(c.empty[6]);
     c.pv = (double)P / bp.view;
-    consts[v] = c;
+    *out = c;
+}
+
+// only launched when no frame is visited (k_bev_cull writes the constants otherwise)
+__global__ void k_bev_consts(const pcacc_bev_params *__restrict__ params, int n_var, int P,
+                             BevConsts *__restrict__ consts) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_var) return;
+    bev_write_consts(params[v], P, consts + v);
 }
 
 __global__ void k_rgb_lut(double *__restrict__ lut) {
@@ -1379,16 +1387,20 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         rc = pcacc_arena_put(h, params + v0, (size_t)nv * sizeof(pcacc_bev_params), &d_params, st);
         if (rc) return rc;
 
-        // per-variant constants (empty-window planes, P/view)
-        h->launches[PCACC_K_REDUCE]++;
-        k_bev_consts<<<(nv + 31) / 32, 32, 0, st>>>((const pcacc_bev_params *)d_params, nv, P, d_consts);
-        PCACC_CUDA(h, cudaGetLastError());
+        // per-variant constants (empty-window planes, P/view): written by k_bev_cull when
+        // there are frames to visit
+        const bool visit = cap > 0 && fhi > flo && max_cnt > 0;
+        if (!visit) {
+            h->launches[PCACC_K_REDUCE]++;
+            k_bev_consts<<<(nv + 31) / 32, 32, 0, st>>>((const pcacc_bev_params *)d_params, nv, P, d_consts);
+            PCACC_CUDA(h, cudaGetLastError());
+        }
 
         const bool want_f64 = out_f64_dev != nullptr;
         __half *o16 = (__half *)out_f16_dev + (int64_t)v0 * 21 * PP;
         double *o64 = want_f64 ? out_f64_dev + (int64_t)v0 * 21 * PP : nullptr;
 
-        if (cap > 0 && fhi > flo && max_cnt > 0) {
+        if (visit) {
             BinArgs a;
             a.ring = h->ring;
             a.frame_off = h->d_frame_off;
