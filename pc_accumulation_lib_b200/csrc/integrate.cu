@@ -9,6 +9,9 @@
 //   sem_pc_accum.py:167-183   update_sem_pcs
 //   nuscenes_oracle_sem_pc_accum.py:223-230,243-250   dynamic flags
 #include <math.h>
+#include <algorithm>
+#include <utility>
+#include <vector>
 #include <string.h>
 
 #include "common.cuh"
@@ -543,16 +546,21 @@ __global__ void k_materialise_done(int64_t *__restrict__ frame_epoch, double *__
 // ---------------------------------------------------------------------------
 // dynamic flags
 // ---------------------------------------------------------------------------
+// One block row per FRAME that has marks (the host groups the (frame, instance) pairs):
+// every point's instance index is read once and compared with the frame's few instances.
 __global__ void __launch_bounds__(IBLOCK)
 k_mark_dynamic(RingDev ring, const int64_t *__restrict__ frame_off,
-               const int64_t *__restrict__ frame_cnt, const int32_t *__restrict__ pair_slot,
-               const int32_t *__restrict__ pair_inst) {
-    int slot = pair_slot[blockIdx.y];
-    int32_t want = pair_inst[blockIdx.y];
-    int64_t cnt = frame_cnt[slot], off = frame_off[slot];
+               const int64_t *__restrict__ frame_cnt, const int32_t *__restrict__ grp /* slot, begin, end */,
+               const int32_t *__restrict__ inst_sorted) {
+    const int slot = grp[3 * blockIdx.y], b = grp[3 * blockIdx.y + 1], e = grp[3 * blockIdx.y + 2];
+    const int64_t cnt = frame_cnt[slot], off = frame_off[slot];
     for (int64_t i = (int64_t)blockIdx.x * IBLOCK + threadIdx.x; i < cnt;
-         i += (int64_t)gridDim.x * IBLOCK)
-        if (ring.inst[off + i] == want) ring.dyn[off + i] = 1;
+         i += (int64_t)gridDim.x * IBLOCK) {
+        const int32_t inst = ring.inst[off + i];
+        bool hit = false;
+        for (int k = b; k < e; k++) hit |= inst == inst_sorted[k];
+        if (hit) ring.dyn[off + i] = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1030,29 +1038,46 @@ extern "C" int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int
     if (n_pairs <= 0) return PCACC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     PCACC_CUDA(h, cudaSetDevice(h->device));
-    std::vector<int32_t> buf(2 * (size_t)n_pairs);
+    // group the pairs by frame slot (stable: order inside a frame is irrelevant)
+    std::vector<std::pair<int32_t, int32_t>> pr((size_t)n_pairs);
     int64_t max_n = 0;
     for (int k = 0; k < n_pairs; k++) {
         FrameHost *f = pcacc_frame(h, frame_ids[k]);
         if (!f) return pcacc_fail(h, PCACC_ERR_ARG, "frame %lld is not live", (long long)frame_ids[k]);
-        buf[k] = (int32_t)(frame_ids[k] % h->max_frames);
-        buf[n_pairs + k] = inst_idx[k];
+        pr[k] = {(int32_t)(frame_ids[k] % h->max_frames), inst_idx[k]};
         int64_t c = f->exact ? f->cnt : f->n_in;
         if (c > max_n) max_n = c;
     }
+    std::sort(pr.begin(), pr.end());
+    std::vector<int32_t> buf;
+    buf.reserve(4 * (size_t)n_pairs);
+    std::vector<int32_t> inst((size_t)n_pairs);
+    int n_grp = 0;
+    for (int k = 0; k < n_pairs; k++) {
+        inst[k] = pr[k].second;
+        if (k == 0 || pr[k].first != pr[k - 1].first) {
+            if (n_grp) buf[3 * (n_grp - 1) + 2] = k;
+            buf.push_back(pr[k].first);
+            buf.push_back(k);
+            buf.push_back(n_pairs);
+            n_grp++;
+        }
+    }
+    const size_t grp_words = buf.size();
+    buf.insert(buf.end(), inst.begin(), inst.end());
     void *dev = nullptr;
     int rc = pcacc_arena_put(h, buf.data(), buf.size() * sizeof(int32_t), &dev, st);
     if (rc) return rc;
-    int64_t bx = (max_n + 4 * IBLOCK - 1) / (4 * IBLOCK);  // grid-stride: 4 rounds per thread
+    int64_t bx = (max_n + IBLOCK - 1) / IBLOCK;
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    for (int k0 = 0; k0 < n_pairs; k0 += 32768) {
-        int ny = n_pairs - k0 < 32768 ? n_pairs - k0 : 32768;
+    if (bx > 256) bx = 256;   // grid-stride beyond that
+    for (int g0 = 0; g0 < n_grp; g0 += 32768) {
+        int ny = n_grp - g0 < 32768 ? n_grp - g0 : 32768;
         dim3 grid((unsigned)bx, (unsigned)ny);
         size_t pe = pcacc_prof_begin(h, PCACC_K_MARK, st);
         k_mark_dynamic<<<grid, IBLOCK, 0, st>>>(h->ring, h->d_frame_off, h->d_frame_cnt,
-                                                (const int32_t *)dev + k0,
-                                                (const int32_t *)dev + n_pairs + k0);
+                                                (const int32_t *)dev + 3 * g0,
+                                                (const int32_t *)dev + grp_words);
         PCACC_CUDA(h, cudaGetLastError());
         pcacc_prof_end(h, PCACC_K_MARK, pe, st);
     }
