@@ -455,6 +455,8 @@ def run_ours(args, rank, world, local_rank, dist):
                 c.close()
             torch.cuda.empty_cache()
             extra['kitti360_long_horizon'] = c3_extra(torch, DeviceCloud, pk)
+            # configs[4]: 1024x1024, elevation max, 100 frames (12 M resident points)
+            extra['highres_1024'] = c3_extra(torch, DeviceCloud, pk, F=100, P=1024, elevation_max=True)
             extra['input_side'] = input_side_extra(torch, DeviceCloud, pk)
 
     if rank == 0:
@@ -482,12 +484,12 @@ def run_ours(args, rank, world, local_rank, dist):
         OUT.flush()
 
 
-def c3_extra(torch, DeviceCloud, pk):
+def c3_extra(torch, DeviceCloud, pk, F=200, P=P, elevation_max=False):
     """BASELINE.json configs[2]: 200 all-points KITTI-360-shaped frames (24 M
     resident points, use_gt_sem path, lazy re-base), one 256x256 BEV at frame
     100 — the primary roofline configuration of SURVEY.md §8(d)."""
     from pc_accumulation_lib_b200.device import make_bev_params
-    F, n_distinct = 200, 8
+    n_distinct = 8
     pcs = [torch.from_numpy(synth.kitti_lidar(synth.seed_for(3, f))).cuda() for f in range(n_distinct)]
     sgs = [torch.from_numpy(synth.kitti_sem_gt(synth.seed_for(3, f), pcs[0].shape[0])[:, 0].copy()).cuda()
            for f in range(n_distinct)]
@@ -528,7 +530,7 @@ def c3_extra(torch, DeviceCloud, pk):
     rot = np.pi - (0.5 * np.pi + np.arctan2(d[1], d[0]))
     R = np.array([[np.cos(rot), -np.sin(rot), 0], [np.sin(rot), np.cos(rot), 0], [0, 0, 1]])
     bp = make_bev_params(first, first + p, first + n_live, origin, R, 0., 0., 80., None, 20., 20., .5,
-                         0, synth.SEM_IDXS)
+                         0, synth.SEM_IDXS, elevation_max)
     out = torch.empty((1, 3, 7, P, P), dtype=torch.float16, device='cuda')
     n_res = cloud.resident_points()
     cloud.profile(True)
@@ -554,7 +556,8 @@ def c3_extra(torch, DeviceCloud, pk):
         'rasterise_frac_of_nominal_8TBps': b_ras / (ms_ras * 1e-3) / 1e9 / 8000.0,
         'rasterise_mandated_GBps': (b_ras + st['binned'] * (29 + 16 * int(np.ceil(2 * np.log2(P) / 8))))
                                    / (ms_ras * 1e-3) / 1e9,
-        'note': 'inputs (0.9 GB ring) exceed L2; 33 B/resident point + 42 B/cell algorithmic',
+        'P': P, 'elevation': 'max' if elevation_max else 'min',
+        'note': 'inputs (%.1f GB ring) exceed L2; 33 B/resident point + 42 B/cell algorithmic' % (n_res * 37e-9),
     }
     cloud.close()
     return res
