@@ -542,9 +542,7 @@ k_bev_bin(BinArgs a) {
             const unsigned long long zb = (unsigned long long)__double_as_longlong(e.z);
             a.tmp_key[c] = key;
             a.tmp_rec[c] = make_uint4((uint32_t)zb, (uint32_t)(zb >> 32), rgbs, __float_as_uint(inten));
-#ifndef EXP_NO_ATOMIC
             atomicAdd(&a.counts[key], 1u);  // result unused: a fire-and-forget reduction
-#endif
         } else {
             a.tmp_key[c] = KEY_INVALID;  // hole: rejected by the exact test
         }
@@ -1445,9 +1443,6 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             k_bev_bin<<<148 * 8, 256, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_BIN, pe, st);
-#ifdef EXP_BIN_ONLY
-            continue;  // experiment builds stop after the bin stage
-#endif
             // scan
             int64_t tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
             rc = pcacc_ensure_tiles(h, tiles);
