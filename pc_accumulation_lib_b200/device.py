@@ -7,6 +7,7 @@ the current stream); every computation happens in libpcacc's sm_100a kernels.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -31,6 +32,35 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise PcaccError(_lib.ERR_CUDA,
                          'no CUDA device: pc_accumulation_lib_b200 has no CPU path')
+
+
+class _PinnedOutPool:
+    """Pinned float16 buffers for results handed to the caller as numpy arrays.  cudaHostAlloc
+    costs about a millisecond per 10 MB, so buffers are recycled: a buffer goes back to the
+    pool when the numpy array created over it (and thereby every view of it) has been
+    collected.  `max_bytes` bounds the pinned memory held by live results; beyond it the
+    caller falls back to a pageable copy."""
+
+    def __init__(self, max_bytes=2 << 30, quantum=1 << 20):
+        self.max_bytes, self.quantum = max_bytes, quantum
+        self.free = {}
+        self.total = 0
+
+    def take(self, nbytes):
+        size = (max(int(nbytes), 1) + self.quantum - 1) // self.quantum * self.quantum
+        lst = self.free.get(size)
+        if lst:
+            return lst.pop()
+        if self.total + size > self.max_bytes:
+            return None
+        self.total += size
+        return torch.empty(size // 2, dtype=torch.float16, pin_memory=True)
+
+    def give(self, buf):
+        self.free.setdefault(buf.numel() * 2, []).append(buf)
+
+
+_OUT_POOL = _PinnedOutPool()
 
 
 class Stager:
@@ -464,20 +494,31 @@ class DeviceCloud:
         return self.planes_to_host_finish(self.planes_to_host_begin(planes))
 
     def planes_to_host_begin(self, planes):
-        """Enqueue the device -> pinned copy; the caller may do host work before `_finish`."""
+        """Enqueue the device -> pinned copy; the caller may do host work before `_finish`.
+        The planes land in a pinned buffer of their own (drawn from a pool, returned to it
+        when the last numpy view of them is garbage-collected), so no second host copy is
+        needed; beyond the pool's cap they go through one shared pinned buffer and a copy."""
         n = planes.numel()
-        buf = getattr(self, '_pin_out', None)
-        if buf is None or buf.numel() < n:
-            buf = self._pin_out = torch.empty(max(n, 1), dtype=torch.float16, pin_memory=True)
-        view = buf[:n].view(planes.shape)
+        own = _OUT_POOL.take(n * 2)
+        if own is not None:
+            view = own[:n].view(planes.shape)
+        else:
+            buf = getattr(self, '_pin_out', None)
+            if buf is None or buf.numel() < n:
+                buf = self._pin_out = torch.empty(max(n, 1), dtype=torch.float16, pin_memory=True)
+            view = buf[:n].view(planes.shape)
         view.copy_(planes, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return view, ev, planes      # `planes` stays referenced until the copy is done
+        return view, ev, planes, own      # `planes` stays referenced until the copy is done
 
     def planes_to_host_finish(self, pending):
-        view, ev, _ = pending
+        view, ev, _, own = pending
         ev.synchronize()
+        if own is not None:
+            out = view.numpy()              # shares the pinned buffer
+            weakref.finalize(out, _OUT_POOL.give, own)
+            return out
         out = np.empty(tuple(view.shape), dtype=np.float16)
         torch.from_numpy(out).copy_(view)       # multi-threaded for large blocks, unlike ndarray.copy
         return out
