@@ -19,6 +19,7 @@
 // 373-480,737-747; bev_generator/sem_bev.py:54-118,196-257,535-554,593-669;
 // window split + origin shift kitti360_sem_pc_accum.py:179-213.
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -862,16 +863,26 @@ __device__ __forceinline__ uint32_t f_pack(uint32_t rgbs) {
 __device__ __forceinline__ uint32_t f_ge(uint32_t ag, uint32_t b) { return ((ag - b) & F_GUARD) >> 9; }
 
 // per-warp shared-memory state of pass A
-struct SmallWarp {
+// Per-cell arrays are indexed [k][cell]: the lanes of a warp (one cell each, or neighbouring
+// cells in pass 1) then hit consecutive banks.  The shared-memory data pipe is this kernel's
+// busiest unit (ncu: 69 % of its peak), a third of its wavefronts were bank-conflict replays
+// of [cell][k] layouts.
+struct __align__(16) SmallWarp {
     uint32_t val[32 * SMALL_T];      // packed r,g,b of the small cells' points, back to back
+    // ---- zeroed together with 16-byte stores --------------------------------------
+    uint32_t cnt[32];                // four 8-bit counts: road present / future, vehicle present / future
+    unsigned long long fx_hi[2][32], fx_lo[2][32];
+    uint32_t med[6][32];             // lo/hi order statistics: present, future, full
+    // --------------------------------------------------------------------------------
+    unsigned long long zc[2][32];
     uint32_t cs[33];                 // first compacted index of each cell (cs[32] = total)
     uint32_t s0[32];                 // first record of each cell in `sorted`
-    uint32_t n_road[32][2], n_veh[32][2];
-    unsigned long long fx_hi[32][2], fx_lo[32][2], zc[32][2];
-    uint32_t med[32][6];             // lo/hi order statistics: present, future, full
     uint8_t meta[32 * SMALL_T];      // cell | window << 5 of each point
     uint8_t np[32], nt[32];
 };
+#define SW_ZERO_BYTES (32 * 4 + 2 * 2 * 32 * 8 + 6 * 32 * 4)
+static_assert(offsetof(SmallWarp, cnt) % 16 == 0 && SW_ZERO_BYTES % 16 == 0 &&
+              offsetof(SmallWarp, zc) == offsetof(SmallWarp, cnt) + SW_ZERO_BYTES, "zeroed block");
 
 // ---------------------------------------------------------------------------
 // pass A: one warp per 32 consecutive cells.  Empty cells take the per-variant
@@ -942,16 +953,13 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     sw.s0[lane] = s01.x;
     sw.np[lane] = (uint8_t)(small ? my_np : 0u);
     sw.nt[lane] = (uint8_t)(small ? my_nt : 0u);
+    {
+        uint4 *z4 = (uint4 *)sw.cnt;
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-        sw.n_road[lane][w] = 0;
-        sw.n_veh[lane][w] = 0;
-        sw.fx_hi[lane][w] = 0;
-        sw.fx_lo[lane][w] = 0;
-        sw.zc[lane][w] = want_max ? 0ull : ~0ull;   // order-encoded -inf / +inf
+        for (int k = 0; k < (SW_ZERO_BYTES / 16 + 31) / 32; k++)
+            if (lane + 32 * k < SW_ZERO_BYTES / 16) z4[lane + 32 * k] = make_uint4(0, 0, 0, 0);
+        sw.zc[0][lane] = sw.zc[1][lane] = want_max ? 0ull : ~0ull;   // order-encoded -inf / +inf
     }
-#pragma unroll
-    for (int k = 0; k < 6; k++) sw.med[lane][k] = 0;
     if (small) {   // tag my points with cell | window << 5
         const uint32_t b = cs_incl - my_nt;
         for (uint32_t j = 0; j < my_nt; j++) sw.meta[b + j] = (uint8_t)(lane | (j >= my_np ? 32u : 0u));
@@ -968,16 +976,18 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
             const uint4 r = sorted[sw.s0[c] + li];
             sw.val[q] = f_pack(r.z);
             const int sem = (int)(r.z >> 24);
+            uint32_t add = 0;
             if (sem == road_cls) {
                 const long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
-                atomicAdd(&sw.n_road[c][w], 1u);
-                atomicAdd(&sw.fx_hi[c][w], (unsigned long long)(fx >> 32));
-                atomicAdd(&sw.fx_lo[c][w], (unsigned long long)(fx & 0xffffffffll));
+                add = 1u << (8 * w);
+                atomicAdd(&sw.fx_hi[w][c], (unsigned long long)(fx >> 32));
+                atomicAdd(&sw.fx_lo[w][c], (unsigned long long)(fx & 0xffffffffll));
             }
-            if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) atomicAdd(&sw.n_veh[c][w], 1u);
+            if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) add += 1u << (16 + 8 * w);
+            if (add) atomicAdd(&sw.cnt[c], add);   // at most SMALL_T per 8-bit field
             const unsigned long long zc =
                 ord_encode(__longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x)));
-            if (want_max) atomicMax(&sw.zc[c][w], zc); else atomicMin(&sw.zc[c][w], zc);
+            if (want_max) atomicMax(&sw.zc[w][c], zc); else atomicMin(&sw.zc[w][c], zc);
         }
         __syncwarp();
         // pass 2: order statistics without sorting.  Point i occupies the ranks [L_i, E_i) of
@@ -1008,16 +1018,16 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
                 const uint32_t klo = (nw - 1) / 2 * F_ONE, khi = nw / 2 * F_ONE;
                 const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
                 const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
-                if (m) atomicOr(&sw.med[c][2 * wi], vi & m);
-                if (h) atomicOr(&sw.med[c][2 * wi + 1], vi & h);
+                if (m) atomicOr(&sw.med[2 * wi][c], vi & m);
+                if (h) atomicOr(&sw.med[2 * wi + 1][c], vi & h);
             }
             {   // full cell
                 const uint32_t E = e1 + e2, L = nt * F_ONE - (g1 + g2);
                 const uint32_t klo = (nt - 1) / 2 * F_ONE, khi = nt / 2 * F_ONE;
                 const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
                 const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
-                if (m) atomicOr(&sw.med[c][4], vi & m);
-                if (h) atomicOr(&sw.med[c][5], vi & h);
+                if (m) atomicOr(&sw.med[4][c], vi & m);
+                if (h) atomicOr(&sw.med[5][c], vi & h);
             }
         }
         __syncwarp();
@@ -1028,19 +1038,24 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     uint32_t nr[2], nv[2];
     long long hi[2], lo[2];
     double ez[2];
+    {
+        const uint32_t cw4 = sw.cnt[lane];
+        nr[0] = cw4 & 255u;
+        nr[1] = (cw4 >> 8) & 255u;
+        nv[0] = (cw4 >> 16) & 255u;
+        nv[1] = cw4 >> 24;
+    }
 #pragma unroll
     for (int w = 0; w < 2; w++) {
-        nr[w] = sw.n_road[lane][w];
-        nv[w] = sw.n_veh[lane][w];
-        hi[w] = (long long)sw.fx_hi[lane][w];
-        lo[w] = (long long)sw.fx_lo[lane][w];
-        ez[w] = ord_decode(sw.zc[lane][w]);   // an empty window keeps the identity of min / max
+        hi[w] = (long long)sw.fx_hi[w][lane];
+        lo[w] = (long long)sw.fx_lo[w][lane];
+        ez[w] = ord_decode(sw.zc[w][lane]);   // an empty window keeps the identity of min / max
     }
     int med2[3][3];
 #pragma unroll
     for (int w = 0; w < 3; w++) {
         // lo + hi per 10-bit field in one add (at most 510 per field)
-        const uint32_t sm = sw.med[lane][2 * w] + sw.med[lane][2 * w + 1];
+        const uint32_t sm = sw.med[2 * w][lane] + sw.med[2 * w + 1][lane];
 #pragma unroll
         for (int c = 0; c < 3; c++) med2[w][c] = (int)((sm >> (10 * c)) & 1023u);
     }
