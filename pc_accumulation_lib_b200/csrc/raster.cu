@@ -663,12 +663,24 @@ k_bev_scatter(uint32_t *__restrict__ cursor, const uint32_t *__restrict__ tmp_ke
     // the reduction reads.  The order inside a segment is arbitrary (see the file header).
     unsigned long long n = *n_append;
     if (n > (unsigned long long)cap) n = (unsigned long long)cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * 256) {
-        const uint32_t key = tmp_key[i];
-        if (key == KEY_INVALID) continue;
-        const uint4 rec = tmp_rec[i];
-        sorted[atomicSub(&cursor[key], 1u) - 1u] = rec;
+    // Records arrive in point order, and neighbouring lidar returns often fall into the same
+    // cell: the lanes of a warp that hold the same key take their slots with ONE atomic (the
+    // cursors of crowded cells are the serial bottleneck of this kernel).
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    const unsigned long long i_first = (unsigned long long)blockIdx.x * 256 + (threadIdx.x & ~31u);
+    for (unsigned long long iw = i_first; iw < n; iw += stride) {   // warp-uniform trip count
+        const unsigned long long i = iw + lane;
+        const uint32_t key = i < n ? tmp_key[i] : KEY_INVALID;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (key != KEY_INVALID) rec = tmp_rec[i];
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t cnt = (uint32_t)__popc(peers), rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if ((int)lane == leader && key != KEY_INVALID) base = atomicSub(&cursor[key], cnt) - cnt;
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key != KEY_INVALID) sorted[base + rank] = rec;
     }
 }
 
