@@ -266,6 +266,8 @@ k_bev_classify(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ uint32_t s_tiles[BIN_MAXF + 1];
     __shared__ uint32_t s_warp[BIN_BLOCK / 32];
+    __shared__ double s_A[MAX_VGROUP][8];
+    __shared__ int s_vpb;
     __shared__ unsigned long long s_base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
@@ -278,12 +280,17 @@ k_bev_classify(BinArgs a) {
         constexpr int PER = BIN_MAXF / BIN_BLOCK;
         uint32_t loc[PER];
         uint32_t sum = 0;
+        const bool mine = (int)threadIdx.x * PER <= a.n_frames;   // few threads own frames
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int f = (int)threadIdx.x * PER + k;
-            const uint32_t t = f < a.n_frames ? a.frame_tiles[f] : 0u;  // 0 = empty or culled
-            loc[k] = sum;
-            sum += t;
+        for (int k = 0; k < PER; k++) loc[k] = 0;
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int f = (int)threadIdx.x * PER + k;
+                const uint32_t t = f < a.n_frames ? a.frame_tiles[f] : 0u;  // 0 = empty or culled
+                loc[k] = sum;
+                sum += t;
+            }
         }
         uint32_t incl = sum;
 #pragma unroll
@@ -298,20 +305,39 @@ k_bev_classify(BinArgs a) {
         for (int w = 0; w < BIN_BLOCK / 32; w++)
             if (w < (int)warp) wbase += s_warp[w];
         const uint32_t excl = wbase + incl - sum;
+        if (mine) {
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int f = (int)threadIdx.x * PER + k;
-            if (f <= a.n_frames) s_tiles[f] = excl + loc[k];
+            for (int k = 0; k < PER; k++) {
+                const int f = (int)threadIdx.x * PER + k;
+                if (f <= a.n_frames) s_tiles[f] = excl + loc[k];
+            }
         }
         __syncthreads();
     }
     const uint32_t total_tiles = s_tiles[a.n_frames];
     if (total_tiles == 0) return;
-    // spread the variants over several work items until the chip is filled
-    int groups = (int)((2u * gridDim.x + total_tiles - 1) / total_tiles);
-    groups = max(1, min(groups, a.n_var));
-    const int vpb = (a.n_var + groups - 1) / groups;
-    groups = (a.n_var + vpb - 1) / vpb;
+    // A work item = one tile x a group of vpb variants.  Few variants per item spread the work
+    // over more blocks but re-read the tile for every group; the block with the most items sets
+    // the kernel's duration, so pick the vpb that minimises  max items per block x (vpb + cost
+    // of loading a tile, about three variant tests).
+    if (threadIdx.x == 0) {
+        uint32_t best = 0xffffffffu;
+        int pick = a.n_var;
+        for (int c = 1; c <= a.n_var; c = (c < a.n_var && 2 * c > a.n_var) ? a.n_var : 2 * c) {
+            const uint32_t g = (uint32_t)((a.n_var + c - 1) / c);
+            const uint32_t per_block = (total_tiles * g + gridDim.x - 1) / gridDim.x;
+            const uint32_t cost = per_block * (uint32_t)(c + 3);
+            if (cost < best) {
+                best = cost;
+                pick = c;
+            }
+            if (c == a.n_var) break;
+        }
+        s_vpb = pick;
+    }
+    __syncthreads();
+    const int vpb = s_vpb;
+    const int groups = (a.n_var + vpb - 1) / vpb;
     const uint32_t n_items = total_tiles * (uint32_t)groups;
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -329,13 +355,23 @@ k_bev_classify(BinArgs a) {
         const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
         const int64_t off = a.frame_off[slot];
         const FrameVar *fv = a.fvar + (int64_t)fl * a.n_var;
+        // the item's candidate maps go to shared memory in one cooperative load: read from
+        // global inside the variant loop, each was a dependent L2 round trip ahead of its tests
+        const bool staged = a.n_var > 1;   // a single variant reads its map directly (no barriers)
+        if (staged) {
+            __syncthreads();   // the previous item's readers are done
+            for (int k = threadIdx.x; k < (v_end - v_begin) * 8; k += BIN_BLOCK)
+                s_A[k >> 3][k & 7] = fv[v_begin + (k >> 3)].A[k & 7];
+            __syncthreads();
+        }
         // z is only streamed when some variant's map mixes it into x / y (a lazily re-based
         // frame, or a rotation that is not about the z axis)
         bool need_z = false;
         for (int v = v_begin; v < v_end; v++) {
             const pcacc_bev_params &bp = s_par[v];
             if (fid >= bp.frame_begin && fid < bp.frame_end)
-                need_z = need_z || (fv[v].A[2] != 0.0) || (fv[v].A[6] != 0.0);
+                need_z = need_z || (staged ? (s_A[v - v_begin][2] != 0.0) || (s_A[v - v_begin][6] != 0.0)
+                                           : (fv[v].A[2] != 0.0) || (fv[v].A[6] != 0.0));
         }
 
         // 4 points per thread: two pairs of neighbours (16 B loads; frame offsets are
@@ -365,7 +401,7 @@ k_bev_classify(BinArgs a) {
             const double lim = __dmul_rn(0.5, bp.view) + GUARD_M;
             double A[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) A[k] = fv[v].A[k];
+            for (int k = 0; k < 8; k++) A[k] = staged ? s_A[v - v_begin][k] : fv[v].A[k];
             unsigned cmask = 0;
 #pragma unroll
             for (int k = 0; k < BIN_ITEMS; k++) {
