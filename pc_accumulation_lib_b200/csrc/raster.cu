@@ -495,6 +495,7 @@ k_bev_bin(BinArgs a) {
     if (n > (unsigned long long)a.cap) n = (unsigned long long)a.cap;
     const int PP = a.P * a.P;
     const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    const int slot_lo = (int)(a.frame_lo % a.max_frames);
 
     // exact evaluation of one candidate whose point data is already in registers
     auto process = [&](unsigned long long c, uint32_t gi32, uint32_t meta, double x, double y, double z,
@@ -502,7 +503,9 @@ k_bev_bin(BinArgs a) {
         const int64_t gi = (int64_t)gi32;
         const int v = (int)(meta & 255u);
         const int64_t fid = a.frame_lo + (int64_t)(meta >> 8);
-        const int slot = (int)(fid % a.max_frames);
+        // (frame_lo + f) % max_frames without a 64-bit division per candidate (f < max_frames)
+        int slot = slot_lo + (int)(meta >> 8);
+        if (slot >= a.max_frames) slot -= a.max_frames;
         const pcacc_bev_params &bp = s_par[v];
         const double pv = s_pv[v];
         const int64_t e0 = a.frame_epoch[slot];
