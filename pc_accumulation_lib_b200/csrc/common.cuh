@@ -220,13 +220,24 @@ __device__ __forceinline__ void aabb_update(unsigned long long *aabb, bool keep,
 template <int BLOCK>
 __device__ __forceinline__ void aabb_update_v(unsigned long long *aabb, double (&v)[6]) {
     __shared__ double s_bb[BLOCK / 32][6];
+    // warp min / max on the order-encoded halves with the REDUX unit (two reductions per
+    // value) instead of five 64-bit shuffle + fmin steps: this reduction was a third of the
+    // integrate kernels' instructions
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            v[k] = fmin(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
-            v[3 + k] = fmax(v[3 + k], __shfl_xor_sync(0xffffffffu, v[3 + k], o));
+    for (int k = 0; k < 6; k++) {
+        double x = v[k];
+        if (x != x) x = k < 3 ? INFINITY : -INFINITY;   // NaN: the identity, as fmin / fmax had it
+        const unsigned long long u = ord_encode(x);
+        const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+        unsigned mh, ml;
+        if (k < 3) {
+            mh = __reduce_min_sync(0xffffffffu, hi);
+            ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        } else {
+            mh = __reduce_max_sync(0xffffffffu, hi);
+            ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
         }
+        v[k] = ord_decode(((unsigned long long)mh << 32) | ml);
     }
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (lane == 0) {
