@@ -1145,6 +1145,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     if (fin) {
         const __half *lut16 = (const __half *)(lut + LUT_TOTAL);
         __half *ob = out16 + o0;
+        const __half eh_rgb = cst.empty_h[2], eh_z = cst.empty_h[3];
 #pragma unroll
         for (int w = 0; w < 3; w++) {
             const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
@@ -1163,13 +1164,21 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
                 plane[6] = ne ? zz : cst.empty[6];
                 store_planes<true>(out16, out64, o0 + (int64_t)ow, PP, plane);
             } else {
-                ob[ow] = lut16[di + nrw];
-                ob[ow + (size_t)PP] = __double2half(I[w]);
+                // branch-free: the table is read for empty windows too (index 0) and the
+                // per-variant fill value selected afterwards
+                __half h[7];
+                h[0] = lut16[di + nrw];
+                h[1] = __double2half(I[w]);
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    ob[ow + (size_t)(2 + k) * PP] = ne ? lut16[med2[w][k]] : cst.empty_h[2];
-                ob[ow + (size_t)5 * PP] = lut16[di + nvw];
-                ob[ow + (size_t)6 * PP] = ne ? __double2half(zz) : cst.empty_h[3];
+                for (int k = 0; k < 3; k++) {
+                    const __half t = lut16[med2[w][k]];
+                    h[2 + k] = ne ? t : eh_rgb;
+                }
+                h[5] = lut16[di + nvw];
+                const __half hz = __double2half(zz);
+                h[6] = ne ? hz : eh_z;
+#pragma unroll
+                for (int p = 0; p < 7; p++) ob[ow + (size_t)p * PP] = h[p];
             }
         }
     }
