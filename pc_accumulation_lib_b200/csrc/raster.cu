@@ -1146,6 +1146,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
         const __half *lut16 = (const __half *)(lut + LUT_TOTAL);
         __half *ob = out16 + o0;
         const __half eh_rgb = cst.empty_h[2], eh_z = cst.empty_h[3];
+        __half *op = ob;
 #pragma unroll
         for (int w = 0; w < 3; w++) {
             const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
@@ -1177,8 +1178,12 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
                 h[5] = lut16[di + nvw];
                 const __half hz = __double2half(zz);
                 h[6] = ne ? hz : eh_z;
+                // the 21 planes of a cell are PP elements apart: walk one pointer
 #pragma unroll
-                for (int p = 0; p < 7; p++) ob[ow + (size_t)p * PP] = h[p];
+                for (int p = 0; p < 7; p++) {
+                    *op = h[p];
+                    op += PP;
+                }
             }
         }
     }
