@@ -518,15 +518,19 @@ k_bev_bin(BinArgs a) {
         // the exact path below.  err: 16 float ulps of the sum of the term magnitudes covers
         // the roundings of A -> float, p -> float and the three FMAs.
         if (bp.R[6] == 0.0 && bp.R[7] == 0.0 && bp.R[8] == 1.0) {
-            const FrameVar &fv = a.fvar[(int64_t)(meta >> 8) * a.n_var + v];
+            // the float32 map of this (frame, variant): two 16-byte loads (32-bit index math:
+            // frames x variants of a launch is far below 2^31)
+            const float4 *af4 = (const float4 *)a.fvar[(meta >> 8) * (uint32_t)a.n_var + (uint32_t)v].Af;
+            const float4 r0 = af4[0], r1 = af4[1];
             const float xf = (float)x, yf = (float)y, zf = (float)z;
-            const float q0 = fmaf(fv.Af[0], xf, fmaf(fv.Af[1], yf, fmaf(fv.Af[2], zf, fv.Af[3])));
-            const float q1 = fmaf(fv.Af[4], xf, fmaf(fv.Af[5], yf, fmaf(fv.Af[6], zf, fv.Af[7])));
-            const float m0 = 1e-5f + 9.6e-7f * (fabsf(fv.Af[0] * xf) + fabsf(fv.Af[1] * yf) +
-                                               fabsf(fv.Af[2] * zf) + fabsf(fv.Af[3]) + (float)bp.view);
-            const float m1 = 1e-5f + 9.6e-7f * (fabsf(fv.Af[4] * xf) + fabsf(fv.Af[5] * yf) +
-                                               fabsf(fv.Af[6] * zf) + fabsf(fv.Af[7]) + (float)bp.view);
-            const float hvf = 0.5f * (float)bp.view;
+            const float q0 = fmaf(r0.x, xf, fmaf(r0.y, yf, fmaf(r0.z, zf, r0.w)));
+            const float q1 = fmaf(r1.x, xf, fmaf(r1.y, yf, fmaf(r1.z, zf, r1.w)));
+            const float viewf = (float)bp.view;
+            const float m0 = 1e-5f + 9.6e-7f * (fabsf(r0.x * xf) + fabsf(r0.y * yf) + fabsf(r0.z * zf) +
+                                               fabsf(r0.w) + viewf);
+            const float m1 = 1e-5f + 9.6e-7f * (fabsf(r1.x * xf) + fabsf(r1.y * yf) + fabsf(r1.z * zf) +
+                                               fabsf(r1.w) + viewf);
+            const float hvf = 0.5f * viewf;
             const float d0 = hvf - fabsf(q0), d1 = hvf - fabsf(q1);   // > 0 inside the view
             if (d0 < -m0 || d1 < -m1) {
                 // certainly outside the view (the guard band let it through): not binned
