@@ -458,6 +458,7 @@ def run_ours(args, rank, world, local_rank, dist):
             # configs[4]: 1024x1024, elevation max, 100 frames (12 M resident points)
             extra['highres_1024'] = c3_extra(torch, DeviceCloud, pk, F=100, P=1024, elevation_max=True)
             extra['input_side'] = input_side_extra(torch, DeviceCloud, pk)
+            extra['kitti360_sequence'] = kitti_seq_extra(torch)
 
     if rank == 0:
         line = {
@@ -561,6 +562,60 @@ def c3_extra(torch, DeviceCloud, pk, F=200, P=P, elevation_max=False):
     }
     cloud.close()
     return res
+
+
+def kitti_seq_extra(torch, F=20, present_idx=10):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case — 20 KITTI-360-shaped
+    frames (120,000 points, 1408x376 camera, class map) through
+    Kitti360SemanticPointCloudAccumulator.integrate (numpy in) and one 256x256 BEV
+    (numpy out), with the ICP pose injected; next to the CPU port on one core."""
+    from pc_accumulation_lib_b200 import Kitti360SemanticPointCloudAccumulator
+    frames = []
+    for f in range(F):
+        seed = synth.seed_for(1, f)
+        frames.append(dict(pc=synth.kitti_lidar(seed), T=synth.kitti_step_transform(seed),
+                           rgb=synth.kitti_rgb(seed), cls=synth.kitti_class_map_fast(seed)))
+    n_pts = sum(fr['pc'].shape[0] for fr in frames)
+
+    def run_gpu():
+        acc = Kitti360SemanticPointCloudAccumulator(
+            1e9, synth.kitti_calib(), 1.0, synth.FakeSemseg([fr['cls'] for fr in frames]),
+            synth.KITTI_FILTERS, synth.SEM_IDXS, False, synth.kitti_bev_params(pixel_size=P),
+            ring_capacity_pts=n_pts // 4 + 4096, ring_max_frames=F + 8)
+        acc.sync_each_integrate = False
+        t0 = time.perf_counter()
+        for fr in frames:
+            acc.integrate([(fr['rgb'], fr['pc'], None, fr['T'])])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        bev = acc.generate_bev(present_idx, 1, True)[0]
+        t2 = time.perf_counter()
+        assert bev['rgb_full'].shape == (3, P, P)
+        n_res = acc.cloud.resident_points()
+        acc.cloud.close()
+        return t1 - t0, t2 - t1, n_res
+
+    run_gpu()
+    ti, tb, n_res = min((run_gpu() for _ in range(3)), key=lambda r: r[0] + r[1])
+    from oracle import oracle as orc          # CPU port, the baseline of this row only
+    bp = synth.kitti_bev_params(pixel_size=P)
+    gp = dict(sem_idxs=synth.SEM_IDXS, view_size=bp['view_size'], pixel_size=P,
+              int_scaler=bp['int_scaler'], int_sep_scaler=bp['int_sep_scaler'],
+              int_mid_threshold=bp['int_mid_threshold'], height_filter=bp['height_filter'], rgb_fill=0)
+    cpu = orc.KittiOracle(1e9, synth.kitti_calib()['p_velo_frame'], synth.KITTI_FILTERS, gp)
+    c0 = time.perf_counter()
+    for fr in frames:
+        cpu.integrate(fr['pc'], fr['rgb'], fr['cls'], fr['T'])
+    c1 = time.perf_counter()
+    cpu.generate_bev(present_idx)
+    c2 = time.perf_counter()
+    return {'frames': F, 'points': n_pts, 'resident_points': n_res,
+            'integrate_ms_per_frame': ti / F * 1e3, 'integrate_points_per_s': n_pts / ti,
+            'bev_ms': tb * 1e3,
+            'cpu_port_integrate_ms_per_frame': (c1 - c0) / F * 1e3, 'cpu_port_bev_ms': (c2 - c1) * 1e3,
+            'cpu_port_cores': 1,
+            'note': 'latency-bound by design (SURVEY.md 8d): one 120 k-point frame is 4 MB of traffic; '
+                    'the literal reference takes 50-82 ms per frame and 14.6 s per BEV (BASELINE.md)'}
 
 
 def input_side_extra(torch, DeviceCloud, pk):
