@@ -1248,14 +1248,63 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
         const uint32_t b0 = start[2 * (int64_t)gc], b1 = start[2 * (int64_t)gc + 1],
                        b2 = start[2 * (int64_t)gc + 2];
         const uint32_t np = b1 - b0, nf = b2 - b1, nt = np + nf;
+        // Cells of at most 32 points (one per lane): the rank intervals of pass A with the
+        // values exchanged by shuffles — about n x 10 instructions instead of the ~800 it takes
+        // to clear and scan nine 256-bin histograms.  Larger cells: histograms.
+        const bool medium = nt <= 32;
+        WinAcc a;
+        acc_init(a, want_max);
+        int m2[3][3];
+        if (medium) {
+            const bool have = lane < nt;
+            const uint4 r = have ? sorted[b0 + lane] : make_uint4(0, 0, 0, 0);
+            const int w = lane >= np ? 1 : 0;
+            if (have) acc_record(a, r, w, road_cls, v0, v1, v2, v3, want_max);
+            // per field: guard bit of (vi|G) - vj = (vi >= vj), of (vi|G) - 1 - vj = (vi > vj)
+            const uint32_t vi = f_pack(r.z), vig = vi | F_GUARD, vig1 = vig - F_ONE;
+            uint32_t e1 = 0, l1 = 0, e2 = 0, l2 = 0;
+            for (uint32_t j = 0; j < np; j++) {
+                const uint32_t vj = __shfl_sync(0xffffffffu, vi, (int)j);
+                e1 += ((vig - vj) & F_GUARD) >> 9;
+                l1 += ((vig1 - vj) & F_GUARD) >> 9;
+            }
+            for (uint32_t j = np; j < nt; j++) {
+                const uint32_t vj = __shfl_sync(0xffffffffu, vi, (int)j);
+                e2 += ((vig - vj) & F_GUARD) >> 9;
+                l2 += ((vig1 - vj) & F_GUARD) >> 9;
+            }
+            uint32_t own_lo = 0, own_hi = 0, all_lo = 0, all_hi = 0;
+            if (have) {
+                {   // own window (its size is at least 1: this lane is in it)
+                    const uint32_t nw = w ? nf : np;
+                    const uint32_t E = w ? e2 : e1, L = w ? l2 : l1;
+                    const uint32_t klo = (nw - 1) / 2 * F_ONE, khi = nw / 2 * F_ONE;
+                    own_lo = vi & ((f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu);
+                    own_hi = vi & ((f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu);
+                }
+                {   // full cell
+                    const uint32_t E = e1 + e2, L = l1 + l2;
+                    const uint32_t klo = (nt - 1) / 2 * F_ONE, khi = nt / 2 * F_ONE;
+                    all_lo = vi & ((f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu);
+                    all_hi = vi & ((f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu);
+                }
+            }
+            // every point that holds the wanted rank carries the same value: OR them together
+            uint32_t sm[3];
+            sm[0] = __reduce_or_sync(0xffffffffu, w == 0 ? own_lo : 0u) + __reduce_or_sync(0xffffffffu, w == 0 ? own_hi : 0u);
+            sm[1] = __reduce_or_sync(0xffffffffu, w == 1 ? own_lo : 0u) + __reduce_or_sync(0xffffffffu, w == 1 ? own_hi : 0u);
+            sm[2] = __reduce_or_sync(0xffffffffu, all_lo) + __reduce_or_sync(0xffffffffu, all_hi);
+#pragma unroll
+            for (int ww = 0; ww < 3; ww++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) m2[ww][c] = (int)((sm[ww] >> (10 * c)) & 1023u);
+        } else {
         {
             uint4 *h4 = (uint4 *)&hist[0][0][0];
 #pragma unroll
             for (int k = 0; k < 12; k++) h4[lane + 32 * k] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
-        WinAcc a;
-        acc_init(a, want_max);
         for (uint32_t i0 = 0; i0 < nt; i0 += 128) {
             // four independent 16 B loads in flight per lane
             uint4 r[4];
@@ -1277,6 +1326,7 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
                 }
             }
         }
+        }   // histogram path: records
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             a.n_road[w] = __reduce_add_sync(0xffffffffu, a.n_road[w]);
@@ -1286,7 +1336,7 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
             a.ext_z[w] = want_max ? warp_max_f64(a.ext_z[w]) : warp_min_f64(a.ext_z[w]);
         }
         __syncwarp();
-        int m2[3][3];
+        if (!medium) {
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             uint32_t cp[8], cf[8];
@@ -1323,6 +1373,7 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
                 m2[w][ch] = v;
             }
         }
+        }   // histogram path: medians
         __syncwarp();
         // lanes 0..2 finalise one window each
         if (lane < 3) {
