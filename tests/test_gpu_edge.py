@@ -273,3 +273,55 @@ def test_probability_map_integrate(dev):
     np.testing.assert_array_equal(b, want)
     assert 0 < c.shape[0] < b.shape[0]            # max_depth drops the far points
     cloud.close()
+
+
+def test_cell_population_sweep(dev):
+    """Every per-cell population from 1 to 70 points, present / future split at every
+    position, colours drawn from a handful of values (ties, even / odd counts): the three
+    reduction paths (rank intervals in pass A up to 15 points, rank intervals over shuffles
+    up to 32, histograms above) against the oracle, planes compared exactly."""
+    from tests.test_gpu_core import bev_params_from, compare_planes, gen_params
+    P, view = 32, 32.0                       # 1 m cells
+    rng = np.random.default_rng(4242)
+    palette = np.array([0, 3, 3, 128, 200, 255, 255, 17])
+    pres, fut = [], []
+    cell = 0
+    for n in range(1, 71):
+        for split in sorted({0, 1, n // 2, n - 1, n}):
+            cx, cy = cell % (P - 2) + 1, cell // (P - 2) + 1       # keep off the border
+            cell += 1
+            pts = np.zeros((n, 10))
+            pts[:, 0] = (cx + rng.uniform(0.1, 0.9, n)) - P / 2
+            pts[:, 1] = (cy + rng.uniform(0.1, 0.9, n)) - P / 2
+            pts[:, 2] = rng.normal(0., 1., n)
+            pts[:, 3] = rng.integers(0, 256, n) / 255.
+            pts[:, 4:7] = palette[rng.integers(0, len(palette), (n, 3))]
+            pts[:, 7] = rng.choice([synth.SEM_IDXS['road'], synth.SEM_IDXS['car'], 8, 2], n)
+            pts[:, 9] = (rng.random(n) < 0.1).astype(float)
+            pres.append(pts[:split])
+            fut.append(pts[split:])
+    assert cell <= (P - 2) * (P - 2)
+    pc_p, pc_f = np.concatenate(pres), np.concatenate(fut)
+    pcs = dict(pc_present=pc_p, pc_future=pc_f, pc_full=np.concatenate([pc_p, pc_f]))
+    ego = [np.array([[0., -2., 0.], [0., -1., 0.], [0., 0., 0.]]), np.array([[0., 0., 0.], [0., 1., 0.]])]
+    trajs = dict(ego_traj_present=ego[0], ego_traj_future=ego[1], ego_traj_full=np.concatenate(ego),
+                 other_trajs_present=[], other_trajs_future=[], other_trajs_full=[])
+    gp = gen_params(synth.kitti_bev_params(pixel_size=P, view_size=view))
+    cloud = dev.DeviceCloud(capacity_pts=pcs['pc_full'].shape[0] + 64, max_frames=8)
+    f0 = cloud.integrate_cloud(pc_p)
+    f1 = cloud.integrate_cloud(pc_f)
+    assert cloud.sync() & ~2 == 0
+    bp = bev_params_from(dev, gp, f0, f1, f1 + 1, np.zeros(3), 0.0)
+    o16, o64, _ = cloud.rasterise([bp], P, want_f64=True)
+    cloud.sync()
+    p2 = {k: v.copy() for k, v in pcs.items()}
+    t2 = {k: ([x.copy() for x in v] if isinstance(v, list) else v.copy()) for k, v in trajs.items()}
+    ref = orc.generate(p2, t2, gp, rot_ang=0.0, do_warping=True, return_f64=True)
+    dbg = ref.pop('_debug')
+    compare_planes(o16[0].cpu().numpy(), o64[0].cpu().numpy(),
+                   {w: dbg[f'planes_f64_{w}'] for w in ('present', 'future', 'full')})
+    # the sweep really covers all three paths
+    counts = np.bincount(dbg['cells_present'][:, 0] * P + dbg['cells_present'][:, 1], minlength=P * P) + \
+        np.bincount(dbg['cells_future'][:, 0] * P + dbg['cells_future'][:, 1], minlength=P * P)
+    assert (counts == 15).any() and (counts == 16).any() and (counts == 32).any() and (counts >= 33).any()
+    cloud.close()
