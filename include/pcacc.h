@@ -262,6 +262,15 @@ int pcacc_preprocess_trajectories(const double *pts, const int32_t *traj_off, in
                                   const double *variants, int n_var, int P, double thresh,
                                   double *out, int32_t *out_cnt);
 
+/* ---- bare events for host-side staging rings -------------------------------
+ * The binding stages every observation through reusable pinned buffers and must know when
+ * the kernels that read a buffer are done before it overwrites it: one event recorded per
+ * integrate on the caller's stream (timing disabled), waited for two integrates later. */
+int pcacc_event_create(void **event);
+int pcacc_event_record(void *event, void *stream);
+int pcacc_event_sync(void *event);   /* NULL: nothing to wait for */
+int pcacc_event_destroy(void *event);
+
 /* ---- the dataloader's input side ----------------------
  * What produces the (N,7) rows and pc_cam_idx that pcacc_integrate_records consumes.
  *

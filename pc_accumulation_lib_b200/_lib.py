@@ -82,6 +82,10 @@ SIGNATURES = {
     'pcacc_raster_stats': (_i32, [_vp, C.POINTER(_i64 * 3), _vp]),
     'pcacc_crop_trajectory': (_i32, [_vp, _i32, _dbl, _dbl, _vp, C.POINTER(_i32)]),
     'pcacc_preprocess_trajectories': (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _dbl, _vp, _vp]),
+    'pcacc_event_create': (_i32, [C.POINTER(_vp)]),
+    'pcacc_event_record': (_i32, [_vp, _vp]),
+    'pcacc_event_sync': (_i32, [_vp]),
+    'pcacc_event_destroy': (_i32, [_vp]),
     'pcacc_assign_boxes': (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_project_cameras': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_profile': (_i32, [_vp, _i32]),

@@ -125,6 +125,33 @@ FrameHost *pcacc_frame(pcacc_t h, int64_t frame_id) {
     return &h->frames[(int)(frame_id % h->max_frames)];
 }
 
+// ---------------------------------------------------------------------------
+// bare events for the host-side staging ring (an Event.record() through PyTorch costs a
+// current_stream() lookup of ~25 us per call; the staging path records one per integrate)
+// ---------------------------------------------------------------------------
+extern "C" int pcacc_event_create(void **event) {
+    if (!event) return PCACC_ERR_ARG;
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return PCACC_ERR_CUDA;
+    }
+    *event = (void *)e;
+    return PCACC_OK;
+}
+extern "C" int pcacc_event_record(void *event, void *stream) {
+    if (!event) return PCACC_ERR_ARG;
+    return cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream) == cudaSuccess ? PCACC_OK : PCACC_ERR_CUDA;
+}
+extern "C" int pcacc_event_sync(void *event) {
+    if (!event) return PCACC_OK;
+    return cudaEventSynchronize((cudaEvent_t)event) == cudaSuccess ? PCACC_OK : PCACC_ERR_CUDA;
+}
+extern "C" int pcacc_event_destroy(void *event) {
+    if (event) cudaEventDestroy((cudaEvent_t)event);
+    return PCACC_OK;
+}
+
 extern "C" const char *pcacc_strerror(int status) {
     switch (status) {
         case PCACC_OK: return "ok";

@@ -77,8 +77,21 @@ class Stager:
         self.device = device
         self._slots = {}     # key -> [[pinned, device, event, ...], [pinned, device, event, ...], turn]
         self._touched = []
-        self._events = [torch.cuda.Event() for _ in range(4)]
+        # bare CUDA events from libpcacc (see pcacc_event_record): four, used in turn
+        self._lib = _lib.load()
+        self._events = []
+        for _ in range(4):
+            ev = C.c_void_p()
+            check(self._lib.pcacc_event_create(C.byref(ev)))
+            self._events.append(ev)
         self._ev_turn = 0
+
+    def __del__(self):
+        try:
+            for ev in self._events:
+                self._lib.pcacc_event_destroy(ev)
+        except Exception:
+            pass
 
     def _slot(self, key, nbytes, need_dev):
         ring = self._slots.get(key)
@@ -89,11 +102,9 @@ class Stager:
         sl = ring[turn]
         if sl is None or sl[0].numel() < nbytes or (need_dev and sl[1] is None):
             cap = max(nbytes, 1) * 5 // 4 + 64
-            ev = torch.cuda.Event()
-            ev.record()
             sl = ring[turn] = [torch.empty(cap, dtype=torch.uint8, pin_memory=True),
                                torch.empty(cap, dtype=torch.uint8, device=self.device)
-                               if need_dev else None, ev]
+                               if need_dev else None, None]     # no reader yet: nothing to wait for
         return sl
 
     def put(self, key, arr, mapped=False):
@@ -118,7 +129,8 @@ class Stager:
             sl += [sig, pin_v, dev_v]
         pin_v, dev_v = sl[4], sl[5]
         if nbytes:
-            sl[2].synchronize()     # everything that read this buffer two puts ago is done
+            if sl[2] is not None:   # everything that read this buffer two puts ago is done
+                self._lib.pcacc_event_sync(sl[2])
             pin_v.copy_(t)          # torch splits large host copies over its thread pool
             if not mapped:
                 dev_v.copy_(pin_v, non_blocking=True)
@@ -128,14 +140,14 @@ class Stager:
     def fence(self):
         """Call after enqueuing the kernels that consume the buffers put since the last fence.
         One event per fence (a ring of four: a slot is reused two fences later), recorded on
-        an explicitly looked-up stream — Event.record() without one costs a
-        torch.cuda.current_stream() call (~25 us) per slot."""
+        torch's current stream through libpcacc — Event.record() costs a
+        torch.cuda.current_stream() call (~25 us)."""
         if not self._touched:
             return
         ring = self._events
         ev = ring[self._ev_turn]
         self._ev_turn = (self._ev_turn + 1) % len(ring)
-        ev.record(torch.cuda.current_stream(self.device))
+        check(self._lib.pcacc_event_record(ev, _stream()))
         for sl in self._touched:
             sl[2] = ev
         self._touched = []
