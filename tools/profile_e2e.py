@@ -41,3 +41,4 @@ pr.enable()
 run()
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(28)
+pstats.Stats(pr).sort_stats('tottime').print_stats(22)
