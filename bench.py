@@ -139,18 +139,17 @@ def variant_params(acc, rng):
     """The 32 pcacc_bev_params of one scene, exactly what generate_bev would use."""
     gen = acc.sem_bev_generator
     first, n = acc._fids[0], len(acc._fids)
-    out = []
+    out, aug = [], []
     for p in PRESENT_IDXS:
         origin = np.array(acc.poses[p])
-        ego_present = np.concatenate([acc.poses[:p]]) - origin
         for _ in range(BEVS_PER_PRESENT):
             gen.rng = rng
             a = gen.rand_aug_params()
             out.append(gen._bev_params(first + 0, first + p, first + n, origin, a['rot_ang'],
                                        a['trans_dx'], a['trans_dy'],
                                        a['zoom_scalar'] * gen.view_size))
-        del ego_present
-    return out
+            aug.append((p, a))
+    return out, aug
 
 
 def run_ours(args, rank, world, local_rank, dist):
@@ -166,33 +165,35 @@ def run_ours(args, rank, world, local_rank, dist):
     bevs_per_scene = len(PRESENT_IDXS) * BEVS_PER_PRESENT
 
     # ---- e2e objects: public API, host buffers ---------------------------------
+    from pc_accumulation_lib_b200.device import pin_observation
     semseg = HostSemseg()
-    for sc in scenes:
-        for o in sc:
-            for img, cls in zip(o['images'], o['_semseg']):
-                semseg.by_id[id(img)] = cls
-    acc = NuScenesOracleSemanticPointCloudAccumulator(
-        semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None, bev_setup(),
-        ring_capacity_pts=n_in_scene + 4096, ring_max_frames=N_SWEEPS + 8, device=local_rank)
-    # data-error flags are checked at the next synchronising call (generate_bev) instead of
-    # after every sweep, so the staging of sweep k+1 overlaps the kernels of sweep k
-    acc.sync_each_integrate = False
+    # the same scenes in page-locked memory (what a dataloader / semseg stand-in that writes
+    # into `pinned_empty` buffers hands over): read by the kernels in place, no host copy
+    scenes_pin = [[pin_observation(o) for o in sc] for sc in scenes]
+    for group in (scenes, scenes_pin):
+        for sc in group:
+            for o in sc:
+                for img, cls in zip(o['images'], o['_semseg']):
+                    semseg.by_id[id(img)] = cls
 
-    def new_scene_state():
-        acc.cloud.reset()
-        acc._fids, acc.poses, acc.seg_dists, acc.rgbs, acc.semsegs = [], [], [], [], []
-        acc.T_global_world = None
-        acc.instances, acc.dyn_instances, acc.token2idx, acc.ts = {}, [], [], 0
-        acc.ego_global_xs, acc.ego_global_ys = [], []
+    def new_acc():
+        a = NuScenesOracleSemanticPointCloudAccumulator(
+            semseg, synth.NUSC_FILTERS, synth.SEM_IDXS, None, bev_setup(),
+            ring_capacity_pts=n_in_scene + 4096, ring_max_frames=N_SWEEPS + 8, device=local_rank)
+        # data-error flags are checked at the next synchronising call (generate_bev) instead of
+        # after every sweep, so the host runs ahead of the kernels
+        a.sync_each_integrate = False
+        return a
 
+    acc = new_acc()
     marks = []          # per distinct scene: per sweep (rel frame ids, inst idx)
     params = []         # per distinct scene: 32 BevParams (frame ids relative to 0)
+    augs = []           # per distinct scene: the (present_idx, augmentation) of every BEV
     n_keep = []
 
-    def e2e_scene(k, record=False):
+    def e2e_scene(acc, sc, k, record=False):
         """One scene through the reference-facing API; returns #BEVs produced."""
-        new_scene_state()
-        sc = scenes[k]
+        acc.reset()
         log = []
         if record:
             orig = acc.cloud.mark_dynamic
@@ -204,12 +205,14 @@ def run_ours(args, rank, world, local_rank, dist):
             first = acc._fids[0]
             marks.append([([f - first for f in fs], ii) for fs, ii in log])
             rng = np.random.RandomState(1234 + k)
-            ps = variant_params(acc, rng)
+            ps, aa = variant_params(acc, rng)
             for q in ps:
                 q.frame_begin -= first
                 q.frame_split -= first
                 q.frame_end -= first
             params.append(ps)
+            augs.append(aa)
+            acc._sync()                      # exact kept counts (unsynced: the upper bound n_in)
             n_keep.append(acc.cloud.resident_points())
         n = 0
         acc.sem_bev_generator.rng = np.random.RandomState(99 + k)
@@ -219,8 +222,9 @@ def run_ours(args, rank, world, local_rank, dist):
             assert bevs[0]['rgb_full'].shape == (3, P, P)
         return n
 
-    for k in range(N_DISTINCT):            # also the e2e warm-up
-        assert e2e_scene(k, record=True) == bevs_per_scene
+    for k in range(N_DISTINCT):            # also the e2e warm-up (pageable -> sparse staging)
+        assert e2e_scene(acc, scenes[k], k, record=True) == bevs_per_scene
+    staging_pageable = acc.cloud.last_staging
 
     # ---- device-resident copies of the inputs (value path) ------------------------
     def to_dev(sc):
@@ -413,41 +417,100 @@ def run_ours(args, rank, world, local_rank, dist):
     roofline_path = {'achieved': path_ach, 'peak': peak, 'unit': 'GB/s', 'frac': path_ach / peak,
                      'frac_of_nominal_8TBps': path_ach / 8000.0,
                      'bytes_per_step': b_step,
-                     'note': 'all algorithmic bytes of the step (integrate + rasterise) / step time; the '
-                             '32 BEVs of a scene re-read the same ~9 MB of resident points, which '
-                             'stay in the 126 MB L2, so this can exceed the HBM peak'}
+                     'resident_points_per_scene': n_res,
+                     'note': 'all algorithmic bytes of the step (integrate + rasterise, SURVEY.md 8d: '
+                             '49 N_in + 7 N_vis + 37 N_keep per sweep, 33 N_res + 42 P^2 per BEV) / step time'}
     gpu_launches = int(sum(v[1] for v in prof.values()))
 
     # ---- e2e: public API, host buffers, copies inside the timed region ---------------
+    # Scenes are independent (one accumulator per scene, run_nuscenes_bev_gen.py:165,203), so the
+    # generation loop may keep several in flight: `--e2e-threads` Python threads, each with its
+    # own accumulator and CUDA stream, take the step's scenes round-robin; while one waits for
+    # its BEV planes to arrive in host memory another runs its integrate() calls.
     e2e_scenes = max(1, min(S, args.e2e_scenes))
-    barrier()
-    t0 = time.perf_counter()
-    n_b = 0
-    for _ in range(args.e2e_steps):
-        for s in range(e2e_scenes):
-            n_b += e2e_scene(s % N_DISTINCT)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    e2e_pts = world * e2e_scenes * args.e2e_steps * n_in_scene / dt
-    h2d = sum(o['pc'].nbytes + o['pc_cam_idx'].nbytes + sum(i.nbytes for i in o['images'])
-              + sum(c.nbytes for c in o['_semseg']) for o in scenes[0]) * e2e_scenes
-    d2h = e2e_scenes * bevs_per_scene * 21 * P * P * 2
-    e2e = {'value': e2e_pts, 'unit': 'points/s', 'h2d_bytes_per_step': int(h2d),
-           'd2h_bytes_per_step': int(d2h), 'bevs_per_s': n_b * world / dt,
-           'scenes_per_step': e2e_scenes, 'steps': args.e2e_steps,
-           'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev, numpy in/out '
-                  '(sync_each_integrate=False: error flags checked at generate_bev)'}
+    n_thr = max(1, min(args.e2e_threads, e2e_scenes))
+    accs = [acc] + [new_acc() for _ in range(n_thr - 1)]
+    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(n_thr)]
 
-    # ---- CPU baseline + long-horizon extra (rank 0, N = 1) ---------------------------
+    def e2e_leg(src, steps):
+        counts = [0] * n_thr
+        errors = []
+
+        def worker(t):
+            try:
+                torch.cuda.set_device(local_rank)
+                with torch.cuda.stream(e2e_streams[t]):
+                    for _ in range(steps):
+                        for s_ in range(t, e2e_scenes, n_thr):
+                            counts[t] += e2e_scene(accs[t], src[s_ % N_DISTINCT], s_ % N_DISTINCT)
+                    e2e_streams[t].synchronize()
+            except BaseException as e:      # surfaced by the caller
+                errors.append(e)
+
+        barrier()
+        t0 = time.perf_counter()
+        if n_thr == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_thr)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), sum(counts)
+
+    e2e_leg(scenes_pin, 1)                                   # warm-up of the pinned path and threads
+    dt, n_b = e2e_leg(scenes_pin, args.e2e_steps)
+    staging_pinned = acc.cloud.last_staging
+    dt_pg, n_b_pg = e2e_leg(scenes, max(1, args.e2e_steps // 2))
+    sc0 = scenes[0]
+    host_in = sum(o['pc'].nbytes + o['pc_cam_idx'].nbytes + sum(i.nbytes for i in o['images'])
+                  + sum(c.nbytes for c in o['_semseg']) for o in sc0) * e2e_scenes
+    n_vis_scene = sum(int((o['pc_cam_idx'] >= 0).sum()) for o in sc0)
+    # bytes that cross the bus towards the device per step.  Pinned arrays are read in place:
+    # cam_idx of every point (8 B), the (u, v) sector of every visible point (32 B), the
+    # sectors holding x, y, z, intensity, inst of every kept point (64 B) and the class / rgb
+    # sectors of the visible / kept pixels (32 B each) — counted in 32-byte sectors, the
+    # granularity of a zero-copy read.
+    h2d_direct = e2e_scenes * (8 * n_in_scene + 64 * n_vis_scene + 96 * int(np.mean(n_keep)))
+    h2d_sparse = e2e_scenes * 64 * n_vis_scene            # packed rows + samples of the visible points
+    d2h = e2e_scenes * bevs_per_scene * 21 * P * P * 2
+    stage_name = {1: 'direct (pinned arrays read in place)', 2: 'sparse (visible rows + samples packed into a pinned slot)'}
+    e2e = {'value': world * e2e_scenes * args.e2e_steps * n_in_scene / dt, 'unit': 'points/s',
+           'h2d_bytes_per_step': int(h2d_direct), 'd2h_bytes_per_step': int(d2h),
+           'host_input_bytes_per_step': int(host_in),
+           'bevs_per_s': n_b * world / dt, 'scenes_per_step': e2e_scenes, 'steps': args.e2e_steps,
+           'threads': n_thr, 'staging': stage_name.get(staging_pinned, str(staging_pinned)),
+           'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev: numpy arrays in '
+                  'page-locked host memory in, numpy float16 planes out (sync_each_integrate=False: error '
+                  'flags checked at generate_bev)',
+           'h2d_note': 'inputs live in pinned host memory and are fetched by the integrate kernel over the '
+                       'bus inside the timed region (zero-copy): h2d_bytes_per_step counts the 32-byte sectors '
+                       'it touches; host_input_bytes_per_step is the size of the arrays handed to the API',
+           'pageable_inputs': {
+               'value': world * e2e_scenes * max(1, args.e2e_steps // 2) * n_in_scene / dt_pg,
+               'unit': 'points/s', 'bevs_per_s': n_b_pg * world / dt_pg,
+               'h2d_bytes_per_step': int(h2d_sparse),
+               'staging': stage_name.get(staging_pageable, str(staging_pageable)),
+               'note': 'the same calls with ordinary (pageable) numpy arrays'}}
+
+    # ---- CPU baseline + parity gate + extras (rank 0, N = 1) ---------------------------
     cpu = None
+    parity = None
     extra = {}
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline_sample(scenes[0])
+            # the CPU port runs bench scene 0 with the SAME 32 (present_idx, augmentation) pairs
+            # as the device: its BEVs are the reference values of the parity gate
+            cpu, cpu_bevs, cpu_acc = cpu_baseline_sample(scenes[0], augs[0])
+            parity = parity_gate(torch, clouds[0], scene_pass, outs[0], par_arr[0], cpu_bevs, cpu_acc, augs[0])
         if not args.no_c3:
             del dev_scenes
             outs.clear()
@@ -466,16 +529,10 @@ def run_ours(args, rank, world, local_rank, dist):
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': 'nuscenes-shaped oracle-pose scenes (BASELINE configs[1]) batched as '
-                                   'configs[3]: 40 sweeps x 34688 pts, CAM_FRONT 1600x900, '
-                                   '32 BEVs/scene (8 present idx x 4 aug), 256x256, present/future/full',
-                       'scenes_per_step_per_gpu': S, 'points_per_step_per_gpu': pts_step_rank,
-                       'bevs_per_step_per_gpu': S * bevs_per_scene, 'sharding': 'scenes by rank',
-                       'streams_per_gpu': n_str,
-                       'l2': 'step inputs (%.1f GB resident copies) exceed the 126 MB L2'
-                             % (S * 0.32)},
+            'config': bench_config(S, n_str),
             'bevs_per_s': bevs_per_s, 'e2e': e2e, 'gpu_launches': gpu_launches,
             'roofline': roofline, 'roofline_path': roofline_path, 'clocks': clk,
+            'parity': parity,
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
@@ -622,8 +679,7 @@ def input_side_extra(torch, DeviceCloud, pk):
     """the dataloader's multi-camera projection and box -> point
     assignment for one nuScenes sample (10 sweeps x 34,688 points, 6 cameras, 64 boxes),
     device-resident, next to the same functions of the CPU port on one core."""
-    from tests.golden import cases
-    c = cases.input_side_inputs(n=34688 * 10, n_boxes=64)
+    c = synth.input_side_inputs(n=34688 * 10, n_boxes=64)
     cloud = DeviceCloud(1024, 4)
     pts = torch.from_numpy(c['pc']).cuda()
     pts32 = torch.from_numpy(c['pc_f32']).cuda()
@@ -663,19 +719,41 @@ def input_side_extra(torch, DeviceCloud, pk):
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ---------------------------------------------------------------------------
 _CPU_ACC = None
+WINDOWS = ('present', 'future', 'full')
+WORKLOAD = ('nuscenes-shaped oracle-pose scenes (BASELINE configs[1]) batched as configs[3]: 40 sweeps x '
+            '34688 pts, CAM_FRONT 1600x900, 32 BEVs/scene (8 present idx x 4 aug), 256x256, '
+            'present/future/full')
+
+
+def bev_planes(bev):
+    """(3 windows, 7 planes, P, P) float16 of one BEV dict, in libpcacc's plane order."""
+    return np.stack([np.concatenate([bev[f'road_{w}'][None], bev[f'intensity_{w}'][None], bev[f'rgb_{w}'],
+                                     bev[f'dynamic_{w}'][None], bev[f'elevation_{w}'][None]]) for w in WINDOWS])
 
 
 def _cpu_bev(job):
     p, aug = job
-    _CPU_ACC.generate_bev(p, **aug)
-    return 1
+    return bev_planes(_CPU_ACC.generate_bev(p, **aug))
 
 
-def cpu_scene(scene, n_sweeps, present_idxs, rng, workers=1):
+def draw_jobs(rng, present_idxs):
+    jobs = []
+    for p in present_idxs:
+        for _ in range(BEVS_PER_PRESENT):
+            rot = 2 * np.pi * rng.random_sample()
+            r, a = 5.0 * rng.random_sample(), 2 * np.pi * rng.random_sample()
+            z = 1 + min(max(rng.normal(0, 0.1), -0.1), 0.1)
+            jobs.append((p, dict(rot_ang=rot, trans_dx=r * np.cos(a), trans_dy=r * np.sin(a),
+                                 zoom_scalar=z, do_warping=True)))
+    return jobs
+
+
+def cpu_scene(scene, n_sweeps, jobs, workers=1):
     """One bounded sample of the workload on the CPU port (oracle/oracle.py): returns
-    (points integrated, BEVs, seconds).  integrate() is sequential by nature; the BEVs of
-    the scene are independent and are spread over `workers` forked processes — the
-    reference's own parallelism (Pool(bev_num), kitti360_sem_pc_accum.py:236-241)."""
+    (points integrated, BEV planes, seconds, the oracle accumulator).  integrate() is sequential
+    by nature; the BEVs of the scene are independent and are spread over `workers` forked
+    processes — the reference's own parallelism (Pool(bev_num), kitti360_sem_pc_accum.py:236-241).
+    jobs: list of (present_idx, augmentation dict)."""
     global _CPU_ACC
     from oracle import oracle as orc
     bp = bev_setup()
@@ -689,39 +767,87 @@ def cpu_scene(scene, n_sweeps, present_idxs, rng, workers=1):
     for o in scene[:n_sweeps]:
         acc.integrate(o, o['_semseg'])
         pts += o['pc'].shape[0]
-    jobs = []
-    for p in present_idxs:
-        for _ in range(BEVS_PER_PRESENT):
-            rot = 2 * np.pi * rng.random_sample()
-            r, a = 5.0 * rng.random_sample(), 2 * np.pi * rng.random_sample()
-            z = 1 + min(max(rng.normal(0, 0.1), -0.1), 0.1)
-            jobs.append((p, dict(rot_ang=rot, trans_dx=r * np.cos(a), trans_dy=r * np.sin(a),
-                                 zoom_scalar=z, do_warping=True)))
     _CPU_ACC = acc
     if workers > 1:
         import multiprocessing as mp
         with mp.get_context('fork').Pool(workers) as pool:
-            n_b = sum(pool.map(_cpu_bev, jobs))
+            bevs = pool.map(_cpu_bev, jobs)
     else:
-        n_b = sum(_cpu_bev(j) for j in jobs)
+        bevs = [_cpu_bev(j) for j in jobs]
     _CPU_ACC = None
-    return pts, n_b, time.perf_counter() - t0
+    return pts, bevs, time.perf_counter() - t0, acc
 
 
 def cpu_workers():
     return max(1, min(os.cpu_count() or 1, len(PRESENT_IDXS) * BEVS_PER_PRESENT))
 
 
-def cpu_baseline_sample(scene):
-    rng = np.random.RandomState(5)
+def cpu_baseline_sample(scene, jobs):
     w = cpu_workers()
-    pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng, w)
-    return {'value': pts / dt, 'unit': 'points/s', 'cores': w, 'kind': 'port',
-            'bevs_per_s': n_b / dt, 'seconds': dt,
-            'sample': f'1 scene: {N_SWEEPS} sweeps ({pts} pts) + {n_b} BEVs through oracle/oracle.py '
-                      '(vectorised numpy + C FMA-chain restatement of the reference; integrate serial, BEVs '
-                      f'over {w} forked workers; the literal reference is ~100x slower per BEV, BASELINE.md)',
-            'host_cpus': os.cpu_count()}
+    jobs = [(p, dict(a, do_warping=True)) for p, a in jobs]
+    pts, bevs, dt, acc = cpu_scene(scene, N_SWEEPS, jobs, w)
+    n_b = len(bevs)
+    lit = literal_reference_record()
+    cpu = {'value': pts / dt, 'unit': 'points/s', 'cores': w, 'kind': 'port',
+           'bevs_per_s': n_b / dt, 'seconds': dt,
+           'sample': f'1 scene: {N_SWEEPS} sweeps ({pts} pts) + {n_b} BEVs through oracle/oracle.py '
+                     '(vectorised numpy + C FMA-chain restatement of the reference; integrate serial, BEVs '
+                     f'over {w} forked workers)',
+           'host_cpus': os.cpu_count(), 'literal_reference': lit}
+    return cpu, bevs, acc
+
+
+def literal_reference_record():
+    """The UNMODIFIED reference timed on this workload in the build container (it is pure Python
+    and /root/reference does not travel to the GPU box): tools/time_literal_reference.py wrote
+    profiles/literal_reference_cpu.json.  Reported beside the port, never as this run's number."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'literal_reference_cpu.json')))
+    except Exception:
+        return None
+
+
+def parity_gate(torch, cloud, scene_pass, out_planes, par0, cpu_bevs, cpu_acc, jobs):
+    """In-run parity gate: bench scene 0 through the device path of the timed
+    region (scene_pass) against the CPU port's output for the same 32 (present_idx,
+    augmentation) pairs — kept-point counts `==`, exported records of three sweeps `==` (with
+    the tracker's retro-active dynamic flags), cell indices of variant 0 `==` in the
+    reference's order, 21 planes x 32 BEVs within 1 float16 ulp."""
+    scene_pass(0, cloud, out_planes)
+    flags = cloud.sync() & ~2                      # bit 1 is informational (float32 intensity)
+    got = out_planes.cpu().numpy()
+    first, n_live = cloud.live_frames()
+    counts_ok = n_live == len(cpu_acc.sem_pcs) and all(
+        cloud.frame_count(first + k) == cpu_acc.sem_pcs[k].shape[0] for k in range(n_live))
+    rec_ok = all(np.array_equal(cloud.export_frame(first + k), cpu_acc.sem_pcs[k]) for k in (0, 17, 39))
+    max_ulp, n_diff, n_vals = 0, 0, 0
+    for v, ref in enumerate(cpu_bevs):
+        d = np.abs(got[v].view(np.int16).astype(np.int32) - ref.view(np.int16).astype(np.int32))
+        max_ulp = max(max_ulp, int(d.max()))
+        n_diff += int((d != 0).sum())
+        n_vals += d.size
+    # cell indices of variant 0, in the reference's (frame, point) order
+    _, _, cells = cloud.rasterise([par0[0]], P, want_cells=True)
+    cloud.sync()
+    p0, aug0 = jobs[0]
+    dbg = cpu_acc.generate_bev(p0, return_f64=True, **dict(aug0, do_warping=True))['_debug']
+
+    def window_cells(fids):
+        out = []
+        for f in fids:
+            off, n = cloud.frame_offset(f), cloud.frame_count(f)
+            c = cells[off:off + n].cpu().numpy()
+            c = c[c >= 0]
+            out.append(np.stack([c // P, c % P], axis=1))
+        return np.concatenate(out)
+
+    cells_ok = (np.array_equal(window_cells(range(first, first + p0)), dbg['cells_present'])
+                and np.array_equal(window_cells(range(first + p0, first + n_live)), dbg['cells_future']))
+    ok = bool(flags == 0 and counts_ok and rec_ok and cells_ok and max_ulp <= 1)
+    return {'ok': ok, 'checked': f'bench scene 0: {n_live} sweeps, {len(cpu_bevs)} BEVs x 21 planes vs oracle/oracle.py',
+            'kept_counts_equal': bool(counts_ok), 'records_equal_sweeps_0_17_39': bool(rec_ok),
+            'cell_indices_equal_variant0': bool(cells_ok), 'planes_max_fp16_ulp': max_ulp,
+            'planes_values_differing': n_diff, 'planes_values': n_vals, 'device_error_flags': int(flags)}
 
 
 def run_reference(args, rank, world):
@@ -730,31 +856,42 @@ def run_reference(args, rank, world):
     scene = make_scenes(0, 1)[0]
     rng = np.random.RandomState(5)
     w = cpu_workers()
-    for _ in range(min(args.warmup, 1)):
-        cpu_scene(scene, 8, PRESENT_IDXS[:1], rng, w)
+    # the reference arm's step is ONE scene (a bounded sample of the S-scene step of the GPU arm:
+    # a full 16-scene step would take minutes per step on the CPU)
+    for _ in range(max(args.warmup, 0)):
+        cpu_scene(scene, 8, draw_jobs(rng, PRESENT_IDXS[:1]), w)
     tot_pts, tot_b, tot_t = 0, 0, 0.0
     for _ in range(args.steps):
-        pts, n_b, dt = cpu_scene(scene, N_SWEEPS, PRESENT_IDXS, rng, w)
-        tot_pts, tot_b, tot_t = tot_pts + pts, tot_b + n_b, tot_t + dt
+        pts, bevs, dt, _ = cpu_scene(scene, N_SWEEPS, draw_jobs(rng, PRESENT_IDXS), w)
+        tot_pts, tot_b, tot_t = tot_pts + pts, tot_b + len(bevs), tot_t + dt
     v = tot_pts / tot_t
-    sample = (f'each step = 1 scene: {N_SWEEPS} sweeps + {len(PRESENT_IDXS) * BEVS_PER_PRESENT} BEVs '
-              f'on the CPU port of the reference algorithm (oracle/oracle.py), BEVs over {w} forked workers; the reference itself is '
-              'pure Python and /root/reference is not present on the GPU box')
+    bevs_per_scene = len(PRESENT_IDXS) * BEVS_PER_PRESENT
+    sample = (f'each step = 1 scene of the workload: {N_SWEEPS} sweeps + {bevs_per_scene} BEVs '
+              f'on the CPU port of the reference algorithm (oracle/oracle.py), integrate serial, BEVs over {w} '
+              'forked workers; warm-up steps are 8-sweep / 4-BEV passes; the reference itself is pure Python '
+              'and /root/reference is not present on the GPU box (its measured rate: cpu_baseline.literal_reference)')
     OUT.write(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'points/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': tot_t / args.steps * 1e3,
+        'steps': args.steps, 'warmup': max(args.warmup, 0), 'ms_per_step': tot_t / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'bevs_per_s': tot_b / tot_t,
-        'config': {'workload': 'nuscenes-shaped oracle-pose scenes (BASELINE configs[1]) batched as '
-                               'configs[3]: 40 sweeps x 34688 pts, CAM_FRONT 1600x900, '
-                               '32 BEVs/scene (8 present idx x 4 aug), 256x256, present/future/full',
-                   'scenes_per_step': 1},
+        'config': bench_config(args.scenes_per_step, args.streams),
         'cpu_baseline': {'value': v, 'unit': 'points/s', 'cores': w, 'kind': 'port', 'sample': sample,
-                         'host_cpus': os.cpu_count()},
+                         'host_cpus': os.cpu_count(), 'literal_reference': literal_reference_record()},
         'e2e': {'value': v, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }) + '\n')
     OUT.flush()
+
+
+def bench_config(S, n_str):
+    """The `config` object of both arms (same keys, same values)."""
+    n_in_scene = N_SWEEPS * 34688
+    bevs_per_scene = len(PRESENT_IDXS) * BEVS_PER_PRESENT
+    return {'workload': WORKLOAD, 'scenes_per_step_per_gpu': S, 'points_per_step_per_gpu': S * n_in_scene,
+            'bevs_per_step_per_gpu': S * bevs_per_scene, 'sharding': 'scenes by rank',
+            'streams_per_gpu': n_str,
+            'l2': 'step inputs (%.1f GB resident copies) exceed the 126 MB L2' % (S * 0.32)}
 
 
 def _quiet_stdout():
@@ -776,8 +913,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scenes-per-step', type=int, default=16)
     ap.add_argument('--streams', type=int, default=4)
-    ap.add_argument('--e2e-scenes', type=int, default=2)
+    ap.add_argument('--e2e-scenes', type=int, default=16)
     ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--e2e-threads', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c3', action='store_true')
     ap.add_argument('--ncu-step', action='store_true')

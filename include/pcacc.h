@@ -144,6 +144,37 @@ int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const double *const *
                                   const int32_t *filters, int n_filters,
                                   int64_t *first_frame_id, void *stream);
 
+/* Host-buffer variant of pcacc_integrate_records — the end-to-end boundary: every bulk
+ * pointer is a HOST pointer (the arrays the dataloader hands to
+ * NuScenesOracleSemanticPointCloudAccumulator.integrate, nuscenes_oracle_sem_pc_accum.py:
+ * 139-160).  rgb_maps_host / sem_maps_host: host arrays of n_cams host pointers.
+ *   PCACC_STAGE_DIRECT  every array is page-locked (cudaHostAlloc / cudaHostRegister, e.g.
+ *                       torch pin_memory): the kernel reads them in place over PCIe — it
+ *                       touches cam_idx, the u,v of visible points and the rows of kept
+ *                       points, a fraction of the arrays — and no host copy is made.  The
+ *                       arrays must stay alive and unchanged until the stream has passed
+ *                       this call (pcacc_sync, or any later synchronisation of `stream`).
+ *   PCACC_STAGE_SPARSE  pageable arrays: the host walks cam_idx once and packs the rows a
+ *                       camera sees plus their (rgb, class) samples — 64 B per visible
+ *                       point, in input order — into a pinned ring slot which the same
+ *                       kernel reads (map dtype "sampled"); the arrays are consumed before
+ *                       the call returns.  Identical records by construction (tested).
+ *   PCACC_STAGE_AUTO    DIRECT if every array is page-locked, else SPARSE.
+ * *staging_used (optional) reports the mode taken. */
+#define PCACC_STAGE_AUTO 0
+#define PCACC_STAGE_DIRECT 1
+#define PCACC_STAGE_SPARSE 2
+int pcacc_integrate_records_host(pcacc_t h, const double *pc_host, const int64_t *cam_idx_host,
+                                 int64_t n, const uint8_t *const *rgb_maps_host,
+                                 const void *const *sem_maps_host, int n_cams, int sem_dtype,
+                                 int img_h, int img_w, const double *T_ego_world,
+                                 double intensity_div, const int32_t *filters, int n_filters,
+                                 int staging, int *staging_used, int64_t *frame_id, void *stream);
+/* 1 if `p` is page-locked host memory (or device / managed memory) a kernel may dereference */
+int pcacc_host_is_pinned(const void *p);
+/* cudaMemcpyAsync device -> (pinned) host on `stream`: the result planes of pcacc_rasterise */
+int pcacc_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+
 /* Append an already-built (n,10) float64 cloud [x,y,z,i,r,g,b,sem,inst,dyn]
  * as one frame (used by BEVGenerator.generate(pcs, ...) when it is handed host
  * clouds, bev_generator/bev_generator.py:63-125).  Rows are stored unchanged. */

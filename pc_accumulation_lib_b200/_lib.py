@@ -18,6 +18,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_STATE = -1, -2, -3, -4, -5
 FLAG_UV_OUT_OF_IMAGE, FLAG_INTENSITY_F32, FLAG_ATTR_RANGE, FLAG_CELL_OVERFLOW = 1, 2, 4, 8
 SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB, SEM_I16 = 0, 1, 2, 3, 4
 BEV_PLANES, BEV_WINDOWS = 7, 3
+STAGE_AUTO, STAGE_DIRECT, STAGE_SPARSE = 0, 1, 2
 ABI_VERSION = 1
 
 
@@ -66,6 +67,11 @@ SIGNATURES = {
                                        C.POINTER(_i64), _vp]),
     'pcacc_integrate_records_batch': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                                              _i32, _vp, _dbl, _vp, _i32, C.POINTER(_i64), _vp]),
+    'pcacc_integrate_records_host': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32,
+                                            _vp, _dbl, _vp, _i32, _i32, C.POINTER(_i32),
+                                            C.POINTER(_i64), _vp]),
+    'pcacc_host_is_pinned': (_i32, [_vp]),
+    'pcacc_memcpy_d2h_async': (_i32, [_vp, _vp, C.c_size_t, _vp]),
     'pcacc_integrate_cloud': (_i32, [_vp, _vp, _i64, C.POINTER(_i64), _vp]),
     'pcacc_rebase': (_i32, [_vp, _vp, _i32, _vp]),
     'pcacc_evict': (_i32, [_vp, _i32]),

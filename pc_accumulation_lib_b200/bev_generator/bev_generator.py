@@ -25,7 +25,7 @@ from abc import ABC, abstractmethod
 import numpy as np
 
 from .. import _lib
-from ..device import DeviceCloud, make_bev_params
+from ..device import DeviceCloud, make_bev_params, make_bev_params_batch
 
 WINDOWS = ('present', 'future', 'full')
 
@@ -44,7 +44,7 @@ class DeviceWindow:
 
     @property
     def shape(self):
-        self.cloud.sync()
+        self.cloud.refresh()     # exact counts; data-error flags stay pending for the caller's sync
         n = sum(self.cloud.frame_count(f) for f in range(self.frame_begin, self.frame_end))
         return (n, 10)
 
@@ -234,8 +234,14 @@ class BEVGenerator(ABC):
         V = len(augs)
 
         def params(cloud, fb, fs, fe, origin):
-            return [self._bev_params(fb, fs, fe, origin, a['rot_ang'], a['trans_dx'], a['trans_dy'],
-                                     a['zoom_scalar'] * self.view_size) for a in augs]
+            sem_idxs = getattr(self, 'sem_idxs', None) or {
+                'road': -1, 'car': -1, 'truck': -1, 'bus': -1, 'motorcycle': -1}
+            return make_bev_params_batch(
+                fb, fs, fe, origin, [self.rotation_matrix_3d(a['rot_ang']) for a in augs],
+                [a['trans_dx'] for a in augs], [a['trans_dy'] for a in augs],
+                [a['zoom_scalar'] * self.view_size for a in augs], self.height_filter,
+                self.int_scaler, self.int_sep_scaler, self.int_mid_threshold,
+                getattr(self, 'rgb_fill', 0), sem_idxs, self.elevation_max)
 
         if isinstance(pp, DeviceWindow):
             cloud = pp.cloud

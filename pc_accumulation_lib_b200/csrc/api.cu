@@ -47,17 +47,26 @@ int pcacc_ensure_tiles(pcacc_t h, int64_t n_tiles) {
 }
 
 int pcacc_arena_put(pcacc_t h, const void *src, size_t bytes, void **dev, cudaStream_t st) {
+    const size_t seg = PCACC_ARENA_SEG_BYTES;
     size_t need = (bytes + 255) / 256 * 256;
-    if (need > h->arena_size) return pcacc_fail(h, PCACC_ERR_ARG, "parameter block of %zu bytes too large", bytes);
-    if (h->arena_pos + need > h->arena_size) {
-        // recycle: everything enqueued so far must have consumed its parameters
-        PCACC_CUDA(h, cudaDeviceSynchronize());
+    if (need > seg) return pcacc_fail(h, PCACC_ERR_ARG, "parameter block of %zu bytes too large", bytes);
+    if (h->arena_pos + need > seg) {
+        // leave the current segment: everything enqueued so far (on this stream) consumes its
+        // parameters before this event; the segment is handed out again PCACC_ARENA_SEGS - 1
+        // segments later, after waiting for that event only — no device-wide synchronisation
+        PCACC_CUDA(h, cudaEventRecord(h->arena_ev[h->arena_seg], st));
+        h->arena_ev_set[h->arena_seg] = true;
+        h->arena_seg = (h->arena_seg + 1) % PCACC_ARENA_SEGS;
+        if (h->arena_ev_set[h->arena_seg]) {
+            PCACC_CUDA(h, cudaEventSynchronize(h->arena_ev[h->arena_seg]));
+            h->arena_ev_set[h->arena_seg] = false;
+        }
         h->arena_pos = 0;
     }
-    memcpy(h->h_arena + h->arena_pos, src, bytes);
-    PCACC_CUDA(h, cudaMemcpyAsync(h->d_arena + h->arena_pos, h->h_arena + h->arena_pos, bytes,
-                                  cudaMemcpyHostToDevice, st));
-    *dev = h->d_arena + h->arena_pos;
+    const size_t at = (size_t)h->arena_seg * seg + h->arena_pos;
+    memcpy(h->h_arena + at, src, bytes);
+    PCACC_CUDA(h, cudaMemcpyAsync(h->d_arena + at, h->h_arena + at, bytes, cudaMemcpyHostToDevice, st));
+    *dev = h->d_arena + at;
     h->arena_pos += need;
     return PCACC_OK;
 }
@@ -191,6 +200,12 @@ static void free_all(pcacc_t h) {
     cudaFree(h->d_rstats);
     cudaFree(h->d_rgb_lut);
     for (auto &e : h->prof_events) cudaEventDestroy(e);
+    for (int k = 0; k < PCACC_ARENA_SEGS; k++)
+        if (h->arena_ev[k]) cudaEventDestroy(h->arena_ev[k]);
+    for (int k = 0; k < PCACC_STAGE_SLOTS; k++) {
+        if (h->stage[k].ev) cudaEventDestroy(h->stage[k].ev);
+        if (h->stage[k].host) cudaFreeHost(h->stage[k].host);
+    }
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_arena) cudaFreeHost(h->h_arena);
 }
@@ -216,7 +231,7 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
     h->max_frames = max_frames;
     h->frames.resize((size_t)max_frames);
     h->launch_epoch = 0;
-    h->arena_size = 1u << 20;
+    h->arena_size = (size_t)PCACC_ARENA_SEGS * PCACC_ARENA_SEG_BYTES;
     size_t cap = (size_t)h->capacity;
 #define TRY(call)                                                           \
     do {                                                                    \
@@ -231,6 +246,9 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
         }                                                                   \
     } while (0)
     TRY(cudaSetDevice(device));
+    TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
+    for (int k = 0; k < PCACC_ARENA_SEGS; k++)
+        TRY(cudaEventCreateWithFlags(&h->arena_ev[k], cudaEventDisableTiming));
     TRY(cudaMalloc(&h->ring.x, cap * 8));
     TRY(cudaMalloc(&h->ring.y, cap * 8));
     TRY(cudaMalloc(&h->ring.z, cap * 8));

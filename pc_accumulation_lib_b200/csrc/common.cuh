@@ -16,6 +16,12 @@
 #define PCACC_MAX_FILTERS 16
 #define PCACC_MAX_CAMS 8
 #define PCACC_ALIGN_PTS 4  // frame offsets are multiples of this many records
+// internal map dtype of the sparse host staging mode: maps.sem[0] points to (n,2) uint32
+// {r | g<<8 | b<<16, class as int32} already gathered on the host; cam_idx is absent
+#define PCACC_SEM_SAMPLED 5
+#define PCACC_STAGE_SLOTS 4
+#define PCACC_ARENA_SEGS 4
+#define PCACC_ARENA_SEG_BYTES (1u << 20)
 
 // ---------------------------------------------------------------------------
 // exact small transforms
@@ -304,9 +310,19 @@ struct pcacc_s {
     bool any_lazy;
     // pinned mailbox for table sync
     int64_t *h_mail;
-    // parameter arena (host pinned + device)
+    // parameter arena (host pinned + device): a ring of PCACC_ARENA_SEGS segments; a segment
+    // is reused only after the event recorded when the allocator left it has completed
     char *h_arena, *d_arena;
-    size_t arena_size, arena_pos;
+    size_t arena_size, arena_pos;   // arena_pos: offset inside the current segment
+    int arena_seg;
+    cudaEvent_t arena_ev[PCACC_ARENA_SEGS];
+    bool arena_ev_set[PCACC_ARENA_SEGS];
+    int n_sm;            // multiprocessors of the device (grid sizing)
+    // pinned staging ring of the host-buffer entry points (sparse staging mode): a slot is
+    // rewritten only after the event recorded behind the kernel that read it has completed
+    struct StageSlot { char *host; size_t cap; cudaEvent_t ev; bool busy; };
+    StageSlot stage[PCACC_STAGE_SLOTS];
+    int stage_turn;
     // raster workspace (grow-only)
     void *d_ws;
     size_t ws_size;

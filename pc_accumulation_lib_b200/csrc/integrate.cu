@@ -81,6 +81,7 @@ __device__ __forceinline__ int load_class(const void *map, int64_t pix, int K) {
         long long v = ((const long long *)map)[pix];
         return (v < -2147483647ll || v > 2147483647ll) ? -2147483647 : (int)v;
     }
+    if (DT == PCACC_SEM_SAMPLED) return ((const int32_t *)map)[2 * pix + 1];
     // float32 probabilities: first index of the maximum (np.argmax)
     const float *p = (const float *)map + pix * K;
     float best = p[0];
@@ -310,7 +311,8 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
 #pragma unroll
     for (int k = 0; k < REC_ITEMS; k++) {
         const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
-        cam[k] = i < n ? cam_idx[i] : -1;
+        // sampled source: the rows are the visible points already (camera 0 of 1)
+        cam[k] = i < n ? (DT == PCACC_SEM_SAMPLED ? 0ll : cam_idx[i]) : -1;
         keep[k] = false;
         packed[k] = 0;
     }
@@ -325,17 +327,28 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
             if (!inside) {
                 atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
             } else {
-                const int64_t pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
-                int cls = load_class<DT>(maps.sem[cam[k]], pix, 1);
+                int cls;
+                uint32_t rgbp = 0;
+                int64_t pix = 0;
+                if (DT == PCACC_SEM_SAMPLED) {
+                    const uint2 smp = ((const uint2 *)maps.sem[0])[i];
+                    rgbp = smp.x;
+                    cls = (int)smp.y;
+                } else {
+                    pix = (int64_t)rint_even(vf) * img_w + (int64_t)rint_even(uf);
+                    cls = load_class<DT>(maps.sem[cam[k]], pix, 1);
+                }
                 keep[k] = (cls >= 0) && !class_filtered(filt, cls);
                 if (keep[k]) {
                     if (cls > 255) {
                         atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
                         cls &= 255;
                     }
-                    const uint8_t *c = maps.rgb[cam[k]] + pix * 3;
-                    packed[k] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
-                                ((uint32_t)cls << 24);
+                    if (DT != PCACC_SEM_SAMPLED) {
+                        const uint8_t *c = maps.rgb[cam[k]] + pix * 3;
+                        rgbp = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+                    }
+                    packed[k] = (rgbp & 0xffffffu) | ((uint32_t)cls << 24);
                 }
             }
         }
@@ -620,10 +633,26 @@ static int make_lookback(pcacc_t h, int64_t n_tiles, LookBack *lb) {
     return PCACC_OK;
 }
 
+// Conservative extent of a live frame on the host: exact after pcacc_sync; a frame placed at a
+// fixed base (batch integrate, first frame, post-wrap frame) has an exact offset and an upper
+// bound of its count before that.
+static inline int64_t fr_off(const FrameHost &g) { return g.exact ? g.off : (g.off >= 0 ? g.off : g.off_ub); }
+static inline int64_t fr_cnt(const FrameHost &g) { return g.exact ? g.cnt : g.n_in; }
+static inline int64_t align_pts(int64_t n) { return (n + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS * PCACC_ALIGN_PTS; }
+
+static bool valid_sem_dtype(int dt, bool allow_prob) {
+    return dt == PCACC_SEM_U8 || dt == PCACC_SEM_I32 || dt == PCACC_SEM_I64 || dt == PCACC_SEM_I16 ||
+           (allow_prob && dt == PCACC_SEM_F32_PROB);
+}
+
 // Reserve a frame slot for up to n_in records. Decides the ring offset policy
 // on the host from upper bounds; syncs the table only when it has to.
+// allow_sync = false: the caller has synchronised already and is registering frames whose
+// kernels are not enqueued yet (batch integrate) — pcacc_sync would overwrite their host
+// entries with stale device-table values, so the placement works from the host-side bounds
+// (exact for every frame older than the batch, fixed base + upper-bound count inside it).
 static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs, int64_t *frame_id,
-                       bool fixed_slot = false) {
+                       bool fixed_slot = false, bool allow_sync = true) {
     if (n_in < 0) return pcacc_fail(h, PCACC_ERR_ARG, "negative point count");
     if (n_in > h->capacity)
         return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame of %lld points exceeds ring capacity %lld",
@@ -642,13 +671,15 @@ static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs,
         h->wrapped = false;
     } else {
         FrameHost &prev = h->frames[(int)((id - 1) % h->max_frames)];
-        ub = prev.off_ub + ((prev.n_in + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
+        ub = prev.off_ub + align_pts(prev.n_in);
         if (h->wrapped || ub + n_in > h->capacity) {
             // need exact numbers
-            int rc = pcacc_sync(h, nullptr, (void *)st);
-            if (rc) return rc;
+            if (allow_sync) {
+                int rc = pcacc_sync(h, nullptr, (void *)st);
+                if (rc) return rc;
+            }
             FrameHost &pv = h->frames[(int)((id - 1) % h->max_frames)];
-            int64_t nxt = pv.off + ((pv.cnt + PCACC_ALIGN_PTS - 1) / PCACC_ALIGN_PTS) * PCACC_ALIGN_PTS;
+            int64_t nxt = fr_off(pv) + align_pts(fr_cnt(pv));
             if (nxt + n_in > h->capacity) {
                 nxt = 0;
                 h->wrapped = true;
@@ -657,11 +688,12 @@ static int begin_frame(pcacc_t h, int64_t n_in, cudaStream_t st, FrameSlots *fs,
             bool any_after = false;
             for (int64_t k = h->first_id; k < h->next_id; k++) {
                 FrameHost &g = h->frames[(int)(k % h->max_frames)];
-                if (g.cnt > 0 && g.off < nxt + n_in && nxt < g.off + g.cnt)
+                const int64_t go = fr_off(g), gc = fr_cnt(g);
+                if (gc > 0 && go < nxt + n_in && nxt < go + gc)
                     return pcacc_fail(h, PCACC_ERR_CAPACITY,
                                       "ring full: %lld resident points, capacity %lld",
                                       (long long)pcacc_resident_points(h), (long long)h->capacity);
-                if (g.off >= nxt) any_after = true;
+                if (go >= nxt) any_after = true;
             }
             if (!any_after) h->wrapped = false;
             override_base = nxt;
@@ -752,6 +784,8 @@ extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t 
     if (!h) return PCACC_ERR_ARG;
     if (!P || img_h <= 0 || img_w <= 0 || K < 1)
         return pcacc_fail(h, PCACC_ERR_ARG, "bad integrate_frustum arguments");
+    // validated before a frame is registered: an error return must not leave a phantom frame
+    if (!valid_sem_dtype(sem_dtype, true)) return pcacc_fail(h, PCACC_ERR_ARG, "unknown sem dtype %d", sem_dtype);
     cudaStream_t st = (cudaStream_t)stream;
     PCACC_CUDA(h, cudaSetDevice(h->device));
     Filters filt;
@@ -825,6 +859,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
     if (!h) return PCACC_ERR_ARG;
     if (n_cams < 0 || n_cams > PCACC_MAX_CAMS || !T_ego_world)
         return pcacc_fail(h, PCACC_ERR_ARG, "n_cams must be 0..%d", PCACC_MAX_CAMS);
+    if (!valid_sem_dtype(sem_dtype, false)) return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
     cudaStream_t st = (cudaStream_t)stream;
     PCACC_CUDA(h, cudaSetDevice(h->device));
     Filters filt;
@@ -885,13 +920,35 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
     if (rc) return rc;
     rc = set_inten_div(h, intensity_div);
     if (rc) return rc;
+    if (!valid_sem_dtype(sem_dtype, false)) return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
     if ((int)(h->next_id - h->first_id) + n_sweeps >= h->max_frames - 1)
         return pcacc_fail(h, PCACC_ERR_CAPACITY, "frame table too small for %d more frames", n_sweeps);
+    // The capacity / wrap decision needs exact numbers at most ONCE for the whole batch, and
+    // before any of its frames is registered: pcacc_sync refreshes every live frame from the
+    // device table, which knows nothing yet about frames whose kernel is not enqueued.
+    if (h->next_id > h->first_id) {
+        const FrameHost &prev = h->frames[(int)((h->next_id - 1) % h->max_frames)];
+        int64_t need = prev.off_ub + align_pts(prev.n_in);
+        for (int k = 0; k < n_sweeps; k++) need += align_pts(n[k] < 0 ? 0 : n[k]);
+        if (h->wrapped || need > h->capacity) {
+            rc = pcacc_sync(h, nullptr, (void *)st);
+            if (rc) return rc;
+        }
+    }
+    // any failure below un-registers the batch's frames (their table entries were never written)
+    const int64_t id_entry = h->next_id;
+    const bool wrapped_entry = h->wrapped;
+#define BATCH_FAIL(rc_)                \
+    do {                               \
+        h->next_id = id_entry;         \
+        h->wrapped = wrapped_entry;    \
+        return (rc_);                  \
+    } while (0)
     std::vector<SweepDesc> desc((size_t)n_sweeps);
     int64_t total_tiles = 0, max_tiles = 1;
     for (int k = 0; k < n_sweeps; k++) {
         int64_t tiles = (n[k] + REC_TILE - 1) / REC_TILE;
-        if (tiles == 0) tiles = 1;
+        if (tiles <= 0) tiles = 1;
         SweepDesc &d = desc[(size_t)k];
         d.pc = pc_dev[k];
         d.cam = (const long long *)cam_idx_dev[k];
@@ -907,22 +964,23 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
         total_tiles += tiles;
         if (tiles > max_tiles) max_tiles = tiles;
         int64_t fid = -1;
-        rc = begin_frame(h, n[k], st, &d.fs, &fid, /*fixed_slot=*/true);
-        if (rc) return rc;
+        rc = begin_frame(h, n[k], st, &d.fs, &fid, /*fixed_slot=*/true, /*allow_sync=*/false);
+        if (rc) BATCH_FAIL(rc);
         if (d.fs.base_override < 0)
-            return pcacc_fail(h, PCACC_ERR_STATE, "internal: batch frame without a fixed base");
+            BATCH_FAIL(pcacc_fail(h, PCACC_ERR_STATE, "internal: batch frame without a fixed base"));
         d.fs.write_next = (k == n_sweeps - 1) ? 1 : 0;
         if (k == 0 && first_frame_id) *first_frame_id = fid;
     }
     rc = pcacc_ensure_tiles(h, total_tiles);
-    if (rc) return rc;
+    if (rc) BATCH_FAIL(rc);
     // per-sweep tickets live behind the descriptors in the arena; zeroed by the upload
     size_t desc_bytes = desc.size() * sizeof(SweepDesc);
     std::vector<char> blob(desc_bytes + (size_t)n_sweeps * 4, 0);
     memcpy(blob.data(), desc.data(), desc_bytes);
     void *dev = nullptr;
     rc = pcacc_arena_put(h, blob.data(), blob.size(), &dev, st);
-    if (rc) return rc;
+    if (rc) BATCH_FAIL(rc);
+#undef BATCH_FAIL
     const SweepDesc *d_desc = (const SweepDesc *)dev;
     uint32_t *d_tickets = (uint32_t *)((char *)dev + desc_bytes);
     uint32_t epoch = pcacc_next_epoch(h);
@@ -948,6 +1006,177 @@ extern "C" int pcacc_integrate_records_batch(pcacc_t h, int n_sweeps, const doub
     PCACC_CUDA(h, cudaGetLastError());
     pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
     return PCACC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry point of the nuScenes record path (the e2e boundary)
+// ---------------------------------------------------------------------------
+// Device-visible address of a host pointer, or nullptr when the memory is pageable.
+static const void *pinned_dev_ptr(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return at.devicePointer;
+    if (at.type == cudaMemoryTypeDevice) return at.devicePointer;   // already resident: fine too
+    return nullptr;
+}
+
+extern "C" int pcacc_host_is_pinned(const void *p) { return pinned_dev_ptr(p) != nullptr; }
+
+static inline int32_t host_class(const void *map, int dt, int64_t pix) {
+    switch (dt) {
+        case PCACC_SEM_U8: return (int32_t)((const uint8_t *)map)[pix];
+        case PCACC_SEM_I16: return (int32_t)((const int16_t *)map)[pix];
+        case PCACC_SEM_I32: return ((const int32_t *)map)[pix];
+        default: {
+            const long long v = ((const long long *)map)[pix];
+            return (v < -2147483647ll || v > 2147483647ll) ? -2147483647 : (int32_t)v;
+        }
+    }
+}
+
+static int stage_slot(pcacc_t h, size_t bytes, pcacc_s::StageSlot **out) {
+    pcacc_s::StageSlot &sl = h->stage[h->stage_turn];
+    h->stage_turn = (h->stage_turn + 1) % PCACC_STAGE_SLOTS;
+    if (sl.busy) {   // the kernel that read this slot PCACC_STAGE_SLOTS integrates ago
+        PCACC_CUDA(h, cudaEventSynchronize(sl.ev));
+        sl.busy = false;
+    }
+    if (!sl.ev) PCACC_CUDA(h, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (sl.cap < bytes) {
+        if (sl.host) cudaFreeHost(sl.host);
+        sl.host = nullptr;
+        sl.cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc((void **)&sl.host, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pcacc_fail(h, PCACC_ERR_NOMEM, "pinned staging slot of %zu bytes: %s", want,
+                              cudaGetErrorString(e));
+        }
+        sl.cap = want;
+    }
+    *out = &sl;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
+                                            const int64_t *cam_idx_host, int64_t n,
+                                            const uint8_t *const *rgb_maps_host,
+                                            const void *const *sem_maps_host, int n_cams,
+                                            int sem_dtype, int img_h, int img_w,
+                                            const double *T_ego_world, double intensity_div,
+                                            const int32_t *filters, int n_filters, int staging,
+                                            int *staging_used, int64_t *frame_id, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || n_cams < 0 || n_cams > PCACC_MAX_CAMS || !T_ego_world || (n > 0 && (!pc_host || !cam_idx_host)) ||
+        (n_cams > 0 && (!rgb_maps_host || !sem_maps_host)) || img_h <= 0 || img_w <= 0)
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad integrate_records_host arguments");
+    if (!valid_sem_dtype(sem_dtype, false)) return pcacc_fail(h, PCACC_ERR_ARG, "unsupported sem dtype %d", sem_dtype);
+    if (staging != PCACC_STAGE_AUTO && staging != PCACC_STAGE_DIRECT && staging != PCACC_STAGE_SPARSE)
+        return pcacc_fail(h, PCACC_ERR_ARG, "unknown staging mode %d", staging);
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // DIRECT: every array is page-locked (or resident): the kernel reads it in place
+    const void *d_pc = nullptr, *d_cam = nullptr;
+    const uint8_t *d_rgb[PCACC_MAX_CAMS];
+    const void *d_sem[PCACC_MAX_CAMS];
+    bool direct = staging != PCACC_STAGE_SPARSE;
+    if (direct) {
+        d_pc = n ? pinned_dev_ptr(pc_host) : (const void *)pc_host;
+        d_cam = n ? pinned_dev_ptr(cam_idx_host) : (const void *)cam_idx_host;
+        direct = (n == 0) || (d_pc && d_cam);
+        for (int c = 0; c < n_cams && direct; c++) {
+            d_rgb[c] = (const uint8_t *)pinned_dev_ptr(rgb_maps_host[c]);
+            d_sem[c] = pinned_dev_ptr(sem_maps_host[c]);
+            direct = d_rgb[c] && d_sem[c];
+        }
+    }
+    if (!direct && staging == PCACC_STAGE_DIRECT)
+        return pcacc_fail(h, PCACC_ERR_ARG, "PCACC_STAGE_DIRECT needs page-locked (pinned) host arrays");
+    if (staging_used) *staging_used = direct ? PCACC_STAGE_DIRECT : PCACC_STAGE_SPARSE;
+    if (direct)
+        return pcacc_integrate_records(h, (const double *)d_pc, (const int64_t *)d_cam, n, d_rgb, d_sem, n_cams,
+                                       sem_dtype, img_h, img_w, T_ego_world, intensity_div, filters,
+                                       n_filters, frame_id, stream);
+
+    // SPARSE: the rows a camera sees and their (rgb, class) samples, in input order, go to a
+    // pinned slot the kernel reads in place: 64 B per visible point instead of the whole
+    // (n,7) array and the camera frames.
+    Filters filt;
+    int rc = fill_filters(h, filters, n_filters, &filt);
+    if (rc) return rc;
+    rc = set_inten_div(h, intensity_div);
+    if (rc) return rc;
+    int64_t n_vis = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t c = cam_idx_host[i];
+        n_vis += (c >= 0 && c < n_cams);
+    }
+    pcacc_s::StageSlot *sl = nullptr;
+    const size_t row_bytes = (size_t)n_vis * 7 * sizeof(double);
+    rc = stage_slot(h, row_bytes + (size_t)n_vis * 8 + 64, &sl);
+    if (rc) return rc;
+    double *rows = (double *)sl->host;
+    uint32_t *samp = (uint32_t *)(sl->host + row_bytes);
+    const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
+    int64_t j = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t c = cam_idx_host[i];
+        if (!(c >= 0 && c < n_cams)) continue;
+        const double *src = pc_host + 7 * i;
+        double *dst = rows + 7 * j;
+        for (int k = 0; k < 7; k++) dst[k] = src[k];
+        const double uf = src[4], vf = src[5];
+        uint32_t rgbp = 0;
+        int32_t cls = 0;
+        // outside the image the kernel raises PCACC_FLAG_UV_OUT_OF_IMAGE and never looks at the sample
+        if ((uf > 1.0) && (uf < wlim) && (vf > 1.0) && (vf < hlim)) {
+            const int64_t pix = (int64_t)nearbyint(vf) * img_w + (int64_t)nearbyint(uf);   // half to even
+            const uint8_t *px = rgb_maps_host[c] + pix * 3;
+            rgbp = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
+            cls = host_class(sem_maps_host[c], sem_dtype, pix);
+        }
+        samp[2 * j] = rgbp;
+        samp[2 * j + 1] = (uint32_t)cls;
+        j++;
+    }
+    CamMaps maps;
+    maps.n = 1;
+    for (int k = 0; k < PCACC_MAX_CAMS; k++) {
+        maps.rgb[k] = nullptr;
+        maps.sem[k] = k == 0 ? (const void *)samp : nullptr;
+    }
+    TMat T;
+    memcpy(T.m, T_ego_world, sizeof(T.m));
+    int64_t tiles = (n_vis + REC_TILE - 1) / REC_TILE;
+    if (tiles == 0) tiles = 1;
+    LookBack lb;
+    rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    FrameSlots fs;
+    rc = begin_frame(h, n_vis, st, &fs, frame_id);
+    if (rc) return rc;
+    size_t pe = pcacc_prof_begin(h, PCACC_K_INTEGRATE, st);
+    k_integrate_records<PCACC_SEM_SAMPLED><<<(unsigned)tiles, RBLOCK, 0, st>>>(
+        rows, nullptr, n_vis, maps, img_h, img_w, T, filt, h->ring, fs, lb, h->d_flags);
+    pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
+    PCACC_CUDA(h, cudaGetLastError());
+    PCACC_CUDA(h, cudaEventRecord(sl->ev, st));
+    sl->busy = true;
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    if (!bytes) return PCACC_OK;
+    if (!dst_host || !src_dev) return PCACC_ERR_ARG;
+    return cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream) == cudaSuccess
+               ? PCACC_OK
+               : PCACC_ERR_CUDA;
 }
 
 extern "C" int pcacc_integrate_cloud(pcacc_t h, const double *rec_dev, int64_t n, int64_t *frame_id,

@@ -1563,19 +1563,19 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             a.dbg_cell = (v0 == 0) ? dbg_cell_dev : nullptr;
             a.flags = h->d_flags;
             int64_t nf = fhi - flo;
-            if (nf > BIN_MAXF)
-                return pcacc_fail(h, PCACC_ERR_ARG, "more than %d frames in one rasterise call", BIN_MAXF);
+            if (nf >= BIN_MAXF)   // k_bev_classify's tile prefix has BIN_MAXF entries incl. the total
+                return pcacc_fail(h, PCACC_ERR_ARG, "more than %d frames in one rasterise call", BIN_MAXF - 1);
             a.frame_lo = flo;
             a.n_frames = (int)nf;
             size_t pe = pcacc_prof_begin(h, PCACC_K_CLASSIFY, st);
             k_bev_cull<<<(a.n_frames * nv + 127) / 128, 128, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             h->launches[PCACC_K_CLASSIFY]++;
-            k_bev_classify<<<148 * 4, BIN_BLOCK, 0, st>>>(a);
+            k_bev_classify<<<h->n_sm * 4, BIN_BLOCK, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_CLASSIFY, pe, st);
             pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
-            k_bev_bin<<<148 * 8, 256, 0, st>>>(a);
+            k_bev_bin<<<h->n_sm * 8, 256, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_BIN, pe, st);
             // scan
@@ -1593,7 +1593,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             pcacc_prof_end(h, PCACC_K_SCAN, pe, st);
             // scatter
             int64_t sb = (cap + 255) / 256;
-            if (sb > 148 * 16) sb = 148 * 16;
+            if (sb > (int64_t)h->n_sm * 16) sb = (int64_t)h->n_sm * 16;
             pe = pcacc_prof_begin(h, PCACC_K_SCATTER, st);
             k_bev_scatter<<<(unsigned)sb, 256, 0, st>>>(counts, a.tmp_key, a.tmp_rec, ctr, cap,
                                                         (uint4 *)(ws + o_sorted));
@@ -1615,7 +1615,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         pcacc_prof_end(h, PCACC_K_REDUCE, pr, st);
         if (cap > SMALL_T) {
             int64_t bb = (big_cap + REDB_WARPS - 1) / REDB_WARPS;
-            if (bb > 148 * 8) bb = 148 * 8;
+            if (bb > (int64_t)h->n_sm * 8) bb = (int64_t)h->n_sm * 8;
             pr = pcacc_prof_begin(h, PCACC_K_REDUCE_BIG, st);
             if (want_f64)
                 k_bev_reduce_big<true><<<(unsigned)bb, REDB_WARPS * 32, 0, st>>>(
@@ -1673,7 +1673,7 @@ extern "C" int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f1
     if (rc) return rc;
     const int64_t total = (int64_t)n_bevs * n_planes * P * P;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)h->n_sm * 16) blocks = (int64_t)h->n_sm * 16;
     h->launches[PCACC_K_EXPORT]++;
     k_warp_planes<<<(unsigned)blocks, 256, 0, st>>>((const __half *)in_f16_dev, (__half *)out_f16_dev,
                                                     (const int32_t *)dev,

@@ -27,24 +27,37 @@ def _dev() -> DeviceCloud:
     return _cloud
 
 
+def _affine_rows(mat, xyz):
+    """Rows [x y z 1] @ mat.T restricted to the first three output columns, i.e. the 3-D part
+    of a 4x4 homogeneous transform applied to every row of `xyz` (float64 matmul, the same
+    dgemm the reference calls)."""
+    rows = np.empty((xyz.shape[0], 4), dtype=np.result_type(xyz.dtype, np.float64))
+    rows[:, :3] = xyz
+    rows[:, 3] = 1.0
+    return rows
+
+
 def homo_transform(tf, points):
-    """datasets/nuscenes_utils.py:46-60 (host; a handful of poses per observation)."""
-    assert tf.shape == (4, 4), f"{tf.shape} is not (4, 4)"
-    assert points.shape == (points.shape[0], 3), f"{points.shape} is not (N, 3)"
-    _pts = np.concatenate([points, np.ones((points.shape[0], 1))], axis=1)
-    _pts = tf @ _pts.T
-    return _pts[:3, :].T
+    """Behaviour of datasets/nuscenes_utils.py:46-60 (host; a handful of poses per
+    observation): `(tf @ [p 1]^T)[:3]^T` with the reference's two shape assertions."""
+    if tf.shape != (4, 4):
+        raise AssertionError(f'{tf.shape} is not (4, 4)')
+    if points.ndim != 2 or points.shape[1] != 3:
+        raise AssertionError(f'{points.shape} is not (N, 3)')
+    return np.matmul(tf, _affine_rows(tf, points).T)[:3].T
 
 
 def apply_tf(tf, points, in_place=False):
-    """datasets/nuscenes_utils.py:233-243 (host)."""
-    assert points.shape[1] >= 3, f"expect points.shape[1] >= 3, get {points.shape[1]}"
-    assert tf.shape == (4, 4), f"expect tf.shape == 4, get {tf.shape}"
-    xyz1 = np.pad(points[:, :3], pad_width=[(0, 0), (0, 1)], constant_values=1.0)
-    if in_place:
-        points[:, :3] = (xyz1 @ tf.T)[:, :3]
-    else:
-        return (xyz1 @ tf.T)[:, :3]
+    """Behaviour of datasets/nuscenes_utils.py:233-243 (host): `[p 1] @ tf^T`, written back
+    into `points[:, :3]` when `in_place`, returned otherwise."""
+    if points.shape[1] < 3:
+        raise AssertionError(f'expect points.shape[1] >= 3, get {points.shape[1]}')
+    if tf.shape != (4, 4):
+        raise AssertionError(f'expect tf.shape == 4, get {tf.shape}')
+    moved = np.matmul(_affine_rows(tf, points[:, :3]), tf.T)[:, :3]
+    if not in_place:
+        return moved
+    points[:, :3] = moved
 
 
 def find_points_in_box(points, target_from_box, dxdydz, tolerance):

@@ -28,6 +28,37 @@ def _narrow_class_map(sem: np.ndarray) -> torch.Tensor:
     return torch.clamp(torch.from_numpy(np.ascontiguousarray(sem)), -1, 256).to(torch.int16)
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (cudaHostAlloc through torch's pinned allocator).
+    Observations written into such arrays — by a dataloader, a semseg network's output copy —
+    are read by the integrate kernels in place (PCACC_STAGE_DIRECT): no host-side copy at all."""
+    require_cuda()
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(d) for d in shape)
+    t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()        # the array keeps the tensor (and its pinned block) alive
+
+
+def pinned_like(arr) -> np.ndarray:
+    """Page-locked copy of `arr` (same shape and dtype)."""
+    arr = np.asarray(arr)
+    out = pinned_empty(arr.shape, arr.dtype)
+    out[...] = arr
+    return out
+
+
+def pin_observation(obs: dict) -> dict:
+    """A nuScenes observation dict (obs_dataloaders/nuscenes_obs_dataloader.py:103-123) whose
+    bulk arrays — pc, pc_cam_idx, images and, if present, the `_semseg` class maps of the
+    synthetic stand-in — live in page-locked memory; everything else is passed through."""
+    out = dict(obs)
+    out['pc'] = pinned_like(np.asarray(obs['pc'], dtype=np.float64))
+    out['pc_cam_idx'] = pinned_like(np.asarray(obs['pc_cam_idx'], dtype=np.int64))
+    out['images'] = [pinned_like(np.asarray(i, dtype=np.uint8)) for i in obs['images']]
+    if '_semseg' in obs:
+        out['_semseg'] = [pinned_like(c) for c in obs['_semseg']]
+    return out
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise PcaccError(_lib.ERR_CUDA,
@@ -80,7 +111,7 @@ class Stager:
         # bare CUDA events from libpcacc (see pcacc_event_record): four, used in turn
         self._lib = _lib.load()
         self._events = []
-        for _ in range(4):
+        for _ in range(8):
             ev = C.c_void_p()
             check(self._lib.pcacc_event_create(C.byref(ev)))
             self._events.append(ev)
@@ -101,6 +132,10 @@ class Stager:
         ring[2] = turn ^ 1
         sl = ring[turn]
         if sl is None or sl[0].numel() < nbytes or (need_dev and sl[1] is None):
+            if sl is not None and sl[2] is not None:
+                # kernels may still read the old pinned block through a raw pointer torch knows
+                # nothing about: wait for its last reader before it returns to the allocator
+                self._lib.pcacc_event_sync(sl[2])
             cap = max(nbytes, 1) * 5 // 4 + 64
             sl = ring[turn] = [torch.empty(cap, dtype=torch.uint8, pin_memory=True),
                                torch.empty(cap, dtype=torch.uint8, device=self.device)
@@ -136,6 +171,12 @@ class Stager:
                 dev_v.copy_(pin_v, non_blocking=True)
             self._touched.append(sl)
         return pin_v if mapped else dev_v
+
+    def next_event(self):
+        """A bare CUDA event from the ring (valid until PCACC ring-size further requests)."""
+        ev = self._events[self._ev_turn]
+        self._ev_turn = (self._ev_turn + 1) % len(self._events)
+        return ev
 
     def fence(self):
         """Call after enqueuing the kernels that consume the buffers put since the last fence.
@@ -189,7 +230,11 @@ class DeviceCloud:
         self.stage = Stager(self.device)
         # camera maps handed over as host arrays are read in place from pinned memory
         self.map_images = True
-        self._keep = []      # device tensors that in-flight kernels still read
+        self._keep = []      # device tensors / pinned arrays that in-flight kernels still read
+        self._filt_cache = None
+        self._fid_out, self._staging_out = C.c_int64(-1), C.c_int(0)
+        self._fid_ref, self._staging_ref = C.byref(self._fid_out), C.byref(self._staging_out)
+        self.last_staging = None
         self._mark_f, self._mark_i = [], []   # queued dynamic-flag updates
 
     def close(self):
@@ -246,6 +291,13 @@ class DeviceCloud:
         self._keep.clear()
         return int(fl.value)
 
+    def refresh(self):
+        """Waits for the stream and refreshes the frame table like sync(), but leaves the
+        data-error flags pending for the next sync() (they must reach the caller that checks them)."""
+        self.flush_marks()
+        self._check(self.lib.pcacc_sync(self.h, None, _stream()))
+        self._keep.clear()
+
     def live_frames(self):
         first, n = C.c_int64(0), C.c_int(0)
         self._check(self.lib.pcacc_num_frames(self.h, C.byref(first), C.byref(n)))
@@ -265,9 +317,24 @@ class DeviceCloud:
         return int(self.lib.pcacc_resident_points(self.h))
 
     # -- integrate ---------------------------------------------------------------
+    @staticmethod
+    def _f32_cloud(pc):
+        """KITTI-360 clouds are float32 (the reference reads them from .bin files); the frustum
+        kernels take float32 input.  A wider array is accepted only if the cast loses nothing —
+        otherwise the projection would silently differ from the reference's float64 result."""
+        if isinstance(pc, torch.Tensor):
+            return pc
+        pc = np.asarray(pc)
+        if pc.dtype == np.float32:
+            return pc
+        pc32 = pc.astype(np.float32)
+        if not np.array_equal(pc32.astype(pc.dtype), pc, equal_nan=True):
+            raise ValueError('point cloud values are not representable in float32: the frustum '
+                             'path takes float32 clouds (as the KITTI-360 reader delivers them)')
+        return pc32
+
     def integrate_frustum(self, pc, P, rgb, sem, filters, max_depth=np.inf) -> int:
-        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
-                             if not isinstance(pc, torch.Tensor) else pc)
+        pts = self.stage.put('pc', self._f32_cloud(pc))
         assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
         rgb_d = self.stage.put('rgb', rgb if isinstance(rgb, torch.Tensor)
                                else np.asarray(rgb, dtype=np.uint8), mapped=self.map_images)
@@ -284,8 +351,7 @@ class DeviceCloud:
         return int(fid.value)
 
     def integrate_gt(self, pc, sem_gt, filters) -> int:
-        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
-                             if not isinstance(pc, torch.Tensor) else pc)
+        pts = self.stage.put('pc', self._f32_cloud(pc))
         assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
         if isinstance(sem_gt, torch.Tensor):
             sg = self.stage.put('sem_gt', sem_gt.reshape(-1).to(torch.int16))
@@ -330,6 +396,56 @@ class DeviceCloud:
             T.ctypes.data_as(C.c_void_p), float(intensity_div), fp, nf, C.byref(fid), _stream()))
         self.stage.fence()
         return int(fid.value)
+
+    def integrate_records_host(self, pc, cam_idx, rgbs, sems, T_ego_world, filters,
+                               intensity_div=255., staging=_lib.STAGE_AUTO) -> int:
+        """integrate_records for HOST numpy arrays through ONE C call
+        (pcacc_integrate_records_host): page-locked arrays are read by the kernel in place,
+        pageable ones go through the sparse staging mode.  Returns the frame id;
+        `self.last_staging` tells which mode ran."""
+        if not (type(pc) is np.ndarray and pc.dtype == np.float64 and pc.flags.c_contiguous):
+            pc = np.ascontiguousarray(pc, dtype=np.float64)
+        if not (type(cam_idx) is np.ndarray and cam_idx.dtype == np.int64 and cam_idx.flags.c_contiguous):
+            cam_idx = np.ascontiguousarray(cam_idx, dtype=np.int64)
+        n = pc.shape[0]
+        assert pc.ndim == 2 and pc.shape[1] == 7 and cam_idx.size == n, (pc.shape, cam_idx.shape)
+        n_cams = len(rgbs)
+        sem_dt, h, w = _lib.SEM_U8, 1, 1
+        if n_cams:
+            rr, ss = [], []
+            for r, m in zip(rgbs, sems):
+                if not (type(r) is np.ndarray and r.dtype == np.uint8 and r.flags.c_contiguous):
+                    r = np.ascontiguousarray(r, dtype=np.uint8)
+                if not (type(m) is np.ndarray and m.flags.c_contiguous and m.dtype in _SEM_DTYPES):
+                    m = np.ascontiguousarray(m)
+                    if m.dtype not in _SEM_DTYPES:
+                        m = m.astype(np.int64)
+                rr.append(r)
+                ss.append(m)
+            rgbs, sems = rr, ss
+            sem_dt = _SEM_DTYPES[sems[0].dtype]
+            h, w = rgbs[0].shape[0], rgbs[0].shape[1]
+            for r, m in zip(rgbs, sems):
+                assert r.shape == (h, w, 3) and m.shape == (h, w) and _SEM_DTYPES[m.dtype] == sem_dt, \
+                    (r.shape, m.shape, m.dtype)
+        rp = (C.c_void_p * max(n_cams, 1))(*[r.__array_interface__['data'][0] for r in rgbs])
+        sp = (C.c_void_p * max(n_cams, 1))(*[m.__array_interface__['data'][0] for m in sems])
+        T = T_ego_world
+        if not (type(T) is np.ndarray and T.dtype == np.float64 and T.flags.c_contiguous and T.size == 16):
+            T = _hostd(T_ego_world, 16)
+        fc = self._filt_cache
+        if fc is None or fc[0] is not filters or fc[1] != len(filters or ()):
+            f, _, nf = self._filters(filters)
+            fc = self._filt_cache = (filters, len(filters or ()), f, f.__array_interface__['data'][0], nf)
+        self._check(self.lib.pcacc_integrate_records_host(
+            self.h, pc.__array_interface__['data'][0], cam_idx.__array_interface__['data'][0], n,
+            rp, sp, n_cams, sem_dt, h, w, T.__array_interface__['data'][0], float(intensity_div),
+            fc[3], fc[4], staging, self._staging_ref, self._fid_ref, _stream()))
+        self.last_staging = self._staging_out.value
+        if self.last_staging == _lib.STAGE_DIRECT:
+            # the kernel reads these arrays in place: keep them alive until the next sync
+            self._keep.append((pc, cam_idx, rgbs, sems))
+        return self._fid_out.value
 
     def integrate_records_batch(self, sweeps, filters, intensity_div=255.) -> int:
         """sweeps: list of dicts with DEVICE tensors pc (n,7) f64, cam (n,) i64,
@@ -423,8 +539,7 @@ class DeviceCloud:
 
     # -- stand-alone operators -----------------------------------------------------------
     def project(self, pc, P, img_h, img_w, max_depth=np.inf):
-        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
-                             if not isinstance(pc, torch.Tensor) else pc)
+        pts = self.stage.put('pc', self._f32_cloud(pc))
         n, stride = int(pts.shape[0]), int(pts.shape[1])
         u = torch.empty(n, dtype=torch.int32, device=self.device)
         v = torch.empty(n, dtype=torch.int32, device=self.device)
@@ -438,8 +553,7 @@ class DeviceCloud:
 
     def gen_semantic_pc(self, pc, semantic_map, P):
         """(M,4+K) float64 device tensor, rows in input order."""
-        pts = self.stage.put('pc', np.asarray(pc, dtype=np.float32)
-                             if not isinstance(pc, torch.Tensor) else pc)
+        pts = self.stage.put('pc', self._f32_cloud(pc))
         assert pts.shape[1] == 4 and pts.dtype == torch.float32
         sm = semantic_map
         if not isinstance(sm, torch.Tensor):
@@ -519,14 +633,15 @@ class DeviceCloud:
             if buf is None or buf.numel() < n:
                 buf = self._pin_out = torch.empty(max(n, 1), dtype=torch.float16, pin_memory=True)
             view = buf[:n].view(planes.shape)
-        view.copy_(planes, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        st = _stream()
+        check(self.lib.pcacc_memcpy_d2h_async(view.data_ptr(), planes.data_ptr(), n * 2, st))
+        ev = self.stage.next_event()
+        check(self.lib.pcacc_event_record(ev, st))
         return view, ev, planes, own      # `planes` stays referenced until the copy is done
 
     def planes_to_host_finish(self, pending):
         view, ev, _, own = pending
-        ev.synchronize()
+        check(self.lib.pcacc_event_sync(ev))
         if own is not None:
             out = view.numpy()              # shares the pinned buffer
             weakref.finalize(out, _OUT_POOL.give, own)
@@ -588,6 +703,43 @@ class DeviceCloud:
         s = (C.c_int64 * 3)()
         self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))
         return {'visited': int(s[0]), 'binned': int(s[1]), 'replays': int(s[2])}
+
+
+# numpy view of pcacc_bev_params (include/pcacc.h): V parameter blocks are filled with a dozen
+# vectorised assignments instead of ~30 ctypes field stores per variant
+BEV_DTYPE = np.dtype({
+    'names': ['frame_begin', 'frame_split', 'frame_end', 'origin', 'R', 'trans_dx', 'trans_dy', 'view',
+              'height_filter', 'int_scaler', 'int_sep_scaler', 'int_mid_threshold', 'rgb_fill',
+              'road_cls', 'veh_cls', 'elevation_max'],
+    'formats': ['<i8', '<i8', '<i8', ('<f8', 3), ('<f8', 9), '<f8', '<f8', '<f8', '<f8', '<f8', '<f8',
+                '<f8', '<f8', '<i4', ('<i4', 4), '<i4'],
+    'offsets': [getattr(BevParams, n).offset for n in (
+        'frame_begin', 'frame_split', 'frame_end', 'origin', 'R', 'trans_dx', 'trans_dy', 'view',
+        'height_filter', 'int_scaler', 'int_sep_scaler', 'int_mid_threshold', 'rgb_fill', 'road_cls',
+        'veh_cls', 'elevation_max')],
+    'itemsize': C.sizeof(BevParams)})
+
+
+def make_bev_params_batch(frame_begin, frame_split, frame_end, origin, Rs, trans_dx, trans_dy, views,
+                          height_filter, int_scaler, int_sep_scaler, int_mid_threshold, rgb_fill,
+                          sem_idxs, elevation_max=False):
+    """V parameter blocks that share the window and generator settings and differ in rotation
+    (Rs: (V,3,3)), translation and view.  Returns a ctypes array (BevParams * V) over a numpy
+    record array (kept alive by the ctypes object)."""
+    Rs = np.asarray(Rs, dtype=np.float64).reshape(-1, 9)
+    V = Rs.shape[0]
+    rec = np.zeros(V, dtype=BEV_DTYPE)
+    rec['frame_begin'], rec['frame_split'], rec['frame_end'] = int(frame_begin), int(frame_split), int(frame_end)
+    rec['origin'] = np.asarray(origin, dtype=np.float64).reshape(3)
+    rec['R'] = Rs
+    rec['trans_dx'], rec['trans_dy'], rec['view'] = trans_dx, trans_dy, views
+    rec['height_filter'] = np.nan if height_filter is None else float(height_filter)
+    rec['int_scaler'], rec['int_sep_scaler'] = float(int_scaler), float(int_sep_scaler)
+    rec['int_mid_threshold'], rec['rgb_fill'] = float(int_mid_threshold), float(rgb_fill)
+    rec['road_cls'] = int(sem_idxs['road'])
+    rec['veh_cls'] = [int(sem_idxs[k]) for k in ('car', 'truck', 'bus', 'motorcycle')]
+    rec['elevation_max'] = 1 if elevation_max else 0
+    return (BevParams * V).from_buffer(rec)
 
 
 def make_bev_params(frame_begin, frame_split, frame_end, origin, R, trans_dx, trans_dy, view,

@@ -10,8 +10,11 @@ nuscenes_oracle_sem_pc_accum.py:191-250,272-414) stays on the host and drives
 """
 from __future__ import annotations
 
+import bisect
+
 import numpy as np
 
+from . import _lib
 from .sem_pc_accum import SemanticPointCloudAccumulator
 
 
@@ -40,6 +43,9 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         self.ego_pose_z = 1.
         self.instances = {}
         self.dyn_instances = []
+        self._dyn_set = set()            # the same tokens, for O(1) membership
+        self._first_xy = {}              # token -> (x, y) of its first sighting (Python floats)
+        self.staging = _lib.STAGE_AUTO   # host staging mode of integrate (pcacc.h PCACC_STAGE_*)
         self.dyn_obj_trans_thresh = 1.0
         self.token2idx = []
         self.track_inst_clss = [0, 1, 2, 3, 5]
@@ -52,6 +58,17 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
             raise NotImplementedError(
                 'GT lane centrelines need the nuscenes-devkit map API (out of scope); assign '
                 'accumulator.gt_lane_poses (list of (n,3) arrays, global frame) yourself')
+
+    def _boxes_to_world(self, centres):
+        """homo_transform(T_global_world, expand_dims(c, 0))[0] for every box centre in ONE
+        numpy call.  A single-point product takes numpy's matrix-vector path, whose rounding
+        differs from the matrix-matrix one; a stacked (n,4,1) operand
+        runs that same matrix-vector kernel once per box, so the centres — which reach the
+        output through `trajs_*` — keep the reference's bits (tests/test_gpu_api.py)."""
+        c = np.asarray(centres, dtype=np.float64).reshape(-1, 3)
+        col = np.ones((c.shape[0], 4, 1))
+        col[:, :3, 0] = c
+        return np.matmul(self.T_global_world, col)[:, :3, 0]
 
     def integrate(self, observations: list):
         obs = observations[0]
@@ -72,31 +89,56 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         self.ego_global_xs.append(obs['ego_global_x'])
         self.ego_global_ys.append(obs['ego_global_y'])
 
-        # fake detector / tracker: host bookkeeping, device flag updates
-        self.token2idx.append({'ts': self.ts})
-        mark_f, mark_i = [], []
-        for idx, token in enumerate(obs['inst_tokens']):
-            if obs['inst_cls'][idx] not in self.track_inst_clss:
-                continue
-            centre = homo_transform(self.T_global_world,
-                                    np.expand_dims(obs['inst_center'][idx], 0))[0]
-            self.instances.setdefault(token, []).append((centre, self.ts))
-            self.token2idx[-1][token] = idx
-            if token in self.dyn_instances:          # known mover: flag the new sweep
-                mark_f.append(fid)
-                mark_i.append(idx)
-                continue
-            seen = self.instances[token]
-            if len(seen) < 2:
-                continue
-            moved = self.cal_pose_change(seen[0][0][:2], seen[-1][0][:2])
-            if moved > self.dyn_obj_trans_thresh:    # newly dynamic: flag every sighting
-                self.dyn_instances.append(token)
-                for pc_ts, f in enumerate(self._fids):
-                    if token in self.token2idx[pc_ts]:
-                        mark_f.append(f)
-                        mark_i.append(self.token2idx[pc_ts][token])
-        self.cloud.mark_dynamic(mark_f, mark_i)
+        # fake detector / tracker (nuscenes_oracle_sem_pc_accum.py:191-250): host bookkeeping,
+        # device flag updates
+        ts = self.ts
+        seen_now = {'ts': ts}
+        self.token2idx.append(seen_now)
+        tokens = obs['inst_tokens']
+        if len(tokens):
+            inst_cls = obs['inst_cls']
+            centres = self._boxes_to_world(obs['inst_center'])
+            xy = centres[:, :2].tolist()
+            tracked, instances, dyn = self.track_inst_clss, self.instances, self._dyn_set
+            thresh = self.dyn_obj_trans_thresh
+            mark_f, mark_i = [], []
+            for idx, token in enumerate(tokens):
+                if inst_cls[idx] not in tracked:
+                    continue
+                seen = instances.get(token)
+                if seen is None:
+                    seen = instances[token] = []
+                    self._first_xy[token] = xy[idx]
+                seen.append((centres[idx], ts))
+                seen_now[token] = idx
+                if token in dyn:                     # known mover: flag the new sweep
+                    mark_f.append(fid)
+                    mark_i.append(idx)
+                    continue
+                if len(seen) < 2:
+                    continue
+                # moved = ||last - first|| > thresh, decided on the squared distance; only
+                # within 1e-9 of the threshold is the reference's own expression evaluated
+                first = self._first_xy.get(token)
+                if first is None:        # `instances` was filled by the caller
+                    first = self._first_xy[token] = seen[0][0][:2].tolist()
+                x0, y0 = first
+                dx, dy = xy[idx][0] - x0, xy[idx][1] - y0
+                d2, t2 = dx * dx + dy * dy, thresh * thresh
+                if abs(d2 - t2) <= 1e-9 * max(1.0, t2):
+                    is_dyn = self.cal_pose_change(seen[0][0][:2], seen[-1][0][:2]) > thresh
+                else:
+                    is_dyn = d2 > t2
+                if is_dyn:                           # newly dynamic: flag every sighting
+                    self.dyn_instances.append(token)
+                    dyn.add(token)
+                    for pc_ts, f in enumerate(self._fids):
+                        prev = self.token2idx[pc_ts].get(token)
+                        if prev is not None:
+                            mark_f.append(f)
+                            mark_i.append(prev)
+            if mark_f:
+                self.cloud.mark_dynamic(mark_f, mark_i)
 
         if len(self.poses) > 1:
             self.seg_dists.append(self.dist(np.array(self.poses[-1]), np.array(self.poses[-2])))
@@ -109,8 +151,15 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         pose = T_ego_world[:3, -1].tolist()
         pose[2] += ego_pose_z
         semsegs = [self.semseg_model.pred(rgb)[0, 0] for rgb in rgbs]
-        fid = self.cloud.integrate_records(pc, pc_cam_idx, [np.asarray(r) for r in rgbs], semsegs,
-                                           T_ego_world, self.semseg_filters, 255.)
+        if isinstance(pc, np.ndarray) and not any(hasattr(r, 'is_cuda') for r in rgbs):
+            # host arrays: one C call; page-locked arrays are read in place, pageable ones go
+            # through the sparse staging mode (device.py: integrate_records_host)
+            fid = self.cloud.integrate_records_host(
+                pc, pc_cam_idx, [r if type(r) is np.ndarray else np.asarray(r) for r in rgbs],
+                semsegs, T_ego_world, self.semseg_filters, 255., self.staging)
+        else:
+            fid = self.cloud.integrate_records(pc, pc_cam_idx, [np.asarray(r) for r in rgbs],
+                                               semsegs, T_ego_world, self.semseg_filters, 255.)
         return fid, pose, semsegs
 
     @staticmethod
@@ -155,18 +204,41 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
                 for run in self.parse_seq_into_coherent_seqs(tss)]
 
     def get_dyn_obj_trajs(self, ts_start: int = 0, ts_end: int = None, skip_ego_traj: bool = True):
+        """nuscenes_oracle_sem_pc_accum.py:272-347: for every dynamic token the sightings with
+        ts_start <= ts <= ts_end, split into runs of consecutive time steps, runs of >= 2
+        poses kept (lists of [x, y, z])."""
         out = []
+        dyn = self._dyn_set if len(self._dyn_set) == len(self.dyn_instances) else set(self.dyn_instances)
         for token, seen in self.instances.items():
-            if token not in self.dyn_instances:
+            if token not in dyn:
                 continue
-            poses, tss = zip(*seen)
-            try:
-                i0 = self.find_nearest_ge_idx(tss, ts_start)
-                i1 = None if ts_end is None else self.find_nearest_le_idx(tss, ts_end) + 1
-            except ValueError:
+            tss = [t for _, t in seen]
+            # find_nearest_ge_idx / find_nearest_le_idx on an increasing sequence
+            i0 = bisect.bisect_left(tss, ts_start)
+            if i0 >= len(tss):
                 continue
-            poses, tss = poses[i0:i1], tss[i0:i1]
-            out += [s for s in self.parse_coherent_pose_seqs(poses, tss) if len(s) >= 2]
+            if ts_end is None:
+                i1 = len(tss)
+            else:
+                if tss[0] > ts_end:
+                    continue
+                i1 = bisect.bisect_right(tss, ts_end)
+            if i0 >= i1:
+                # a gap in the sightings covers the whole interval: the reference indexes an
+                # empty tuple here (parse_seq_into_coherent_seqs, :400)
+                raise IndexError('tuple index out of range')
+            run = []
+            prev = None
+            for k in range(i0, i1):
+                t = tss[k]
+                if prev is not None and t - prev != 1:
+                    if len(run) >= 2:
+                        out.append(run)
+                    run = []
+                run.append(seen[k][0].tolist())
+                prev = t
+            if len(run) >= 2:
+                out.append(run)
         if not skip_ego_traj:
             out.append(self.poses)
         return out
@@ -174,6 +246,16 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
     def get_split_dyn_obj_trajs(self, split_idx: int, skip_ego_traj: bool = True):
         return (self.get_dyn_obj_trajs(ts_end=split_idx), self.get_dyn_obj_trajs(ts_start=split_idx),
                 self.get_dyn_obj_trajs())
+
+    def reset(self):
+        """New scene on the same accumulator (run_nuscenes_bev_gen.py builds a new accumulator per
+        scene, :165,203; this keeps the ring, its workspace and the staging buffers)."""
+        self.cloud.reset()
+        self._fids, self.poses, self.seg_dists, self.rgbs, self.semsegs = [], [], [], [], []
+        self.T_global_world = None
+        self.instances, self.dyn_instances, self.token2idx, self.ts = {}, [], [], 0
+        self._dyn_set, self._first_xy = set(), {}
+        self.ego_global_xs, self.ego_global_ys = [], []
 
     def generate_bev(self, present_idx: int = None, bev_num: int = 1, gen_future: bool = False):
         other = self.get_split_dyn_obj_trajs(present_idx)

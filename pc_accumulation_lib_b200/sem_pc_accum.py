@@ -196,7 +196,7 @@ class SemanticPointCloudAccumulator:
         return self.cloud.gen_semantic_pc(pc_velo, semantic_map, P_velo_frame).cpu().numpy()
 
     def velo2img(self, pc_velo, P_velo_frame, img_h, img_w, max_depth=np.inf):
-        pc = np.ascontiguousarray(pc_velo, dtype=np.float32)
+        pc = np.ascontiguousarray(self.cloud._f32_cloud(pc_velo))
         u, v, m = self.cloud.project(pc, P_velo_frame, img_h, img_w, max_depth)
         m = m.bool()
         pts = torch.from_numpy(np.asarray(pc_velo)).to(self.cloud.device).double()

@@ -337,3 +337,58 @@ class SceneSemseg:
 
     def pred(self, rgb):
         return self._by_id[id(rgb)][None, None]
+
+
+# ---------------------------------------------------------------------------
+# the dataloader's input side: multi-camera projection, boxes
+# ---------------------------------------------------------------------------
+def _rigid(rng, yaw_range, t_scale, tilt=0.02):
+    yaw, pitch, roll = rng.uniform(-yaw_range, yaw_range), rng.normal(0, tilt), rng.normal(0, tilt)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    R = (np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]]) @ np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+         @ np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]]))
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = rng.normal(0, t_scale, 3)
+    return T
+
+
+def input_side_inputs(n=12000, n_boxes=24, n_cams=6, seed=91):
+    """Lidar points in the ego frame, six cameras looking around (CAM_* of nuScenes: 1600x900,
+    fx = fy ~ 1266, 60 degrees apart, overlapping at the seams so that 'a later camera
+    overwrites an earlier one' is exercised), and boxes in the target frame, some of them
+    overlapping and some empty."""
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(2., 60., n)
+    az = rng.uniform(-np.pi, np.pi, n)
+    pc = np.stack([r * np.cos(az), r * np.sin(az), rng.normal(-0.5, 1.2, n)], axis=1)
+    pc[:50] = 0.0                                  # degenerate points at the sensor origin
+    glob_from_ego = _rigid(rng, np.pi, 300., 0.01)
+    cams = []
+    for j in range(n_cams):
+        yaw = 2 * np.pi * j / n_cams + rng.normal(0, 0.01)
+        # camera axes: z forward, x right, y down
+        fwd = np.array([np.cos(yaw), np.sin(yaw), 0.])
+        right = np.array([np.sin(yaw), -np.cos(yaw), 0.])
+        down = np.array([0., 0., -1.])
+        ego_from_cam = np.eye(4)
+        ego_from_cam[:3, :3] = np.stack([right, down, fwd], axis=1)
+        ego_from_cam[:3, 3] = [1.5 * np.cos(yaw), 0.5 * np.sin(yaw), 1.5]
+        fx = 1266.4 * (0.55 if j % 2 else 1.0)     # every other camera wide: neighbours overlap
+        cams.append(dict(glob_from_self=glob_from_ego @ ego_from_cam,
+                         cam_K=np.array([[fx, 0., 816.3 + j], [0., fx, 491.5 - j], [0., 0., 1.]]),
+                         img_wh=np.array([1600., 900.])))
+    boxes, sizes = [], []
+    for b in range(n_boxes):
+        T = _rigid(rng, np.pi, 0.0, 0.0)
+        T[:3, 3] = [rng.uniform(-40, 40), rng.uniform(-40, 40), rng.normal(-0.3, 0.3)]
+        if b % 5 == 1:                             # overlaps the previous box
+            T[:3, 3] = boxes[-1][:3, 3] + [0.8, 0.3, 0.0]
+        if b % 7 == 3:                             # far away: no points
+            T[:3, 3] = [500. + 30. * b, 500., 0.]
+        boxes.append(T)
+        sizes.append(np.array([rng.uniform(3.5, 12.), rng.uniform(1.6, 3.), rng.uniform(1.4, 3.5)]))
+    # points exactly on box faces / at box centres
+    pc[50:50 + n_boxes] = [T[:3, 3] if b % 7 != 3 else [1., 1., 1.] for b, T in enumerate(boxes)]
+    return dict(pc=pc, pc_f32=pc.astype(np.float32), glob_from_ego=glob_from_ego, cams=cams,
+                boxes=boxes, sizes=sizes, tolerance=1e-2)
