@@ -7,7 +7,7 @@ is not built or no CUDA device is present — there is no CPU path.
 """
 __all__ = ['Kitti360SemanticPointCloudAccumulator', 'NuScenesOracleSemanticPointCloudAccumulator',
            'SemanticPointCloudAccumulator', 'SemBEVGenerator', 'RGBBEVGenerator', 'BEVGenerator',
-           'DeviceCloud', 'AsyncBevWriter']
+           'DeviceCloud', 'AsyncBevWriter', 'pinned_empty', 'pinned_like', 'pin_observation']
 
 
 def __getattr__(name):
@@ -26,7 +26,7 @@ def __getattr__(name):
     if name == 'AsyncBevWriter':
         from .sem_pc_accum import AsyncBevWriter as c
         return c
-    if name == 'DeviceCloud':
-        from .device import DeviceCloud as c
-        return c
+    if name in ('DeviceCloud', 'pinned_empty', 'pinned_like', 'pin_observation'):
+        from . import device as m
+        return getattr(m, name)
     raise AttributeError(name)

@@ -954,11 +954,13 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     __shared__ SmallWarp s_sw[RED_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
-    // blockIdx.y = variant, blockIdx.x = 32*RED_WARPS consecutive cells of it (PP % 32 == 0)
+    // blockIdx.y = variant, blockIdx.x = 32*RED_WARPS consecutive cells of it; when PP is not a
+    // multiple of 32 the lanes past the last cell of the last warp are idle (valid = false)
     const int var = (int)blockIdx.y;
     const int cw = ((int)blockIdx.x * RED_WARPS + (int)warp) * 32;
     if (cw >= PP) return;
-    const int cell_in = cw + (int)lane;
+    const bool valid = cw + (int)lane < PP;
+    const int cell_in = valid ? cw + (int)lane : PP - 1;
     const pcacc_bev_params &bp = params[var];
     const BevConsts &cst = consts[var];
     const bool want_max = bp.elevation_max != 0;
@@ -967,14 +969,16 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     const uint32_t gc = (uint32_t)var * (uint32_t)PP + (uint32_t)cell_in;
     const uint2 s01 = ((const uint2 *)start)[gc];
     uint32_t s2 = __shfl_down_sync(0xffffffffu, s01.x, 1);
-    if (lane == 31) s2 = start[2 * (size_t)gc + 2];
-    const uint32_t my_np = s01.y - s01.x, my_nf = s2 - s01.y, my_nt = my_np + my_nf;
+    if (lane == 31 || cw + (int)lane + 1 >= PP) s2 = start[2 * (size_t)gc + 2];
+    const uint32_t my_np = valid ? s01.y - s01.x : 0u, my_nf = valid ? s2 - s01.y : 0u, my_nt = my_np + my_nf;
     const int64_t o0 = ((int64_t)var * 3 * 7) * PP + cell_in;
 
     // all 32 cells empty: nothing to read
     if (__ballot_sync(0xffffffffu, my_nt != 0) == 0) {
+        if (valid) {
 #pragma unroll
-        for (int w = 0; w < 3; w++) store_empty<F64OUT>(out16, out64, o0 + (int64_t)w * 7 * PP, PP, cst);
+            for (int w = 0; w < 3; w++) store_empty<F64OUT>(out16, out64, o0 + (int64_t)w * 7 * PP, PP, cst);
+        }
         return;
     }
 
@@ -1089,7 +1093,7 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
     }
 
     // back to one cell per lane (large cells are written by pass B)
-    const bool fin = my_nt <= SMALL_T;
+    const bool fin = valid && my_nt <= SMALL_T;
     uint32_t nr[2], nv[2];
     long long hi[2], lo[2];
     double ez[2];
@@ -1449,8 +1453,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
                                void *out_f16_dev, double *out_f64_dev, int32_t *dbg_cell_dev,
                                void *stream) {
     if (!h) return PCACC_ERR_ARG;
-    if (!params || n_variants <= 0 || P <= 0 || (P * P) % 32 != 0 || !out_f16_dev)
-        return pcacc_fail(h, PCACC_ERR_ARG, "bad rasterise arguments (P*P must be a multiple of 32)");
+    if (!params || n_variants <= 0 || P <= 0 || P > 16384 || !out_f16_dev)
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad rasterise arguments");
     if (h->inten_div == 0.0) h->inten_div = 1.0;
     cudaStream_t st = (cudaStream_t)stream;
     PCACC_CUDA(h, cudaSetDevice(h->device));
@@ -1601,7 +1605,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             pcacc_prof_end(h, PCACC_K_SCATTER, pe, st);
         }
         // reduce + finalise (also correct on all-zero counters: every cell empty)
-        const dim3 blocks((unsigned)((PP / 32 + RED_WARPS - 1) / RED_WARPS), (unsigned)nv);
+        const dim3 blocks((unsigned)(((PP + 31) / 32 + RED_WARPS - 1) / RED_WARPS), (unsigned)nv);
         size_t pr = pcacc_prof_begin(h, PCACC_K_REDUCE, st);
         if (want_f64)
             k_bev_reduce<true><<<blocks, RED_WARPS * 32, 0, st>>>(

@@ -158,3 +158,79 @@ def test_async_writer_files_are_the_reference_format(tmp_path):
     wr.submit(bevs[0], 'x', str(tmp_path / 'missing_dir'))
     with pytest.raises(IOError):
         wr.close()
+
+
+def test_tracker_helpers_keep_reference_semantics():
+    """Host bookkeeping of the nuScenes accumulator that was restructured for speed: the batched
+    box transform keeps the single-point product's bits, and the trajectory extraction equals
+    the reference's find_nearest_* / parse_* composition (nuscenes_oracle_sem_pc_accum.py:
+    272-414) on random sighting patterns."""
+    from oracle import oracle as orc
+    from pc_accumulation_lib_b200 import NuScenesOracleSemanticPointCloudAccumulator as Acc
+    rng = np.random.default_rng(3)
+    acc = Acc.__new__(Acc)
+    for _ in range(20):
+        T = np.linalg.inv(rng.normal(size=(4, 4)) * 10.)
+        T[3] = [0., 0., 0., 1.]
+        acc.T_global_world = T
+        c = rng.normal(size=(30, 3)) * 500.
+        want = np.stack([orc.homo_transform(T, c[i:i + 1])[0] for i in range(c.shape[0])])
+        np.testing.assert_array_equal(acc._boxes_to_world(list(c)), want)
+
+    def reference_trajs(instances, dyn, ts_start=0, ts_end=None):
+        out = []
+        for token, seen in instances.items():
+            if token not in dyn:
+                continue
+            poses, tss = zip(*seen)
+            try:
+                i0 = Acc.find_nearest_ge_idx(tss, ts_start)
+                i1 = None if ts_end is None else Acc.find_nearest_le_idx(tss, ts_end) + 1
+            except ValueError:
+                continue
+            poses, tss = poses[i0:i1], tss[i0:i1]
+            for run in Acc.parse_seq_into_coherent_seqs(tss):
+                if len(run) >= 2:
+                    out.append([poses[k].tolist() for k in run])
+        return out
+
+    for trial in range(200):
+        instances, dyn = {}, []
+        for t in range(int(rng.integers(1, 6))):
+            ts = np.flatnonzero(rng.random(30) < rng.uniform(0.3, 0.95))
+            if ts.size == 0:
+                continue
+            instances[f'tok{t}'] = [(rng.normal(size=3), int(k)) for k in ts]
+            if rng.random() < 0.7:
+                dyn.append(f'tok{t}')
+        acc.instances, acc.dyn_instances, acc._dyn_set, acc.poses = instances, dyn, set(dyn), [[0., 0., 0.]]
+        split = int(rng.integers(0, 30))
+        for kw in (dict(ts_end=split), dict(ts_start=split), dict()):
+            try:
+                want = reference_trajs(instances, dyn, **kw)
+            except IndexError:
+                with pytest.raises(IndexError):
+                    acc.get_dyn_obj_trajs(**kw)
+                continue
+            assert acc.get_dyn_obj_trajs(**kw) == want
+
+
+def test_dataset_mirror_transforms_match_oracle():
+    from oracle import oracle as orc
+    from pc_accumulation_lib_b200.datasets import nuscenes_utils as nu
+    rng = np.random.default_rng(9)
+    T = np.linalg.inv(rng.normal(size=(4, 4)))
+    T[3] = [0., 0., 0., 1.]
+    for n in (1, 2, 257):
+        pts = rng.normal(size=(n, 3)) * 100.
+        np.testing.assert_array_equal(nu.homo_transform(T, pts), orc.homo_transform(T, pts))
+        np.testing.assert_array_equal(nu.apply_tf(T, pts), orc.apply_tf(T, pts))
+        q = np.concatenate([pts, rng.normal(size=(n, 2))], axis=1)
+        want = q.copy()
+        want[:, :3] = orc.apply_tf(T, pts)
+        assert nu.apply_tf(T, q, in_place=True) is None
+        np.testing.assert_array_equal(q, want)
+    with pytest.raises(AssertionError):
+        nu.homo_transform(np.eye(3), np.zeros((2, 3)))
+    with pytest.raises(AssertionError):
+        nu.homo_transform(np.eye(4), np.zeros((2, 4)))

@@ -87,9 +87,10 @@ def _long_horizon(dev, F, eager=False):
     return cloud, poses, sgs_d, N
 
 
-def test_full_size_long_horizon_properties(dev):
-    """configs[2]: 200 frames x 120,000 points (24 M resident), one 256x256 BEV at frame 100."""
-    P, F = 256, 200
+@pytest.mark.parametrize('F,P,emax', [(200, 256, False), (100, 1024, True)])
+def test_full_size_long_horizon_properties(dev, F, P, emax):
+    """configs[2]: 200 frames x 120,000 points (24 M resident), one 256x256 BEV at frame 100;
+    configs[4]: 100 frames (12 M resident) at 1024x1024 with elevation max."""
     cloud, poses, sgs_d, N = _long_horizon(dev, F)
     assert cloud.resident_points() == F * N          # kitti_sem_gt draws unfiltered classes only
     first, n_live = cloud.live_frames()
@@ -102,7 +103,7 @@ def test_full_size_long_horizon_properties(dev):
     sem = synth.SEM_IDXS
 
     def params(fb, fs, fe, Rm, dx=0., dy=0.):
-        return dev.make_bev_params(fb, fs, fe, origin, Rm, dx, dy, 80., None, 20., 20., .5, 0, sem)
+        return dev.make_bev_params(fb, fs, fe, origin, Rm, dx, dy, 80., None, 20., 20., .5, 0, sem, emax)
 
     bp = params(first, first + p, first + F, R, 1.25, -0.5)
     o16, _, cells = cloud.rasterise([bp], P, want_cells=True)
@@ -165,4 +166,107 @@ def test_full_size_long_horizon_properties(dev):
     same = (r90[0].view(torch.int16) == want.contiguous().view(torch.int16))
     # a coordinate exactly on a cell boundary would break the symmetry of floor(); none expected
     assert bool(same.all().item()), int((~same).sum().item())
+    cloud.close()
+
+
+def test_full_size_kitti360_sequence_matches_oracle():
+    """configs[0] at full size through the reference-facing class: 20 frames x 120,000 points,
+    camera 1408x376, class map, frustum path (kitti360_sem_pc_accum.py:41-88) and one 256x256
+    BEV at present_idx = 10 (:166-243) against the oracle — records of every frame `==`, cell
+    indices `==`, planes <= 1e-5 before / <= 1 ulp after the float16 cast."""
+    from pc_accumulation_lib_b200 import Kitti360SemanticPointCloudAccumulator
+    P, F, p_idx = 256, 20, 10
+    frames = []
+    for f in range(F):
+        seed = synth.seed_for(1, f)
+        frames.append(dict(pc=synth.kitti_lidar(seed), T=synth.kitti_step_transform(seed),
+                           rgb=synth.kitti_rgb(seed), cls=synth.kitti_class_map_fast(seed)))
+    assert frames[0]['pc'].shape == (120000, 4) and frames[0]['rgb'].shape == (376, 1408, 3)
+    bev_params = synth.kitti_bev_params(pixel_size=P)
+    gp = gen_params(bev_params)
+    ref = orc.KittiOracle(1e9, synth.kitti_calib()['p_velo_frame'], synth.KITTI_FILTERS, gp)
+    for fr in frames:
+        ref.integrate(fr['pc'], fr['rgb'], fr['cls'], fr['T'])
+    want = ref.generate_bev(p_idx, return_f64=True)
+    dbg = want.pop('_debug')
+    for eager in (False, True):
+        acc = Kitti360SemanticPointCloudAccumulator(
+            1e9, synth.kitti_calib(), 1.0, synth.FakeSemseg([fr['cls'] for fr in frames]),
+            synth.KITTI_FILTERS, synth.SEM_IDXS, False, bev_params,
+            ring_capacity_pts=F * 120000 // 4, ring_max_frames=F + 8)
+        acc.eager_rebase = eager
+        for fr in frames:
+            assert acc.integrate([(fr['rgb'], fr['pc'], None, fr['T'])]) == 0
+        np.testing.assert_array_equal(np.array(acc.poses), np.array(ref.poses))
+        assert len(acc.sem_pcs) == F
+        for k in range(F):
+            np.testing.assert_array_equal(acc.sem_pcs[k], ref.sem_pcs[k], err_msg=f'frame {k}')
+        bev = acc.generate_bev(p_idx, 1, True)[0]
+        for k, w in want.items():
+            if isinstance(w, list):
+                assert len(bev[k]) == len(w)
+                for a, b in zip(bev[k], w):
+                    np.testing.assert_array_equal(np.asarray(a), np.asarray(b), err_msg=k)
+                continue
+            d = np.abs(bev[k].view(np.int16).astype(np.int32) - w.view(np.int16).astype(np.int32))
+            assert d.max() <= 1, (k, int(d.max()))
+        # the same window through the C ABI with the float64 planes and the cell indices
+        cloud = acc.cloud
+        first = acc._fids[0]
+        origin = np.array(acc.poses[p_idx])
+        rot = orc.heading_rot_ang(np.array(acc.poses[:p_idx]) - origin)
+        from pc_accumulation_lib_b200 import device as dev_mod
+        bp = bev_params_from(dev_mod, gp, first, first + p_idx, first + F, origin, rot)
+        o16, o64, cells = cloud.rasterise([bp], P, want_f64=True, want_cells=True)
+        cloud.sync()
+        compare_planes(o16[0].cpu().numpy(), o64[0].cpu().numpy(),
+                       {w: dbg[f'planes_f64_{w}'] for w in ('present', 'future', 'full')},
+                       exact=(0, 2, 3, 4, 5, 6) if eager else (0, 2, 3, 4, 5))
+        fids = list(range(first, first + F))
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[:p_idx], P), dbg['cells_present'])
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[p_idx:], P), dbg['cells_future'])
+        cloud.close()
+
+
+def test_full_size_highres_1024_matches_oracle(dev):
+    """configs[4] against the oracle at 10 frames x 120,000 all-points frames (1.2 M resident,
+    lazily re-based), P = 1024, V = 80, 5 % of the vehicle-class points flagged dynamic,
+    elevation in reference mode (min) and north-star mode (max).  (The 100-frame window is
+    covered by test_full_size_long_horizon_properties[100-1024-True].)"""
+    P, F, split = 1024, 10, 5
+    rng = np.random.default_rng(5)
+    ref = orc.KittiOracle(1e9, synth.kitti_calib()['p_velo_frame'], synth.KITTI_FILTERS,
+                          gen_params(synth.kitti_bev_params(pixel_size=P)), use_gt_sem=True)
+    cloud = dev.DeviceCloud(F * 120000 + 1024, F + 8)
+    fids = []
+    for f in range(F):
+        seed = synth.seed_for(5, f)
+        pc = synth.kitti_lidar(seed)
+        sg = synth.kitti_sem_gt(seed, pc.shape[0], unfiltered_only=False)
+        T = synth.kitti_step_transform(seed)
+        ref.integrate(pc, None, None, T, sg)
+        rec = ref.sem_pcs[-1]
+        veh = np.isin(rec[:, 7], [13, 14, 15, 17])
+        rec[veh & (rng.random(rec.shape[0]) < 0.05), 9] = 1.
+        if f:
+            cloud.rebase(T, eager=False)
+        fids.append(cloud.integrate_cloud(rec.copy()))       # rec is re-based in place by the oracle later
+    assert cloud.sync() & ~2 == 0
+    assert cloud.resident_points() == sum(s.shape[0] for s in ref.sem_pcs) > 1_000_000
+    for k in (0, F // 2, F - 1):
+        np.testing.assert_array_equal(cloud.export_frame(fids[k]), ref.sem_pcs[k], err_msg=f'frame {k}')
+    origin = np.array(ref.poses[split])
+    rot = orc.heading_rot_ang(np.array(ref.poses[:split]) - origin)
+    for mode in ('min', 'max'):
+        gp = gen_params(synth.kitti_bev_params(pixel_size=P), elevation_mode=mode)
+        ref.gen_params = gp
+        bp = bev_params_from(dev, gp, fids[0], fids[split], fids[-1] + 1, origin, rot)
+        o16, o64, cells = cloud.rasterise([bp], P, want_f64=True, want_cells=True)
+        cloud.sync()
+        dbg = ref.generate_bev(split, return_f64=True)['_debug']
+        compare_planes(o16[0].cpu().numpy(), o64[0].cpu().numpy(),
+                       {w: dbg[f'planes_f64_{w}'] for w in ('present', 'future', 'full')},
+                       exact=(0, 2, 3, 4, 5))                  # elevation: 1e-13 m under lazy re-base
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[:split], P), dbg['cells_present'])
+        np.testing.assert_array_equal(window_cells(cloud, cells, fids[split:], P), dbg['cells_future'])
     cloud.close()
