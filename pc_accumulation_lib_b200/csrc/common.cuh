@@ -323,6 +323,8 @@ struct pcacc_s {
     struct StageSlot { char *host; size_t cap; cudaEvent_t ev; bool busy; };
     StageSlot stage[PCACC_STAGE_SLOTS];
     int stage_turn;
+    std::vector<uint32_t> stage_idx;   // scratch of the sparse staging pass
+    std::vector<int64_t> stage_pix;
     // raster workspace (grow-only)
     void *d_ws;
     size_t ws_size;

@@ -1104,6 +1104,7 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
                                        sem_dtype, img_h, img_w, T_ego_world, intensity_div, filters,
                                        n_filters, frame_id, stream);
 
+    const int sem_bytes = sem_dtype == PCACC_SEM_U8 ? 1 : sem_dtype == PCACC_SEM_I16 ? 2 : sem_dtype == PCACC_SEM_I32 ? 4 : 8;
     // SPARSE: the rows a camera sees and their (rgb, class) samples, in input order, go to a
     // pinned slot the kernel reads in place: 64 B per visible point instead of the whole
     // (n,7) array and the camera frames.
@@ -1112,38 +1113,48 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
     if (rc) return rc;
     rc = set_inten_div(h, intensity_div);
     if (rc) return rc;
-    int64_t n_vis = 0;
+    // pass 1: the visible points, their pixel addresses, and a prefetch of the two cache lines
+    // each of them will read (the gathers are the only cache-missing part of the staging)
+    std::vector<uint32_t> &vidx = h->stage_idx;
+    std::vector<int64_t> &vpix = h->stage_pix;
+    vidx.clear();
+    vpix.clear();
+    const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
     for (int64_t i = 0; i < n; i++) {
         const int64_t c = cam_idx_host[i];
-        n_vis += (c >= 0 && c < n_cams);
+        if (!(c >= 0 && c < n_cams)) continue;
+        const double uf = pc_host[7 * i + 4], vf = pc_host[7 * i + 5];
+        int64_t pix = -1;
+        // outside the image the kernel raises PCACC_FLAG_UV_OUT_OF_IMAGE and never looks at the sample
+        if ((uf > 1.0) && (uf < wlim) && (vf > 1.0) && (vf < hlim)) {
+            pix = (int64_t)nearbyint(vf) * img_w + (int64_t)nearbyint(uf);   // half to even
+            __builtin_prefetch(rgb_maps_host[c] + pix * 3);
+            __builtin_prefetch((const char *)sem_maps_host[c] + pix * sem_bytes);
+        }
+        vidx.push_back((uint32_t)i);
+        vpix.push_back(pix);
     }
+    const int64_t n_vis = (int64_t)vidx.size();
     pcacc_s::StageSlot *sl = nullptr;
     const size_t row_bytes = (size_t)n_vis * 7 * sizeof(double);
     rc = stage_slot(h, row_bytes + (size_t)n_vis * 8 + 64, &sl);
     if (rc) return rc;
     double *rows = (double *)sl->host;
     uint32_t *samp = (uint32_t *)(sl->host + row_bytes);
-    const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
-    int64_t j = 0;
-    for (int64_t i = 0; i < n; i++) {
-        const int64_t c = cam_idx_host[i];
-        if (!(c >= 0 && c < n_cams)) continue;
-        const double *src = pc_host + 7 * i;
-        double *dst = rows + 7 * j;
-        for (int k = 0; k < 7; k++) dst[k] = src[k];
-        const double uf = src[4], vf = src[5];
+    // pass 2: rows and samples, in input order
+    for (int64_t j = 0; j < n_vis; j++) {
+        const int64_t i = vidx[(size_t)j];
+        memcpy(rows + 7 * j, pc_host + 7 * i, 7 * sizeof(double));
+        const int64_t c = cam_idx_host[i], pix = vpix[(size_t)j];
         uint32_t rgbp = 0;
         int32_t cls = 0;
-        // outside the image the kernel raises PCACC_FLAG_UV_OUT_OF_IMAGE and never looks at the sample
-        if ((uf > 1.0) && (uf < wlim) && (vf > 1.0) && (vf < hlim)) {
-            const int64_t pix = (int64_t)nearbyint(vf) * img_w + (int64_t)nearbyint(uf);   // half to even
+        if (pix >= 0) {
             const uint8_t *px = rgb_maps_host[c] + pix * 3;
             rgbp = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
             cls = host_class(sem_maps_host[c], sem_dtype, pix);
         }
         samp[2 * j] = rgbp;
         samp[2 * j + 1] = (uint32_t)cls;
-        j++;
     }
     CamMaps maps;
     maps.n = 1;

@@ -45,6 +45,7 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         self.dyn_instances = []
         self._dyn_set = set()            # the same tokens, for O(1) membership
         self._first_xy = {}              # token -> (x, y) of its first sighting (Python floats)
+        self._pose_lists = {}            # token -> ([[x, y, z], ...], [ts, ...]) mirror of `instances`
         self.staging = _lib.STAGE_AUTO   # host staging mode of integrate (pcacc.h PCACC_STAGE_*)
         self.dyn_obj_trans_thresh = 1.0
         self.token2idx = []
@@ -98,7 +99,7 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         if len(tokens):
             inst_cls = obs['inst_cls']
             centres = self._boxes_to_world(obs['inst_center'])
-            xy = centres[:, :2].tolist()
+            xyz = centres.tolist()
             tracked, instances, dyn = self.track_inst_clss, self.instances, self._dyn_set
             thresh = self.dyn_obj_trans_thresh
             mark_f, mark_i = [], []
@@ -108,8 +109,13 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
                 seen = instances.get(token)
                 if seen is None:
                     seen = instances[token] = []
-                    self._first_xy[token] = xy[idx]
+                    self._first_xy[token] = xyz[idx][:2]
+                    self._pose_lists[token] = ([], [])
                 seen.append((centres[idx], ts))
+                cached = self._pose_lists.get(token)
+                if cached is not None:
+                    cached[0].append(xyz[idx])
+                    cached[1].append(ts)
                 seen_now[token] = idx
                 if token in dyn:                     # known mover: flag the new sweep
                     mark_f.append(fid)
@@ -123,7 +129,7 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
                 if first is None:        # `instances` was filled by the caller
                     first = self._first_xy[token] = seen[0][0][:2].tolist()
                 x0, y0 = first
-                dx, dy = xy[idx][0] - x0, xy[idx][1] - y0
+                dx, dy = xyz[idx][0] - x0, xyz[idx][1] - y0
                 d2, t2 = dx * dx + dy * dy, thresh * thresh
                 if abs(d2 - t2) <= 1e-9 * max(1.0, t2):
                     is_dyn = self.cal_pose_change(seen[0][0][:2], seen[-1][0][:2]) > thresh
@@ -212,7 +218,11 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         for token, seen in self.instances.items():
             if token not in dyn:
                 continue
-            tss = [t for _, t in seen]
+            cached = self._pose_lists.get(token)
+            if cached is not None and len(cached[1]) == len(seen):
+                plist, tss = cached          # [x, y, z] lists kept since integrate()
+            else:                            # `instances` was filled by the caller
+                plist, tss = [p.tolist() for p, _ in seen], [t for _, t in seen]
             # find_nearest_ge_idx / find_nearest_le_idx on an increasing sequence
             i0 = bisect.bisect_left(tss, ts_start)
             if i0 >= len(tss):
@@ -235,7 +245,7 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
                     if len(run) >= 2:
                         out.append(run)
                     run = []
-                run.append(seen[k][0].tolist())
+                run.append(plist[k][:])
                 prev = t
             if len(run) >= 2:
                 out.append(run)
@@ -254,7 +264,7 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         self._fids, self.poses, self.seg_dists, self.rgbs, self.semsegs = [], [], [], [], []
         self.T_global_world = None
         self.instances, self.dyn_instances, self.token2idx, self.ts = {}, [], [], 0
-        self._dyn_set, self._first_xy = set(), {}
+        self._dyn_set, self._first_xy, self._pose_lists = set(), {}, {}
         self.ego_global_xs, self.ego_global_ys = [], []
 
     def generate_bev(self, present_idx: int = None, bev_num: int = 1, gen_future: bool = False):

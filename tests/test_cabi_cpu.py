@@ -204,6 +204,7 @@ def test_tracker_helpers_keep_reference_semantics():
             if rng.random() < 0.7:
                 dyn.append(f'tok{t}')
         acc.instances, acc.dyn_instances, acc._dyn_set, acc.poses = instances, dyn, set(dyn), [[0., 0., 0.]]
+        acc._pose_lists = {}
         split = int(rng.integers(0, 30))
         for kw in (dict(ts_end=split), dict(ts_start=split), dict()):
             try:

@@ -168,9 +168,10 @@ def test_batch_integrate_into_nearly_full_and_wrapped_ring(dev):
             got[:, 9] = want[k][:, 9]
             np.testing.assert_array_equal(got, want[k], err_msg=f'frame {k}')
 
-    # (a) upper bounds of the batch exceed the capacity, the exact counts fit: the second batch
-    #     lands behind the first one's exact end and wraps once for its later sweeps
-    cloud = dev.DeviceCloud(capacity_pts=int(3.5 * n_in), max_frames=64)
+    # (a) the upper bounds of the second batch exceed the capacity, placed behind the first
+    #     batch's EXACT end it fits: one sync for the whole batch, in-batch frames keep their
+    #     host-side bounds
+    cloud = dev.DeviceCloud(capacity_pts=int(5.2 * n_in), max_frames=64)
     f0 = cloud.integrate_records_batch(sweeps[:3], synth.NUSC_FILTERS, 255.)
     f1 = cloud.integrate_records_batch(sweeps[3:6], synth.NUSC_FILTERS, 255.)
     assert cloud.sync() == 0
@@ -180,14 +181,15 @@ def test_batch_integrate_into_nearly_full_and_wrapped_ring(dev):
     for a in range(6):                                   # live frames never overlap
         for b in range(a + 1, 6):
             assert offs[a][0] + offs[a][1] <= offs[b][0] or offs[b][0] + offs[b][1] <= offs[a][0]
-    # (b) evict the oldest frames, batch again into the wrapped ring
+    # (b) evict the oldest frames; the next batch's second sweep wraps to offset 0
     cloud.evict(4)
     f2 = cloud.integrate_records_batch(sweeps[6:8], synth.NUSC_FILTERS, 255.)
     assert cloud.sync() == 0
     first, n_live = cloud.live_frames()
     assert (first, n_live) == (f0 + 4, 4)
     check(cloud, first, [4, 5, 6, 7])
-    # (c) a batch that cannot fit fails cleanly and leaves no phantom frames behind
+    assert cloud.frame_offset(f2 + 1) == 0 and cloud.frame_offset(f2) > cloud.frame_offset(f2 - 1)
+    # (c) a batch into the wrapped ring that cannot fit fails cleanly and leaves no phantom frames
     with pytest.raises(_lib.PcaccError) as e:
         cloud.integrate_records_batch(sweeps[:4], synth.NUSC_FILTERS, 255.)
     assert e.value.status == _lib.ERR_CAPACITY
