@@ -305,8 +305,35 @@ def run_ours(args, rank, world, local_rank, dist):
             OUT.write(json.dumps({'ncu_step': True, 'scenes': S, 'streams': n_str}) + '\n')
             OUT.flush()
         return
+    # Per-kernel device times.  (1) every kernel class timed ALONE: CUDA events around each launch
+    # on ONE stream, untimed passes after the warm-up — this picks the dominant stage and gives its
+    # own duration.  (2) inside the timed region only the dominant stage's launches carry events
+    # (two cudaEventRecord per launch: timing every class there costs host time the throughput
+    # measurement would pay for); with several streams that in-region duration also spans the other
+    # streams' kernels sharing the SMs, so it is reported beside the alone figure, not instead.
+    STAGES = {'bev_reduce': ('bev_reduce', 'bev_reduce_big'), 'bev_bin': ('bev_bin', 'bev_classify'),
+              'integrate': ('integrate',), 'scan': ('scan',), 'bev_scatter': ('bev_scatter',),
+              'mark_dynamic': ('mark_dynamic',)}
+
+    def by_stage(prof):
+        return {st: (sum(prof[k][0] for k in ks), prof[ks[0]][1]) for st, ks in STAGES.items()}
+
+    torch.cuda.synchronize()
+    clouds[0].profile(True)
+    clouds[0].profile_read()
+    own = [s for s in range(S) if s % n_str == 0]
+    n_alone = 3
+    for _ in range(n_alone):
+        for s in own:
+            scene_pass(s, clouds[0], outs[0])
+        torch.cuda.synchronize()
+        clouds[0]._keep.clear()
+    alone_raw = clouds[0].profile_read()
+    clouds[0].profile(False)
+    alone = by_stage(alone_raw)
+    dom = max(alone, key=lambda k: alone[k][0])
     for c in clouds:
-        c.profile(True)
+        c.profile(STAGES[dom])
         c.profile_read()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -332,22 +359,6 @@ def run_ours(args, rank, world, local_rank, dist):
         extended += 1
     clk = clocks.stop()
     clk['untimed_steps_added_for_sampling'] = extended
-    # the same kernels timed ALONE (one stream, untimed extra pass): inside the timed region
-    # the scenes of 4 streams overlap, so an event pair around one launch also spans the
-    # other streams' kernels it shared the SMs with
-    alone = {}
-    if n_str > 1:
-        torch.cuda.synchronize()
-        clouds[0].profile(True)
-        clouds[0].profile_read()
-        own = [s for s in range(S) if s % n_str == 0]
-        for _ in range(2):
-            for s in own:
-                scene_pass(s, clouds[0], outs[0])
-            torch.cuda.synchronize()
-            clouds[0]._keep.clear()
-        alone = clouds[0].profile_read()
-        clouds[0].profile(False)
     # the only collective of the run: summary statistics (sum of work, max of time)
     pts_step_rank = S * n_in_scene
     tot = parallel.reduce_stats(dist, {'points': pts_step_rank * args.steps,
@@ -369,49 +380,34 @@ def run_ours(args, rank, world, local_rank, dist):
     }
     # stages made of two kernels are timed as one stage: reduce = small-cell pass + queued
     # large-cell pass; bin = streaming crop test + exact per-candidate pass
-    prof_raw = dict(prof)
-    prof['bev_reduce'] = (prof['bev_reduce'][0] + prof.pop('bev_reduce_big')[0], prof['bev_reduce'][1])
-    prof['bev_bin'] = (prof['bev_bin'][0] + prof.pop('bev_classify')[0], prof['bev_bin'][1])
-    dom = max(prof, key=lambda k: prof[k][0])
-    dom_ms = prof[dom][0]
-    # a stage runs once per scene pass (its class may count helper launches too: k_bev_consts,
-    # k_bev_cull), so time per stage execution = class time / scene passes
-    dom_n = S * args.steps
+    region = by_stage(prof)
+    n_passes = n_alone * len(own)
     peak = pk['hbm_gbs']
-    ach = (alg.get(dom, 0.0) / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n and dom_ms > 0 else 0.0
+    us_alone = alone[dom][0] / n_passes * 1e3
+    us_region = region[dom][0] / max(S * args.steps, 1) * 1e3
+    ach = alg.get(dom, 0.0) / (us_alone * 1e-6) / 1e9 if us_alone > 0 else 0.0
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
     except Exception:
         pass
-    kname = {'bev_bin': 'k_bev_classify+k_bev_bin', 'bev_reduce': 'k_bev_reduce+k_bev_reduce_big',
+    kname = {'bev_bin': 'k_bev_classify+k_bev_bin', 'bev_reduce': 'k_bev_reduce_chunk+k_bev_reduce_big',
              'integrate': 'k_integrate_records_batch'}.get(dom, 'k_' + dom)
+    alone_sum = max(sum(v[0] for v in alone.values()), 1e-9)
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' (burst copy)',
-                'launch_us': dom_ms / max(dom_n, 1) * 1e3, 'launches_timed': dom_n,
-                # kernels of different streams overlap: the share is of the summed kernel time
-                'share_of_step': dom_ms / max(sum(v[0] for v in prof.values()), 1e-9),
-                'kernel_ms': {k: round(v[0], 3) for k, v in prof_raw.items() if v[1]},
-                'kernel_launches': {k: v[1] for k, v in prof_raw.items() if v[1]}}
-    if alone:
-        a = dict(alone)
-        a['bev_reduce'] = (a['bev_reduce'][0] + a.pop('bev_reduce_big')[0], a['bev_reduce'][1])
-        a['bev_bin'] = (a['bev_bin'][0] + a.pop('bev_classify')[0], a['bev_bin'][1])
-        if a.get(dom, (0, 0))[1]:
-            # With several streams an event pair around one launch also spans the other
-            # streams' kernels that shared the SMs, so the in-region duration is not the
-            # kernel's own.  Headline = the same launches timed alone; the in-region figures
-            # (which give the stage's share of the step) are kept beside it.
-            us = a[dom][0] / (2 * len(own)) * 1e3
-            roofline['timed_region_overlapped'] = {
-                'launch_us': roofline['launch_us'], 'achieved': roofline['achieved'],
-                'frac': roofline['frac'], 'streams': n_str}
-            roofline['launch_us'] = us
-            roofline['achieved'] = alg.get(dom, 0.0) / (us * 1e-6) / 1e9
-            roofline['frac'] = roofline['achieved'] / peak
-            roofline['timing'] = ('CUDA events around the same launches on ONE stream, %d scene passes '
-                                  'right after the timed region; timed_region_overlapped = events '
-                                  'inside the timed region, where %d streams overlap' % (2 * len(own), n_str))
+                'launch_us': us_alone, 'launches_timed': n_passes,
+                'algorithmic_bytes_per_launch': alg.get(dom, 0.0),
+                'share_of_step': alone[dom][0] / alone_sum,
+                'kernel_us_alone': {k: round(v[0] / n_passes * 1e3, 2) for k, v in alone_raw.items() if v[1]},
+                'kernel_launches_per_step': {k: int(v[1] / n_passes * S) for k, v in alone_raw.items() if v[1]},
+                'timed_region_overlapped': {
+                    'launch_us': us_region, 'launches_timed': S * args.steps, 'streams': n_str,
+                    'achieved': alg.get(dom, 0.0) / (us_region * 1e-6) / 1e9 if us_region > 0 else None,
+                    'frac': alg.get(dom, 0.0) / (us_region * 1e-6) / 1e9 / peak if us_region > 0 else None},
+                'timing': ('launch_us: CUDA events around the stage\'s launches on ONE stream, %d scene passes '
+                           'right before the timed region; timed_region_overlapped: events around the same '
+                           'launches inside the timed region, where %d streams share the SMs' % (n_passes, n_str))}
     b_step = S * (alg['integrate'] + alg['bev_bin'] + alg['bev_reduce'])
     path_ach = b_step * args.steps / (ms_total * 1e-3) / 1e9
     roofline_path = {'achieved': path_ach, 'peak': peak, 'unit': 'GB/s', 'frac': path_ach / peak,
@@ -420,7 +416,7 @@ def run_ours(args, rank, world, local_rank, dist):
                      'resident_points_per_scene': n_res,
                      'note': 'all algorithmic bytes of the step (integrate + rasterise, SURVEY.md 8d: '
                              '49 N_in + 7 N_vis + 37 N_keep per sweep, 33 N_res + 42 P^2 per BEV) / step time'}
-    gpu_launches = int(sum(v[1] for v in prof.values()))
+    gpu_launches = int(sum(v[1] for v in prof.values()))   # launch counts cover every class, timed or not
 
     # ---- e2e: public API, host buffers, copies inside the timed region ---------------
     # Scenes are independent (one accumulator per scene, run_nuscenes_bev_gen.py:165,203), so the

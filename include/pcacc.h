@@ -262,6 +262,13 @@ int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_variants, i
 int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f16_dev, int n_bevs, int n_planes,
                       int P, const int32_t *imap, const int32_t *jmap, void *stream);
 
+/* Implementation switches for A/B measurements and equivalence tests (results are bit-identical
+ * either way).  PCACC_OPT_REDUCE_STRIPS = 1: the per-cell reduction of float16-only output runs
+ * the 32-cell strip kernel (k_bev_reduce) instead of the 128-cell chunk kernel
+ * (k_bev_reduce_chunk, the default whenever P*P is a multiple of 128). */
+#define PCACC_OPT_REDUCE_STRIPS 1
+int pcacc_set_option(pcacc_t h, int option, int value);
+
 /* ring position (record index) of a live frame's first point, for dbg_cell_dev */
 int pcacc_frame_offset(pcacc_t h, int64_t frame_id, int64_t *offset);
 
@@ -348,9 +355,11 @@ int pcacc_project_cameras(pcacc_t h, const double *pc_ego_dev, int64_t n, int64_
 #define PCACC_K_CLASSIFY 9  /* k_bev_classify (streaming crop test over the ring) */
 #define PCACC_N_KERNELS 10
 
-/* enable=1: every kernel launch of this handle is bracketed by CUDA events on
- * its launch stream. */
-int pcacc_profile(pcacc_t h, int enable);
+/* class_mask: bit k set = every launch of kernel class k of this handle is bracketed by CUDA
+ * events on its launch stream (two cudaEventRecord calls per launch: time only the classes
+ * you need inside a throughput measurement).  0 = off, PCACC_PROFILE_ALL = every class. */
+#define PCACC_PROFILE_ALL ((1 << PCACC_N_KERNELS) - 1)
+int pcacc_profile(pcacc_t h, int class_mask);
 /* Synchronises, then returns and clears the accumulated per-class device time
  * (ms, from the events) and launch counts since the last read.  launches[] is
  * counted whether or not event timing is enabled. */

@@ -19,6 +19,7 @@ FLAG_UV_OUT_OF_IMAGE, FLAG_INTENSITY_F32, FLAG_ATTR_RANGE, FLAG_CELL_OVERFLOW = 
 SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB, SEM_I16 = 0, 1, 2, 3, 4
 BEV_PLANES, BEV_WINDOWS = 7, 3
 STAGE_AUTO, STAGE_DIRECT, STAGE_SPARSE = 0, 1, 2
+OPT_REDUCE_STRIPS = 1
 ABI_VERSION = 1
 
 
@@ -75,6 +76,7 @@ SIGNATURES = {
     'pcacc_integrate_cloud': (_i32, [_vp, _vp, _i64, C.POINTER(_i64), _vp]),
     'pcacc_rebase': (_i32, [_vp, _vp, _i32, _vp]),
     'pcacc_evict': (_i32, [_vp, _i32]),
+    'pcacc_set_option': (_i32, [_vp, _i32, _i32]),
     'pcacc_mark_dynamic': (_i32, [_vp, _vp, _vp, _i32, _vp]),
     'pcacc_sync': (_i32, [_vp, C.POINTER(C.c_uint32), _vp]),
     'pcacc_num_frames': (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i32)]),

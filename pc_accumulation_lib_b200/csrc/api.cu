@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -73,7 +74,7 @@ int pcacc_arena_put(pcacc_t h, const void *src, size_t bytes, void **dev, cudaSt
 
 size_t pcacc_prof_begin(pcacc_t h, int kernel, cudaStream_t st) {
     h->launches[kernel]++;
-    if (!h->prof_on) return 0;
+    if (!((h->prof_mask >> kernel) & 1u)) return 0;
     if (h->prof_used + 2 > h->prof_events.size()) {
         size_t old = h->prof_events.size();
         h->prof_events.resize(old + 1024);
@@ -86,7 +87,7 @@ size_t pcacc_prof_begin(pcacc_t h, int kernel, cudaStream_t st) {
 }
 
 void pcacc_prof_end(pcacc_t h, int kernel, size_t ev0, cudaStream_t st) {
-    if (!h->prof_on) return;
+    if (!((h->prof_mask >> kernel) & 1u)) return;
     cudaEventRecord(h->prof_events[ev0 + 1], st);
     h->prof_spans.push_back({kernel, ev0, ev0 + 1});
     if (h->prof_spans.size() >= 16384) pcacc_prof_flush(h);
@@ -106,11 +107,11 @@ int pcacc_prof_flush(pcacc_t h) {
     return PCACC_OK;
 }
 
-extern "C" int pcacc_profile(pcacc_t h, int enable) {
+extern "C" int pcacc_profile(pcacc_t h, int class_mask) {
     if (!h) return PCACC_ERR_ARG;
     PCACC_CUDA(h, cudaSetDevice(h->device));
-    if (!enable && h->prof_on) pcacc_prof_flush(h);
-    h->prof_on = enable != 0;
+    if (h->prof_mask) pcacc_prof_flush(h);
+    h->prof_mask = (uint32_t)class_mask & ((1u << PCACC_N_KERNELS) - 1u);
     return PCACC_OK;
 }
 
@@ -284,6 +285,10 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
     TRY(cudaMallocHost(&h->h_mail, (size_t)(3 * max_frames + 8) * 8));
     TRY(cudaMallocHost(&h->h_arena, h->arena_size));
 #undef TRY
+    {   // A/B switch for profiling runs (see pcacc_set_option)
+        const char *e = getenv("PCACC_REDUCE_STRIPS");
+        h->reduce_strips = e && e[0] == '1';
+    }
     int rc = pcacc_ensure_tiles(h, 4096);
     if (!rc) rc = pcacc_init_tables(h);
     if (rc) {
@@ -312,6 +317,14 @@ extern "C" int pcacc_reset(pcacc_t h, void *stream) {
     h->any_lazy = false;
     h->inten_div = 0.0;
     return PCACC_OK;
+}
+
+extern "C" int pcacc_set_option(pcacc_t h, int option, int value) {
+    if (!h) return PCACC_ERR_ARG;
+    switch (option) {
+        case PCACC_OPT_REDUCE_STRIPS: h->reduce_strips = value != 0; return PCACC_OK;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown option %d", option);
+    }
 }
 
 extern "C" int pcacc_evict(pcacc_t h, int n_frames) {

@@ -333,9 +333,10 @@ struct pcacc_s {
     int64_t last_visit_ub;
     double inten_div;    // stored intensity / inten_div = reference intensity; 0 = not set yet
     uint32_t pending_flags;
+    bool reduce_strips;   // debugging / A-B switch: 1 = the 32-cell strip kernel for float16 output too
     // launch accounting + optional per-kernel CUDA-event timing
     int64_t launches[PCACC_N_KERNELS];
-    bool prof_on;
+    uint32_t prof_mask;   // bit k: launches of kernel class k are bracketed by events
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used;
     struct ProfSpan { int kernel; size_t ev0, ev1; };

@@ -1198,6 +1198,332 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
 }
 
 // ---------------------------------------------------------------------------
+// pass A, chunked (float16 output only, P*P a multiple of CH_CELLS): one warp per CH_CELLS
+// consecutive cells.  In the dataset-generation workload a 32-cell strip holds ~16 points in
+// ~7 non-empty cells, and k_bev_reduce pays its fixed per-strip work (segment scans, zeroing,
+// the 21-plane finalisation of 32 lanes) for every strip that is not completely empty.  Here
+// the non-empty small cells of a 128-cell chunk are compacted first and reduced 32 at a time
+// (lane = one non-empty cell: the finalisation never runs for an empty cell), results go to
+// a shared-memory tile of the chunk's 21 x 128 planes that starts out as the empty-window
+// constants and leaves as 21 fully coalesced 256-byte row pieces.
+// ---------------------------------------------------------------------------
+#define CH_CELLS 128
+#define CH_PER_LANE (CH_CELLS / 32)
+#define CH_WARPS 2
+
+// per-warp state of one group of <= 32 small cells.  Arrays are [k][cell] (see SmallWarp).
+// Every accumulator is a 32-bit word updated with native shared-memory atomics: the 64-bit
+// ones of k_bev_reduce compile to compare-and-swap loops (ATOMS.CAST.SPIN).
+struct __align__(16) GroupWarp {
+    uint32_t val[32 * SMALL_T];      // packed r,g,b of the points; later the intensity evaluation slots
+    // ---- zeroed together with 16-byte stores --------------------------------------
+    uint32_t cnt[32];                // four 8-bit counts: road present / future, vehicle present / future
+    uint32_t fx0[2][32], fx1[2][32]; // raw road intensity sums, 2^-40 fixed point, in three 21-bit limbs:
+    int32_t fx2[2][32];              //   fx = fx0 + fx1 * 2^21 + fx2 * 2^42 (fx2 signed)
+    uint32_t med[6][32];             // lo/hi order statistics: present, future, full
+    // --------------------------------------------------------------------------------
+    uint32_t zc[2][32];              // order-encoded float16 of the extreme z per window
+    uint32_t cs[33];                 // first compacted index of each cell (cs[32] = total)
+    uint32_t s0[32];                 // first record of each cell in `sorted`
+    uint8_t meta[32 * SMALL_T];      // cell | window << 5 of each point
+    uint8_t np[32], nt[32];
+};
+#define GW_ZERO_BYTES (32 * 4 + 3 * 2 * 32 * 4 + 6 * 32 * 4)
+static_assert(offsetof(GroupWarp, cnt) % 16 == 0 && GW_ZERO_BYTES % 16 == 0 &&
+              offsetof(GroupWarp, zc) == offsetof(GroupWarp, cnt) + GW_ZERO_BYTES, "zeroed block");
+
+struct __align__(16) ChunkWarp {
+    GroupWarp gw;
+    uint32_t g_s0[CH_CELLS];     // compacted non-empty small cells: first record in `sorted`
+    uint8_t g_cell[CH_CELLS];    // ... cell index inside the chunk
+    uint8_t g_np[CH_CELLS], g_nt[CH_CELLS];
+};
+
+// float16 bits <-> unsigned keys with the same order (rounding to float16 is monotone, so
+// the float16 of the smallest z is the smallest float16: the extreme can be taken after the cast)
+__device__ __forceinline__ uint32_t h_ord(__half h) {
+    const uint32_t b = __half_as_ushort(h);
+    return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+}
+__device__ __forceinline__ __half h_unord(uint32_t u) {
+    const uint32_t b = (u & 0x8000u) ? (u & 0x7fffu) : (~u & 0xffffu);
+    return __ushort_as_half((unsigned short)b);
+}
+
+__global__ void __launch_bounds__(CH_WARPS * 32, 12)
+k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
+                   const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
+                   const double *__restrict__ lut, int P, double intensity_div,
+                   uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_count,
+                   __half *__restrict__ out16) {
+    __shared__ ChunkWarp s_cw[CH_WARPS];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int PP = P * P;
+    const int var = (int)blockIdx.y;
+    const int c0 = ((int)blockIdx.x * CH_WARPS + (int)warp) * CH_CELLS;
+    if (c0 >= PP) return;
+    ChunkWarp &cw = s_cw[warp];
+    GroupWarp &sw = cw.gw;
+    const pcacc_bev_params &bp = params[var];
+    const BevConsts &cst = consts[var];
+    const bool want_max = bp.elevation_max != 0;
+
+    // segment bounds of my CH_PER_LANE cells: words 2*gc .. 2*gc + 2*CH_PER_LANE (coalesced 16 B loads)
+    const uint32_t gc0 = (uint32_t)var * (uint32_t)PP + (uint32_t)c0 + CH_PER_LANE * lane;
+    uint32_t sb[2 * CH_PER_LANE + 1];
+    {
+        const uint4 *s4 = (const uint4 *)(start + 2 * (size_t)gc0);
+#pragma unroll
+        for (int k = 0; k < CH_PER_LANE / 2; k++) {
+            const uint4 v = s4[k];
+            sb[4 * k] = v.x; sb[4 * k + 1] = v.y; sb[4 * k + 2] = v.z; sb[4 * k + 3] = v.w;
+        }
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, sb[0], 1);
+        if (lane == 31) nxt = start[2 * (size_t)gc0 + 2 * CH_PER_LANE];
+        sb[2 * CH_PER_LANE] = nxt;
+    }
+    uint32_t c_np[CH_PER_LANE], c_nt[CH_PER_LANE];
+    uint32_t n_big = 0, n_small = 0;
+#pragma unroll
+    for (int k = 0; k < CH_PER_LANE; k++) {
+        c_np[k] = sb[2 * k + 1] - sb[2 * k];
+        c_nt[k] = sb[2 * k + 2] - sb[2 * k];
+        n_big += c_nt[k] > SMALL_T;
+        n_small += c_nt[k] > 0 && c_nt[k] <= SMALL_T;
+    }
+    // The empty-window constants go out first, for the whole chunk: plane p of window w of the
+    // chunk is CH_CELLS halves = 32 lanes x 8 bytes.  The non-empty cells overwrite theirs
+    // afterwards (ordered by the __syncwarp below).
+    __half *const ob = out16 + ((int64_t)var * 21) * PP + c0;
+    static_assert(CH_PER_LANE == 4, "one uint2 of four halves per lane and plane");
+    {
+        const uint32_t r = __half_as_ushort(cst.empty_h[0]), i = __half_as_ushort(cst.empty_h[1]),
+                       g = __half_as_ushort(cst.empty_h[2]), z = __half_as_ushort(cst.empty_h[3]);
+        const uint2 e_road = make_uint2(r | (r << 16), r | (r << 16)), e_int = make_uint2(i | (i << 16), i | (i << 16)),
+                    e_rgb = make_uint2(g | (g << 16), g | (g << 16)), e_z = make_uint2(z | (z << 16), z | (z << 16));
+        __half *o = ob + CH_PER_LANE * lane;
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+#pragma unroll
+            for (int pl = 0; pl < 7; pl++) {
+                *(uint2 *)o = pl == 0 || pl == 5 ? e_road : pl == 1 ? e_int : pl == 6 ? e_z : e_rgb;
+                o += PP;
+            }
+        }
+    }
+    // queue the large cells for pass B; compact the small non-empty ones
+    {
+        uint32_t incl = n_big | (n_small << 16);     // both scans in one (<= 128 each)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot == 0) return;                        // nothing but empty cells
+        const uint32_t excl = incl - (n_big | (n_small << 16));
+        uint32_t bbase = 0;
+        if ((tot & 0xffffu) != 0) {
+            if (lane == 0) bbase = atomicAdd(big_count, tot & 0xffffu);
+            bbase = __shfl_sync(0xffffffffu, bbase, 0);
+        }
+        uint32_t bi = bbase + (excl & 0xffffu), si = excl >> 16;
+#pragma unroll
+        for (int k = 0; k < CH_PER_LANE; k++) {
+            if (c_nt[k] > SMALL_T) {
+                big_list[bi++] = gc0 + k;
+            } else if (c_nt[k] > 0) {
+                cw.g_s0[si] = sb[2 * k];
+                cw.g_cell[si] = (uint8_t)(CH_PER_LANE * lane + k);
+                cw.g_np[si] = (uint8_t)c_np[k];
+                cw.g_nt[si] = (uint8_t)c_nt[k];
+                si++;
+            }
+        }
+        n_small = tot >> 16;      // now: the chunk's total
+    }
+    __syncwarp();                 // lists visible; constant stores ordered before the overwrites
+
+    const int road_cls = bp.road_cls, v0 = bp.veh_cls[0], v1 = bp.veh_cls[1], v2 = bp.veh_cls[2],
+              v3 = bp.veh_cls[3];
+    const __half *lut16 = (const __half *)(lut + LUT_TOTAL);
+    const __half eh_rgb = cst.empty_h[2], eh_z = cst.empty_h[3], eh_int = cst.empty_h[1];
+    const uint32_t z_init = want_max ? 0u : 0xffffffffu;
+    for (uint32_t g0 = 0; g0 < n_small; g0 += 32) {
+        // ---- one group of <= 32 non-empty small cells: lane = cell --------------------------
+        const bool have = g0 + lane < n_small;
+        const uint32_t my_np = have ? cw.g_np[g0 + lane] : 0u, my_nt = have ? cw.g_nt[g0 + lane] : 0u;
+        const uint32_t my_nf = my_nt - my_np;
+        uint32_t cs_incl = my_nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, cs_incl, o);
+            if (lane >= (unsigned)o) cs_incl += t;
+        }
+        const uint32_t T = __shfl_sync(0xffffffffu, cs_incl, 31);
+        sw.cs[lane] = cs_incl - my_nt;
+        if (lane == 31) sw.cs[32] = T;
+        sw.s0[lane] = have ? cw.g_s0[g0 + lane] : 0u;
+        sw.np[lane] = (uint8_t)my_np;
+        sw.nt[lane] = (uint8_t)my_nt;
+        {
+            uint4 *z4 = (uint4 *)sw.cnt;
+#pragma unroll
+            for (int k = 0; k < (GW_ZERO_BYTES / 16 + 31) / 32; k++)
+                if (lane + 32 * k < GW_ZERO_BYTES / 16) z4[lane + 32 * k] = make_uint4(0, 0, 0, 0);
+            sw.zc[0][lane] = sw.zc[1][lane] = z_init;
+        }
+        {
+            const uint32_t b = cs_incl - my_nt;
+            for (uint32_t j = 0; j < my_nt; j++) sw.meta[b + j] = (uint8_t)(lane | (j >= my_np ? 32u : 0u));
+        }
+        __syncwarp();
+        // pass 1: statistics, one record per lane and round
+        for (uint32_t q = lane; q < T; q += 32) {
+            const int c = sw.meta[q] & 31, w = sw.meta[q] >> 5;
+            const uint32_t li = q - sw.cs[c];
+            const uint4 r = sorted[sw.s0[c] + li];
+            sw.val[q] = f_pack(r.z);
+            const int sem = (int)(r.z >> 24);
+            uint32_t add = 0;
+            if (sem == road_cls) {
+                const long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
+                add = 1u << (8 * w);
+                atomicAdd(&sw.fx0[w][c], (uint32_t)fx & 0x1fffffu);
+                atomicAdd(&sw.fx1[w][c], (uint32_t)(fx >> 21) & 0x1fffffu);
+                atomicAdd(&sw.fx2[w][c], (int32_t)(fx >> 42));
+            }
+            if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) add += 1u << (16 + 8 * w);
+            if (add) atomicAdd(&sw.cnt[c], add);
+            const uint32_t zk =
+                h_ord(__double2half(__longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x))));
+            if (want_max) atomicMax(&sw.zc[w][c], zk); else atomicMin(&sw.zc[w][c], zk);
+        }
+        __syncwarp();
+        // pass 2: rank intervals (see k_bev_reduce)
+        for (uint32_t q = lane; q < T; q += 32) {
+            const int c = sw.meta[q] & 31, wi = sw.meta[q] >> 5;
+            const uint32_t base = sw.cs[c], np = sw.np[c], nt = sw.nt[c], nf = nt - np;
+            const uint32_t vi = sw.val[q], vig = vi | F_GUARD;
+            if (nt == 1) {                      // the commonest cell: its one point is every median
+                sw.med[2 * wi][c] = vi;
+                sw.med[2 * wi + 1][c] = vi;
+                sw.med[4][c] = vi;
+                sw.med[5][c] = vi;
+                continue;
+            }
+            uint32_t e1 = 0, g1 = 0, e2 = 0, g2 = 0;
+#pragma unroll 2
+            for (uint32_t j = 0; j < np; j++) {
+                const uint32_t vj = sw.val[base + j];
+                e1 += f_ge(vig, vj);
+                g1 += f_ge(vj | F_GUARD, vi);
+            }
+#pragma unroll 2
+            for (uint32_t j = np; j < nt; j++) {
+                const uint32_t vj = sw.val[base + j];
+                e2 += f_ge(vig, vj);
+                g2 += f_ge(vj | F_GUARD, vi);
+            }
+            {
+                const uint32_t nw = wi ? nf : np;
+                const uint32_t E = wi ? e2 : e1, L = nw * F_ONE - (wi ? g2 : g1);
+                const uint32_t klo = (nw - 1) / 2 * F_ONE, khi = nw / 2 * F_ONE;
+                const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
+                const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
+                if (m) atomicOr(&sw.med[2 * wi][c], vi & m);
+                if (h) atomicOr(&sw.med[2 * wi + 1][c], vi & h);
+            }
+            {
+                const uint32_t E = e1 + e2, L = nt * F_ONE - (g1 + g2);
+                const uint32_t klo = (nt - 1) / 2 * F_ONE, khi = nt / 2 * F_ONE;
+                const uint32_t m = (f_ge(klo | F_GUARD, L) & f_ge(E | F_GUARD, klo + F_ONE)) * 0x3ffu;
+                const uint32_t h = (f_ge(khi | F_GUARD, L) & f_ge(E | F_GUARD, khi + F_ONE)) * 0x3ffu;
+                if (m) atomicOr(&sw.med[4][c], vi & m);
+                if (h) atomicOr(&sw.med[5][c], vi & h);
+            }
+        }
+        __syncwarp();
+
+        uint32_t nr[2], nv[2];
+        uint32_t zk[2];
+        {
+            const uint32_t cw4 = sw.cnt[lane];
+            nr[0] = cw4 & 255u;
+            nr[1] = (cw4 >> 8) & 255u;
+            nv[0] = (cw4 >> 16) & 255u;
+            nv[1] = cw4 >> 24;
+        }
+        zk[0] = sw.zc[0][lane];
+        zk[1] = sw.zc[1][lane];
+        uint32_t med2[3];
+#pragma unroll
+        for (int w = 0; w < 3; w++) med2[w] = sw.med[2 * w][lane] + sw.med[2 * w + 1][lane];
+
+        // intensity: (cell, window) pairs with road points compacted over the warp
+        const bool need0 = have && nr[0] != 0, need1 = have && nr[1] != 0, need2 = need0 && need1;
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1),
+                       m2 = __ballot_sync(0xffffffffu, need2);
+        const uint32_t b1 = (uint32_t)__popc(m0), b2 = b1 + (uint32_t)__popc(m1), tot = b2 + (uint32_t)__popc(m2);
+        const uint32_t k0 = (uint32_t)__popc(m0 & lt), k1 = b1 + (uint32_t)__popc(m1 & lt),
+                       k2 = b2 + (uint32_t)__popc(m2 & lt);
+        // slot = the three limb sums (the exact integer sum; converted by the evaluating lane) + count
+        uint4 *e_sl = (uint4 *)sw.val;
+        static_assert(sizeof(sw.val) >= 96 * sizeof(uint4), "evaluation slots");
+        {
+            const uint32_t a0 = sw.fx0[0][lane], a1 = sw.fx1[0][lane], c0_ = sw.fx0[1][lane], c1_ = sw.fx1[1][lane];
+            const int32_t a2 = sw.fx2[0][lane], c2_ = sw.fx2[1][lane];
+            if (need0) e_sl[k0] = make_uint4(a0, a1, (uint32_t)a2, nr[0]);
+            if (need1) e_sl[k1] = make_uint4(c0_, c1_, (uint32_t)c2_, nr[1]);
+            if (need2) e_sl[k2] = make_uint4(a0 + c0_, a1 + c1_, (uint32_t)(a2 + c2_), nr[0] + nr[1]);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < tot; i += 32) {
+            const uint4 sl = e_sl[i];
+            // S = l0 + l1 2^21 + l2 2^42 rounded once, as fx_to_double rounds hi 2^32 + lo
+            const double raw = __dmul_rn(__dadd_rn(__dmul_rn((double)(int32_t)sl.z, 4398046511104.0),
+                                                   (double)(((long long)sl.y << 21) + (long long)sl.x)), FX_INV);
+            const double val = intensity_plane(bp, raw, sl.w, intensity_div);
+            ((__half *)e_sl)[8 * i] = __double2half(val);     // in place: slot i is read by this lane only
+        }
+        __syncwarp();
+        __half I[3];
+        I[0] = need0 ? ((const __half *)e_sl)[8 * k0] : eh_int;
+        I[1] = need1 ? ((const __half *)e_sl)[8 * k1] : eh_int;
+        I[2] = need2 ? ((const __half *)e_sl)[8 * k2] : (need0 ? I[0] : I[1]);
+
+        if (have) {
+            __half *o = ob + cw.g_cell[g0 + lane];
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                const uint32_t nw = (w == 0) ? my_np : (w == 1) ? my_nf : my_nt;
+                const uint32_t nrw = (w < 2) ? nr[w & 1] : nr[0] + nr[1], nvw = (w < 2) ? nv[w & 1] : nv[0] + nv[1];
+                const uint32_t zz = (w < 2) ? zk[w & 1] : (want_max ? max(zk[0], zk[1]) : min(zk[0], zk[1]));
+                const bool ne = nw != 0;
+                const uint32_t di = DIR_LUT_OFF + nw * 16;
+                __half h[7];
+                h[0] = lut16[di + nrw];
+                h[1] = I[w];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const __half t = lut16[(med2[w] >> (10 * k)) & 1023u];
+                    h[2 + k] = ne ? t : eh_rgb;
+                }
+                h[5] = lut16[di + nvw];
+                h[6] = ne ? h_unord(zz) : eh_z;
+#pragma unroll
+                for (int pl = 0; pl < 7; pl++) {
+                    *o = h[pl];
+                    o += PP;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // pass B: one warp per queued large cell (dynamic queue), 256-bin shared-memory
 // histograms per window and channel.
 // ---------------------------------------------------------------------------
@@ -1611,6 +1937,11 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             k_bev_reduce<true><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, o64);
+        else if (PP % CH_CELLS == 0 && !h->reduce_strips)
+            k_bev_reduce_chunk<<<dim3((unsigned)((PP / CH_CELLS + CH_WARPS - 1) / CH_WARPS), (unsigned)nv),
+                                 CH_WARPS * 32, 0, st>>>(
+                counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
+                h->d_rgb_lut, P, h->inten_div, big_list, big_count, o16);
         else
             k_bev_reduce<false><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,

@@ -235,6 +235,7 @@ class DeviceCloud:
         self._fid_out, self._staging_out = C.c_int64(-1), C.c_int(0)
         self._fid_ref, self._staging_ref = C.byref(self._fid_out), C.byref(self._staging_out)
         self.last_staging = None
+        self._dirty = True    # frames or flags may have changed since the last sync()
         self._mark_f, self._mark_i = [], []   # queued dynamic-flag updates
 
     def close(self):
@@ -279,6 +280,7 @@ class DeviceCloud:
 
     # -- lifetime --------------------------------------------------------------
     def reset(self):
+        self._dirty = True
         self._mark_f, self._mark_i = [], []
         self._check(self.lib.pcacc_reset(self.h, _stream()))
 
@@ -289,6 +291,7 @@ class DeviceCloud:
         fl = C.c_uint32(0)
         self._check(self.lib.pcacc_sync(self.h, C.byref(fl), _stream()))
         self._keep.clear()
+        self._dirty = False
         return int(fl.value)
 
     def refresh(self):
@@ -334,6 +337,7 @@ class DeviceCloud:
         return pc32
 
     def integrate_frustum(self, pc, P, rgb, sem, filters, max_depth=np.inf) -> int:
+        self._dirty = True
         pts = self.stage.put('pc', self._f32_cloud(pc))
         assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
         rgb_d = self.stage.put('rgb', rgb if isinstance(rgb, torch.Tensor)
@@ -351,6 +355,7 @@ class DeviceCloud:
         return int(fid.value)
 
     def integrate_gt(self, pc, sem_gt, filters) -> int:
+        self._dirty = True
         pts = self.stage.put('pc', self._f32_cloud(pc))
         assert pts.dim() == 2 and pts.shape[1] == 4 and pts.dtype == torch.float32
         if isinstance(sem_gt, torch.Tensor):
@@ -367,6 +372,7 @@ class DeviceCloud:
 
     def integrate_records(self, pc, cam_idx, rgbs, sems, T_ego_world, filters,
                           intensity_div=255.) -> int:
+        self._dirty = True
         pcd = self.stage.put('pc', pc if isinstance(pc, torch.Tensor)
                              else np.asarray(pc, dtype=np.float64))
         assert pcd.dim() == 2 and pcd.shape[1] == 7 and pcd.dtype == torch.float64
@@ -403,6 +409,7 @@ class DeviceCloud:
         (pcacc_integrate_records_host): page-locked arrays are read by the kernel in place,
         pageable ones go through the sparse staging mode.  Returns the frame id;
         `self.last_staging` tells which mode ran."""
+        self._dirty = True
         if not (type(pc) is np.ndarray and pc.dtype == np.float64 and pc.flags.c_contiguous):
             pc = np.ascontiguousarray(pc, dtype=np.float64)
         if not (type(cam_idx) is np.ndarray and cam_idx.dtype == np.int64 and cam_idx.flags.c_contiguous):
@@ -476,12 +483,14 @@ class DeviceCloud:
         return {'args': args, 'keep': (sweeps, pcp, cmp_, nn, rp, sp, T, f)}
 
     def integrate_prepared(self, prep) -> int:
+        self._dirty = True
         fid = C.c_int64(-1)
         self._check(self.lib.pcacc_integrate_records_batch(self.h, *prep['args'], C.byref(fid),
                                                            _stream()))
         return int(fid.value)
 
     def integrate_cloud(self, rec) -> int:
+        self._dirty = True
         r = self.stage.put('cloud', rec if isinstance(rec, torch.Tensor)
                            else np.asarray(rec, dtype=np.float64))
         assert r.dim() == 2 and r.shape[1] == 10 and r.dtype == torch.float64
@@ -493,6 +502,7 @@ class DeviceCloud:
 
     # -- state updates -------------------------------------------------------------
     def rebase(self, T_new_prev, eager=False):
+        self._dirty = True
         T = _hostd(T_new_prev, 16)
         self._check(self.lib.pcacc_rebase(self.h, T.ctypes.data_as(C.c_void_p),
                                           1 if eager else 0, _stream()))
@@ -593,8 +603,19 @@ class DeviceCloud:
                                              _ptr(cells), _stream()))
         return out, o64, cells
 
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.pcacc_set_option(self.h, int(option), int(value)))
+
     def profile(self, enable=True):
-        self._check(self.lib.pcacc_profile(self.h, 1 if enable else 0))
+        """enable: False = off, True = every kernel class, or an iterable of class names
+        (_lib.KERNEL_CLASSES) to time only those."""
+        if enable is True:
+            mask = (1 << len(_lib.KERNEL_CLASSES)) - 1
+        elif not enable:
+            mask = 0
+        else:
+            mask = sum(1 << _lib.KERNEL_CLASSES.index(k) for k in enable)
+        self._check(self.lib.pcacc_profile(self.h, mask))
 
     def profile_read(self):
         """{kernel class: (device ms from CUDA events, launches)} since the last read."""

@@ -96,6 +96,8 @@ class SemanticPointCloudAccumulator:
         return self.cloud.export_frame(fid)
 
     def _sync(self):
+        if not self.cloud._dirty:
+            return 0          # nothing was enqueued since the last sync: table and flags are current
         flags = self.cloud.sync()
         if flags & _lib.FLAG_UV_OUT_OF_IMAGE:
             raise AssertionError('pts_uv must be all inside image')
@@ -208,17 +210,24 @@ class SemanticPointCloudAccumulator:
 
     # -- shared part of generate_bev (kitti360_sem_pc_accum.py:166-243) -------
     def _window_inputs(self, present_idx, gen_future, other_trajs=None, gt_lanes=None):
+        """The reference's window split (kitti360_sem_pc_accum.py:179-213): frame ranges instead
+        of concatenated clouds; trajectories shifted by the present pose."""
         n = len(self.poses)
-        origin = np.array(self.poses[-1] if present_idx is None else self.poses[present_idx])
+        poses = np.array(self.poses, dtype=np.float64).reshape(n, 3)
+        origin = poses[-1 if present_idx is None else present_idx].copy()
         lo, hi, _ = slice(None, present_idx).indices(n)
         flo, fhi, _ = slice(present_idx, None).indices(n)
         if hi <= lo:
             raise ValueError('need at least one array to concatenate')
         first = self._fids[0]
+        shifted = poses - origin
+
+        def shift(ts):
+            return [np.array(t, dtype=np.float64) - origin for t in ts] if ts else []
+
         pcs = {'pc_present': DeviceWindow(self.cloud, first + lo, first + hi, origin)}
-        trajs = {'ego_traj_present': np.concatenate([self.poses[:present_idx]]) - origin,
-                 'other_trajs_present': [np.concatenate([t]) - origin
-                                         for t in (other_trajs[0] if other_trajs else [])]}
+        trajs = {'ego_traj_present': shifted[:present_idx],
+                 'other_trajs_present': shift(other_trajs[0] if other_trajs else None)}
         if gt_lanes is not None:
             trajs['gt_lanes'] = [lane - origin for lane in gt_lanes]
         if gen_future:
@@ -226,12 +235,10 @@ class SemanticPointCloudAccumulator:
                 raise ValueError('need at least one array to concatenate')
             pcs['pc_future'] = DeviceWindow(self.cloud, first + flo, first + fhi, origin)
             pcs['pc_full'] = DeviceWindow(self.cloud, first, first + n, origin)
-            trajs['ego_traj_future'] = np.concatenate([self.poses[present_idx:]]) - origin
-            trajs['ego_traj_full'] = np.concatenate([self.poses]) - origin
-            trajs['other_trajs_future'] = [np.concatenate([t]) - origin
-                                           for t in (other_trajs[1] if other_trajs else [])]
-            trajs['other_trajs_full'] = [np.concatenate([t]) - origin
-                                         for t in (other_trajs[2] if other_trajs else [])]
+            trajs['ego_traj_future'] = shifted[present_idx:]
+            trajs['ego_traj_full'] = shifted
+            trajs['other_trajs_future'] = shift(other_trajs[1] if other_trajs else None)
+            trajs['other_trajs_full'] = shift(other_trajs[2] if other_trajs else None)
         else:
             pcs['pc_future'] = pcs['pc_full'] = None
             for k in ('ego_traj_future', 'other_trajs_future', 'ego_traj_full',
