@@ -518,6 +518,8 @@ def run_ours(args, rank, world, local_rank, dist):
             extra['highres_1024'] = c3_extra(torch, DeviceCloud, pk, F=100, P=1024, elevation_max=True)
             extra['input_side'] = input_side_extra(torch, DeviceCloud, pk)
             extra['kitti360_sequence'] = kitti_seq_extra(torch)
+            extra['kitti360_prob_maps'] = prob_map_extra(torch, DeviceCloud, pk)
+            extra['writer'] = writer_extra(torch)
 
     if rank == 0:
         line = {
@@ -669,6 +671,101 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
             'cpu_port_cores': 1,
             'note': 'latency-bound by design (SURVEY.md 8d): one 120 k-point frame is 4 MB of traffic; '
                     'the literal reference takes 50-82 ms per frame and 14.6 s per BEV (BASELINE.md)'}
+
+
+def prob_map_extra(torch, DeviceCloud, pk, n_frames=8):
+    """North-star gather variant (sem_pc_accum.py:323-345 with K = 19): the semantic
+    input is the (376,1408,19) float32 probability map, the class is its argmax at the projected
+    pixel.  120,000-point frames, maps resident in HBM (8 distinct maps = 322 MB > L2).  Rows of 19
+    floats (76 B, scalar loads), rows padded to 20 floats (80 B, 16-byte vector loads) and the
+    class-index map (1 B) through the same kernel; algorithmic bytes 16 N + (3 + 4K) N_vis + 37 N_keep."""
+    P_mat = synth.kitti_calib()['p_velo_frame']
+    frames = []
+    for f in range(n_frames):
+        seed = synth.seed_for(1, f)
+        prob = synth.kitti_prob_map(seed)
+        frames.append(dict(
+            pc=torch.from_numpy(synth.kitti_lidar(seed)).cuda(), rgb=torch.from_numpy(synth.kitti_rgb(seed)).cuda(),
+            p19=torch.from_numpy(prob).cuda(),
+            p20=torch.from_numpy(np.concatenate([prob, np.zeros(prob.shape[:2] + (1,), np.float32)], axis=2)).cuda(),
+            cls=torch.from_numpy(np.argmax(prob, axis=2).astype(np.uint8)).cuda()))
+    N = int(frames[0]['pc'].shape[0])
+    cloud = DeviceCloud(n_frames * N + 1024, n_frames + 8)
+
+    def run(key):
+        cloud.reset()
+        for fr in frames:
+            cloud.integrate_frustum(fr['pc'], P_mat, fr['rgb'], fr[key], synth.KITTI_FILTERS)
+        cloud._keep.clear()
+
+    def timed(key, n=20):
+        for _ in range(3):
+            run(key)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            run(key)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (n * n_frames) * 1e3          # us per frame
+
+    out = {'points_per_frame': N, 'frames_in_flight': n_frames}
+    counts = {}
+    for key, K in (('cls', 1), ('p19', 19), ('p20', 20)):
+        us = timed(key)
+        cloud.sync()
+        n_keep = cloud.resident_points() / n_frames
+        counts[key] = n_keep
+        u, v, m = cloud.project(frames[0]['pc'], P_mat, synth.KITTI_IMG_H, synth.KITTI_IMG_W)
+        n_vis = float(m.sum().item())
+        gather = 3 + (1 if K == 1 else 4 * K)
+        alg = 16.0 * N + gather * n_vis + 37.0 * n_keep
+        out[key] = {'K': K, 'us_per_frame': us, 'points_per_s': N / (us * 1e-6), 'n_vis': n_vis,
+                    'n_keep': n_keep, 'algorithmic_bytes_per_frame': alg,
+                    'alg_GBps': alg / (us * 1e-6) / 1e9, 'frac_of_hbm_peak': alg / (us * 1e-6) / 1e9 / pk['hbm_gbs']}
+    assert counts['cls'] == counts['p19'] == counts['p20'], counts     # same classes either way
+    out['note'] = ('frames back to back on one stream (launch-latency bound: a frame is ~4 MB of traffic); the '
+                   'gather touches N_vis rows of 76-80 B of a 40 MB map, i.e. 3.7 % of it')
+    cloud.close()
+    return out
+
+
+def writer_extra(torch, n_bevs=32, levels=(1, 6, 9)):
+    """write_compressed_pickle (sem_pc_accum.py:280-294) at device rates — the
+    threaded writer on this host's cores at gzip levels 1 / 6 / 9, on real BEV dicts of the bench
+    workload (2.75 MB of float16 planes each).  BEVs/s next to the e2e generation rate."""
+    import shutil
+    import tempfile
+    from pc_accumulation_lib_b200 import NuScenesOracleSemanticPointCloudAccumulator as Acc
+    scene = make_scenes(0, 1)[0]
+    acc = Acc(synth.SceneSemseg(), synth.NUSC_FILTERS, synth.SEM_IDXS, None, bev_setup(),
+              ring_capacity_pts=sum(o['pc'].shape[0] for o in scene) + 4096, ring_max_frames=N_SWEEPS + 8)
+    for o in scene:
+        acc.semseg_model.register(o)
+        acc.integrate([o])
+    acc.sem_bev_generator.rng = np.random.RandomState(3)
+    bevs = []
+    for p in PRESENT_IDXS:
+        bevs += acc.generate_bev(p, BEVS_PER_PRESENT, True)
+    bevs = bevs[:n_bevs]
+    acc.cloud.close()
+    raw = sum(v.nbytes for v in bevs[0].values() if isinstance(v, np.ndarray))
+    n_thr = max(1, min(32, os.cpu_count() or 1))
+    res = {'threads': n_thr, 'bevs': len(bevs), 'raw_bytes_per_bev': raw, 'levels': {}}
+    for lvl in levels:
+        d = tempfile.mkdtemp(prefix='pcacc_writer_')
+        try:
+            t0 = time.perf_counter()
+            with Acc.async_writer(n_threads=n_thr, compresslevel=lvl, max_pending=2 * n_thr) as wr:
+                for k, b in enumerate(bevs):
+                    wr.submit(b, f'bev_{k:04d}.pkl', d)
+            dt = time.perf_counter() - t0
+            res['levels'][str(lvl)] = {'bevs_per_s': len(bevs) / dt, 'raw_MB_per_s': raw * len(bevs) / dt / 1e6,
+                                       'file_bytes_per_bev': wr.bytes_written / max(wr.n_written, 1)}
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return res
 
 
 def input_side_extra(torch, DeviceCloud, pk):

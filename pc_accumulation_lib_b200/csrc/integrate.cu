@@ -82,10 +82,50 @@ __device__ __forceinline__ int load_class(const void *map, int64_t pix, int K) {
         return (v < -2147483647ll || v > 2147483647ll) ? -2147483647 : (int)v;
     }
     if (DT == PCACC_SEM_SAMPLED) return ((const int32_t *)map)[2 * pix + 1];
-    // float32 probabilities: first index of the maximum (np.argmax)
+    // float32 probabilities: first index of the maximum (np.argmax).  All loads of the row are
+    // issued before the first compare.  A row of K floats starts at byte 4*K*pix: when K is a
+    // multiple of 4 (a producer that pads 19 classes to 20 with a zero channel) and the map is
+    // 16-byte aligned the row is read with K/4 vector loads, otherwise with K scalar loads
+    // (a 76-byte row straddles three or four 32-byte sectors either way; L1 keeps them).
     const float *p = (const float *)map + pix * K;
-    float best = p[0];
+    float best;
     int arg = 0;
+    if ((K & 3) == 0 && K <= 32 && ((uintptr_t)map & 15u) == 0) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (4 * k < K) v[k] = __ldg((const float4 *)p + k);
+        best = v[0].x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (4 * k < K) {
+                const float c[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (c[j] > best) {
+                        best = c[j];
+                        arg = 4 * k + j;
+                    }
+                }
+            }
+        }
+        return arg;
+    }
+    if (K == 19) {      // the semseg head of the reference (19 Cityscapes classes): fully unrolled
+        float c[19];
+#pragma unroll
+        for (int k = 0; k < 19; k++) c[k] = __ldg(p + k);
+        best = c[0];
+#pragma unroll
+        for (int k = 1; k < 19; k++) {
+            if (c[k] > best) {
+                best = c[k];
+                arg = k;
+            }
+        }
+        return arg;
+    }
+    best = p[0];
     for (int k = 1; k < K; k++) {
         float v = p[k];
         if (v > best) {

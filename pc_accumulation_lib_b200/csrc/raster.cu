@@ -1250,10 +1250,10 @@ __device__ __forceinline__ __half h_unord(uint32_t u) {
     return __ushort_as_half((unsigned short)b);
 }
 
-__global__ void __launch_bounds__(CH_WARPS * 32, 12)
+__global__ void __launch_bounds__(CH_WARPS * 32, 16)
 k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
                    const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
-                   const double *__restrict__ lut, int P, double intensity_div,
+                   const double *__restrict__ lut, int P, double intensity_div, uint32_t small_t,
                    uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_count,
                    __half *__restrict__ out16) {
     __shared__ ChunkWarp s_cw[CH_WARPS];
@@ -1288,8 +1288,8 @@ k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__
     for (int k = 0; k < CH_PER_LANE; k++) {
         c_np[k] = sb[2 * k + 1] - sb[2 * k];
         c_nt[k] = sb[2 * k + 2] - sb[2 * k];
-        n_big += c_nt[k] > SMALL_T;
-        n_small += c_nt[k] > 0 && c_nt[k] <= SMALL_T;
+        n_big += c_nt[k] > small_t;
+        n_small += c_nt[k] > 0 && c_nt[k] <= small_t;
     }
     // The empty-window constants go out first, for the whole chunk: plane p of window w of the
     // chunk is CH_CELLS halves = 32 lanes x 8 bytes.  The non-empty cells overwrite theirs
@@ -1330,7 +1330,7 @@ k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__
         uint32_t bi = bbase + (excl & 0xffffu), si = excl >> 16;
 #pragma unroll
         for (int k = 0; k < CH_PER_LANE; k++) {
-            if (c_nt[k] > SMALL_T) {
+            if (c_nt[k] > small_t) {
                 big_list[bi++] = gc0 + k;
             } else if (c_nt[k] > 0) {
                 cw.g_s0[si] = sb[2 * k];
@@ -1786,6 +1786,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
     PCACC_CUDA(h, cudaSetDevice(h->device));
     const int64_t PP = (int64_t)P * P;
 
+    const bool want_f64_early = out_f64_dev != nullptr;
     for (int v0 = 0; v0 < n_variants; v0 += MAX_VGROUP) {
         const int nv = n_variants - v0 < MAX_VGROUP ? n_variants - v0 : MAX_VGROUP;
         if ((int64_t)nv * PP * 2 + 1 > 0xffffffffll)
@@ -1832,8 +1833,15 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         size_t o_consts = align_up(o_sorted + (size_t)cap * 16, 256);
         size_t o_fvar = align_up(o_consts + (size_t)nv * sizeof(BevConsts), 256);
         size_t o_big = align_up(o_fvar + (size_t)(fhi > flo ? fhi - flo : 0) * nv * sizeof(FrameVar), 256);
-        // a cell is "large" only above SMALL_T points, so the queue never exceeds cap / (SMALL_T+1)
-        int64_t big_cap = cap / (SMALL_T + 1) + 1;
+        // Cells above small_t points are queued for pass B (one warp per cell, dynamically
+        // balanced); the rest is reduced 32 cells per warp by pass A.  (Measured on the
+        // long-horizon window, one variant = 512 chunk warps: small_t = 4 takes pass A from 35 to
+        // 12 us but pass B from 94 to 128 us — a warp per 5..15-point cell costs more than the
+        // group reduction it replaces — so the threshold stays at SMALL_T for every launch.)
+        const bool chunked = !want_f64_early && PP % CH_CELLS == 0 && !h->reduce_strips;
+        const uint32_t small_t = (uint32_t)SMALL_T;
+        // so the queue never exceeds cap / (small_t + 1)
+        int64_t big_cap = cap / (small_t + 1) + 1;
         if (big_cap > (int64_t)nv * PP) big_cap = (int64_t)nv * PP;
         size_t total = align_up(o_big + (size_t)big_cap * 4, 256);
         int rc = ensure_ws(h, total);
@@ -1937,18 +1945,18 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             k_bev_reduce<true><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, o64);
-        else if (PP % CH_CELLS == 0 && !h->reduce_strips)
+        else if (chunked)
             k_bev_reduce_chunk<<<dim3((unsigned)((PP / CH_CELLS + CH_WARPS - 1) / CH_WARPS), (unsigned)nv),
                                  CH_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
-                h->d_rgb_lut, P, h->inten_div, big_list, big_count, o16);
+                h->d_rgb_lut, P, h->inten_div, small_t, big_list, big_count, o16);
         else
             k_bev_reduce<false><<<blocks, RED_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, nullptr);
         PCACC_CUDA(h, cudaGetLastError());
         pcacc_prof_end(h, PCACC_K_REDUCE, pr, st);
-        if (cap > SMALL_T) {
+        if (cap > (int64_t)small_t) {
             int64_t bb = (big_cap + REDB_WARPS - 1) / REDB_WARPS;
             if (bb > (int64_t)h->n_sm * 8) bb = (int64_t)h->n_sm * 8;
             pr = pcacc_prof_begin(h, PCACC_K_REDUCE_BIG, st);

@@ -272,6 +272,21 @@ def test_probability_map_integrate(dev):
     np.testing.assert_array_equal(a, want)
     np.testing.assert_array_equal(b, want)
     assert 0 < c.shape[0] < b.shape[0]            # max_depth drops the far points
+    # the same probabilities padded to 20 channels (zero channel: 16-byte rows, vector loads),
+    # with ties (first maximum wins, np.argmax), and a 7-channel map (generic loop)
+    pad = np.concatenate([prob, np.zeros(prob.shape[:2] + (1,), dtype=np.float32)], axis=2)
+    pad[::3, ::5, :] = 0.25                       # all-equal rows: argmax = 0
+    pad[1::3, 2::5, 7] = pad[1::3, 2::5, 3] = 2.0  # two equal maxima: the first one (3)
+    cls_pad = np.argmax(pad, axis=2).astype(np.int64)
+    small = np.ascontiguousarray(prob[:, :, :7])
+    cloud.reset()
+    fd = cloud.integrate_frustum(pc, P, rgb, np.ascontiguousarray(pad), synth.KITTI_FILTERS)
+    fe = cloud.integrate_frustum(pc, P, rgb, small, synth.KITTI_FILTERS)
+    assert cloud.sync() == 0
+    np.testing.assert_array_equal(cloud.export_frame(fd), orc.kitti_obs2sem(pc, rgb, cls_pad, P, synth.KITTI_FILTERS))
+    np.testing.assert_array_equal(cloud.export_frame(fe),
+                                  orc.kitti_obs2sem(pc, rgb, np.argmax(small, axis=2).astype(np.int64), P,
+                                                    synth.KITTI_FILTERS))
     cloud.close()
 
 
