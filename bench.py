@@ -631,8 +631,11 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
         frames.append(dict(pc=synth.kitti_lidar(seed), T=synth.kitti_step_transform(seed),
                            rgb=synth.kitti_rgb(seed), cls=synth.kitti_class_map_fast(seed)))
     n_pts = sum(fr['pc'].shape[0] for fr in frames)
+    from pc_accumulation_lib_b200 import pinned_like
+    frames_pin = [dict(pc=pinned_like(fr['pc']), T=fr['T'], rgb=pinned_like(fr['rgb']), cls=pinned_like(fr['cls']))
+                  for fr in frames]
 
-    def run_gpu():
+    def run_gpu(frames=frames):
         acc = Kitti360SemanticPointCloudAccumulator(
             1e9, synth.kitti_calib(), 1.0, synth.FakeSemseg([fr['cls'] for fr in frames]),
             synth.KITTI_FILTERS, synth.SEM_IDXS, False, synth.kitti_bev_params(pixel_size=P),
@@ -652,6 +655,8 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
 
     run_gpu()
     ti, tb, n_res = min((run_gpu() for _ in range(3)), key=lambda r: r[0] + r[1])
+    run_gpu(frames_pin)
+    ti_pin, tb_pin, _ = min((run_gpu(frames_pin) for _ in range(3)), key=lambda r: r[0] + r[1])
     from oracle import oracle as orc          # CPU port, the baseline of this row only
     bp = synth.kitti_bev_params(pixel_size=P)
     gp = dict(sem_idxs=synth.SEM_IDXS, view_size=bp['view_size'], pixel_size=P,
@@ -667,6 +672,9 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
     return {'frames': F, 'points': n_pts, 'resident_points': n_res,
             'integrate_ms_per_frame': ti / F * 1e3, 'integrate_points_per_s': n_pts / ti,
             'bev_ms': tb * 1e3,
+            'pinned_inputs': {'integrate_ms_per_frame': ti_pin / F * 1e3, 'integrate_points_per_s': n_pts / ti_pin,
+                              'bev_ms': tb_pin * 1e3,
+                              'note': 'arrays in page-locked memory: no staging copy (camera maps read in place)'},
             'cpu_port_integrate_ms_per_frame': (c1 - c0) / F * 1e3, 'cpu_port_bev_ms': (c2 - c1) * 1e3,
             'cpu_port_cores': 1,
             'note': 'latency-bound by design (SURVEY.md 8d): one 120 k-point frame is 4 MB of traffic; '
@@ -714,6 +722,15 @@ def prob_map_extra(torch, DeviceCloud, pk, n_frames=8):
     counts = {}
     for key, K in (('cls', 1), ('p19', 19), ('p20', 20)):
         us = timed(key)
+        # the kernel's own duration: CUDA events around each launch (the loop above is bound by
+        # the host's call rate, ~15 us per integrate call)
+        cloud.profile(('integrate',))
+        cloud.profile_read()
+        for _ in range(5):
+            run(key)
+        pr = cloud.profile_read()['integrate']
+        cloud.profile(False)
+        k_us = pr[0] / max(pr[1], 1) * 1e3
         cloud.sync()
         n_keep = cloud.resident_points() / n_frames
         counts[key] = n_keep
@@ -721,9 +738,11 @@ def prob_map_extra(torch, DeviceCloud, pk, n_frames=8):
         n_vis = float(m.sum().item())
         gather = 3 + (1 if K == 1 else 4 * K)
         alg = 16.0 * N + gather * n_vis + 37.0 * n_keep
-        out[key] = {'K': K, 'us_per_frame': us, 'points_per_s': N / (us * 1e-6), 'n_vis': n_vis,
+        out[key] = {'K': K, 'us_per_frame_host_call_rate': us, 'kernel_us': k_us,
+                    'points_per_s': N / (us * 1e-6), 'n_vis': n_vis,
                     'n_keep': n_keep, 'algorithmic_bytes_per_frame': alg,
-                    'alg_GBps': alg / (us * 1e-6) / 1e9, 'frac_of_hbm_peak': alg / (us * 1e-6) / 1e9 / pk['hbm_gbs']}
+                    'kernel_alg_GBps': alg / (k_us * 1e-6) / 1e9,
+                    'kernel_frac_of_hbm_peak': alg / (k_us * 1e-6) / 1e9 / pk['hbm_gbs']}
     assert counts['cls'] == counts['p19'] == counts['p20'], counts     # same classes either way
     out['note'] = ('frames back to back on one stream (launch-latency bound: a frame is ~4 MB of traffic); the '
                    'gather touches N_vis rows of 76-80 B of a 40 MB map, i.e. 3.7 % of it')

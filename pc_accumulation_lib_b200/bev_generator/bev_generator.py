@@ -203,6 +203,13 @@ class BEVGenerator(ABC):
                                self.int_mid_threshold, getattr(self, 'rgb_fill', 0), sem_idxs,
                                self.elevation_max)
 
+    def _rot_of(self, aug):
+        """rotation_matrix_3d(aug['rot_ang']), computed once per augmentation dict."""
+        R = aug.get('_R')
+        if R is None:
+            R = aug['_R'] = self.rotation_matrix_3d(aug['rot_ang'])
+        return R
+
     def _scratch_cloud(self, n_pts):
         if self._scratch is None or self._scratch.capacity < n_pts + 16:
             if self._scratch is not None:
@@ -237,7 +244,7 @@ class BEVGenerator(ABC):
             sem_idxs = getattr(self, 'sem_idxs', None) or {
                 'road': -1, 'car': -1, 'truck': -1, 'bus': -1, 'motorcycle': -1}
             return make_bev_params_batch(
-                fb, fs, fe, origin, [self.rotation_matrix_3d(a['rot_ang']) for a in augs],
+                fb, fs, fe, origin, [self._rot_of(a) for a in augs],
                 [a['trans_dx'] for a in augs], [a['trans_dy'] for a in augs],
                 [a['zoom_scalar'] * self.view_size for a in augs], self.height_filter,
                 self.int_scaler, self.int_sep_scaler, self.int_mid_threshold,
@@ -356,33 +363,38 @@ class BEVGenerator(ABC):
         arrs = []
         for g in groups:
             for t in g:
-                t = np.asarray(t, dtype=np.float64)
-                arrs.append(t.reshape(-1, 3) if t.size else np.zeros((0, 3)))
+                if not (type(t) is np.ndarray and t.dtype == np.float64 and t.ndim == 2 and t.shape[1] == 3):
+                    t = np.asarray(t, dtype=np.float64)
+                    t = t.reshape(-1, 3) if t.size else np.zeros((0, 3))
+                arrs.append(t)
         n_traj, n_var = len(arrs), len(augs)
-        off = np.zeros(n_traj + 1, dtype=np.int32)
-        if n_traj:
-            np.cumsum([a.shape[0] for a in arrs], out=off[1:])
-        N = int(off[-1])
-        pts = np.ascontiguousarray(np.concatenate(arrs, axis=0)) if N else np.zeros((0, 3))
+        lens = [a.shape[0] for a in arrs]
+        off_l = [0]
+        for n in lens:
+            off_l.append(off_l[-1] + n)
+        off = np.array(off_l, dtype=np.int32)
+        N = off_l[-1]
+        pts = np.concatenate(arrs, axis=0) if N else np.zeros((0, 3))
         var = np.empty((n_var, 12), dtype=np.float64)
         for v, a in enumerate(augs):
-            var[v, :9] = self.rotation_matrix_3d(a['rot_ang']).reshape(9)
+            var[v, :9] = self._rot_of(a).reshape(9)
             var[v, 9], var[v, 10] = a['trans_dx'], a['trans_dy']
             var[v, 11] = a['zoom_scalar'] * self.view_size
         out = np.empty((n_var, 2 * N, 3), dtype=np.float64)
         cnt = np.zeros((n_var, max(n_traj, 1)), dtype=np.int32)
         _lib.check(_lib.load().pcacc_preprocess_trajectories(
-            pts.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), n_traj,
-            var.ctypes.data_as(C.c_void_p), n_var, int(self.pixel_size), 1e-4,
-            out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+            pts.ctypes.data, off.ctypes.data, n_traj, var.ctypes.data, n_var, int(self.pixel_size), 1e-4,
+            out.ctypes.data, cnt.ctypes.data))
+        cnt_l = cnt.tolist()
         res = []
         for v in range(n_var):
             per_group, t = [], 0
             for g in groups:
                 lst = []
+                ov, cv = out[v], cnt_l[v]
                 for _ in g:
-                    b = 2 * int(off[t])
-                    lst.append(out[v, b:b + int(cnt[v, t])])
+                    b = 2 * off_l[t]
+                    lst.append(ov[b:b + cv[t]])
                     t += 1
                 per_group.append(lst)
             res.append(per_group)

@@ -108,6 +108,7 @@ class Stager:
         self.device = device
         self._slots = {}     # key -> [[pinned, device, event, ...], [pinned, device, event, ...], turn]
         self._touched = []
+        self.keepalive = []   # caller-owned pinned arrays handed to kernels / DMA; cleared by the owner after a sync
         # bare CUDA events from libpcacc (see pcacc_event_record): four, used in turn
         self._lib = _lib.load()
         self._events = []
@@ -153,6 +154,20 @@ class Stager:
         else:
             t = torch.from_numpy(np.ascontiguousarray(arr))
         nbytes = t.numel() * t.element_size()
+        if nbytes and self._lib.pcacc_host_is_pinned(t.data_ptr()):
+            # the caller's array is page-locked already (pinned_empty / pin_memory): no staging
+            # copy.  mapped: the kernel reads it in place; otherwise one DMA straight from it.
+            # The caller keeps `keepalive` entries until the stream has passed the consumers.
+            self.keepalive.append(t)
+            if mapped:
+                return t
+            sl = self._slot(key, nbytes, True)
+            dev_v = sl[1][:nbytes].view(t.dtype).view(t.shape)
+            if sl[2] is not None:
+                self._lib.pcacc_event_sync(sl[2])
+            dev_v.copy_(t, non_blocking=True)
+            self._touched.append(sl)
+            return dev_v
         sl = self._slot(key, nbytes, not mapped)
         # typed views of the slot's buffers are cached: observations of one stream keep
         # their shapes, and a dozen tensor-view calls per put cost more than the copy
@@ -228,9 +243,9 @@ class DeviceCloud:
                                     C.byref(h)))
         self.h = h
         self.stage = Stager(self.device)
+        self._keep = self.stage.keepalive   # one list: everything in-flight work still reads
         # camera maps handed over as host arrays are read in place from pinned memory
         self.map_images = True
-        self._keep = []      # device tensors / pinned arrays that in-flight kernels still read
         self._filt_cache = None
         self._fid_out, self._staging_out = C.c_int64(-1), C.c_int(0)
         self._fid_ref, self._staging_ref = C.byref(self._fid_out), C.byref(self._staging_out)

@@ -237,18 +237,17 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
                 # a gap in the sightings covers the whole interval: the reference indexes an
                 # empty tuple here (parse_seq_into_coherent_seqs, :400)
                 raise IndexError('tuple index out of range')
-            run = []
-            prev = None
-            for k in range(i0, i1):
-                t = tss[k]
-                if prev is not None and t - prev != 1:
-                    if len(run) >= 2:
-                        out.append(run)
-                    run = []
-                run.append(plist[k][:])
-                prev = t
-            if len(run) >= 2:
-                out.append(run)
+            # runs of consecutive time steps; the usual case is one unbroken run
+            if tss[i1 - 1] - tss[i0] == i1 - 1 - i0:
+                if i1 - i0 >= 2:
+                    out.append([p[:] for p in plist[i0:i1]])
+                continue
+            a = i0
+            for k in range(i0 + 1, i1 + 1):
+                if k == i1 or tss[k] - tss[k - 1] != 1:
+                    if k - a >= 2:
+                        out.append([p[:] for p in plist[a:k]])
+                    a = k
         if not skip_ego_traj:
             out.append(self.poses)
         return out

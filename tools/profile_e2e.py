@@ -48,7 +48,8 @@ for _ in range(3):
           f'({tb/8*1e3:.3f} ms/call) -> {n_in/(ti+tw+tb)/1e6:.1f} M points/s')
 pr = cProfile.Profile()
 pr.enable()
-run()
+for _ in range(20):          # 20 scenes: pstats prints milliseconds, per-scene = value / 20
+    run()
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
 pstats.Stats(pr).sort_stats('tottime').print_stats(25)
