@@ -462,6 +462,11 @@ def run_ours(args, rank, world, local_rank, dist):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()), sum(counts)
 
+    if n_thr > 1:
+        # a thread coming back from a blocking C call (event wait, launch) gets the GIL only when
+        # the running thread reaches its switch interval: the default 5 ms is longer than a whole
+        # generate_bev call
+        sys.setswitchinterval(args.switch_interval)
     e2e_leg(scenes_pin, 1)                                   # warm-up of the pinned path and threads
     dt, n_b = e2e_leg(scenes_pin, args.e2e_steps)
     staging_pinned = acc.cloud.last_staging
@@ -483,7 +488,7 @@ def run_ours(args, rank, world, local_rank, dist):
            'h2d_bytes_per_step': int(h2d_direct), 'd2h_bytes_per_step': int(d2h),
            'host_input_bytes_per_step': int(host_in),
            'bevs_per_s': n_b * world / dt, 'scenes_per_step': e2e_scenes, 'steps': args.e2e_steps,
-           'threads': n_thr, 'staging': stage_name.get(staging_pinned, str(staging_pinned)),
+           'threads': n_thr, 'gil_switch_interval_s': args.switch_interval if n_thr > 1 else None, 'staging': stage_name.get(staging_pinned, str(staging_pinned)),
            'api': 'NuScenesOracleSemanticPointCloudAccumulator.integrate / generate_bev: numpy arrays in '
                   'page-locked host memory in, numpy float16 planes out (sync_each_integrate=False: error '
                   'flags checked at generate_bev)',
@@ -1028,6 +1033,7 @@ def main():
     ap.add_argument('--e2e-scenes', type=int, default=16)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--e2e-threads', type=int, default=2)
+    ap.add_argument('--switch-interval', type=float, default=1e-4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c3', action='store_true')
     ap.add_argument('--ncu-step', action='store_true')

@@ -308,7 +308,6 @@ class BEVGenerator(ABC):
         device-side replacement of the reference's Pool(bev_num).map
         (kitti360_sem_pc_accum.py:236-241)."""
         ego_p, ego_f, ego_a = self.extract_ego_traj_dict(trajs)
-        oth_p, oth_f, oth_a = self.extract_other_traj_dicts(trajs)
         _, pc_future, _ = self.extract_pc_dict(pcs)
         if pc_future is None:
             # the reference dies here too: trajs_future is never bound
@@ -333,6 +332,8 @@ class BEVGenerator(ABC):
         # the device works (rasterise, warp, copy to pinned memory) while the host prepares
         # the trajectories
         pending, has_future, cloud = self._rasterise_windows_begin(pcs, full, warps)
+        # (a lazily filled trajs dict extracts the other objects' trajectories here, under the kernels)
+        oth_p, oth_f, oth_a = self.extract_other_traj_dicts(trajs)
         groups = [[ego_p] + list(oth_p), [ego_f] + list(oth_f), [ego_a] + list(oth_a)]
         if 'gt_lanes' in trajs:
             groups.append(list(self.extract_gt_lane_dicts(trajs)))

@@ -340,38 +340,67 @@ k_bev_classify(BinArgs a) {
     const int groups = (a.n_var + vpb - 1) / vpb;
     const uint32_t n_items = total_tiles * (uint32_t)groups;
 
+    // The per-item bookkeeping is block-uniform: warp 0 does it once — which frame the tile
+    // belongs to (every lane probes a slice of the tile prefix), the frame's ring offset and
+    // count, whether z has to be streamed — and hands it over in shared memory.  Done by every
+    // thread (a binary search over s_tiles, two 64-bit modulos, dependent loads of the frame
+    // table) it was a third of this kernel's instructions.
+    __shared__ struct {
+        long long off, cnt, tile0, fid;
+        int fl, v_begin, v_end, need_z;
+    } s_item;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t tile_lin = item % total_tiles;
-        const int v_begin = (int)(item / total_tiles) * vpb;
-        const int v_end = min(a.n_var, v_begin + vpb);
-        int fl = 0, fh = a.n_frames;  // largest f with s_tiles[f] <= tile_lin
-        while (fh - fl > 1) {
-            const int m = (fl + fh) >> 1;
-            if (s_tiles[m] <= tile_lin) fl = m; else fh = m;
+        __syncthreads();   // the previous item's readers of s_item / s_A are done
+        if (warp == 0) {
+            const uint32_t grp = groups == 1 ? 0u : item / total_tiles;
+            const uint32_t tile_lin = item - grp * total_tiles;
+            int fl = 0;   // the frame f with s_tiles[f] <= tile_lin < s_tiles[f + 1] (tiles > 0 there)
+            for (int f0 = 0; f0 < a.n_frames; f0 += 32) {
+                const int f = f0 + (int)lane;
+                const bool hit = f < a.n_frames && s_tiles[f] <= tile_lin && tile_lin < s_tiles[f + 1];
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    fl = f0 + __ffs(m) - 1;
+                    break;
+                }
+            }
+            const int vb = (int)grp * vpb, ve = min(a.n_var, vb + vpb);
+            const long long fid = a.frame_lo + fl;
+            int slot = (int)(a.frame_lo % a.max_frames) + fl;
+            if (slot >= a.max_frames) slot -= a.max_frames;
+            // z is only streamed when some variant's map mixes it into x / y (a lazily re-based
+            // frame, or a rotation that is not about the z axis)
+            bool nz = false;
+            const FrameVar *fvw = a.fvar + (int64_t)fl * a.n_var;
+            for (int v = vb + (int)lane; v < ve; v += 32) {
+                const pcacc_bev_params &bp = s_par[v];
+                if (fid >= bp.frame_begin && fid < bp.frame_end)
+                    nz = nz || (fvw[v].A[2] != 0.0) || (fvw[v].A[6] != 0.0);
+            }
+            nz = __any_sync(0xffffffffu, nz);
+            if (lane == 0) {
+                s_item.off = a.frame_off[slot];
+                s_item.cnt = a.frame_cnt[slot];
+                s_item.tile0 = (long long)(tile_lin - s_tiles[fl]) * BIN_TILE;
+                s_item.fid = fid;
+                s_item.fl = fl;
+                s_item.v_begin = vb;
+                s_item.v_end = ve;
+                s_item.need_z = nz ? 1 : 0;
+            }
         }
-        const int64_t fid = a.frame_lo + fl;
-        const int slot = (int)(fid % a.max_frames);
-        const int64_t cnt = a.frame_cnt[slot];
-        const int64_t tile0 = (int64_t)(tile_lin - s_tiles[fl]) * BIN_TILE;
-        const int64_t off = a.frame_off[slot];
+        __syncthreads();
+        const int fl = s_item.fl, v_begin = s_item.v_begin, v_end = s_item.v_end;
+        const int64_t fid = s_item.fid, cnt = s_item.cnt, tile0 = s_item.tile0, off = s_item.off;
+        const bool need_z = s_item.need_z != 0;
         const FrameVar *fv = a.fvar + (int64_t)fl * a.n_var;
         // the item's candidate maps go to shared memory in one cooperative load: read from
         // global inside the variant loop, each was a dependent L2 round trip ahead of its tests
-        const bool staged = a.n_var > 1;   // a single variant reads its map directly (no barriers)
+        const bool staged = a.n_var > 1;   // a single variant reads its map directly
         if (staged) {
-            __syncthreads();   // the previous item's readers are done
             for (int k = threadIdx.x; k < (v_end - v_begin) * 8; k += BIN_BLOCK)
                 s_A[k >> 3][k & 7] = fv[v_begin + (k >> 3)].A[k & 7];
             __syncthreads();
-        }
-        // z is only streamed when some variant's map mixes it into x / y (a lazily re-based
-        // frame, or a rotation that is not about the z axis)
-        bool need_z = false;
-        for (int v = v_begin; v < v_end; v++) {
-            const pcacc_bev_params &bp = s_par[v];
-            if (fid >= bp.frame_begin && fid < bp.frame_end)
-                need_z = need_z || (staged ? (s_A[v - v_begin][2] != 0.0) || (s_A[v - v_begin][6] != 0.0)
-                                           : (fv[v].A[2] != 0.0) || (fv[v].A[6] != 0.0));
         }
 
         // 4 points per thread: two pairs of neighbours (16 B loads; frame offsets are

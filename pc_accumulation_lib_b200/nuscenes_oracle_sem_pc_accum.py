@@ -267,6 +267,6 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         self.ego_global_xs, self.ego_global_ys = [], []
 
     def generate_bev(self, present_idx: int = None, bev_num: int = 1, gen_future: bool = False):
-        other = self.get_split_dyn_obj_trajs(present_idx)
-        pcs, trajs = self._window_inputs(present_idx, gen_future, other, self.gt_lane_poses)
+        pcs, trajs = self._window_inputs(present_idx, gen_future,
+                                         lambda: self.get_split_dyn_obj_trajs(present_idx), self.gt_lane_poses)
         return self._generate(pcs, trajs, bev_num)

@@ -27,6 +27,44 @@ from .bev_generator import DeviceWindow, SemBEVGenerator
 from .device import DeviceCloud
 
 
+class _LazyTrajs(dict):
+    """The `trajs` dict of BEVGenerator.generate whose other-object / lane entries are computed
+    on first use (`_fill`); the ego entries are there from the start."""
+    _fill = None
+
+    def _materialise(self):
+        fill, self._fill = self._fill, None
+        if fill is not None:
+            self.update(fill())
+
+    def __missing__(self, key):
+        if self._fill is None:
+            raise KeyError(key)
+        self._materialise()
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        if not dict.__contains__(self, key) and self._fill is not None:
+            self._materialise()
+        return dict.__contains__(self, key)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._materialise()
+        return dict.__len__(self)
+
+
 class SemPcsView(Sequence):
     """`accumulator.sem_pcs`: list-like view of the live frames."""
 
@@ -214,7 +252,10 @@ class SemanticPointCloudAccumulator:
     # -- shared part of generate_bev (kitti360_sem_pc_accum.py:166-243) -------
     def _window_inputs(self, present_idx, gen_future, other_trajs=None, gt_lanes=None):
         """The reference's window split (kitti360_sem_pc_accum.py:179-213): frame ranges instead
-        of concatenated clouds; trajectories shifted by the present pose."""
+        of concatenated clouds; trajectories shifted by the present pose.  `other_trajs` may be a
+        callable returning the (present, future, full) lists: the dict then produces the
+        other-object entries on first access, which the generator makes after it has enqueued the
+        device work (their extraction is host-only work that overlaps the kernels)."""
         n = len(self.poses)
         poses = np.array(self.poses, dtype=np.float64).reshape(n, 3)
         origin = poses[-1 if present_idx is None else present_idx].copy()
@@ -224,15 +265,9 @@ class SemanticPointCloudAccumulator:
             raise ValueError('need at least one array to concatenate')
         first = self._fids[0]
         shifted = poses - origin
-
-        def shift(ts):
-            return [np.array(t, dtype=np.float64) - origin for t in ts] if ts else []
-
         pcs = {'pc_present': DeviceWindow(self.cloud, first + lo, first + hi, origin)}
-        trajs = {'ego_traj_present': shifted[:present_idx],
-                 'other_trajs_present': shift(other_trajs[0] if other_trajs else None)}
-        if gt_lanes is not None:
-            trajs['gt_lanes'] = [lane - origin for lane in gt_lanes]
+        trajs = _LazyTrajs()
+        trajs['ego_traj_present'] = shifted[:present_idx]
         if gen_future:
             if fhi <= flo:
                 raise ValueError('need at least one array to concatenate')
@@ -240,13 +275,27 @@ class SemanticPointCloudAccumulator:
             pcs['pc_full'] = DeviceWindow(self.cloud, first, first + n, origin)
             trajs['ego_traj_future'] = shifted[present_idx:]
             trajs['ego_traj_full'] = shifted
-            trajs['other_trajs_future'] = shift(other_trajs[1] if other_trajs else None)
-            trajs['other_trajs_full'] = shift(other_trajs[2] if other_trajs else None)
         else:
             pcs['pc_future'] = pcs['pc_full'] = None
-            for k in ('ego_traj_future', 'other_trajs_future', 'ego_traj_full',
-                      'other_trajs_full'):
-                trajs[k] = None
+            trajs['ego_traj_future'] = trajs['ego_traj_full'] = None
+
+        def fill():
+            others = other_trajs() if callable(other_trajs) else other_trajs
+
+            def shift(ts):
+                return [np.array(t, dtype=np.float64) - origin for t in ts] if ts else []
+
+            out = {'other_trajs_present': shift(others[0] if others else None)}
+            if gt_lanes is not None:
+                out['gt_lanes'] = [lane - origin for lane in gt_lanes]
+            if gen_future:
+                out['other_trajs_future'] = shift(others[1] if others else None)
+                out['other_trajs_full'] = shift(others[2] if others else None)
+            else:
+                out['other_trajs_future'] = out['other_trajs_full'] = None
+            return out
+
+        trajs._fill = fill
         return pcs, trajs
 
     def _generate(self, pcs, trajs, bev_num):
