@@ -399,6 +399,10 @@ def run_ours(args, rank, world, local_rank, dist):
                 'launch_us': us_alone, 'launches_timed': n_passes,
                 'algorithmic_bytes_per_launch': alg.get(dom, 0.0),
                 'share_of_step': alone[dom][0] / alone_sum,
+                'stages': {st: {'launch_us': round(v[0] / n_passes * 1e3, 2),
+                                'algorithmic_bytes_per_launch': alg.get(st),
+                                'frac': (alg[st] / (v[0] / n_passes * 1e-3) / 1e9 / peak) if st in alg and v[0] > 0 else None}
+                           for st, v in alone.items()},
                 'kernel_us_alone': {k: round(v[0] / n_passes * 1e3, 2) for k, v in alone_raw.items() if v[1]},
                 'kernel_launches_per_step': {k: int(v[1] / n_passes * S) for k, v in alone_raw.items() if v[1]},
                 'timed_region_overlapped': {

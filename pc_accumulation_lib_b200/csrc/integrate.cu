@@ -1350,7 +1350,9 @@ extern "C" int pcacc_mark_dynamic(pcacc_t h, const int64_t *frame_ids, const int
     if (rc) return rc;
     int64_t bx = (max_n + IBLOCK - 1) / IBLOCK;
     if (bx < 1) bx = 1;
-    if (bx > 256) bx = 256;   // grid-stride beyond that
+    // grid-stride beyond a few blocks per frame: unsynchronised frames only have upper bounds
+    // of their counts (often 10x the kept points) and a block without work still costs a launch slot
+    if (bx > 16) bx = 16;
     for (int g0 = 0; g0 < n_grp; g0 += 32768) {
         int ny = n_grp - g0 < 32768 ? n_grp - g0 : 32768;
         dim3 grid((unsigned)bx, (unsigned)ny);

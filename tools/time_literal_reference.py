@@ -71,6 +71,31 @@ def main():
                                     'bevs_per_s': bevs_per_scene / t_scene_port},
         'port_over_literal': t_scene / t_scene_port,
     }
+    # BASELINE.json configs[0]: 20 KITTI-360-shaped frames (120,000 points, 1408x376) + one 256^2 BEV
+    F, p_idx = 20, 10
+    frames = []
+    for f in range(F):
+        seed = synth.seed_for(1, f)
+        frames.append(dict(pc=synth.kitti_lidar(seed), T=synth.kitti_step_transform(seed),
+                           rgb=synth.kitti_rgb(seed), cls=synth.kitti_class_map_fast(seed)))
+    kacc = ref_loader.make_kitti_accum(ref, 1e9, synth.kitti_calib(), synth.KITTI_FILTERS, synth.SEM_IDXS,
+                                       synth.kitti_bev_params(pixel_size=256),
+                                       synth.FakeSemseg([fr['cls'] for fr in frames]), use_gt_sem=False)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(sink):
+        for fr in frames:
+            ref_loader.ICP_QUEUE.append(fr['T'])
+            kacc.integrate([(fr['rgb'], fr['pc'], None)])
+    t_kint = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(sink):
+        kacc.generate_bev(p_idx, 1, True)
+    t_kbev = time.perf_counter() - t0
+    out['kitti360_sequence'] = {
+        'what': 'configs[0]: 20 frames x 120000 pts through Kitti360SemanticPointCloudAccumulator.integrate '
+                '(ICP scripted, semseg stand-in) + generate_bev(10, 1, True)',
+        'integrate_ms_per_frame': t_kint / F * 1e3, 'integrate_points_per_s': F * 120000 / t_kint,
+        'bev_s': t_kbev, 'resident_points': int(sum(s.shape[0] for s in kacc.sem_pcs))}
     path = os.path.join(ROOT, 'profiles', 'literal_reference_cpu.json')
     json.dump(out, open(path, 'w'), indent=1)
     print(json.dumps(out, indent=1))
