@@ -294,6 +294,14 @@ def run_ours(args, rank, world, local_rank, dist):
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
+    # host time to ENQUEUE a step (no synchronisation inside): close to ms_per_step means the
+    # device path is bound by the launching thread as much as by the GPU.  (Enqueuing from 2-8
+    # host threads was measured: 2.28-2.62 ms per step against 2.07 ms from one thread.)
+    t_h0 = time.perf_counter()
+    for _ in range(3):
+        device_step()
+    host_enqueue_ms = (time.perf_counter() - t_h0) / 3 * 1e3
+    barrier()
     if args.ncu_step:
         # profiling aid (never a bench value): one step between cudaProfilerStart/Stop, for
         #   ncu --profile-from-start off ... python bench.py --ncu-step --streams 1 --scenes-per-step 1
@@ -537,6 +545,7 @@ def run_ours(args, rank, world, local_rank, dist):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': bench_config(S, n_str),
+            'host_enqueue_ms_per_step': host_enqueue_ms,
             'bevs_per_s': bevs_per_s, 'e2e': e2e, 'gpu_launches': gpu_launches,
             'roofline': roofline, 'roofline_path': roofline_path, 'clocks': clk,
             'parity': parity,
