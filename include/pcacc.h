@@ -267,6 +267,9 @@ int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f16_dev, int 
  * the 32-cell strip kernel (k_bev_reduce) instead of the 128-cell chunk kernel
  * (k_bev_reduce_chunk, the default whenever P*P is a multiple of 128). */
 #define PCACC_OPT_REDUCE_STRIPS 1
+/* PCACC_OPT_CLASSIFY_SINGLE = 1: candidate selection runs k_bev_classify (block per variant) for
+ * every batch size instead of k_bev_classify_mv (warp per variant, batches of >= 8 variants). */
+#define PCACC_OPT_CLASSIFY_SINGLE 2
 int pcacc_set_option(pcacc_t h, int option, int value);
 
 /* ring position (record index) of a live frame's first point, for dbg_cell_dev */

@@ -19,7 +19,7 @@ FLAG_UV_OUT_OF_IMAGE, FLAG_INTENSITY_F32, FLAG_ATTR_RANGE, FLAG_CELL_OVERFLOW = 
 SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB, SEM_I16 = 0, 1, 2, 3, 4
 BEV_PLANES, BEV_WINDOWS = 7, 3
 STAGE_AUTO, STAGE_DIRECT, STAGE_SPARSE = 0, 1, 2
-OPT_REDUCE_STRIPS = 1
+OPT_REDUCE_STRIPS, OPT_CLASSIFY_SINGLE = 1, 2
 ABI_VERSION = 1
 
 

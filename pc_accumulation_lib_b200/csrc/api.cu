@@ -288,6 +288,11 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
     {   // A/B switch for profiling runs (see pcacc_set_option)
         const char *e = getenv("PCACC_REDUCE_STRIPS");
         h->reduce_strips = e && e[0] == '1';
+        const char *c = getenv("PCACC_CLS_MULT"), *b = getenv("PCACC_BIN_MULT");
+        h->cls_mult = c && atoi(c) > 0 ? atoi(c) : 4;
+        h->bin_mult = b && atoi(b) > 0 ? atoi(b) : 8;   // (4 = one wave: 23.0 vs 25 us on the bench workload, but 123 vs 103 us on the long-horizon window)
+        const char *cs = getenv("PCACC_CLASSIFY_SINGLE");
+        h->classify_single = cs && cs[0] == '1';
     }
     int rc = pcacc_ensure_tiles(h, 4096);
     if (!rc) rc = pcacc_init_tables(h);
@@ -323,6 +328,7 @@ extern "C" int pcacc_set_option(pcacc_t h, int option, int value) {
     if (!h) return PCACC_ERR_ARG;
     switch (option) {
         case PCACC_OPT_REDUCE_STRIPS: h->reduce_strips = value != 0; return PCACC_OK;
+        case PCACC_OPT_CLASSIFY_SINGLE: h->classify_single = value != 0; return PCACC_OK;
         default: return pcacc_fail(h, PCACC_ERR_ARG, "unknown option %d", option);
     }
 }

@@ -333,6 +333,8 @@ struct pcacc_s {
     int64_t last_visit_ub;
     double inten_div;    // stored intensity / inten_div = reference intensity; 0 = not set yet
     uint32_t pending_flags;
+    int cls_mult, bin_mult;   // grid size of k_bev_classify / k_bev_bin in multiples of the SM count
+    bool classify_single;     // A/B switch: 1 = k_bev_classify for every variant count
     bool reduce_strips;   // debugging / A-B switch: 1 = the 32-cell strip kernel for float16 output too
     // launch accounting + optional per-kernel CUDA-event timing
     int64_t launches[PCACC_N_KERNELS];

@@ -478,6 +478,181 @@ k_bev_classify(BinArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// pass 1a for batches of variants (n_var >= CLS_MV_MIN) — k_bev_classify_mv.  k_bev_classify lets
+// the whole block cooperate on one variant at a time: a block-wide scan, a returning atomic and two
+// barriers per (tile, variant), i.e. a chain of ~1 us round trips per variant.  Here a work item is
+// one tile x CLS_MV_W variants: the block stages the tile's x / y (/ z) in shared memory once, then
+// every warp takes ONE variant and works alone — it counts its candidates over the 1024 points,
+// reserves their slots with one atomic, and walks the tile a second time to write them (the test is
+// a handful of FMAs; repeating it is cheaper than keeping 32 masks per lane).  No barrier inside an
+// item, eight independent chains per block.
+// ---------------------------------------------------------------------------
+#define CLS_MV_W (BIN_BLOCK / 32)   /* variants per item = warps per block */
+#define CLS_MV_MIN 8
+
+__global__ void __launch_bounds__(BIN_BLOCK, 4)
+k_bev_classify_mv(BinArgs a) {
+    __shared__ pcacc_bev_params s_par[MAX_VGROUP];
+    __shared__ uint32_t s_tiles[BIN_MAXF + 1];
+    __shared__ uint32_t s_warp[BIN_BLOCK / 32];
+    __shared__ __align__(16) double s_x[BIN_TILE], s_y[BIN_TILE], s_z[BIN_TILE];
+    __shared__ struct {
+        long long off, cnt, tile0, fid;
+        int fl, v_begin, v_end, need_z;
+    } s_item;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    {   // stage all variant parameters; exclusive prefix of tiles per frame (as k_bev_classify)
+        const uint32_t *src = (const uint32_t *)a.params;
+        uint32_t *dst = (uint32_t *)s_par;
+        const int words = a.n_var * (int)(sizeof(pcacc_bev_params) / 4);
+        for (int k = threadIdx.x; k < words; k += BIN_BLOCK) dst[k] = src[k];
+        constexpr int PER = BIN_MAXF / BIN_BLOCK;
+        uint32_t loc[PER];
+        uint32_t sum = 0;
+        const bool mine = (int)threadIdx.x * PER <= a.n_frames;
+#pragma unroll
+        for (int k = 0; k < PER; k++) loc[k] = 0;
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int f = (int)threadIdx.x * PER + k;
+                const uint32_t t = f < a.n_frames ? a.frame_tiles[f] : 0u;
+                loc[k] = sum;
+                sum += t;
+            }
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < BIN_BLOCK / 32; w++)
+            if (w < (int)warp) wbase += s_warp[w];
+        const uint32_t excl = wbase + incl - sum;
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int f = (int)threadIdx.x * PER + k;
+                if (f <= a.n_frames) s_tiles[f] = excl + loc[k];
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t total_tiles = s_tiles[a.n_frames];
+    if (total_tiles == 0) return;
+    const uint32_t groups = (uint32_t)((a.n_var + CLS_MV_W - 1) / CLS_MV_W);
+    const uint32_t n_items = total_tiles * groups;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        __syncthreads();   // the previous item's readers of s_item / the tile are done
+        if (warp == 0) {
+            // consecutive items share the tile (its lines stay in L2 for the other groups)
+            const uint32_t tile_lin = item / groups, grp = item - tile_lin * groups;
+            int fl = 0;
+            for (int f0 = 0; f0 < a.n_frames; f0 += 32) {
+                const int f = f0 + (int)lane;
+                const bool hit = f < a.n_frames && s_tiles[f] <= tile_lin && tile_lin < s_tiles[f + 1];
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    fl = f0 + __ffs(m) - 1;
+                    break;
+                }
+            }
+            const int vb = (int)grp * CLS_MV_W, ve = min(a.n_var, vb + CLS_MV_W);
+            const long long fid = a.frame_lo + fl;
+            int slot = (int)(a.frame_lo % a.max_frames) + fl;
+            if (slot >= a.max_frames) slot -= a.max_frames;
+            bool nz = false;
+            const FrameVar *fvw = a.fvar + (int64_t)fl * a.n_var;
+            for (int v = vb + (int)lane; v < ve; v += 32) {
+                const pcacc_bev_params &bp = s_par[v];
+                if (fid >= bp.frame_begin && fid < bp.frame_end)
+                    nz = nz || (fvw[v].A[2] != 0.0) || (fvw[v].A[6] != 0.0);
+            }
+            nz = __any_sync(0xffffffffu, nz);
+            if (lane == 0) {
+                s_item.off = a.frame_off[slot];
+                s_item.cnt = a.frame_cnt[slot];
+                s_item.tile0 = (long long)(tile_lin - s_tiles[fl]) * BIN_TILE;
+                s_item.fid = fid;
+                s_item.fl = fl;
+                s_item.v_begin = vb;
+                s_item.v_end = ve;
+                s_item.need_z = nz ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        const int fl = s_item.fl;
+        const int64_t fid = s_item.fid, cnt = s_item.cnt, tile0 = s_item.tile0, off = s_item.off;
+        const bool need_z = s_item.need_z != 0;
+        const int n_here = (int)min((int64_t)BIN_TILE, cnt - tile0);   // points of this tile (>= 1)
+        {   // the tile: pairs of neighbours, 16 B loads (frame offsets are multiples of 4 records)
+#pragma unroll
+            for (int h = 0; h < BIN_ITEMS / 2; h++) {
+                const int i0 = h * (2 * BIN_BLOCK) + 2 * (int)threadIdx.x;
+                double2 X = make_double2(0, 0), Y = make_double2(0, 0), Z = make_double2(0, 0);
+                if (i0 < n_here) {
+                    X = *(const double2 *)(a.ring.x + off + tile0 + i0);
+                    Y = *(const double2 *)(a.ring.y + off + tile0 + i0);
+                    if (need_z) Z = *(const double2 *)(a.ring.z + off + tile0 + i0);
+                }
+                *(double2 *)&s_x[i0] = X;
+                *(double2 *)&s_y[i0] = Y;
+                *(double2 *)&s_z[i0] = Z;
+            }
+        }
+        __syncthreads();
+        const int v = s_item.v_begin + (int)warp;
+        if (v >= s_item.v_end) continue;
+        const pcacc_bev_params &bp = s_par[v];
+        if (!(fid >= bp.frame_begin && fid < bp.frame_end)) continue;   // warp-uniform
+        // candidate = within the view plus a guard band; k_bev_bin takes the real decision
+        const double lim = __dmul_rn(0.5, bp.view) + GUARD_M;
+        double A[8];
+        {
+            const double *Ag = a.fvar[(int64_t)fl * a.n_var + v].A;
+#pragma unroll
+            for (int k = 0; k < 8; k++) A[k] = Ag[k];
+        }
+        const int n_round = (n_here + 31) >> 5;
+        uint32_t total = 0;
+        for (int r = 0; r < n_round; r++) {
+            const int i = (r << 5) + (int)lane;
+            const double q0 = fma(A[0], s_x[i], fma(A[1], s_y[i], fma(A[2], s_z[i], A[3])));
+            const double q1 = fma(A[4], s_x[i], fma(A[5], s_y[i], fma(A[6], s_z[i], A[7])));
+            const bool c = i < n_here && (fabs(q0) < lim) && (fabs(q1) < lim);   // NaN fails
+            total += (uint32_t)__popc(__ballot_sync(0xffffffffu, c));
+        }
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.n_append, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t meta = (uint32_t)v | ((uint32_t)fl << 8);
+        const uint32_t gi0 = (uint32_t)(off + tile0);
+        for (int r = 0; r < n_round; r++) {
+            const int i = (r << 5) + (int)lane;
+            const double q0 = fma(A[0], s_x[i], fma(A[1], s_y[i], fma(A[2], s_z[i], A[3])));
+            const double q1 = fma(A[4], s_x[i], fma(A[5], s_y[i], fma(A[6], s_z[i], A[7])));
+            const bool c = i < n_here && (fabs(q0) < lim) && (fabs(q1) < lim);
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            if (c) {
+                const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                if ((int64_t)pos < a.cap) {
+                    a.cand_gi[pos] = gi0 + (uint32_t)i;
+                    a.cand_meta[pos] = meta;
+                }
+            }
+            base += (unsigned long long)__popc(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // pass 1b — k_bev_bin: one thread per candidate, no block synchronisation: exact
 // per-point work (lazy matrix + guard band / chain replay, height filter, pos2grid,
 // static filter), the cell counter (its old value is the rank in the cell segment) and
@@ -1938,11 +2113,14 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
             k_bev_cull<<<(a.n_frames * nv + 127) / 128, 128, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             h->launches[PCACC_K_CLASSIFY]++;
-            k_bev_classify<<<h->n_sm * 4, BIN_BLOCK, 0, st>>>(a);
+            if (nv >= CLS_MV_MIN && !h->classify_single)
+                k_bev_classify_mv<<<h->n_sm * h->cls_mult, BIN_BLOCK, 0, st>>>(a);
+            else
+                k_bev_classify<<<h->n_sm * h->cls_mult, BIN_BLOCK, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_CLASSIFY, pe, st);
             pe = pcacc_prof_begin(h, PCACC_K_BIN, st);
-            k_bev_bin<<<h->n_sm * 8, 256, 0, st>>>(a);
+            k_bev_bin<<<h->n_sm * h->bin_mult, 256, 0, st>>>(a);
             PCACC_CUDA(h, cudaGetLastError());
             pcacc_prof_end(h, PCACC_K_BIN, pe, st);
             // scan

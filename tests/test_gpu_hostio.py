@@ -254,7 +254,9 @@ def test_float64_cloud_must_be_float32_representable(dev):
 
 def test_chunk_and_strip_reduce_kernels_agree(dev):
     """k_bev_reduce_chunk (default for float16-only output) against k_bev_reduce (strips) and the
-    float64-output instantiation on sparse, crowded and empty grids: identical float16 bits."""
+    float64-output instantiation on sparse, crowded and empty grids: identical float16 bits.  Nine
+    variants per call, so the candidate selection runs k_bev_classify_mv; the last pass repeats it
+    with k_bev_classify (block per variant)."""
     from tests.test_gpu_edge import rand_cloud
     rng = np.random.default_rng(31)
     for P, n, spread in ((256, 40000, 30.), (64, 60000, 6.), (128, 3000, 40.), (1024, 200000, 25.)):
@@ -264,7 +266,7 @@ def test_chunk_and_strip_reduce_kernels_agree(dev):
         cloud.sync()
         gp = gen_params(synth.kitti_bev_params(pixel_size=P, view_size=80))
         bps = [bev_params_from(dev, gp, fids[0], fids[1], fids[1] + 1, np.array([0.5, 0.25, 0.1]),
-                               0.3 * k, 0.7 * k, -0.4 * k, 1.0 + 0.02 * k) for k in range(5)]
+                               0.3 * k, 0.7 * k, -0.4 * k, 1.0 + 0.02 * k) for k in range(9)]
         bps[4].elevation_max = 1
         bps[3].rgb_fill = 37.0
         a, _, _ = cloud.rasterise(bps, P)
@@ -273,6 +275,11 @@ def test_chunk_and_strip_reduce_kernels_agree(dev):
         cloud.set_option(_lib.OPT_REDUCE_STRIPS, 0)
         c, _, _ = cloud.rasterise(bps, P, want_f64=True)
         cloud.sync()
+        cloud.set_option(_lib.OPT_CLASSIFY_SINGLE, 1)
+        d, _, _ = cloud.rasterise(bps, P)
+        cloud.set_option(_lib.OPT_CLASSIFY_SINGLE, 0)
+        cloud.sync()
         assert torch.equal(a.view(torch.int16), b.view(torch.int16)), P
         assert torch.equal(a.view(torch.int16), c.view(torch.int16)), P
+        assert torch.equal(a.view(torch.int16), d.view(torch.int16)), P
         cloud.close()
