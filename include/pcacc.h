@@ -54,6 +54,9 @@ typedef enum {
 #define PCACC_SEM_I64 2
 #define PCACC_SEM_I16 4
 #define PCACC_SEM_F32_PROB 3 /* (H,W,K) float32 class probabilities: class = first argmax over K */
+/* image dtypes accepted by pcacc_pts_feat_from_img in addition to the integer codes above */
+#define PCACC_IMG_F32 6
+#define PCACC_IMG_F64 7
 
 const char *pcacc_strerror(int status);
 const char *pcacc_last_error(pcacc_t h);
@@ -343,6 +346,28 @@ int pcacc_project_cameras(pcacc_t h, const double *pc_ego_dev, int64_t n, int64_
                           const double *glob_from_ego, const double *cam_from_glob,
                           const double *cam_K, const double *img_wh, int n_cams, double depth_thres,
                           double *out_uv_dev, int64_t *out_cam_idx_dev, void *stream);
+
+/* pts_feat_from_img, datasets/nuscenes_utils.py:181-214, both branches: for n points with pixel
+ * coordinates uv_dev (n,2) float64 and an image img_dev (H,W,C) of img_dtype, out_dev (n,C)
+ * float64 = img[rint(v), rint(u)] (bilinear = 0, half-to-even like np.round) or the four-neighbour
+ * blend with the reference's weights in its operation order (bilinear = 1; an integral u or v
+ * gives the reference's 0/0).  The reference's bounds assertion (1 < uv < wh - 1) comes back as
+ * PCACC_FLAG_UV_OUT_OF_IMAGE from pcacc_sync.  The reference multiplies (N,) weights with (N,C)
+ * features, which numpy only broadcasts for a 2-D image; every channel gets the per-point weights
+ * here. */
+int pcacc_pts_feat_from_img(pcacc_t h, const double *uv_dev, int64_t n, const void *img_dev,
+                            int img_dtype, int img_h, int img_w, int channels, int bilinear,
+                            double *out_dev, void *stream);
+
+/* static_obj_partitioning_by_elev, bev_generator/sem_bev.py:556-591: pc_dev (n,10) float64 rows
+ * whose columns 0, 1 are grid coordinates; per-cell minimum z (row P-1-j, column i), then column 8
+ * of every point more than elev_thresh above its cell's minimum is set to 1 IN PLACE.
+ * elevmap_dev (P,P) float64 (0 where unobserved), obs_mask_dev (P,P) uint8, scratch_dev: P*P
+ * uint64.  Grid coordinates outside [-P, P) (the reference's IndexError) or a NaN z raise
+ * PCACC_FLAG_ATTR_RANGE. */
+int pcacc_static_obj_partitioning(pcacc_t h, double *pc_dev, int64_t n, int P, double elev_thresh,
+                                  double *elevmap_dev, uint8_t *obs_mask_dev,
+                                  unsigned long long *scratch_dev, void *stream);
 
 /* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
  * Kernel classes of this library. */

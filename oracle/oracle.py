@@ -265,6 +265,50 @@ def project_to_cameras(pc_in_ego, glob_from_ego, cams, depth_thres=1e-3):
     return pc_uv, pc_cam_idx
 
 
+def pts_feat_from_img(pts_uv, img, method='bilinear'):
+    """datasets/nuscenes_utils.py:181-214, both branches.  Bilinear: the reference's expression
+    per channel (it only broadcasts for a 2-D image; there this IS its arithmetic)."""
+    img_wh = np.array([img.shape[1], img.shape[0]], dtype=float)
+    assert np.all((pts_uv > 1) & (pts_uv < img_wh - 1)), "pts_uv must be all inside image"
+    if method == 'nearest':
+        uv_ = np.round(pts_uv).astype(int)
+        return img[uv_[:, 1], uv_[:, 0]]
+    u, v = pts_uv[:, 0], pts_uv[:, 1]
+    u_floor, u_ceil = np.floor(u), np.ceil(u)
+    v_floor, v_ceil = np.floor(v), np.ceil(v)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        total = (u_ceil - u_floor) * (v_ceil - v_floor)
+        w_ff = (u_ceil - u) * (v_ceil - v) / total
+        w_cc = (u - u_floor) * (v - v_floor) / total
+        w_fc = (u - u_floor) * (v_ceil - v) / total
+        w_cf = 1. - (w_ff + w_cc + w_fc)
+        uf, vf, uc, vc = u_floor.astype(int), v_floor.astype(int), u_ceil.astype(int), v_ceil.astype(int)
+        if img.ndim == 2:
+            return w_ff * img[vf, uf] + w_cc * img[vc, uc] + w_cf * img[vc, uf] + w_fc * img[vf, uc]
+        return (w_ff[:, None] * img[vf, uf] + w_cc[:, None] * img[vc, uc] + w_cf[:, None] * img[vc, uf]
+                + w_fc[:, None] * img[vf, uc])
+
+
+def static_obj_partitioning_by_elev(pc, P, elev_thresh):
+    """bev_generator/sem_bev.py:556-591, vectorised: per-cell minimum z (row P-1-j, column i,
+    indices truncated like .astype(int) and wrapped once like numpy's negative indices), then
+    column 8 = 1 where z > min + thresh.  Mutates pc like the reference."""
+    i = pc[:, 0].astype(int)
+    j_rev = P - 1 - pc[:, 1].astype(int)
+    if np.any((i < -P) | (i >= P) | (j_rev < -P) | (j_rev >= P)):
+        raise IndexError('index out of bounds')
+    i = np.where(i < 0, i + P, i)
+    j_rev = np.where(j_rev < 0, j_rev + P, j_rev)
+    cell = j_rev * P + i
+    zmin = np.full(P * P, np.inf)
+    np.minimum.at(zmin, cell, pc[:, 2])
+    obs = np.zeros(P * P, dtype=bool)
+    obs[cell] = True
+    elevmap = np.where(obs, zmin, 0.).reshape(P, P)
+    pc[pc[:, 2] > zmin[cell] + elev_thresh, 8] = 1
+    return pc[pc[:, 8] == 0], pc[pc[:, 8] == 1], elevmap, obs.reshape(P, P)
+
+
 # ---------------------------------------------------------------------------
 #  a14-a20: the BEV generator
 # ---------------------------------------------------------------------------

@@ -17,6 +17,7 @@ OK = 0
 ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_STATE = -1, -2, -3, -4, -5
 FLAG_UV_OUT_OF_IMAGE, FLAG_INTENSITY_F32, FLAG_ATTR_RANGE, FLAG_CELL_OVERFLOW = 1, 2, 4, 8
 SEM_U8, SEM_I32, SEM_I64, SEM_F32_PROB, SEM_I16 = 0, 1, 2, 3, 4
+IMG_F32, IMG_F64 = 6, 7
 BEV_PLANES, BEV_WINDOWS = 7, 3
 STAGE_AUTO, STAGE_DIRECT, STAGE_SPARSE = 0, 1, 2
 OPT_REDUCE_STRIPS, OPT_CLASSIFY_SINGLE = 1, 2
@@ -96,6 +97,8 @@ SIGNATURES = {
     'pcacc_event_destroy': (_i32, [_vp]),
     'pcacc_assign_boxes': (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_project_cameras': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    'pcacc_pts_feat_from_img': (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'pcacc_static_obj_partitioning': (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp, _vp]),
     'pcacc_profile': (_i32, [_vp, _i32]),
     'pcacc_profile_read': (_i32, [_vp, C.POINTER(_dbl * 10), C.POINTER(_i64 * 10)]),
 }

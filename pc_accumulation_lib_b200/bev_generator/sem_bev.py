@@ -69,3 +69,19 @@ class SemBEVGenerator(BEVGenerator):
             self.view_size, self.height_filter = saved
         tw = {'present': trajs_present, 'future': trajs_future, 'full': trajs_full}
         return self._assemble(planes, 0, tw, gt_lane_trajs, has_future)
+
+    def static_obj_partitioning_by_elev(self, pc, elev_thresh: float):
+        """bev_generator/sem_bev.py:556-591 (unused by the reference's own pipeline): per-cell
+        minimum z of a cloud in grid coordinates, points more than `elev_thresh` above it get
+        column 8 set to 1 IN PLACE -> (pc_static, pc_dynamic, elevmap, elevmap_obs_mask).
+        Runs in `pcacc_static_obj_partitioning`."""
+        from .bev_generator import DeviceCloud
+        from .. import _lib
+        if self._scratch is None:
+            self._scratch = DeviceCloud(1024, max_frames=8)
+        flagged, elev, obs = self._scratch.static_obj_partitioning(pc, self.pixel_size, elev_thresh)
+        if self._scratch.sync() & _lib.FLAG_ATTR_RANGE:
+            raise IndexError('grid index out of bounds for the elevation map (or NaN z)')
+        out = flagged.cpu().numpy()
+        pc[:, 8] = out[:, 8]
+        return pc[pc[:, 8] == 0], pc[pc[:, 8] == 1], elev.cpu().numpy(), obs.cpu().numpy()

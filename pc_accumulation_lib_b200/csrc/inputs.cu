@@ -178,3 +178,166 @@ extern "C" int pcacc_project_cameras(pcacc_t h, const double *pc_ego_dev, int64_
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }
+
+// ---------------------------------------------------------------------------
+// pts_feat_from_img, datasets/nuscenes_utils.py:181-214 — both branches.
+// One thread per (point, channel).  'nearest': img[rint(v), rint(u)] (half to even).
+// 'bilinear': the reference's weights in its own operation order, every product and sum
+// rounded separately (numpy evaluates the expression element-wise without contraction):
+//   total = (uc - uf) * (vc - vf);  w_ff = (uc - u) * (vc - v) / total;  w_cc = (u - uf) * (v - vf) / total;
+//   w_fc = (u - uf) * (vc - v) / total;  w_cf = 1 - (w_ff + w_cc + w_fc);
+//   feat = ((w_ff * I[vf,uf] + w_cc * I[vc,uc]) + w_cf * I[vc,uf]) + w_fc * I[vf,uc]
+// (an integral u or v makes total 0 and the result NaN / inf, as in the reference).  The
+// reference multiplies (N,) weights with (N,C) features, which numpy only broadcasts for a 2-D
+// image; here every channel gets the per-point weights, which is that result for C = 1.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double img_at(const T *img, int64_t pix, int C, int c) {
+    return (double)img[pix * C + c];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(INB)
+k_pts_feat(const double *__restrict__ uv, int64_t n, const T *__restrict__ img, int H, int W, int C,
+           int bilinear, double *__restrict__ out, uint32_t *__restrict__ flags) {
+    const int64_t t = (int64_t)blockIdx.x * INB + threadIdx.x;
+    if (t >= n * C) return;
+    const int64_t i = t / C;
+    const int c = (int)(t - i * C);
+    const double u = uv[2 * i], v = uv[2 * i + 1];
+    // assert np.all((pts_uv > 1) & (pts_uv < img_wh - 1))
+    const bool inside = (u > 1.0) && (u < (double)W - 1.0) && (v > 1.0) && (v < (double)H - 1.0);
+    if (!inside) {
+        if (c == 0) atomicOr(flags, PCACC_FLAG_UV_OUT_OF_IMAGE);
+        out[t] = 0.0;
+        return;
+    }
+    if (!bilinear) {
+        const int64_t pix = (int64_t)rint_even(v) * W + (int64_t)rint_even(u);
+        out[t] = img_at(img, pix, C, c);
+        return;
+    }
+    const double uf = floor(u), uc = ceil(u), vf = floor(v), vc = ceil(v);
+    const double total = __dmul_rn(__dsub_rn(uc, uf), __dsub_rn(vc, vf));
+    const double w_ff = __ddiv_rn(__dmul_rn(__dsub_rn(uc, u), __dsub_rn(vc, v)), total);
+    const double w_cc = __ddiv_rn(__dmul_rn(__dsub_rn(u, uf), __dsub_rn(v, vf)), total);
+    const double w_fc = __ddiv_rn(__dmul_rn(__dsub_rn(u, uf), __dsub_rn(vc, v)), total);
+    const double w_cf = __dsub_rn(1.0, __dadd_rn(__dadd_rn(w_ff, w_cc), w_fc));
+    const int64_t iuf = (int64_t)uf, iuc = (int64_t)uc, ivf = (int64_t)vf, ivc = (int64_t)vc;
+    const double a = __dmul_rn(w_ff, img_at(img, ivf * W + iuf, C, c));
+    const double b = __dmul_rn(w_cc, img_at(img, ivc * W + iuc, C, c));
+    const double d = __dmul_rn(w_cf, img_at(img, ivc * W + iuf, C, c));
+    const double e = __dmul_rn(w_fc, img_at(img, ivf * W + iuc, C, c));
+    out[t] = __dadd_rn(__dadd_rn(__dadd_rn(a, b), d), e);
+}
+
+extern "C" int pcacc_pts_feat_from_img(pcacc_t h, const double *uv_dev, int64_t n, const void *img_dev,
+                                       int img_dtype, int img_h, int img_w, int channels, int bilinear,
+                                       double *out_dev, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || img_h <= 0 || img_w <= 0 || channels <= 0 || (n > 0 && (!uv_dev || !img_dev || !out_dev)))
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad pts_feat_from_img arguments");
+    if (n == 0) return PCACC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    const int64_t blocks = (n * channels + INB - 1) / INB;
+    h->launches[PCACC_K_INTEGRATE]++;
+#define LAUNCH_PF(T)                                                                                    \
+    k_pts_feat<T><<<(unsigned)blocks, INB, 0, st>>>(uv_dev, n, (const T *)img_dev, img_h, img_w, channels, \
+                                                    bilinear, out_dev, h->d_flags)
+    switch (img_dtype) {
+        case PCACC_SEM_U8: LAUNCH_PF(uint8_t); break;
+        case PCACC_SEM_I16: LAUNCH_PF(int16_t); break;
+        case PCACC_SEM_I32: LAUNCH_PF(int32_t); break;
+        case PCACC_SEM_I64: LAUNCH_PF(long long); break;
+        case PCACC_IMG_F32: LAUNCH_PF(float); break;
+        case PCACC_IMG_F64: LAUNCH_PF(double); break;
+        default: return pcacc_fail(h, PCACC_ERR_ARG, "unsupported image dtype %d", img_dtype);
+    }
+#undef LAUNCH_PF
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// static_obj_partitioning_by_elev, bev_generator/sem_bev.py:556-591: per-cell minimum z of
+// the (grid-coordinate) cloud, then every point more than elev_thresh above its cell's
+// minimum gets column 8 set to 1.  pc rows are the (M,10) float64 records whose columns 0, 1
+// hold grid coordinates (output of pos2grid); `.astype(int)` truncates toward zero and numpy
+// wraps negative indices once, which is mirrored; anything outside [-P, P) is the reference's
+// IndexError and raises PCACC_FLAG_ATTR_RANGE here.  The minimum is order-independent except
+// for NaN z (the reference keeps a NaN that arrives first): NaN z raises the same flag.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_index(double g, int P, int &idx) {
+    if (!(g > -2147483648.0 && g < 2147483647.0)) return false;   // NaN / inf / beyond int
+    int i = (int)g;   // truncation toward zero, as ndarray.astype(int)
+    if (i < -P || i >= P) return false;
+    idx = i < 0 ? i + P : i;
+    return true;
+}
+
+__global__ void __launch_bounds__(INB)
+k_elev_min(const double *__restrict__ pc, int64_t n, int P, unsigned long long *__restrict__ zmin,
+           uint32_t *__restrict__ flags) {
+    const int64_t t = (int64_t)blockIdx.x * INB + threadIdx.x;
+    if (t >= n) return;
+    const double *r = pc + t * 10;
+    int i, j;
+    const double z = r[2];
+    // j_rev = P - 1 - j is what is indexed (and wrapped) in the reference
+    double jr = (double)(P - 1) - trunc(r[1]);
+    if (!grid_index(r[0], P, i) || !(r[1] > -2147483648.0 && r[1] < 2147483647.0) || !grid_index(jr, P, j) ||
+        z != z) {
+        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+        return;
+    }
+    atomicMin(&zmin[(int64_t)j * P + i], ord_encode(z));
+}
+
+__global__ void __launch_bounds__(INB)
+k_elev_flag(double *__restrict__ pc, int64_t n, int P, double elev_thresh,
+            const unsigned long long *__restrict__ zmin) {
+    const int64_t t = (int64_t)blockIdx.x * INB + threadIdx.x;
+    if (t >= n) return;
+    double *r = pc + t * 10;
+    int i, j;
+    double jr = (double)(P - 1) - trunc(r[1]);
+    if (!grid_index(r[0], P, i) || !(r[1] > -2147483648.0 && r[1] < 2147483647.0) || !grid_index(jr, P, j) ||
+        r[2] != r[2])
+        return;
+    const double m = ord_decode(zmin[(int64_t)j * P + i]);
+    if (r[2] > __dadd_rn(m, elev_thresh)) r[8] = 1.0;
+}
+
+__global__ void __launch_bounds__(INB)
+k_elev_export(const unsigned long long *__restrict__ zmin, int64_t cells, double *__restrict__ elevmap,
+              uint8_t *__restrict__ obs) {
+    const int64_t t = (int64_t)blockIdx.x * INB + threadIdx.x;
+    if (t >= cells) return;
+    const unsigned long long u = zmin[t];
+    const bool seen = u != AABB_EMPTY_MIN;
+    elevmap[t] = seen ? ord_decode(u) : 0.0;
+    obs[t] = seen ? 1 : 0;
+}
+
+extern "C" int pcacc_static_obj_partitioning(pcacc_t h, double *pc_dev, int64_t n, int P, double elev_thresh,
+                                             double *elevmap_dev, uint8_t *obs_mask_dev,
+                                             unsigned long long *scratch_dev, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || P <= 0 || !elevmap_dev || !obs_mask_dev || !scratch_dev || (n > 0 && !pc_dev))
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad static_obj_partitioning arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    const int64_t cells = (int64_t)P * P;
+    PCACC_CUDA(h, cudaMemsetAsync(scratch_dev, 0xff, (size_t)cells * 8, st));   // AABB_EMPTY_MIN everywhere
+    h->launches[PCACC_K_EXPORT] += 3;
+    if (n > 0) {
+        const int64_t nb = (n + INB - 1) / INB;
+        k_elev_min<<<(unsigned)nb, INB, 0, st>>>(pc_dev, n, P, scratch_dev, h->d_flags);
+        k_elev_flag<<<(unsigned)nb, INB, 0, st>>>(pc_dev, n, P, elev_thresh, scratch_dev);
+    }
+    k_elev_export<<<(unsigned)((cells + INB - 1) / INB), INB, 0, st>>>(scratch_dev, cells, elevmap_dev,
+                                                                     obs_mask_dev);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}

@@ -5,10 +5,8 @@ u, v, inst]` and `pc_cam_idx`.  Same function names and argument meaning; the pe
 runs in libpcacc (`pcacc_assign_boxes`, `pcacc_project_cameras`), the 4x4 inverses and the
 small bookkeeping stay in numpy exactly as the reference has them.
 
-`pts_feat_from_img(..., 'bilinear')` is not mirrored: the reference's bilinear branch
-multiplies (N,) weights with (N,C) features and only broadcasts for C == N
-(datasets/nuscenes_utils.py:206-208); the accumulator uses 'nearest', which is part of
-`pcacc_integrate_records`.
+`pts_feat_from_img` (both branches) runs in `pcacc_pts_feat_from_img`; the accumulator's own
+'nearest' gather is fused into `pcacc_integrate_records`.
 """
 from __future__ import annotations
 
@@ -58,6 +56,26 @@ def apply_tf(tf, points, in_place=False):
     if not in_place:
         return moved
     points[:, :3] = moved
+
+
+def pts_feat_from_img(pts_uv, img, method='bilinear'):
+    """datasets/nuscenes_utils.py:181-214 -> (N, C) array ((N,) for a 2-D image).  'nearest':
+    `img[round(v), round(u)]`; 'bilinear': the reference's four weights in its operation order.
+    The reference multiplies (N,) weights with (N, C) features, which numpy only broadcasts for a
+    2-D image — there the results are bit-equal (tests); for C channels every channel gets the
+    per-point weights.  Coordinates outside `1 < uv < wh - 1` raise the reference's AssertionError."""
+    if not isinstance(img, np.ndarray):
+        raise AssertionError(f'{type(img)} is not supported')
+    if method not in ('bilinear', 'nearest'):
+        raise AssertionError(f'{method} is not supported')
+    dev = _dev()
+    out = dev.pts_feat_from_img(np.ascontiguousarray(pts_uv, dtype=np.float64), img, method)
+    if dev.sync() & 1:          # PCACC_FLAG_UV_OUT_OF_IMAGE
+        raise AssertionError('pts_uv must be all inside image')
+    res = out.cpu().numpy()
+    if method == 'nearest':
+        return res.astype(img.dtype)      # a pure gather keeps the image's dtype
+    return res
 
 
 def find_points_in_box(points, target_from_box, dxdydz, tolerance):

@@ -735,6 +735,47 @@ class DeviceCloud:
         self.stage.fence()
         return uv, cam
 
+    def pts_feat_from_img(self, pts_uv, img, method='bilinear'):
+        """datasets/nuscenes_utils.py:181-214 on the device -> (n, C) float64 CUDA tensor ((n,) for a
+        2-D image, as the reference's fancy indexing gives)."""
+        assert method in ('bilinear', 'nearest'), f'{method} is not supported'
+        uv = self.stage.put('feat_uv', pts_uv if isinstance(pts_uv, torch.Tensor)
+                            else np.asarray(pts_uv, dtype=np.float64)).contiguous()
+        assert uv.dtype == torch.float64 and uv.dim() == 2 and uv.shape[1] == 2
+        im = img if isinstance(img, torch.Tensor) else np.ascontiguousarray(img)
+        codes = {torch.uint8: _lib.SEM_U8, torch.int16: _lib.SEM_I16, torch.int32: _lib.SEM_I32,
+                 torch.int64: _lib.SEM_I64, torch.float32: _lib.IMG_F32, torch.float64: _lib.IMG_F64}
+        imd = self.stage.put('feat_img', im).contiguous()
+        if imd.dtype not in codes:
+            imd = imd.double()
+        two_d = imd.dim() == 2
+        h, w = int(imd.shape[0]), int(imd.shape[1])
+        c = 1 if two_d else int(imd.shape[2])
+        n = int(uv.shape[0])
+        out = torch.empty((n, c), dtype=torch.float64, device=self.device)
+        self._check(self.lib.pcacc_pts_feat_from_img(self.h, _ptr(uv), n, _ptr(imd), codes[imd.dtype], h, w,
+                                                     c, 1 if method == 'bilinear' else 0, _ptr(out),
+                                                     _stream()))
+        self.stage.fence()
+        self._dirty = True
+        return out[:, 0] if two_d else out
+
+    def static_obj_partitioning(self, pc, P: int, elev_thresh: float):
+        """bev_generator/sem_bev.py:556-591 on the device.  pc: (n,10) float64 rows with grid
+        coordinates in columns 0, 1 -> (pc with column 8 flagged, elevmap (P,P) float64, observed
+        mask (P,P) bool) as CUDA tensors."""
+        t = pc if isinstance(pc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pc, dtype=np.float64))
+        t = t.to(self.device).contiguous().clone()
+        assert t.dtype == torch.float64 and t.dim() == 2 and t.shape[1] == 10
+        elev = torch.empty((P, P), dtype=torch.float64, device=self.device)
+        obs = torch.empty((P, P), dtype=torch.uint8, device=self.device)
+        scratch = torch.empty(P * P, dtype=torch.int64, device=self.device)
+        self._check(self.lib.pcacc_static_obj_partitioning(self.h, _ptr(t), int(t.shape[0]), int(P),
+                                                           float(elev_thresh), _ptr(elev), _ptr(obs),
+                                                           _ptr(scratch), _stream()))
+        self._dirty = True
+        return t, elev, obs.bool()
+
     def raster_stats(self):
         s = (C.c_int64 * 3)()
         self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))

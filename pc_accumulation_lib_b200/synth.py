@@ -392,3 +392,28 @@ def input_side_inputs(n=12000, n_boxes=24, n_cams=6, seed=91):
     pc[50:50 + n_boxes] = [T[:3, 3] if b % 7 != 3 else [1., 1., 1.] for b, T in enumerate(boxes)]
     return dict(pc=pc, pc_f32=pc.astype(np.float32), glob_from_ego=glob_from_ego, cams=cams,
                 boxes=boxes, sizes=sizes, tolerance=1e-2)
+
+
+def helper_inputs(seed=123, n=4000, P=48):
+    """Inputs of the two stand-alone helpers of SURVEY.md 8f rank 4: pixel coordinates strictly
+    inside a 97 x 61 image (some with integral u or v: the bilinear 0/0), a float64 single-channel
+    image, an int64 4-channel image, and a cloud in grid coordinates with stacked points per cell."""
+    rng = np.random.default_rng(seed)
+    H, W = 61, 97
+    uv = np.stack([rng.uniform(1.001, W - 1.001, n), rng.uniform(1.001, H - 1.001, n)], axis=1)
+    uv[:40, 0] = np.floor(uv[:40, 0]) + 0.5            # exact halves: np.round to even
+    uv[40:60, 1] = np.floor(uv[40:60, 1])              # integral v: total == 0 in the bilinear branch
+    uv[60:70] = np.floor(uv[60:70]) + [0.0, 0.25]      # integral u
+    uv = np.clip(uv, 1.001, None)
+    img2d = rng.normal(0., 50., (H, W))
+    img4 = rng.integers(0, 256, (H, W, 4)).astype(np.int64)
+    pc = np.zeros((n, 10))
+    pc[:, 0:2] = np.floor(rng.uniform(0, P, (n, 2)))
+    pc[:200, 0:2] = [5., 7.]                            # a crowded cell
+    pc[200:230, 0] += 0.75                              # fractional grid coordinates truncate
+    pc[:, 2] = rng.normal(0., 1.5, n)
+    pc[:, 3] = rng.uniform(0., 1., n)
+    pc[:, 7] = rng.integers(0, 19, n)
+    pc[::17, 8] = 1.                                    # already flagged
+    pc[5::29, 8] = 3.                                   # neither 0 nor 1: dropped from both outputs
+    return dict(uv=uv, img2d=img2d, img4=img4, pc=pc, P=P, elev_thresh=0.8)

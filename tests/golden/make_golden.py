@@ -245,8 +245,30 @@ def gen_input_side(ref, name):
     save(name, out)
 
 
+def gen_helpers(ref, name):
+    """The two stand-alone helpers of SURVEY.md 8f rank 4, run unmodified: pts_feat_from_img (nearest on
+    a 4-channel image; bilinear on a 2-D image, the only shape the reference's broadcasting handles) and
+    SemBEVGenerator.static_obj_partitioning_by_elev."""
+    c = synth.helper_inputs()
+    nu = ref.nusc_utils
+    out = {'nearest4': nu.pts_feat_from_img(c['uv'], c['img4'], 'nearest')}
+    with np.errstate(divide='ignore', invalid='ignore'):
+        out['bilinear2d'] = nu.pts_feat_from_img(c['uv'], c['img2d'], 'bilinear')
+    g = ref.SemBEVGenerator(synth.SEM_IDXS, 40., c['P'])
+    pc = c['pc'].copy()
+    with quiet():
+        st, dy, elev, obs = g.static_obj_partitioning_by_elev(pc, c['elev_thresh'])
+    out.update(pc_after=pc, pc_static=st, pc_dynamic=dy, elevmap=elev, obs=obs)
+    out['input_digest'] = np.frombuffer(cases.digest(c['uv'], c['img2d'], c['img4'], c['pc']).encode(),
+                                        dtype=np.uint8)
+    save(name, out)
+
+
 def main():
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'helpers':
+        gen_helpers(ref, 'helpers.npz')
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'input_side':
         gen_input_side(ref, 'input_side.npz')
         return
@@ -264,6 +286,7 @@ def main():
                    view=51.2)
     gen_bev_warp(ref, 'bev_warp.npz')
     gen_input_side(ref, 'input_side.npz')
+    gen_helpers(ref, 'helpers.npz')
 
 
 if __name__ == '__main__':

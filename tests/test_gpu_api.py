@@ -8,6 +8,7 @@ import pytest
 
 torch = pytest.importorskip('torch')
 
+from oracle import oracle as orc                                               # noqa: E402
 from pc_accumulation_lib_b200 import synth                                     # noqa: E402
 from tests.conftest import assert_bev_equal, load_golden, unpack_bev, unpack_sem_pcs  # noqa: E402
 from tests.golden import cases                                                 # noqa: E402
@@ -260,3 +261,45 @@ def test_input_side_kernels_match_reference_golden():
     want = np.where(g['box_f64'] >= 0, g['box_f64'] + 11 * len(c['boxes']), -1)
     np.testing.assert_array_equal(box, want)
     np.testing.assert_array_equal(cnt, np.tile(g['cnt_f64'], 12))
+
+
+def test_standalone_helpers_match_reference_golden():
+    """pts_feat_from_img (both branches) and static_obj_partitioning_by_elev through the drop-in
+    functions against outputs of the unmodified reference (tests/golden/helpers.npz)."""
+    from pc_accumulation_lib_b200.bev_generator import SemBEVGenerator
+    from pc_accumulation_lib_b200.datasets import nuscenes_utils as nu
+    g = load_golden('helpers.npz')
+    c = synth.helper_inputs()
+    near = nu.pts_feat_from_img(c['uv'], c['img4'], 'nearest')
+    assert near.dtype == g['nearest4'].dtype
+    np.testing.assert_array_equal(near, g['nearest4'])
+    b = nu.pts_feat_from_img(c['uv'], c['img2d'], 'bilinear')
+    assert b.shape == g['bilinear2d'].shape
+    assert np.array_equal(b, g['bilinear2d'], equal_nan=True)
+    # per-channel blend of a multi-channel image == the 2-D result of each channel
+    b4 = nu.pts_feat_from_img(c['uv'], c['img4'].astype(np.float64), 'bilinear')
+    for ch in range(4):
+        want = orc.pts_feat_from_img(c['uv'], np.ascontiguousarray(c['img4'][:, :, ch].astype(np.float64)), 'bilinear')
+        assert np.array_equal(b4[:, ch], want, equal_nan=True), ch
+    bad = c['uv'].copy()
+    bad[3, 0] = 0.5
+    with pytest.raises(AssertionError):
+        nu.pts_feat_from_img(bad, c['img2d'], 'nearest')
+    with pytest.raises(AssertionError):
+        nu.pts_feat_from_img(c['uv'], c['img2d'], 'cubic')
+
+    gen = SemBEVGenerator(synth.SEM_IDXS, 40., c['P'])
+    pc = c['pc'].copy()
+    st, dy, el, ob = gen.static_obj_partitioning_by_elev(pc, c['elev_thresh'])
+    for got, key in ((pc, 'pc_after'), (st, 'pc_static'), (dy, 'pc_dynamic'), (el, 'elevmap'), (ob, 'obs')):
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
+    # negative grid coordinates wrap once like numpy's indexing; beyond that the reference raises
+    pc2 = c['pc'].copy()
+    pc2[0, 0] = -3.
+    want = pc2.copy()
+    orc.static_obj_partitioning_by_elev(want, c['P'], c['elev_thresh'])
+    gen.static_obj_partitioning_by_elev(pc2, c['elev_thresh'])
+    np.testing.assert_array_equal(pc2, want)
+    pc2[0, 0] = float(c['P'])
+    with pytest.raises(IndexError):
+        gen.static_obj_partitioning_by_elev(pc2, c['elev_thresh'])

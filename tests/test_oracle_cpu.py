@@ -179,3 +179,19 @@ def test_input_side_matches_reference_golden():
     # the seams are seen by two cameras: the later one must have won
     seen = np.stack([g[f'mask_cam{j}'] for j in range(len(c['cams']))])
     assert (seen.sum(axis=0) > 1).sum() > 100
+
+
+def test_standalone_helpers_match_reference_golden():
+    """SURVEY.md 8f rank 4 remainder: pts_feat_from_img (nearest + bilinear) and
+    static_obj_partitioning_by_elev against outputs of the unmodified reference."""
+    from pc_accumulation_lib_b200 import synth
+    g = load_golden('helpers.npz')
+    c = synth.helper_inputs()
+    np.testing.assert_array_equal(orc.pts_feat_from_img(c['uv'], c['img4'], 'nearest'), g['nearest4'])
+    b = orc.pts_feat_from_img(c['uv'], c['img2d'], 'bilinear')
+    assert np.array_equal(b, g['bilinear2d'], equal_nan=True)
+    assert (~np.isfinite(b)).sum() > 0          # integral coordinates: the reference's 0/0
+    pc = c['pc'].copy()
+    st, dy, el, ob = orc.static_obj_partitioning_by_elev(pc, c['P'], c['elev_thresh'])
+    for got, key in ((pc, 'pc_after'), (st, 'pc_static'), (dy, 'pc_dynamic'), (el, 'elevmap'), (ob, 'obs')):
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
