@@ -474,13 +474,27 @@ class BEVGenerator(ABC):
     def warp_points(self, pnt_list, a_1, a_2, b_1, b_2, I, J):
         return [self.warp_point(p[0], p[1], a_1, a_2, b_1, b_2, I, J) for p in pnt_list]
 
+    @staticmethod
+    def _warp_axis(v, c_1, c_2, n):
+        """warp_point's inverse map for a whole coordinate column: the same numpy ufuncs applied
+        element-wise give the same bits as the reference's per-point calls."""
+        import math
+        if math.isclose(c_2, 0.0, abs_tol=1e-6):
+            w = np.array(v, dtype=np.float64)
+        else:
+            w = np.rint((-c_1 + np.sqrt(c_1 ** 2 + 4.0 * c_2 * v)) / (2 * c_2))
+            if np.isnan(w).any():
+                raise ValueError('cannot convert float NaN to integer')   # int(np.rint(nan)) in the reference
+        return np.where(w < 0, 0, np.where(w >= n, n - 1, w))
+
     def warp_sparse_points(self, pnts, a_1, a_2, b_1, b_2, i_mid, j_mid, i_warp, j_warp):
         # the j warp is applied reversed, as in the reference (bev_generator.py:530-533)
         b_1_rev, b_2_rev = self.cal_warp_params(self.pixel_size - j_warp, j_mid, self.pixel_size - 1)
-        out = self.warp_points(list(zip(pnts[:, 0], pnts[:, 1])), a_1, a_2, b_1_rev, b_2_rev,
-                               self.pixel_size, self.pixel_size)
-        pnts[:, 0] = [i for i, _ in out]
-        pnts[:, 1] = [j for _, j in out]
+        if pnts.shape[0]:
+            x = self._warp_axis(pnts[:, 0], a_1, a_2, self.pixel_size)
+            y = self._warp_axis(pnts[:, 1], b_1_rev, b_2_rev, self.pixel_size)
+            pnts[:, 0] = x
+            pnts[:, 1] = y
         return pnts
 
     def warp_trajs(self, trajs, a_1, a_2, b_1, b_2, i_mid, j_mid, i_warp, j_warp):
