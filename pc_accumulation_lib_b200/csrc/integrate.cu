@@ -336,7 +336,7 @@ struct TMat {
 // One tile (1024 consecutive points) of the nuScenes record path.  Item k of thread t is
 // point tile*1024 + k*128 + t.  Only the two pixel coordinates are read for every point;
 // xyz / intensity / instance of the (few) kept points are fetched after the gather.
-template <int DT>
+template <int DT, int ITEMS>
 __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
                                              const long long *__restrict__ cam_idx, int64_t n,
                                              const CamMaps &maps, int img_h, int img_w,
@@ -345,21 +345,21 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
                                              unsigned long long *state, uint32_t epoch, uint32_t tile,
                                              uint32_t n_tiles, int64_t base,
                                              uint32_t *__restrict__ flags, uint32_t *s_cnt) {
-    bool keep[REC_ITEMS];
-    uint32_t packed[REC_ITEMS];
-    long long cam[REC_ITEMS];
+    bool keep[ITEMS];
+    uint32_t packed[ITEMS];
+    long long cam[ITEMS];
 #pragma unroll
-    for (int k = 0; k < REC_ITEMS; k++) {
-        const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
+    for (int k = 0; k < ITEMS; k++) {
+        const int64_t i = (int64_t)tile * (RBLOCK * ITEMS) + k * RBLOCK + threadIdx.x;
         // sampled source: the rows are the visible points already (camera 0 of 1)
         cam[k] = i < n ? (DT == PCACC_SEM_SAMPLED ? 0ll : cam_idx[i]) : -1;
         keep[k] = false;
         packed[k] = 0;
     }
 #pragma unroll
-    for (int k = 0; k < REC_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         if (cam[k] >= 0 && cam[k] < maps.n) {
-            const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
+            const int64_t i = (int64_t)tile * (RBLOCK * ITEMS) + k * RBLOCK + threadIdx.x;
             const double uf = pc[i * 7 + 4], vf = pc[i * 7 + 5];
             // pts_feat_from_img bounds assertion, datasets/nuscenes_utils.py:190-195
             const bool inside = (uf > 1.0) && (uf < (double)img_w - 1.0) && (vf > 1.0) &&
@@ -393,13 +393,13 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
             }
         }
     }
-    uint32_t rank[REC_ITEMS], tile_end;
-    compact_rank_multi<RBLOCK, REC_ITEMS>(keep, state, epoch, tile, s_cnt, rank, &tile_end);
+    uint32_t rank[ITEMS], tile_end;
+    compact_rank_multi<RBLOCK, ITEMS>(keep, state, epoch, tile, s_cnt, rank, &tile_end);
     double bb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int k = 0; k < REC_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         if (keep[k]) {
-            const int64_t i = (int64_t)tile * REC_TILE + k * RBLOCK + threadIdx.x;
+            const int64_t i = (int64_t)tile * (RBLOCK * ITEMS) + k * RBLOCK + threadIdx.x;
             const double *row = pc + i * 7;
             double wx, wy, wz;
             affine_chain(T, 4, row[0], row[1], row[2], wx, wy, wz);
@@ -426,16 +426,22 @@ __device__ __forceinline__ void records_tile(const double *__restrict__ pc,
     if (tile == n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
+// Per-sweep launch: a sweep of 34,688 points is 34 tiles of 1024 — 34 blocks, each a chain of
+// dependent reads (cam_idx -> u, v -> class -> rgb / row) that go over the bus when the arrays are
+// page-locked host memory.  Two points per thread (256-point tiles, 136 blocks) put four times as
+// many chains in flight; the batched kernel below keeps 8 points per thread (its 40 sweeps fill
+// the machine already).
+#define REC_ITEMS_SWEEP 2
 template <int DT>
 __global__ void __launch_bounds__(RBLOCK)
 k_integrate_records(const double *__restrict__ pc, const long long *__restrict__ cam_idx, int64_t n,
                     CamMaps maps, int img_h, int img_w, TMat T, Filters filt, RingDev ring,
                     FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_cnt[REC_ITEMS * RBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[REC_ITEMS_SWEEP * RBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
     const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
-    records_tile<DT>(pc, cam_idx, n, maps, img_h, img_w, T.m, filt, ring, fs, lb.state, lb.epoch, tile,
-                     lb.n_tiles, frame_base(fs), flags, s_cnt);
+    records_tile<DT, REC_ITEMS_SWEEP>(pc, cam_idx, n, maps, img_h, img_w, T.m, filt, ring, fs, lb.state, lb.epoch,
+                                      tile, lb.n_tiles, frame_base(fs), flags, s_cnt);
 }
 
 // ---------------------------------------------------------------------------
@@ -476,7 +482,7 @@ k_integrate_records_batch(const SweepDesc *__restrict__ sweeps, int img_h, int i
     const SweepDesc &sw = sweeps[blockIdx.y];
     if (blockIdx.x >= sw.n_tiles) return;
     const uint32_t tile = lb_take_ticket(tickets + blockIdx.y, sw.n_tiles, &s_tile);
-    records_tile<DT>(sw.pc, sw.cam, sw.n, sw.maps, img_h, img_w, sw.T.m, filt, ring, sw.fs,
+    records_tile<DT, REC_ITEMS>(sw.pc, sw.cam, sw.n, sw.maps, img_h, img_w, sw.T.m, filt, ring, sw.fs,
                      state + sw.state_off, epoch, tile, sw.n_tiles, sw.fs.base_override, flags, s_cnt);
 }
 
@@ -915,7 +921,7 @@ extern "C" int pcacc_integrate_records(pcacc_t h, const double *pc_dev, const in
     }
     TMat T;
     memcpy(T.m, T_ego_world, sizeof(T.m));
-    int64_t tiles = (n + REC_TILE - 1) / REC_TILE;
+    int64_t tiles = (n + RBLOCK * REC_ITEMS_SWEEP - 1) / (RBLOCK * REC_ITEMS_SWEEP);
     if (tiles == 0) tiles = 1;
     LookBack lb;
     rc = make_lookback(h, tiles, &lb);
@@ -1160,7 +1166,12 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
     vidx.clear();
     vpix.clear();
     const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
+    const int64_t ahead = 48;   // rows of visible points are scattered 56-byte reads: fetch them early
     for (int64_t i = 0; i < n; i++) {
+        if (i + ahead < n) {
+            const int64_t ca = cam_idx_host[i + ahead];
+            if (ca >= 0 && ca < n_cams) __builtin_prefetch(pc_host + 7 * (i + ahead));
+        }
         const int64_t c = cam_idx_host[i];
         if (!(c >= 0 && c < n_cams)) continue;
         const double uf = pc_host[7 * i + 4], vf = pc_host[7 * i + 5];
@@ -1204,7 +1215,7 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
     }
     TMat T;
     memcpy(T.m, T_ego_world, sizeof(T.m));
-    int64_t tiles = (n_vis + REC_TILE - 1) / REC_TILE;
+    int64_t tiles = (n_vis + RBLOCK * REC_ITEMS_SWEEP - 1) / (RBLOCK * REC_ITEMS_SWEEP);
     if (tiles == 0) tiles = 1;
     LookBack lb;
     rc = make_lookback(h, tiles, &lb);
