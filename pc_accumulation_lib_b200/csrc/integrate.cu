@@ -1159,21 +1159,28 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
     if (rc) return rc;
     rc = set_inten_div(h, intensity_div);
     if (rc) return rc;
-    // pass 1: the visible points, their pixel addresses, and a prefetch of the two cache lines
-    // each of them will read (the gathers are the only cache-missing part of the staging)
+    // pass 0: indices of the points a camera sees — a branch-free compaction (one point in ten is
+    // visible, in no predictable pattern: a branch per point costs more than the store it avoids)
     std::vector<uint32_t> &vidx = h->stage_idx;
     std::vector<int64_t> &vpix = h->stage_pix;
-    vidx.clear();
-    vpix.clear();
-    const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
-    const int64_t ahead = 48;   // rows of visible points are scattered 56-byte reads: fetch them early
-    for (int64_t i = 0; i < n; i++) {
-        if (i + ahead < n) {
-            const int64_t ca = cam_idx_host[i + ahead];
-            if (ca >= 0 && ca < n_cams) __builtin_prefetch(pc_host + 7 * (i + ahead));
+    vidx.resize((size_t)n + 1);
+    size_t nv = 0;
+    {
+        uint32_t *vi = vidx.data();
+        const uint64_t nc = (uint64_t)n_cams;
+        for (int64_t i = 0; i < n; i++) {
+            vi[nv] = (uint32_t)i;
+            nv += (uint64_t)cam_idx_host[i] < nc;     // 0 <= c < n_cams in one unsigned compare
         }
-        const int64_t c = cam_idx_host[i];
-        if (!(c >= 0 && c < n_cams)) continue;
+    }
+    vidx.resize(nv);
+    vpix.resize(nv);
+    // pass 1: pixel addresses of the visible points and a prefetch of the two cache lines each of
+    // them will read (the gathers are the cache-missing part of the staging; the iterations are
+    // independent, so the row reads of this pass overlap as well)
+    const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
+    for (size_t k = 0; k < nv; k++) {
+        const int64_t i = vidx[k], c = cam_idx_host[i];
         const double uf = pc_host[7 * i + 4], vf = pc_host[7 * i + 5];
         int64_t pix = -1;
         // outside the image the kernel raises PCACC_FLAG_UV_OUT_OF_IMAGE and never looks at the sample
@@ -1182,8 +1189,7 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
             __builtin_prefetch(rgb_maps_host[c] + pix * 3);
             __builtin_prefetch((const char *)sem_maps_host[c] + pix * sem_bytes);
         }
-        vidx.push_back((uint32_t)i);
-        vpix.push_back(pix);
+        vpix[k] = pix;
     }
     const int64_t n_vis = (int64_t)vidx.size();
     pcacc_s::StageSlot *sl = nullptr;
