@@ -273,6 +273,9 @@ int pcacc_warp_planes(pcacc_t h, const void *in_f16_dev, void *out_f16_dev, int 
 /* PCACC_OPT_CLASSIFY_SINGLE = 1: candidate selection runs k_bev_classify (block per variant) for
  * every batch size instead of k_bev_classify_mv (warp per variant, batches of >= 8 variants). */
 #define PCACC_OPT_CLASSIFY_SINGLE 2
+/* (Profiling runs can set the same switches, and the grid sizes of k_bev_classify / k_bev_bin in
+ * multiples of the SM count, through the environment read by pcacc_create: PCACC_REDUCE_STRIPS=1,
+ * PCACC_CLASSIFY_SINGLE=1, PCACC_CLS_MULT=<n>, PCACC_BIN_MULT=<n>.) */
 int pcacc_set_option(pcacc_t h, int option, int value);
 
 /* ring position (record index) of a live frame's first point, for dbg_cell_dev */
