@@ -1411,9 +1411,12 @@ k_bev_reduce(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorte
 // a shared-memory tile of the chunk's 21 x 128 planes that starts out as the empty-window
 // constants and leaves as 21 fully coalesced 256-byte row pieces.
 // ---------------------------------------------------------------------------
-#define CH_CELLS 128
-#define CH_PER_LANE (CH_CELLS / 32)
 #define CH_WARPS 2
+#ifndef CH_CPL
+#define CH_CPL 4          /* cells per lane: a chunk is 32 * CH_CPL consecutive cells (8: 62 us, 16: 96 us against 52 us: fewer groups, but longer serial chains per warp) */
+#endif
+#define CH_CELLS (32 * CH_CPL)
+#define CH_PER_LANE CH_CPL
 
 // per-warp state of one group of <= 32 small cells.  Arrays are [k][cell] (see SmallWarp).
 // Every accumulator is a 32-bit word updated with native shared-memory atomics: the 64-bit
@@ -1439,7 +1442,7 @@ static_assert(offsetof(GroupWarp, cnt) % 16 == 0 && GW_ZERO_BYTES % 16 == 0 &&
 struct __align__(16) ChunkWarp {
     GroupWarp gw;
     uint32_t g_s0[CH_CELLS];     // compacted non-empty small cells: first record in `sorted`
-    uint8_t g_cell[CH_CELLS];    // ... cell index inside the chunk
+    uint16_t g_cell[CH_CELLS];   // ... cell index inside the chunk
     uint8_t g_np[CH_CELLS], g_nt[CH_CELLS];
 };
 
@@ -1463,9 +1466,20 @@ k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__
     __shared__ ChunkWarp s_cw[CH_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int PP = P * P;
-    const int var = (int)blockIdx.y;
-    const int c0 = ((int)blockIdx.x * CH_WARPS + (int)warp) * CH_CELLS;
-    if (c0 >= PP) return;
+    // Longest chunks first: the points are densest around the ego vehicle, i.e. in the middle
+    // rows of the grid, and a chunk there is four groups of serial work while one at the rim is
+    // 21 stores.  Blocks are dispatched x-fastest, so x = variant and y walks the chunks from the
+    // centre row outwards — the dense chunks of every variant start in the first wave instead of
+    // forming the kernel's tail.
+    const int var = (int)blockIdx.x;
+    const int n_ch = PP / CH_CELLS;
+    const int ord = (int)blockIdx.y * CH_WARPS + (int)warp;
+    if (ord >= n_ch) return;
+    const int mid = n_ch >> 1;
+    int chunk = (ord & 1) ? mid - ((ord + 1) >> 1) : mid + (ord >> 1);
+    if (chunk < 0) chunk += n_ch;            // odd chunk counts: the last odd step wraps below 0
+    if (chunk >= n_ch) chunk -= n_ch;
+    const int c0 = chunk * CH_CELLS;
     ChunkWarp &cw = s_cw[warp];
     GroupWarp &sw = cw.gw;
     const pcacc_bev_params &bp = params[var];
@@ -1499,18 +1513,23 @@ k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__
     // chunk is CH_CELLS halves = 32 lanes x 8 bytes.  The non-empty cells overwrite theirs
     // afterwards (ordered by the __syncwarp below).
     __half *const ob = out16 + ((int64_t)var * 21) * PP + c0;
-    static_assert(CH_PER_LANE == 4, "one uint2 of four halves per lane and plane");
+    static_assert(CH_PER_LANE == 4 || CH_PER_LANE % 8 == 0, "8- or 16-byte pieces per lane and plane");
     {
         const uint32_t r = __half_as_ushort(cst.empty_h[0]), i = __half_as_ushort(cst.empty_h[1]),
                        g = __half_as_ushort(cst.empty_h[2]), z = __half_as_ushort(cst.empty_h[3]);
-        const uint2 e_road = make_uint2(r | (r << 16), r | (r << 16)), e_int = make_uint2(i | (i << 16), i | (i << 16)),
-                    e_rgb = make_uint2(g | (g << 16), g | (g << 16)), e_z = make_uint2(z | (z << 16), z | (z << 16));
+        const uint32_t e_road = r | (r << 16), e_int = i | (i << 16), e_rgb = g | (g << 16), e_z = z | (z << 16);
         __half *o = ob + CH_PER_LANE * lane;
 #pragma unroll
         for (int w = 0; w < 3; w++) {
 #pragma unroll
             for (int pl = 0; pl < 7; pl++) {
-                *(uint2 *)o = pl == 0 || pl == 5 ? e_road : pl == 1 ? e_int : pl == 6 ? e_z : e_rgb;
+                const uint32_t e = pl == 0 || pl == 5 ? e_road : pl == 1 ? e_int : pl == 6 ? e_z : e_rgb;
+                if (CH_PER_LANE == 4) {
+                    *(uint2 *)o = make_uint2(e, e);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CH_PER_LANE / 8; q++) *(uint4 *)(o + 8 * q) = make_uint4(e, e, e, e);
+                }
                 o += PP;
             }
         }
@@ -1538,7 +1557,7 @@ k_bev_reduce_chunk(const uint32_t *__restrict__ start, const uint4 *__restrict__
                 big_list[bi++] = gc0 + k;
             } else if (c_nt[k] > 0) {
                 cw.g_s0[si] = sb[2 * k];
-                cw.g_cell[si] = (uint8_t)(CH_PER_LANE * lane + k);
+                cw.g_cell[si] = (uint16_t)(CH_PER_LANE * lane + k);
                 cw.g_np[si] = (uint8_t)c_np[k];
                 cw.g_nt[si] = (uint8_t)c_nt[k];
                 si++;
@@ -2042,7 +2061,8 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
         // long-horizon window, one variant = 512 chunk warps: small_t = 4 takes pass A from 35 to
         // 12 us but pass B from 94 to 128 us — a warp per 5..15-point cell costs more than the
         // group reduction it replaces — so the threshold stays at SMALL_T for every launch.)
-        const bool chunked = !want_f64_early && PP % CH_CELLS == 0 && !h->reduce_strips;
+        const bool chunked = !want_f64_early && PP % CH_CELLS == 0 && !h->reduce_strips &&
+                             (PP / CH_CELLS + CH_WARPS - 1) / CH_WARPS <= 65535;   // grid.y
         const uint32_t small_t = (uint32_t)SMALL_T;
         // so the queue never exceeds cap / (small_t + 1)
         int64_t big_cap = cap / (small_t + 1) + 1;
@@ -2153,7 +2173,7 @@ extern "C" int pcacc_rasterise(pcacc_t h, const pcacc_bev_params *params, int n_
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, nv, P, h->inten_div, big_list, big_count, o16, o64);
         else if (chunked)
-            k_bev_reduce_chunk<<<dim3((unsigned)((PP / CH_CELLS + CH_WARPS - 1) / CH_WARPS), (unsigned)nv),
+            k_bev_reduce_chunk<<<dim3((unsigned)nv, (unsigned)((PP / CH_CELLS + CH_WARPS - 1) / CH_WARPS)),
                                  CH_WARPS * 32, 0, st>>>(
                 counts, (const uint4 *)(ws + o_sorted), (const pcacc_bev_params *)d_params, d_consts,
                 h->d_rgb_lut, P, h->inten_div, small_t, big_list, big_count, o16);
