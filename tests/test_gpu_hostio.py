@@ -283,3 +283,42 @@ def test_chunk_and_strip_reduce_kernels_agree(dev):
         assert torch.equal(a.view(torch.int16), c.view(torch.int16)), P
         assert torch.equal(a.view(torch.int16), d.view(torch.int16)), P
         cloud.close()
+
+
+def test_multi_camera_staging_modes_match_oracle(dev):
+    """Three cameras (the golden scene has one): the visible points are spread over cameras 0..2
+    with different frames and class maps of a narrow dtype; device gather, sparse staging and
+    in-place (page-locked) staging all give the oracle's records."""
+    rng = np.random.default_rng(17)
+    o = cases.nusc_seq_inputs()[2]
+    pc, cam0 = o['pc'], o['pc_cam_idx']
+    vis = np.flatnonzero(cam0 >= 0)
+    cam = cam0.copy()
+    cam[vis] = rng.integers(0, 3, vis.size)
+    cam[vis[::11]] = -1                                  # some visible points dropped again
+    h, w = o['images'][0].shape[:2]
+    rgbs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(3)]
+    sems = [rng.integers(0, 19, (h, w)).astype(np.int16) for _ in range(3)]
+    T = np.linalg.inv(cases.nusc_seq_inputs()[0]['ego_at_lidar_ts']) @ o['ego_at_lidar_ts']
+    want, _ = orc.nusc_obs2sem(pc, cam, rgbs, [s.astype(np.int64) for s in sems], T, synth.NUSC_FILTERS)
+    assert want.shape[0] > 200
+    cloud = dev.DeviceCloud(pc.shape[0] * 4 + 64, 16)
+    f0 = cloud.integrate_records(torch.from_numpy(pc).cuda(), torch.from_numpy(cam).cuda(),
+                                 [torch.from_numpy(r).cuda() for r in rgbs],
+                                 [torch.from_numpy(s).cuda() for s in sems], T, synth.NUSC_FILTERS, 255.)
+    f1 = cloud.integrate_records_host(pc, cam, rgbs, sems, T, synth.NUSC_FILTERS, 255., _lib.STAGE_SPARSE)
+    pin = [dev.pinned_like(a) for a in (pc, cam)]
+    f2 = cloud.integrate_records_host(pin[0], pin[1], [dev.pinned_like(r) for r in rgbs],
+                                      [dev.pinned_like(s) for s in sems], T, synth.NUSC_FILTERS, 255.,
+                                      _lib.STAGE_DIRECT)
+    # a camera index beyond the list is "seen by no camera" on every path
+    cam_bad = cam.copy()
+    cam_bad[vis[:5]] = 7
+    f3 = cloud.integrate_records_host(pc, cam_bad, rgbs, sems, T, synth.NUSC_FILTERS, 255., _lib.STAGE_SPARSE)
+    assert cloud.sync() == 0
+    for f in (f0, f1, f2):
+        np.testing.assert_array_equal(cloud.export_frame(f), want)
+    want_bad, _ = orc.nusc_obs2sem(pc, np.where(cam_bad == 7, -1, cam_bad), rgbs,
+                                   [s.astype(np.int64) for s in sems], T, synth.NUSC_FILTERS)
+    np.testing.assert_array_equal(cloud.export_frame(f3), want_bad)
+    cloud.close()
