@@ -1180,6 +1180,11 @@ extern "C" int pcacc_integrate_records_host(pcacc_t h, const double *pc_host,
     // independent, so the row reads of this pass overlap as well)
     const double wlim = (double)img_w - 1.0, hlim = (double)img_h - 1.0;
     for (size_t k = 0; k < nv; k++) {
+        if (k + 24 < nv) {   // the rows are ~560 bytes apart: no hardware prefetcher follows them
+            const double *nxt = pc_host + 7 * (int64_t)vidx[k + 24];
+            __builtin_prefetch(nxt);
+            __builtin_prefetch(nxt + 6);
+        }
         const int64_t i = vidx[k], c = cam_idx_host[i];
         const double uf = pc_host[7 * i + 4], vf = pc_host[7 * i + 5];
         int64_t pix = -1;
