@@ -492,6 +492,7 @@ def run_ours(args, rank, world, local_rank, dist):
     e2e_leg(scenes_pin, 1)                                   # warm-up of the pinned path and threads
     dt, n_b = e2e_leg(scenes_pin, args.e2e_steps)
     staging_pinned = acc.cloud.last_staging
+    e2e_leg(scenes, 1)                                       # warm-up: every thread's staging slots exist
     dt_pg, n_b_pg = e2e_leg(scenes, max(1, args.e2e_steps // 2))
     sc0 = scenes[0]
     host_in = sum(o['pc'].nbytes + o['pc_cam_idx'].nbytes + sum(i.nbytes for i in o['images'])
