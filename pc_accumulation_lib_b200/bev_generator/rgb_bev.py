@@ -2,8 +2,9 @@
 `bev_generator/rgb_bev.py` (`rgb_present`, `rgb_future`, `poses_present`,
 `poses_future`).  The reference accumulator never constructs it
 (sem_pc_accum.py:120-121 raises), so only `generate_bev` on pre-processed
-clouds is offered; the per-cell median raster is the same kernel as
-SemBEVGenerator's RGB planes (rgb_bev.py:133-183 == sem_bev.py:619-669)."""
+clouds is offered (with and without the polynomial warp); the per-cell median
+raster is the same kernel as SemBEVGenerator's RGB planes (rgb_bev.py:133-183 ==
+sem_bev.py:619-669), the warp is `pcacc_warp_planes`."""
 from __future__ import annotations
 
 import numpy as np
@@ -21,8 +22,9 @@ class RGBBEVGenerator(BEVGenerator):
         raise NotImplementedError('RGBBEVGenerator only offers generate_bev()')
 
     def generate_bev(self, pc_present, pc_future, poses_present, poses_future, do_warping=False):
-        if do_warping:
-            raise NotImplementedError('polynomial warp is not on the B200 path yet')
+        """rgb_bev.py:27-95: per-cell RGB medians / 255 of two pre-processed clouds (grid coordinates
+        in columns 0, 1; r, g, b in columns 4..6), optionally pushed through one polynomial warp
+        together with the pose lists (drawn like the reference: two normal draws, two sign draws)."""
         P = self.pixel_size
 
         def centre(pc):
@@ -40,8 +42,15 @@ class RGBBEVGenerator(BEVGenerator):
         self.view_size, self.height_filter = float(P), None
         try:
             aug = [dict(rot_ang=0., trans_dx=0., trans_dy=0., zoom_scalar=1., do_warping=True)]
-            planes, _ = self._rasterise_windows(pcs, aug)
+            warp = self.draw_warp() if do_warping else None
+            planes, _ = self._rasterise_windows(pcs, aug, [warp] if warp else None)
         finally:
             self.view_size, self.height_filter = saved
+        if warp is not None:
+            w = warp
+            poses_present = self.warp_sparse_points(poses_present, w['a_1'], w['a_2'], w['b_1'], w['b_2'],
+                                                    w['i_mid'], w['j_mid'], w['i_warp'], w['j_warp'])
+            poses_future = self.warp_sparse_points(poses_future, w['a_1'], w['a_2'], w['b_1'], w['b_2'],
+                                                   w['i_mid'], w['j_mid'], w['i_warp'], w['j_warp'])
         return {'rgb_present': planes[0, 0, 2:5], 'rgb_future': planes[0, 1, 2:5],
                 'poses_present': poses_present, 'poses_future': poses_future}

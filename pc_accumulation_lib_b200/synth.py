@@ -417,3 +417,19 @@ def helper_inputs(seed=123, n=4000, P=48):
     pc[::17, 8] = 1.                                    # already flagged
     pc[5::29, 8] = 3.                                   # neither 0 nor 1: dropped from both outputs
     return dict(uv=uv, img2d=img2d, img4=img4, pc=pc, P=P, elev_thresh=0.8)
+
+
+def rgb_bev_inputs(seed=31, P=32, n=3000):
+    """Pre-processed clouds (grid coordinates, r g b in columns 4..6) and pose lists for
+    RGBBEVGenerator.generate_bev."""
+    rng = np.random.default_rng(seed)
+
+    def cloud(m):
+        pc = np.zeros((m, 7))
+        pc[:, 0:2] = rng.integers(0, P, (m, 2))
+        pc[:, 2] = rng.normal(0, 1, m)
+        pc[:, 4:7] = rng.integers(0, 256, (m, 3))
+        return pc
+    poses_p = np.stack([np.linspace(3, P - 4, 9), np.linspace(5, P - 6, 9), np.zeros(9)], axis=1).round()
+    poses_f = np.stack([np.linspace(P - 4, 2, 7), np.linspace(4, P - 3, 7), np.zeros(7)], axis=1).round()
+    return dict(P=P, pc_present=cloud(n), pc_future=cloud(n // 2), poses_present=poses_p, poses_future=poses_f)

@@ -264,8 +264,35 @@ def gen_helpers(ref, name):
     save(name, out)
 
 
+def gen_rgb_bev(ref, name, seeds=(5, 6)):
+    """bev_generator/rgb_bev.py run unmodified: generate_bev without and with the polynomial warp
+    (global numpy / `random` RNGs seeded right before each call)."""
+    import random
+    from bev_generator import rgb_bev as ref_rgb        # importable after ref_loader.load()
+    c = synth.rgb_bev_inputs()
+    g = ref_rgb.RGBBEVGenerator(40., c['P'])
+    out = {'seeds': np.array(seeds, dtype=np.int64)}
+    with quiet():
+        bev = g.generate_bev(c['pc_present'].copy(), c['pc_future'].copy(), c['poses_present'].copy(),
+                             c['poses_future'].copy(), do_warping=False)
+    for k, v in bev.items():
+        out[f'plain_{k}'] = np.asarray(v)
+    for s in seeds:
+        np.random.seed(s)
+        random.seed(s)
+        with quiet():
+            bev = g.generate_bev(c['pc_present'].copy(), c['pc_future'].copy(), c['poses_present'].copy(),
+                                 c['poses_future'].copy(), do_warping=True)
+        for k, v in bev.items():
+            out[f'warp{s}_{k}'] = np.asarray(v)
+    save(name, out)
+
+
 def main():
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'rgb_bev':
+        gen_rgb_bev(ref, 'rgb_bev.npz')
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'helpers':
         gen_helpers(ref, 'helpers.npz')
         return
@@ -287,6 +314,7 @@ def main():
     gen_bev_warp(ref, 'bev_warp.npz')
     gen_input_side(ref, 'input_side.npz')
     gen_helpers(ref, 'helpers.npz')
+    gen_rgb_bev(ref, 'rgb_bev.npz')
 
 
 if __name__ == '__main__':

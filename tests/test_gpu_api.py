@@ -197,6 +197,29 @@ def test_rgb_bev_generator():
             np.testing.assert_array_equal(out[key][ch], want)
 
 
+def test_rgb_bev_generator_matches_reference_golden():
+    """RGBBEVGenerator.generate_bev without and with the polynomial warp against the unmodified
+    reference (tests/golden/rgb_bev.npz): planes bit-equal (medians / 255 in float16), warped poses equal."""
+    import random
+    from pc_accumulation_lib_b200 import RGBBEVGenerator
+    g = load_golden('rgb_bev.npz')
+    c = synth.rgb_bev_inputs()
+    bg = RGBBEVGenerator(40., c['P'])
+
+    def call(warp):
+        return bg.generate_bev(c['pc_present'].copy(), c['pc_future'].copy(), c['poses_present'].copy(),
+                               c['poses_future'].copy(), do_warping=warp)
+    out = call(False)
+    for k in ('rgb_present', 'rgb_future', 'poses_present', 'poses_future'):
+        np.testing.assert_array_equal(np.asarray(out[k]), g[f'plain_{k}'], err_msg=k)
+    for s in g['seeds']:
+        bg.rng, bg.py_rng = np.random.RandomState(int(s)), random.Random(int(s))
+        out = call(True)
+        for k in ('rgb_present', 'rgb_future', 'poses_present', 'poses_future'):
+            np.testing.assert_array_equal(np.asarray(out[k]), g[f'warp{int(s)}_{k}'], err_msg=f'{k} seed {s}')
+    assert not np.array_equal(g['warp5_rgb_present'], g['plain_rgb_present'])     # the warp does something
+
+
 def test_missing_cuda_or_library_fails_loudly(monkeypatch):
     from pc_accumulation_lib_b200 import _lib
     monkeypatch.setattr(_lib, '_lib', None)
