@@ -372,6 +372,66 @@ int pcacc_static_obj_partitioning(pcacc_t h, double *pc_dev, int64_t n, int P, d
                                   double *elevmap_dev, uint8_t *obs_mask_dev,
                                   unsigned long long *scratch_dev, void *stream);
 
+/* ---- the rasteriser's steps as stand-alone operators --------------------------------------
+ * pcacc_rasterise fuses these; the reference exposes each as a public method, so each has an
+ * entry point with the method's argument meaning.  Clouds are (n, cols) float64 rows on the
+ * device, x, y, z in columns 0..2. */
+
+/* get_elevation_map, bev_generator/sem_bev.py:535-553: per-cell minimum z (row P-1-j, column i;
+ * 0 where unobserved) and the observed mask; index rules and flags of
+ * pcacc_static_obj_partitioning. */
+int pcacc_elevation_map(pcacc_t h, const double *pc_dev, int64_t n, int cols, int P,
+                        double *elevmap_dev, uint8_t *obs_mask_dev, unsigned long long *scratch_dev,
+                        void *stream);
+
+/* velo2frame, sem_pc_accum.py:347-366: out_dev (n,3) float64 = rows of the (3,4) host matrix P
+ * times [x y z 1] for the first three columns of pts_dev (n, stride) float32 (pts_f64 = 0) or
+ * float64 (1). */
+int pcacc_velo2frame(pcacc_t h, const void *pts_dev, int pts_f64, int64_t n, int stride, const double *P,
+                     double *out_dev, void *stream);
+
+/* preprocess_pc_and_trajs (cloud part), geometric_transform and crop_view,
+ * bev_generator/bev_generator.py:127-160, 207-256, 737-747, in the reference's order: rotation by the
+ * (3,3) host matrix rot and translation (skipped when rot is NULL), strict crop of x then y to
+ * +-crop_view/2 (NaN = no crop), z < height_filter (NaN = off), pos2grid of columns 0, 1 over
+ * grid_view metres and P pixels (NaN = stay metric).  Kept rows go to out_dev in input order with
+ * their other columns untouched; *n_kept_dev = their number. */
+int pcacc_preprocess_pc(pcacc_t h, const double *pc_dev, int64_t n, int cols, const double *rot,
+                        double trans_dx, double trans_dy, double crop_view, double height_filter,
+                        double grid_view, int P, double *out_dev, int64_t *n_kept_dev, void *stream);
+
+/* partition_semantic_pc + gen_gridmap_count_map (+ gen_sem_probmap / gen_intensity_map),
+ * bev_generator/bev_generator.py:373-453: a point is "selected" when column sem_col equals one of
+ * sems[0..n_sems) (n_sems < 0: every point).  np.histogram2d's binning over [0,P]x[0,P] of the
+ * grid coordinates in columns 1, 0, flipped along the first axis.  Any of the three (P,P) float64
+ * outputs may be NULL: count_sel_dev / count_rest_dev = number of selected / other points per cell,
+ * wsum_sel_dev = sum over the selected points of column weight_col (or of weights_dev[point] when
+ * weight_col < 0; order-dependent rounding, ~1e-16 relative).  finish: 0 = raw maps; 1 = the
+ * Dirichlet expectation with a uniform prior of the two counts, in place (gen_sem_probmap);
+ * 2 = wsum / (count_sel + 1) in place (gen_intensity_map). */
+int pcacc_cell_stats(pcacc_t h, const double *pc_dev, int64_t n, int cols, int P, int sem_col,
+                     const int32_t *sems, int n_sems, int weight_col, const double *weights_dev,
+                     int finish, double *count_sel_dev, double *count_rest_dev, double *wsum_sel_dev,
+                     void *stream);
+
+/* partition_semantic_pc, bev_generator/bev_generator.py:411-432: rows whose column sem_col equals
+ * one of sems[0..n_sems) go to out_sel_dev, the others to out_rest_dev (both (n, cols), input
+ * order); *n_sel_dev = number of selected rows (the others number n - that). */
+int pcacc_partition_semantic_pc(pcacc_t h, const double *pc_dev, int64_t n, int cols, int sem_col,
+                                const int32_t *sems, int n_sems, double *out_sel_dev,
+                                double *out_rest_dev, int64_t *n_sel_dev, void *stream);
+
+/* dirichlet_dist_expectation, bev_generator/bev_generator.py:455-481, in place on maps_dev
+ * (n_maps, cells) float64. */
+int pcacc_dirichlet_expectation(pcacc_t h, double *maps_dev, int n_maps, int64_t cells,
+                                double obs_weight, void *stream);
+
+/* road_marking_transform (sigmoid_only = 0) and sigmoid (1), bev_generator/sem_bev.py:593-617,
+ * elementwise on n float64 values. */
+int pcacc_road_marking(pcacc_t h, const double *in_dev, int64_t n, double int_scaler,
+                       double int_sep_scaler, double int_mid_threshold, int sigmoid_only,
+                       double *out_dev, void *stream);
+
 /* ---- accounting / profiling (bench.py: gpu_launches, roofline) -------------
  * Kernel classes of this library. */
 #define PCACC_K_INTEGRATE 0 /* k_integrate_frustum / _gt / _records / _cloud, k_gen_semantic_pc, k_project */

@@ -490,6 +490,102 @@ PLANES = ('road', 'intensity', 'r', 'g', 'b', 'dynamic', 'elevation')
 
 
 # ---------------------------------------------------------------------------
+#  the per-plane steps of generate_bev as the stand-alone methods the reference exposes
+# ---------------------------------------------------------------------------
+def crop_view(pc, view):
+    """bev_generator/bev_generator.py:239-256: strict crop of x, then of y."""
+    pc = pc[(pc[:, 0] > -0.5 * view) & (pc[:, 0] < 0.5 * view)]
+    return pc[(pc[:, 1] > -0.5 * view) & (pc[:, 1] < 0.5 * view)]
+
+
+def geometric_transform_pc(pc, R, dx, dy, view):
+    """bev_generator/bev_generator.py:207-237, cloud branch (on a copy)."""
+    pc = pc.copy()
+    pc[:, :3] = rot33(R, pc[:, :3]) if pc.shape[0] != 1 else np.matmul(R, pc[:, :3].T).T
+    pc[:, 0] += dx
+    pc[:, 1] += dy
+    return crop_view(pc, view)
+
+
+def partition_semantic_pc(pc, sems, sem_col):
+    """bev_generator/bev_generator.py:411-432."""
+    hit = np.isin(pc[:, sem_col], np.asarray(sems, dtype=np.float64))
+    return pc[hit], pc[~hit]
+
+
+def gridmap_count_map(pc, P, weights=None):
+    """bev_generator/bev_generator.py:434-453 without np.histogram2d: P unit bins over [0, P] a side
+    (the right edge belongs to the last bin, everything else outside and NaN is dropped), first
+    axis = column 1 flipped, second axis = column 0; weights are summed in point order."""
+    def bins(v):
+        ok = (v >= 0) & (v <= P)
+        b = np.where(ok, np.minimum(np.nan_to_num(v, nan=0.), P - 1), 0).astype(np.int64)
+        return ok, b
+    ok_j, bj = bins(pc[:, 1])
+    ok_i, bi = bins(pc[:, 0])
+    ok = ok_j & ok_i
+    cell = ((P - 1 - bj) * P + bi)[ok]
+    w = None if weights is None else np.asarray(weights, dtype=np.float64)[ok]
+    return np.bincount(cell, weights=w, minlength=P * P).astype(np.float64).reshape(P, P)
+
+
+def dirichlet_expectation(gridmaps, obs_weight=1):
+    """bev_generator/bev_generator.py:455-481."""
+    g = np.stack(gridmaps).astype(np.float64) * obs_weight + 1.
+    a0 = g[0].copy()
+    for k in range(1, g.shape[0]):
+        a0 = a0 + g[k]
+    return [g[k] / a0 for k in range(g.shape[0])]
+
+
+def sem_probmap(pc, P, sems, sem_col=7):
+    """bev_generator/bev_generator.py:373-391."""
+    a, b = partition_semantic_pc(pc, sems, sem_col)
+    return dirichlet_expectation([gridmap_count_map(a, P), gridmap_count_map(b, P)])[0]
+
+
+def intensity_map(pc, P, sem, sem_col=7):
+    """bev_generator/bev_generator.py:393-409."""
+    a, _ = partition_semantic_pc(pc, [sem], sem_col)
+    return gridmap_count_map(a, P, weights=a[:, 3]) / (gridmap_count_map(a, P) + 1)
+
+
+def sigmoid(z):
+    """bev_generator/sem_bev.py:615-617."""
+    return 1 / (1 + np.exp(-np.asarray(z, dtype=np.float64)))
+
+
+def road_marking_transform(inten, int_scaler, int_sep_scaler, int_mid_threshold):
+    """bev_generator/sem_bev.py:593-613."""
+    out = int_scaler * sigmoid(int_sep_scaler * (np.asarray(inten, dtype=np.float64) - int_mid_threshold))
+    out[out > 1.] = 1.
+    return out
+
+
+def elevation_map(pc, P):
+    """bev_generator/sem_bev.py:535-553 (per-cell minimum z, observed mask)."""
+    q = np.zeros((pc.shape[0], 10))
+    q[:, :3] = pc[:, :3]
+    _, _, elev, obs = static_obj_partitioning_by_elev(q, P, np.inf)
+    return elev, obs
+
+
+def rgb_maps(pc, P, rgb_fill=0):
+    """bev_generator/sem_bev.py:619-669 == rgb_bev.py:133-183: per-cell medians of columns 4..6."""
+    i = pc[:, 0].astype(int)
+    j_rev = P - 1 - pc[:, 1].astype(int)
+    if np.any((i < -P) | (i >= P) | (j_rev < -P) | (j_rev >= P)):
+        raise IndexError('index out of bounds')
+    cell = np.where(j_rev < 0, j_rev + P, j_rev) * P + np.where(i < 0, i + P, i)
+    out = []
+    for ch in (4, 5, 6):
+        med = _segment_median(cell, pc[:, ch], P * P)
+        med[np.isnan(med)] = rgb_fill
+        out.append(med.reshape(P, P))
+    return tuple(out)
+
+
+# ---------------------------------------------------------------------------
 #  polynomial warp (bev_generator/bev_generator.py:482-698), SURVEY §8f rank 1
 # ---------------------------------------------------------------------------
 def cal_warp_params(idx_0, idx_1, idx_max):

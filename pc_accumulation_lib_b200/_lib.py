@@ -99,6 +99,15 @@ SIGNATURES = {
     'pcacc_project_cameras': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_pts_feat_from_img': (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'pcacc_static_obj_partitioning': (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp, _vp]),
+    'pcacc_elevation_map': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    'pcacc_velo2frame': (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    'pcacc_preprocess_pc': (_i32, [_vp, _vp, _i64, _i32, _vp, _dbl, _dbl, _dbl, _dbl, _dbl, _i32,
+                                   _vp, _vp, _vp]),
+    'pcacc_cell_stats': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp,
+                                _vp, _vp, _vp]),
+    'pcacc_partition_semantic_pc': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    'pcacc_dirichlet_expectation': (_i32, [_vp, _vp, _i32, _i64, _dbl, _vp]),
+    'pcacc_road_marking': (_i32, [_vp, _vp, _i64, _dbl, _dbl, _dbl, _i32, _vp, _vp]),
     'pcacc_profile': (_i32, [_vp, _i32]),
     'pcacc_profile_read': (_i32, [_vp, C.POINTER(_dbl * 10), C.POINTER(_i64 * 10)]),
 }

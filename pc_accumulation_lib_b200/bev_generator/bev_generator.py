@@ -49,6 +49,26 @@ class DeviceWindow:
         return (n, 10)
 
 
+_OPS = {}
+
+
+def _ops_cloud() -> DeviceCloud:
+    """One small DeviceCloud per (process, device) whose handle serves the stand-alone operators
+    (static methods of the reference have no generator instance to hang it on)."""
+    import torch
+    key = (os.getpid(), torch.cuda.current_device())
+    c = _OPS.get(key)
+    if c is None:
+        c = _OPS[key] = DeviceCloud(1024, max_frames=8)
+    return c
+
+
+def _to_like(like, t):
+    """Results go back in the kind of the input: numpy in -> numpy out, CUDA tensor in -> tensor out."""
+    import torch
+    return t if isinstance(like, torch.Tensor) else t.cpu().numpy()
+
+
 class BEVGenerator(ABC):
     def __init__(self,
                  view_size: int,
@@ -146,15 +166,100 @@ class BEVGenerator(ABC):
 
     def geometric_transform(self, pc_mat, rot_ang, trans_dx, trans_dy, aug_view_size,
                             is_traj=False):
-        """Trajectories only on the host; clouds go through generate()."""
-        if not is_traj:
-            raise NotImplementedError(
-                'point clouds are transformed on the device: use generate()')
+        """bev_generator.py:207-237.  Trajectories are rotated and shifted on the host and cropped by
+        `pcacc_crop_trajectory`; clouds go through `pcacc_preprocess_pc` (rotation, translation and
+        crop in one kernel; rows of any width, kept rows in input order).  The reference also leaves
+        the rotated coordinates in the caller's array; the cloud branch here does not touch it."""
         R = self.rotation_matrix_3d(rot_ang)
+        if not is_traj:
+            return _to_like(pc_mat, _ops_cloud().preprocess_pc(pc_mat, R, trans_dx, trans_dy, aug_view_size))
         pc_mat[:, :3] = np.matmul(R, pc_mat[:, :3].T).T
         pc_mat[:, 0] += trans_dx
         pc_mat[:, 1] += trans_dy
         return self.crop_trajectory(pc_mat, aug_view_size)
+
+    @staticmethod
+    def crop_view(pc_mat, aug_view_size: float):
+        """bev_generator.py:239-256: rows with |x| and |y| strictly inside aug_view_size / 2."""
+        return _to_like(pc_mat, _ops_cloud().preprocess_pc(pc_mat, crop_view=aug_view_size))
+
+    def preprocess_pc_and_trajs(self, pc, trajs, rot_ang, trans_dx, trans_dy, aug_view_size):
+        """bev_generator.py:127-160: the cloud through one `pcacc_preprocess_pc` launch (rotation,
+        translation, crop, height filter, pos2grid), the trajectories through `preprocess_trajs`."""
+        pc = _to_like(pc, _ops_cloud().preprocess_pc(
+            pc, self.rotation_matrix_3d(rot_ang), trans_dx, trans_dy, aug_view_size, self.height_filter,
+            aug_view_size, self.pixel_size))
+        return pc, self.preprocess_trajs(trajs, rot_ang, trans_dx, trans_dy, aug_view_size)
+
+    # ------------------------------------------------------------------
+    # per-plane steps of generate_bev as stand-alone operators (fused in pcacc_rasterise)
+    # ------------------------------------------------------------------
+    def gen_sem_probmap(self, pc, sem_clss: list):
+        """bev_generator.py:373-391: Dirichlet expectation of (points of sem_clss, other points) per cell."""
+        sems = [self.sem_idxs[c] for c in sem_clss]
+        m = _ops_cloud().cell_stats(pc, self.pixel_size, sems, self.sem_idx, finish=1, want=('sel', 'rest'))
+        return _to_like(pc, m['sel'])
+
+    def gen_intensity_map(self, pc, sem_cls: str):
+        """bev_generator.py:393-409: summed intensity (column 3) of the class's points / (count + 1)."""
+        m = _ops_cloud().cell_stats(pc, self.pixel_size, [self.sem_idxs[sem_cls]], self.sem_idx,
+                                    weight_col=3, finish=2, want=('sel', 'wsum'))
+        return _to_like(pc, m['wsum'])
+
+    @staticmethod
+    def partition_semantic_pc(pc_mat, sems: list, sem_idx: int):
+        """bev_generator.py:411-432 -> (rows whose column sem_idx is in sems, the other rows), both in
+        input order (`pcacc_partition_semantic_pc`: one scan ranks both halves)."""
+        a, b = _ops_cloud().partition_semantic_pc(pc_mat, sems, sem_idx)
+        return _to_like(pc_mat, a), _to_like(pc_mat, b)
+
+    def gen_gridmap_count_map(self, pc, weights=None):
+        """bev_generator.py:434-453: np.histogram2d of the grid coordinates (optionally weighted),
+        flipped to image rows."""
+        if weights is None:
+            m = _ops_cloud().cell_stats(pc, self.pixel_size, want=('sel',))
+            return _to_like(pc, m['sel'])
+        m = _ops_cloud().cell_stats(pc, self.pixel_size, weights=weights, want=('wsum',))
+        return _to_like(pc, m['wsum'])
+
+    @staticmethod
+    def dirichlet_dist_expectation(gridmaps, obs_weight=1):
+        """bev_generator.py:455-481 -> list of posterior maps."""
+        m = _ops_cloud().dirichlet_expectation(gridmaps, obs_weight)
+        like = gridmaps if not isinstance(gridmaps, (list, tuple)) else gridmaps[0]
+        return [_to_like(like, m[g]) for g in range(m.shape[0])]
+
+    def get_rgb_maps(self, pc):
+        """sem_bev.py:619-669 == rgb_bev.py:133-183: per-cell medians of the r, g, b columns (4..6) of a cloud in grid
+        coordinates, `rgb_fill` where a cell is empty -> (red_map, green_map, blue_map) float64.
+        The medians come out of the rasteriser's RGB planes (float64 copy, median / 255): a median of
+        0..255 integers is a multiple of 1/2, so round(2 * 255 * plane) / 2 recovers it exactly; empty
+        cells are told apart by rasterising with a fill value no colour can produce."""
+        P = self.pixel_size
+        c = self._pad10(np.array(pc.cpu().numpy() if hasattr(pc, 'cpu') else pc, dtype=np.float64))
+        c[:, 7:] = 0.
+        c[:, 0] = c[:, 0] + 0.5 - 0.5 * P
+        c[:, 1] = c[:, 1] + 0.5 - 0.5 * P
+        fill = getattr(self, 'rgb_fill', 0)
+        saved = self.view_size, self.height_filter
+        self.view_size, self.height_filter, self.rgb_fill = float(P), None, -1.
+        try:
+            cloud = self._scratch_cloud(c.shape[0])
+            fid = cloud.integrate_cloud(c)
+            prm = self._bev_params(fid, fid + 1, fid + 1, np.zeros(3), 0., 0., 0., float(P))
+            _, p64, _ = cloud.rasterise([prm], P, want_f64=True)
+            if cloud.sync() & _lib.FLAG_ATTR_RANGE:
+                raise ValueError('r, g, b must be integers in 0..255')
+        finally:
+            (self.view_size, self.height_filter), self.rgb_fill = saved, fill
+        med = (p64[0, 0, 2:5] * 510.).round() / 2.
+        med = med.where(med >= 0., med.new_tensor(float(fill)))
+        med = med if hasattr(pc, 'cpu') else med.cpu().numpy()
+        return med[0], med[1], med[2]
+
+    @staticmethod
+    def extract_aug_dict(augs: dict):
+        return augs['max_translation_radius'], augs['zoom_threshold']
 
     def preprocess_trajs(self, trajs, rot_ang, trans_dx, trans_dy, aug_view_size):
         out = []

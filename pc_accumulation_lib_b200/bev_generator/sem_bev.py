@@ -6,7 +6,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .bev_generator import BEVGenerator, WINDOWS
+from .. import _lib
+from .bev_generator import BEVGenerator, WINDOWS, _ops_cloud, _to_like
 
 
 class SemBEVGenerator(BEVGenerator):
@@ -76,7 +77,6 @@ class SemBEVGenerator(BEVGenerator):
         column 8 set to 1 IN PLACE -> (pc_static, pc_dynamic, elevmap, elevmap_obs_mask).
         Runs in `pcacc_static_obj_partitioning`."""
         from .bev_generator import DeviceCloud
-        from .. import _lib
         if self._scratch is None:
             self._scratch = DeviceCloud(1024, max_frames=8)
         flagged, elev, obs = self._scratch.static_obj_partitioning(pc, self.pixel_size, elev_thresh)
@@ -85,3 +85,25 @@ class SemBEVGenerator(BEVGenerator):
         out = flagged.cpu().numpy()
         pc[:, 8] = out[:, 8]
         return pc[pc[:, 8] == 0], pc[pc[:, 8] == 1], elev.cpu().numpy(), obs.cpu().numpy()
+
+    # -- the per-plane steps of generate_bev as stand-alone operators ----------------------
+    def road_marking_transform(self, intensity_map, int_scaler: float, int_sep_scaler: float,
+                               int_mid_threshold: float):
+        """sem_bev.py:593-613: int_scaler * sigmoid(int_sep_scaler * (I - int_mid_threshold)) capped
+        at 1, elementwise (`pcacc_road_marking`)."""
+        return _to_like(intensity_map, _ops_cloud().road_marking(intensity_map, int_scaler, int_sep_scaler,
+                                                                 int_mid_threshold))
+
+    @staticmethod
+    def sigmoid(z):
+        """sem_bev.py:615-617."""
+        return _to_like(z, _ops_cloud().road_marking(z, sigmoid_only=True))
+
+    def get_elevation_map(self, pc):
+        """sem_bev.py:535-553: per-cell minimum z of a cloud in grid coordinates -> (elevmap,
+        elevmap_obs_mask) (`pcacc_elevation_map`; index rules of static_obj_partitioning_by_elev)."""
+        ops = _ops_cloud()
+        elev, obs = ops.elevation_map(pc, self.pixel_size)
+        if ops.sync() & _lib.FLAG_ATTR_RANGE:
+            raise IndexError('grid index out of bounds for the elevation map (or NaN z)')
+        return _to_like(pc, elev), _to_like(pc, obs)

@@ -277,11 +277,11 @@ __device__ __forceinline__ bool grid_index(double g, int P, int &idx) {
 }
 
 __global__ void __launch_bounds__(INB)
-k_elev_min(const double *__restrict__ pc, int64_t n, int P, unsigned long long *__restrict__ zmin,
+k_elev_min(const double *__restrict__ pc, int64_t n, int cols, int P, unsigned long long *__restrict__ zmin,
            uint32_t *__restrict__ flags) {
     const int64_t t = (int64_t)blockIdx.x * INB + threadIdx.x;
     if (t >= n) return;
-    const double *r = pc + t * 10;
+    const double *r = pc + t * cols;
     int i, j;
     const double z = r[2];
     // j_rev = P - 1 - j is what is indexed (and wrapped) in the reference
@@ -333,9 +333,31 @@ extern "C" int pcacc_static_obj_partitioning(pcacc_t h, double *pc_dev, int64_t 
     h->launches[PCACC_K_EXPORT] += 3;
     if (n > 0) {
         const int64_t nb = (n + INB - 1) / INB;
-        k_elev_min<<<(unsigned)nb, INB, 0, st>>>(pc_dev, n, P, scratch_dev, h->d_flags);
+        k_elev_min<<<(unsigned)nb, INB, 0, st>>>(pc_dev, n, 10, P, scratch_dev, h->d_flags);
         k_elev_flag<<<(unsigned)nb, INB, 0, st>>>(pc_dev, n, P, elev_thresh, scratch_dev);
     }
+    k_elev_export<<<(unsigned)((cells + INB - 1) / INB), INB, 0, st>>>(scratch_dev, cells, elevmap_dev,
+                                                                     obs_mask_dev);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+// get_elevation_map, bev_generator/sem_bev.py:535-553: the per-cell minimum z alone, for rows of
+// any width (x, y, z in columns 0..2).
+extern "C" int pcacc_elevation_map(pcacc_t h, const double *pc_dev, int64_t n, int cols, int P,
+                                   double *elevmap_dev, uint8_t *obs_mask_dev,
+                                   unsigned long long *scratch_dev, void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || cols < 3 || P <= 0 || !elevmap_dev || !obs_mask_dev || !scratch_dev || (n > 0 && !pc_dev))
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad elevation_map arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    const int64_t cells = (int64_t)P * P;
+    PCACC_CUDA(h, cudaMemsetAsync(scratch_dev, 0xff, (size_t)cells * 8, st));
+    h->launches[PCACC_K_EXPORT] += 2;
+    if (n > 0)
+        k_elev_min<<<(unsigned)((n + INB - 1) / INB), INB, 0, st>>>(pc_dev, n, cols, P, scratch_dev,
+                                                                     h->d_flags);
     k_elev_export<<<(unsigned)((cells + INB - 1) / INB), INB, 0, st>>>(scratch_dev, cells, elevmap_dev,
                                                                      obs_mask_dev);
     PCACC_CUDA(h, cudaGetLastError());

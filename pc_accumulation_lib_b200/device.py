@@ -776,6 +776,122 @@ class DeviceCloud:
         self._dirty = True
         return t, elev, obs.bool()
 
+    # -- the rasteriser's steps as stand-alone operators (include/pcacc.h) ----------------
+    def _rows64(self, pc, min_cols=3):
+        """(n, cols) float64 contiguous CUDA tensor of a numpy array / tensor (no copy when it is one)."""
+        t = pc if isinstance(pc, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(pc, dtype=np.float64))
+        t = t.to(device=self.device, dtype=torch.float64).contiguous()
+        assert t.dim() == 2 and t.shape[1] >= min_cols, f'expected (n, >={min_cols}) rows'
+        return t
+
+    def elevation_map(self, pc, P: int):
+        """get_elevation_map, bev_generator/sem_bev.py:535-553 -> (elevmap (P,P) float64, observed
+        mask (P,P) bool) CUDA tensors."""
+        t = self._rows64(pc)
+        elev = torch.empty((P, P), dtype=torch.float64, device=self.device)
+        obs = torch.empty((P, P), dtype=torch.uint8, device=self.device)
+        scratch = torch.empty(P * P, dtype=torch.int64, device=self.device)
+        self._check(self.lib.pcacc_elevation_map(self.h, _ptr(t), int(t.shape[0]), int(t.shape[1]), int(P),
+                                                 _ptr(elev), _ptr(obs), _ptr(scratch), _stream()))
+        self._dirty = True
+        return elev, obs.bool()
+
+    def velo2frame(self, pc_velo, P_velo_frame):
+        """sem_pc_accum.py:347-366 -> (n,3) float64 CUDA tensor."""
+        t = pc_velo if isinstance(pc_velo, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pc_velo))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.double()
+        t = t.to(self.device).contiguous()
+        assert t.dim() == 2 and t.shape[1] >= 3
+        n = int(t.shape[0])
+        out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        Pm = _hostd(P_velo_frame, 12)
+        self._check(self.lib.pcacc_velo2frame(self.h, _ptr(t), int(t.dtype == torch.float64), n,
+                                              int(t.shape[1]), Pm.ctypes.data_as(C.c_void_p), _ptr(out),
+                                              _stream()))
+        return out
+
+    def preprocess_pc(self, pc, rot=None, trans_dx=0., trans_dy=0., crop_view=None, height_filter=None,
+                      grid_view=None, P=0):
+        """bev_generator/bev_generator.py:127-160, 207-256, 737-747 for a cloud: rotate + translate
+        (rot (3,3) or None), crop, height filter, pos2grid; None switches a step off.  -> kept rows,
+        input order, CUDA tensor."""
+        t = self._rows64(pc)
+        n, cols = int(t.shape[0]), int(t.shape[1])
+        out = torch.empty_like(t)
+        nk = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nan = float('nan')
+        R = None if rot is None else _hostd(rot, 9)
+        self._check(self.lib.pcacc_preprocess_pc(
+            self.h, _ptr(t), n, cols, None if R is None else R.ctypes.data_as(C.c_void_p),
+            float(trans_dx), float(trans_dy), nan if crop_view is None else float(crop_view),
+            nan if height_filter is None else float(height_filter),
+            nan if grid_view is None else float(grid_view), int(P), _ptr(out), _ptr(nk), _stream()))
+        return out[:int(nk.item())]
+
+    def cell_stats(self, pc, P: int, sems=None, sem_col=7, weight_col=-1, weights=None, finish=0,
+                   want=('sel', 'rest', 'wsum')):
+        """pcacc_cell_stats: per-cell counts of the selected / other points and the selected points'
+        weight sum -> dict of (P,P) float64 CUDA tensors for the names in `want`."""
+        t = self._rows64(pc, 2)
+        n, cols = int(t.shape[0]), int(t.shape[1])
+        maps = {k: torch.empty((P, P), dtype=torch.float64, device=self.device) for k in want}
+        if sems is None:
+            sarr, ns = None, -1
+        else:
+            sarr = np.ascontiguousarray(np.asarray(list(sems), dtype=np.int32))
+            ns = int(sarr.shape[0])
+        w = None
+        if weights is not None:
+            w = weights if isinstance(weights, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(weights, dtype=np.float64))
+            w = w.to(device=self.device, dtype=torch.float64).contiguous()
+            assert w.numel() == n, 'one weight per point'
+        self._check(self.lib.pcacc_cell_stats(
+            self.h, _ptr(t), n, cols, int(P), int(sem_col),
+            None if sarr is None or ns == 0 else sarr.ctypes.data_as(C.c_void_p), ns, int(weight_col),
+            _ptr(w), int(finish), _ptr(maps.get('sel')), _ptr(maps.get('rest')), _ptr(maps.get('wsum')),
+            _stream()))
+        return maps
+
+    def partition_semantic_pc(self, pc, sems, sem_col: int):
+        """bev_generator/bev_generator.py:411-432 -> (selected rows, other rows) CUDA tensors."""
+        t = self._rows64(pc, 1)
+        n, cols = int(t.shape[0]), int(t.shape[1])
+        a, b = torch.empty_like(t), torch.empty_like(t)
+        nk = torch.zeros(1, dtype=torch.int64, device=self.device)
+        sarr = np.ascontiguousarray(np.asarray(list(sems), dtype=np.int32))
+        self._check(self.lib.pcacc_partition_semantic_pc(
+            self.h, _ptr(t), n, cols, int(sem_col),
+            sarr.ctypes.data_as(C.c_void_p) if sarr.size else None, int(sarr.size), _ptr(a), _ptr(b),
+            _ptr(nk), _stream()))
+        k = int(nk.item())
+        return a[:k], b[:n - k]
+
+    def dirichlet_expectation(self, gridmaps, obs_weight=1.):
+        """bev_generator/bev_generator.py:455-481 -> (G, ...) float64 CUDA tensor."""
+        if isinstance(gridmaps, torch.Tensor):
+            m = gridmaps.to(device=self.device, dtype=torch.float64).contiguous().clone()
+        else:
+            m = torch.from_numpy(np.ascontiguousarray(np.stack(gridmaps), dtype=np.float64)).to(self.device)
+        G = int(m.shape[0])
+        self._check(self.lib.pcacc_dirichlet_expectation(self.h, _ptr(m), G, int(m.numel() // max(G, 1)),
+                                                         float(obs_weight), _stream()))
+        return m
+
+    def road_marking(self, values, int_scaler=1., int_sep_scaler=1., int_mid_threshold=0.5,
+                     sigmoid_only=False):
+        """sem_bev.py:593-617 elementwise -> float64 CUDA tensor of the input's shape."""
+        v = values if isinstance(values, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(values, dtype=np.float64))
+        v = v.to(device=self.device, dtype=torch.float64).contiguous()
+        out = torch.empty_like(v)
+        self._check(self.lib.pcacc_road_marking(self.h, _ptr(v), int(v.numel()), float(int_scaler),
+                                                float(int_sep_scaler), float(int_mid_threshold),
+                                                int(bool(sigmoid_only)), _ptr(out), _stream()))
+        return out
+
     def raster_stats(self):
         s = (C.c_int64 * 3)()
         self._check(self.lib.pcacc_raster_stats(self.h, C.byref(s), _stream()))

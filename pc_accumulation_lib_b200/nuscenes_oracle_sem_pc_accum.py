@@ -195,6 +195,11 @@ class NuScenesOracleSemanticPointCloudAccumulator(SemanticPointCloudAccumulator)
         return len(array) - 1
 
     @staticmethod
+    def get_tf_pose(inst_tf):
+        """(x, y, z) of a (4,4) instance pose matrix (nuscenes_oracle_sem_pc_accum.py:701-709)."""
+        return inst_tf[:3, -1]
+
+    @staticmethod
     def parse_seq_into_coherent_seqs(ts):
         runs = [[]]
         prev = ts[0] - 1

@@ -150,6 +150,10 @@ class SemanticPointCloudAccumulator:
     def obs2sem_vec_space(self, *a, **k):
         raise NotImplementedError()
 
+    def generate_bev(self, *a, **k):
+        """Dataset-specific (kitti360_sem_pc_accum.py:166-243, nuscenes_oracle_sem_pc_accum.py:421-530)."""
+        raise NotImplementedError()
+
     # -- pose / cloud updates (sem_pc_accum.py:156-209) ------------------
     def update_poses(self, T_new_prev):
         self.poses = [list(np.matmul(T_new_prev, np.array([p + [1]]).T)[:, 0][:-1])
@@ -246,8 +250,24 @@ class SemanticPointCloudAccumulator:
         out = torch.cat([pts, u.double()[:, None], v.double()[:, None]], dim=1)
         return out[m].cpu().numpy()
 
+    @staticmethod
+    def velo2frame(pc_velo, P_velo_frame):
+        """sem_pc_accum.py:347-366: (N,3) points times the (3,4) matrix in homogeneous
+        coordinates -> (N,3) float64 (`pcacc_velo2frame`)."""
+        from .bev_generator.bev_generator import _ops_cloud, _to_like
+        return _to_like(pc_velo, _ops_cloud().velo2frame(pc_velo, P_velo_frame))
+
     def viz_sem_vec_space(self, *a, **k):
         raise NotImplementedError('Open3D visualisation is outside the B200 hot path')
+
+    def viz_sem_pc(self, *a, **k):
+        raise NotImplementedError('Open3D visualisation is outside the B200 hot path')
+
+    def viz_bev(self, *a, **k):
+        raise NotImplementedError('plotting is outside the B200 hot path')
+
+    def pc2pcd(self, *a, **k):
+        raise NotImplementedError('Open3D point cloud objects are outside the B200 hot path')
 
     # -- shared part of generate_bev (kitti360_sem_pc_accum.py:166-243) -------
     def _window_inputs(self, present_idx, gen_future, other_trajs=None, gt_lanes=None):

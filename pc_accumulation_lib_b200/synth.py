@@ -433,3 +433,46 @@ def rgb_bev_inputs(seed=31, P=32, n=3000):
     poses_p = np.stack([np.linspace(3, P - 4, 9), np.linspace(5, P - 6, 9), np.zeros(9)], axis=1).round()
     poses_f = np.stack([np.linspace(P - 4, 2, 7), np.linspace(4, P - 3, 7), np.zeros(7)], axis=1).round()
     return dict(P=P, pc_present=cloud(n), pc_future=cloud(n // 2), poses_present=poses_p, poses_future=poses_f)
+
+
+def standalone_inputs(seed=77, n=6000, P=48, view=37.2):
+    """Inputs of the stand-alone per-step methods (crop_view, geometric_transform,
+    preprocess_pc_and_trajs, gen_gridmap_count_map, gen_sem_probmap, gen_intensity_map,
+    partition_semantic_pc, dirichlet_dist_expectation, road_marking_transform, get_elevation_map,
+    get_rgb_maps, velo2frame): a metric (n,10) cloud with points on the crop boundary and a NaN row,
+    and a cloud in grid coordinates with the histogram's edge cases (a coordinate equal to P,
+    fractional and negative coordinates, NaN)."""
+    rng = np.random.default_rng(seed)
+    pc = np.zeros((n, 10))
+    pc[:, 0:2] = rng.uniform(-30., 30., (n, 2))
+    pc[:, 2] = rng.normal(0., 1.2, n)
+    pc[:, 3] = rng.uniform(0., 1., n)
+    pc[:, 4:7] = rng.integers(0, 256, (n, 3))
+    pc[:, 7] = rng.integers(0, 19, n)
+    pc[:, 8] = rng.integers(-1, 40, n)
+    pc[:, 9] = rng.integers(0, 2, n)
+    pc[0, 0:2] = [0.5 * view, 0.]            # on the boundary: strict comparisons drop it
+    pc[1, 0:2] = [0., -0.5 * view]
+    pc[2, 0] = np.nan
+    pc[3, 2] = np.inf
+    grid = np.zeros((n, 10))
+    grid[:, 0:2] = np.floor(rng.uniform(0, P, (n, 2)))
+    grid[:300, 0:2] = [11., 30.]             # a crowded cell
+    grid[:, 2] = rng.normal(0., 1.5, n)
+    grid[:, 3] = rng.uniform(0., 1., n)
+    grid[:, 4:7] = rng.integers(0, 256, (n, 3))
+    grid[:, 7] = rng.integers(0, 19, n)
+    edges = grid.copy()
+    edges[300:320, 0] = P                    # right edge: histogram2d's last bin
+    edges[320:330, 1] = P
+    edges[330:340, 0] = -1.                  # outside
+    edges[340:350, 1] = P + 1.
+    edges[350:380, 0:2] += 0.6               # fractional
+    edges[380, 0] = np.nan
+    vals = rng.normal(0.3, 0.4, (P, P))
+    maps = [rng.integers(0, 9, (P, P)).astype(np.float64) for _ in range(3)]
+    P34 = np.concatenate([rng.normal(0., 1., (3, 3)), rng.normal(0., 5., (3, 1))], axis=1)
+    pts32 = rng.normal(0., 20., (n, 4)).astype(np.float32)
+    return dict(pc=pc, grid=grid, edges=edges, P=P, view=view, rot_ang=0.7, dx=1.5, dy=-2.25,
+                height_filter=1.1, vals=vals, maps=maps, P34=P34, pts32=pts32,
+                weights=rng.uniform(-1., 2., n))

@@ -288,8 +288,48 @@ def gen_rgb_bev(ref, name, seeds=(5, 6)):
     save(name, out)
 
 
+def gen_standalone(ref, name):
+    """The per-step public methods of BEVGenerator / SemBEVGenerator / SemanticPointCloudAccumulator that
+    the fused rasteriser replaces, each run unmodified on synth.standalone_inputs()."""
+    c = synth.standalone_inputs()
+    P, view = c['P'], c['view']
+    g = ref.SemBEVGenerator(synth.SEM_IDXS, 40., P, height_filter=c['height_filter'], rgb_fill=7)
+    out = {}
+    with quiet():
+        out['crop_view'] = g.crop_view(c['pc'].copy(), view)
+        out['geometric_transform'] = g.geometric_transform(c['pc'].copy(), c['rot_ang'], c['dx'], c['dy'], view)
+        pc_g, _ = g.preprocess_pc_and_trajs(c['pc'].copy(), [], c['rot_ang'], c['dx'], c['dy'], view)
+        out['preprocess_pc'] = pc_g
+        out['count_map'] = g.gen_gridmap_count_map(c['edges'])
+        out['count_map_weighted'] = g.gen_gridmap_count_map(c['edges'], weights=c['weights'])
+        out['sem_probmap_road'] = g.gen_sem_probmap(c['edges'], ['road'])
+        out['sem_probmap_veh'] = g.gen_sem_probmap(c['edges'], ['car', 'truck', 'bus', 'motorcycle'])
+        out['intensity_map'] = g.gen_intensity_map(c['edges'], 'road')
+        a, b = g.partition_semantic_pc(c['edges'], [synth.SEM_IDXS['car'], synth.SEM_IDXS['bus']], 7)
+        out['partition_sel'], out['partition_rest'] = a, b
+        post = g.dirichlet_dist_expectation([m.copy() for m in c['maps']], obs_weight=2)
+        out['dirichlet'] = np.stack(post)
+        out['road_marking'] = g.road_marking_transform(c['vals'].copy(), 1., 30., 0.12)
+        out['road_marking_kitti'] = g.road_marking_transform(c['vals'].copy(), 20., 20., 0.5)
+        out['sigmoid'] = g.sigmoid(c['vals'])
+        elev, obs = g.get_elevation_map(c['grid'])
+        out['elevmap'], out['elev_obs'] = elev, obs
+        r, gg, b_ = g.get_rgb_maps(c['grid'])
+        out['rgb_maps'] = np.stack([r, gg, b_])
+        vf = ref.KittiAccum.velo2frame
+        out['velo2frame32'] = vf(c['pts32'][:, :3], c['P34'])
+        out['velo2frame64'] = vf(c['pc'][4:, :3], c['P34'])
+    out['input_digest'] = np.frombuffer(cases.digest(c['pc'], c['grid'], c['edges'], c['vals'], c['P34'],
+                                                     c['pts32'], c['weights'], *c['maps']).encode(),
+                                        dtype=np.uint8)
+    save(name, out)
+
+
 def main():
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'standalone':
+        gen_standalone(ref, 'standalone.npz')
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'rgb_bev':
         gen_rgb_bev(ref, 'rgb_bev.npz')
         return

@@ -326,3 +326,74 @@ def test_standalone_helpers_match_reference_golden():
     pc2[0, 0] = float(c['P'])
     with pytest.raises(IndexError):
         gen.static_obj_partitioning_by_elev(pc2, c['elev_thresh'])
+
+
+def test_per_step_methods_match_reference_golden():
+    """Every per-step public method of the generators / accumulator that pcacc_rasterise fuses, called
+    stand-alone with the reference's arguments, against outputs of the unmodified reference
+    (tests/golden/standalone.npz): bit-exact except the weighted histogram and the intensity map (float64
+    atomics: summation order) and exp (device libm vs numpy, <= 2 ulp)."""
+    import torch
+    from pc_accumulation_lib_b200 import SemanticPointCloudAccumulator
+    from pc_accumulation_lib_b200.bev_generator import SemBEVGenerator, RGBBEVGenerator
+    g = load_golden('standalone.npz')
+    c = synth.standalone_inputs()
+    P, view = c['P'], c['view']
+    S = synth.SEM_IDXS
+    gen = SemBEVGenerator(S, 40., P, height_filter=c['height_filter'], rgb_fill=7)
+    eq = np.testing.assert_array_equal
+
+    eq(gen.crop_view(c['pc'].copy(), view), g['crop_view'])
+    eq(SemBEVGenerator.crop_view(c['pc'].copy(), view), g['crop_view'])         # static in the reference
+    eq(gen.geometric_transform(c['pc'].copy(), c['rot_ang'], c['dx'], c['dy'], view), g['geometric_transform'])
+    pc_g, trajs = gen.preprocess_pc_and_trajs(c['pc'].copy(), [], c['rot_ang'], c['dx'], c['dy'], view)
+    eq(pc_g, g['preprocess_pc'])
+    assert trajs == []
+    # rows of another width (the reference takes (N, 3 + M)) and an empty cloud
+    eq(gen.crop_view(c['pc'][:, :4].copy(), view), g['crop_view'][:, :4])
+    assert gen.crop_view(np.zeros((0, 10)), view).shape == (0, 10)
+
+    eq(gen.gen_gridmap_count_map(c['edges']), g['count_map'])
+    np.testing.assert_allclose(gen.gen_gridmap_count_map(c['edges'], weights=c['weights']),
+                               g['count_map_weighted'], rtol=0, atol=1e-12)
+    eq(gen.gen_sem_probmap(c['edges'], ['road']), g['sem_probmap_road'])
+    eq(gen.gen_sem_probmap(c['edges'], ['car', 'truck', 'bus', 'motorcycle']), g['sem_probmap_veh'])
+    np.testing.assert_allclose(gen.gen_intensity_map(c['edges'], 'road'), g['intensity_map'], rtol=0, atol=1e-13)
+    a, b = gen.partition_semantic_pc(c['edges'], [S['car'], S['bus']], 7)
+    assert np.array_equal(a, g['partition_sel'], equal_nan=True)
+    assert np.array_equal(b, g['partition_rest'], equal_nan=True)
+    a0, b0 = gen.partition_semantic_pc(c['edges'], [], 7)
+    assert a0.shape == (0, 10) and np.array_equal(b0, c['edges'], equal_nan=True)
+    post = gen.dirichlet_dist_expectation([m.copy() for m in c['maps']], obs_weight=2)
+    assert isinstance(post, list) and len(post) == 3
+    eq(np.stack(post), g['dirichlet'])
+    for key, args in (('road_marking', (1., 30., 0.12)), ('road_marking_kitti', (20., 20., 0.5))):
+        got = gen.road_marking_transform(c['vals'].copy(), *args)
+        np.testing.assert_allclose(got, g[key], rtol=1e-15, atol=0)
+        assert got.max() <= 1.
+    np.testing.assert_allclose(gen.sigmoid(c['vals']), g['sigmoid'], rtol=1e-15, atol=0)
+    assert gen.extract_aug_dict({'max_translation_radius': 3., 'zoom_threshold': .2}) == (3., .2)
+
+    elev, obs = gen.get_elevation_map(c['grid'])
+    eq(elev, g['elevmap'])
+    eq(obs, g['elev_obs'])
+    assert obs.dtype == np.bool_
+    bad = c['grid'].copy()
+    bad[7, 0] = P
+    with pytest.raises(IndexError):
+        gen.get_elevation_map(bad)
+    eq(np.stack(gen.get_rgb_maps(c['grid'])), g['rgb_maps'])
+    assert gen.rgb_fill == 7
+    rgen = RGBBEVGenerator(40., P, rgb_fill=7)
+    eq(np.stack(rgen.get_rgb_maps(c['grid'][:, :7])), g['rgb_maps'])
+
+    vf = SemanticPointCloudAccumulator.velo2frame
+    np.testing.assert_allclose(vf(c['pts32'][:, :3], c['P34']), g['velo2frame32'], rtol=1e-13, atol=1e-12)
+    np.testing.assert_allclose(vf(c['pc'][4:, :3], c['P34']), g['velo2frame64'], rtol=1e-13, atol=1e-12)
+    eq(vf(c['pts32'][:, :3], c['P34']), orc.velo2frame(c['pts32'][:, :3], c['P34']))
+
+    # CUDA tensors in -> CUDA tensors out, no host round trip
+    t = torch.from_numpy(c['edges']).cuda()
+    m = gen.gen_sem_probmap(t, ['road'])
+    assert isinstance(m, torch.Tensor) and m.is_cuda
+    eq(m.cpu().numpy(), g['sem_probmap_road'])

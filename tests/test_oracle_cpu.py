@@ -195,3 +195,44 @@ def test_standalone_helpers_match_reference_golden():
     st, dy, el, ob = orc.static_obj_partitioning_by_elev(pc, c['P'], c['elev_thresh'])
     for got, key in ((pc, 'pc_after'), (st, 'pc_static'), (dy, 'pc_dynamic'), (el, 'elevmap'), (ob, 'obs')):
         np.testing.assert_array_equal(got, g[key], err_msg=key)
+
+
+def test_per_step_methods_match_reference_golden():
+    """The per-step public methods the fused rasteriser replaces (crop_view ... velo2frame): the
+    oracle's restatements against outputs of the unmodified reference (tests/golden/standalone.npz)."""
+    from pc_accumulation_lib_b200 import synth
+    g = load_golden('standalone.npz')
+    c = synth.standalone_inputs()
+    P, view = c['P'], c['view']
+    R = orc.rotation_matrix_3d(c['rot_ang'])
+    S = synth.SEM_IDXS
+    eq = np.testing.assert_array_equal
+    eq(orc.crop_view(c['pc'], view), g['crop_view'])
+    assert g['crop_view'].shape[0] < c['pc'].shape[0] - 100
+    eq(orc.geometric_transform_pc(c['pc'], R, c['dx'], c['dy'], view), g['geometric_transform'])
+    eq(orc.preprocess_pc(c['pc'], R, c['dx'], c['dy'], view, P, c['height_filter']), g['preprocess_pc'])
+    eq(orc.gridmap_count_map(c['edges'], P), g['count_map'])
+    assert g['count_map'].sum() == c['edges'].shape[0] - 21       # 10 + 10 outside, one NaN
+    np.testing.assert_allclose(orc.gridmap_count_map(c['edges'], P, c['weights']), g['count_map_weighted'],
+                               rtol=0, atol=1e-12)
+    eq(orc.sem_probmap(c['edges'], P, [S['road']]), g['sem_probmap_road'])
+    eq(orc.sem_probmap(c['edges'], P, [S[k] for k in ('car', 'truck', 'bus', 'motorcycle')]),
+       g['sem_probmap_veh'])
+    np.testing.assert_allclose(orc.intensity_map(c['edges'], P, S['road']), g['intensity_map'], rtol=0,
+                               atol=1e-13)
+    a, b = orc.partition_semantic_pc(c['edges'], [S['car'], S['bus']], 7)
+    assert np.array_equal(a, g['partition_sel'], equal_nan=True)
+    assert np.array_equal(b, g['partition_rest'], equal_nan=True)
+    eq(np.stack(orc.dirichlet_expectation(c['maps'], 2)), g['dirichlet'])
+    eq(orc.road_marking_transform(c['vals'], 1., 30., 0.12), g['road_marking'])
+    eq(orc.road_marking_transform(c['vals'], 20., 20., 0.5), g['road_marking_kitti'])
+    eq(orc.sigmoid(c['vals']), g['sigmoid'])
+    elev, obs = orc.elevation_map(c['grid'], P)
+    eq(elev, g['elevmap'])
+    eq(obs, g['elev_obs'])
+    eq(np.stack(orc.rgb_maps(c['grid'], P, rgb_fill=7)), g['rgb_maps'])
+    assert (g['rgb_maps'] % 1 == 0.5).sum() > 10                  # even counts: half-integer medians
+    np.testing.assert_allclose(orc.velo2frame(c['pts32'][:, :3], c['P34']), g['velo2frame32'], rtol=1e-13,
+                               atol=1e-12)
+    np.testing.assert_allclose(orc.velo2frame(c['pc'][4:, :3], c['P34']), g['velo2frame64'], rtol=1e-13,
+                               atol=1e-12)
