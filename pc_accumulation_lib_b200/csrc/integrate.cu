@@ -44,10 +44,13 @@ struct LookBack {
     uint32_t n_tiles;
 };
 
+// All PCACC_MAX_FILTERS slots are compared (statically indexed, predicated on k < n): a loop bounded
+// by f.n indexes the by-value kernel parameter dynamically, which makes the compiler copy the struct
+// to local memory and read it back through L1 for every point.
 __device__ __forceinline__ bool class_filtered(const Filters &f, int cls) {
     bool hit = false;
-#pragma unroll 4
-    for (int k = 0; k < f.n; k++) hit |= (cls == f.v[k]);
+#pragma unroll
+    for (int k = 0; k < PCACC_MAX_FILTERS; k++) hit |= (k < f.n) && (cls == f.v[k]);
     return hit;
 }
 

@@ -683,7 +683,10 @@ __device__ __forceinline__ Eval exact_candidate(const BinArgs &a, const pcacc_be
     return e;
 }
 
-__global__ void __launch_bounds__(256, 4)
+#ifndef BIN_OCC
+#define BIN_OCC 3
+#endif
+__global__ void __launch_bounds__(256, BIN_OCC)
 k_bev_bin(BinArgs a) {
     __shared__ pcacc_bev_params s_par[MAX_VGROUP];
     __shared__ double s_pv[MAX_VGROUP];
@@ -796,22 +799,29 @@ k_bev_bin(BinArgs a) {
         }
     };
 
-    // two candidates per iteration: both points' loads are in flight before either is used
-    for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < n; c += 2 * stride) {
-        const unsigned long long c2 = c + stride;
-        const bool two = c2 < n;
-        const uint32_t gA = a.cand_gi[c], mA = a.cand_meta[c];
-        const uint32_t gB = two ? a.cand_gi[c2] : gA, mB = two ? a.cand_meta[c2] : mA;
-        const double xA = a.ring.x[gA], yA = a.ring.y[gA], zA = a.ring.z[gA];
-        const uint32_t rA = a.ring.rgbs[gA];
-        const float iA = a.ring.inten[gA];
-        const uint32_t dA = a.ring.dyn[gA];
-        const double xB = a.ring.x[gB], yB = a.ring.y[gB], zB = a.ring.z[gB];
-        const uint32_t rB = a.ring.rgbs[gB];
-        const float iB = a.ring.inten[gB];
-        const uint32_t dB = a.ring.dyn[gB];
-        process(c, gA, mA, xA, yA, zA, rA, iA, dA);
-        if (two) process(c2, gB, mB, xB, yB, zB, rB, iB, dB);
+    // Software pipeline over the thread's candidates c, c + stride, ...: while candidate k is
+    // evaluated, the gathers of k + 1 and the list entry of k + 2 are in flight (the list entry is the
+    // address of the gathers, the gathers feed the evaluation: taken one after the other, each
+    // candidate paid both round trips).
+    struct Pt { double x, y, z; uint32_t rgbs, dyn; float inten; };
+    auto gather = [&](uint32_t g) {
+        Pt p;
+        p.x = a.ring.x[g]; p.y = a.ring.y[g]; p.z = a.ring.z[g];
+        p.rgbs = a.ring.rgbs[g]; p.inten = a.ring.inten[g]; p.dyn = a.ring.dyn[g];
+        return p;
+    };
+    unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n) return;
+    uint32_t g0 = a.cand_gi[c], m0 = a.cand_meta[c];
+    uint32_t g1 = g0, m1 = m0;
+    if (c + stride < n) { g1 = a.cand_gi[c + stride]; m1 = a.cand_meta[c + stride]; }
+    Pt p0 = gather(g0);
+    for (; c < n; c += stride) {
+        const Pt p1 = gather(g1);                       // valid address even past the end (a repeat)
+        uint32_t g2 = g1, m2 = m1;
+        if (c + 2 * stride < n) { g2 = a.cand_gi[c + 2 * stride]; m2 = a.cand_meta[c + 2 * stride]; }
+        process(c, g0, m0, p0.x, p0.y, p0.z, p0.rgbs, p0.inten, p0.dyn);
+        p0 = p1; g0 = g1; m0 = m1; g1 = g2; m1 = m2;
     }
 }
 
@@ -978,21 +988,33 @@ __device__ __forceinline__ void acc_init(WinAcc &a, bool want_max) {
     }
 }
 
+// w selects the window with conditional moves, not with an index: indexed, the accumulators lived in
+// local memory and every record paid a load-modify-store round trip through L1 per field.
 __device__ __forceinline__ void acc_record(WinAcc &a, const uint4 &r, int w, int road_cls, int v0,
                                            int v1, int v2, int v3, bool want_max) {
     const double z = __longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x));
     const int sem = (int)(r.z >> 24);
+    const bool w1 = w != 0;
     if (sem == road_cls) {
         // raw float32 intensity: exact in 2^-40 fixed point for |v| >= 2^-17
-        long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
-        a.fx_hi[w] += fx >> 32;
-        a.fx_lo[w] += fx & 0xffffffffll;
-        a.n_road[w]++;
+        const long long fx = __double2ll_rn(__dmul_rn((double)__uint_as_float(r.w), FX_SCALE));
+        const long long hi = fx >> 32, lo = fx & 0xffffffffll;
+        a.fx_hi[0] += w1 ? 0ll : hi;
+        a.fx_hi[1] += w1 ? hi : 0ll;
+        a.fx_lo[0] += w1 ? 0ll : lo;
+        a.fx_lo[1] += w1 ? lo : 0ll;
+        a.n_road[0] += w1 ? 0u : 1u;
+        a.n_road[1] += w1 ? 1u : 0u;
     }
-    if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) a.n_veh[w]++;
-    a.ext_z[w] = want_max ? fmax(a.ext_z[w], z) : fmin(a.ext_z[w], z);
+    if ((sem == v0) || (sem == v1) || (sem == v2) || (sem == v3)) {
+        a.n_veh[0] += w1 ? 0u : 1u;
+        a.n_veh[1] += w1 ? 1u : 0u;
+    }
+    const double e0 = want_max ? fmax(a.ext_z[0], z) : fmin(a.ext_z[0], z);
+    const double e1 = want_max ? fmax(a.ext_z[1], z) : fmin(a.ext_z[1], z);
+    a.ext_z[0] = w1 ? a.ext_z[0] : e0;
+    a.ext_z[1] = w1 ? e1 : a.ext_z[1];
 }
-
 
 // (m2 * 0.5) / 255. for m2 = twice the median, 0..510: filled once per handle
 #define RGB_LUT_N 511
@@ -1774,32 +1796,83 @@ __device__ __forceinline__ double warp_max_f64(double v) {
     return ord_decode(((unsigned long long)mh << 32) | ml);
 }
 
+// parked (cell, window) statistics of k_bev_reduce_big, one warp's worth
+struct BigPend {
+    long long fx_hi[32], fx_lo[32];
+    double ez[32];
+    uint32_t nw[32], nr[32], nv[32], med[32], gc[32];   // med: three 10-bit doubled medians | window << 30
+};
+
 template <bool F64OUT>
-__global__ void __launch_bounds__(REDB_WARPS * 32)
+__device__ __forceinline__ void big_flush(const BigPend &pd, uint32_t n, unsigned lane,
+                                          const pcacc_bev_params *__restrict__ params,
+                                          const BevConsts *__restrict__ consts, const double *__restrict__ lut,
+                                          int PP, double intensity_div, __half *__restrict__ out16,
+                                          double *__restrict__ out64) {
+    if (lane < n) {
+        const uint32_t gc = pd.gc[lane], m = pd.med[lane];
+        const int w = (int)(m >> 30);
+        const int var = (int)(gc / (uint32_t)PP);
+        const int cell_in = (int)(gc - (uint32_t)var * (uint32_t)PP);
+        const int md[3] = {(int)(m & 1023u), (int)((m >> 10) & 1023u), (int)((m >> 20) & 1023u)};
+        double plane[7];
+        window_planes<false>(params[var], consts[var], lut, pd.nw[lane], pd.nr[lane], pd.nv[lane], pd.fx_hi[lane],
+                             pd.fx_lo[lane], pd.ez[lane], md, intensity_div, plane);
+        store_planes<F64OUT>(out16, out64, (((int64_t)var * 3 + w) * 7) * PP + cell_in, PP, plane);
+    }
+}
+
+#ifndef REDB_BATCH
+#define REDB_BATCH 1   /* queue entries per ticket (4: 109 vs 94 us on the long-horizon window, 8: 123) */
+#endif
+template <bool F64OUT>
+__global__ void __launch_bounds__(REDB_WARPS * 32, 7)
 k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ sorted,
                  const pcacc_bev_params *__restrict__ params, const BevConsts *__restrict__ consts,
                  const double *__restrict__ lut, int P, double intensity_div,
                  const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
                  uint32_t *__restrict__ next, __half *__restrict__ out16, double *__restrict__ out64) {
     __shared__ __align__(16) uint32_t s_hist[REDB_WARPS][2][3][256];
+    __shared__ BigPend s_pend[REDB_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t(*hist)[3][256] = s_hist[warp];
+    BigPend &pd = s_pend[warp];
+    uint32_t pend_n = 0;
     const int PP = P * P;
     const uint32_t n_big = *big_count;
+    // Cells are drawn from the queue REDB_BATCH at a time: one ticket, then the cells' ids, segment
+    // bounds and a prefetch of their first records fetched by one lane each, side by side.  Drawn one
+    // by one, every cell paid four dependent round trips (ticket -> id -> bounds -> records) before
+    // its first record arrived, and with 28 warps per SM that chain, not the arithmetic, set the
+    // kernel's duration.
     while (true) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(next, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= n_big) break;
-        const uint32_t gc = big_list[q];
+        uint32_t q0 = 0;
+        if (lane == 0) q0 = atomicAdd(next, (uint32_t)REDB_BATCH);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= n_big) break;
+        const uint32_t n_batch = min((uint32_t)REDB_BATCH, n_big - q0);
+        uint32_t l_gc = 0, l_b0 = 0, l_b1 = 0, l_b2 = 0;
+        if (lane < n_batch) {
+            l_gc = big_list[q0 + lane];
+            l_b0 = start[2 * (int64_t)l_gc];
+            l_b1 = start[2 * (int64_t)l_gc + 1];
+            l_b2 = start[2 * (int64_t)l_gc + 2];
+            const char *rec = (const char *)(sorted + l_b0);
+            const uint32_t bytes = min((l_b2 - l_b0) * 16u, 2048u);
+            for (uint32_t o = 0; o < bytes; o += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
+        }
+#pragma unroll 1
+    for (uint32_t bi = 0; bi < n_batch; bi++) {
+        const uint32_t gc = __shfl_sync(0xffffffffu, l_gc, (int)bi);
         const int var = (int)(gc / (uint32_t)PP);
         const int cell_in = (int)(gc - (uint32_t)var * (uint32_t)PP);
         const pcacc_bev_params &bp = params[var];
         const bool want_max = bp.elevation_max != 0;
         const int road_cls = bp.road_cls, v0 = bp.veh_cls[0], v1 = bp.veh_cls[1], v2 = bp.veh_cls[2],
                   v3 = bp.veh_cls[3];
-        const uint32_t b0 = start[2 * (int64_t)gc], b1 = start[2 * (int64_t)gc + 1],
-                       b2 = start[2 * (int64_t)gc + 2];
+        const uint32_t b0 = __shfl_sync(0xffffffffu, l_b0, (int)bi), b1 = __shfl_sync(0xffffffffu, l_b1, (int)bi),
+                       b2 = __shfl_sync(0xffffffffu, l_b2, (int)bi);
         const uint32_t np = b1 - b0, nf = b2 - b1, nt = np + nf;
         // Cells of at most 32 points (one per lane): the rank intervals of pass A with the
         // values exchanged by shuffles — about n x 10 instructions instead of the ~800 it takes
@@ -1928,36 +2001,52 @@ k_bev_reduce_big(const uint32_t *__restrict__ start, const uint4 *__restrict__ s
         }
         }   // histogram path: medians
         __syncwarp();
-        // lanes 0..2 finalise one window each
-        if (lane < 3) {
-            const int w = (int)lane;
-            const BevConsts &cst = consts[var];
-            const uint32_t nw = (w == 0) ? np : (w == 1) ? nf : nt;
-            const int64_t o = (((int64_t)var * 3 + w) * 7) * PP + cell_in;
-            if (nw == 0) {
-                store_empty<F64OUT>(out16, out64, o, PP, cst);
-            } else {
-                double plane[7];
-                int md[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) md[c] = (w == 0) ? m2[0][c] : (w == 1) ? m2[1][c] : m2[2][c];
-                if (w < 2) {
-                    const int ww = w & 1;
-                    window_planes<false>(bp, cst, lut, nw, ww ? a.n_road[1] : a.n_road[0],
-                                  ww ? a.n_veh[1] : a.n_veh[0], ww ? a.fx_hi[1] : a.fx_hi[0],
-                                  ww ? a.fx_lo[1] : a.fx_lo[0], ww ? a.ext_z[1] : a.ext_z[0], md,
-                                  intensity_div, plane);
+        // The windows' statistics are parked in shared memory and finalised 32 at a time with one
+        // lane per (cell, window): done on the spot, three lanes ran the float64 divisions and the
+        // sigmoid of a cell while 29 waited — 28 % of this kernel's instructions on the 24 M-point
+        // window.  Empty windows only store constants and are not parked.
+        {
+            const uint32_t k0 = np != 0 ? 1u : 0u, k1 = nf != 0 ? 1u : 0u;
+            if (lane < 3) {
+                const int w = (int)lane;
+                const uint32_t nw = (w == 0) ? np : (w == 1) ? nf : nt;
+                if (nw == 0) {
+                    store_empty<F64OUT>(out16, out64, (((int64_t)var * 3 + w) * 7) * PP + cell_in, PP, consts[var]);
                 } else {
-                    window_planes<false>(bp, cst, lut, nw, a.n_road[0] + a.n_road[1], a.n_veh[0] + a.n_veh[1],
-                                  a.fx_hi[0] + a.fx_hi[1], a.fx_lo[0] + a.fx_lo[1],
-                                  want_max ? fmax(a.ext_z[0], a.ext_z[1]) : fmin(a.ext_z[0], a.ext_z[1]),
-                                  md, intensity_div, plane);
+                    const uint32_t e = pend_n + (w == 0 ? 0u : w == 1 ? k0 : k0 + k1);
+                    const int ww = w & 1;
+                    pd.nw[e] = nw;
+                    pd.gc[e] = gc;
+                    const uint32_t mp0 = (uint32_t)m2[0][0] | ((uint32_t)m2[0][1] << 10) | ((uint32_t)m2[0][2] << 20),
+                                   mp1 = (uint32_t)m2[1][0] | ((uint32_t)m2[1][1] << 10) | ((uint32_t)m2[1][2] << 20),
+                                   mp2 = (uint32_t)m2[2][0] | ((uint32_t)m2[2][1] << 10) | ((uint32_t)m2[2][2] << 20);
+                    pd.med[e] = ((w == 0) ? mp0 : (w == 1) ? mp1 : mp2) | ((uint32_t)w << 30);
+                    if (w < 2) {
+                        pd.nr[e] = ww ? a.n_road[1] : a.n_road[0];
+                        pd.nv[e] = ww ? a.n_veh[1] : a.n_veh[0];
+                        pd.fx_hi[e] = ww ? a.fx_hi[1] : a.fx_hi[0];
+                        pd.fx_lo[e] = ww ? a.fx_lo[1] : a.fx_lo[0];
+                        pd.ez[e] = ww ? a.ext_z[1] : a.ext_z[0];
+                    } else {
+                        pd.nr[e] = a.n_road[0] + a.n_road[1];
+                        pd.nv[e] = a.n_veh[0] + a.n_veh[1];
+                        pd.fx_hi[e] = a.fx_hi[0] + a.fx_hi[1];
+                        pd.fx_lo[e] = a.fx_lo[0] + a.fx_lo[1];
+                        pd.ez[e] = want_max ? fmax(a.ext_z[0], a.ext_z[1]) : fmin(a.ext_z[0], a.ext_z[1]);
+                    }
                 }
-                store_planes<F64OUT>(out16, out64, o, PP, plane);
             }
+            pend_n += k0 + k1 + 1u;      // a queued cell is never empty: its full window always counts
         }
         __syncwarp();
+        if (pend_n > 29u) {
+            big_flush<F64OUT>(pd, pend_n, lane, params, consts, lut, PP, intensity_div, out16, out64);
+            pend_n = 0;
+            __syncwarp();
+        }
+    }   // cells of the batch
     }
+    if (pend_n) big_flush<F64OUT>(pd, pend_n, lane, params, consts, lut, PP, intensity_div, out16, out64);
 }
 
 // ===========================================================================

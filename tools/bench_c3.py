@@ -77,3 +77,11 @@ torch.cuda.profiler.start()
 cloud.rasterise(bps, a.P, out=out)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+if os.environ.get('C3_CELL_STATS'):
+    _, _, cells = cloud.rasterise(bps[:1], a.P, want_cells=True)
+    c = cells[cells >= 0].long()
+    cnt = torch.bincount(c, minlength=a.P * a.P)
+    s = torch.sort(cnt, descending=True).values
+    print('cells non-empty', int((cnt > 0).sum()), 'points', int(cnt.sum()), 'largest', s[:12].tolist(),
+          'quantiles 50/90/99/99.9 %', [int(torch.quantile(cnt[cnt > 0].float(), q)) for q in (0.5, 0.9, 0.99, 0.999)],
+          '> 15:', int((cnt > 15).sum()), '> 32:', int((cnt > 32).sum()), '> 1024:', int((cnt > 1024).sum()))
