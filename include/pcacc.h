@@ -402,13 +402,15 @@ int pcacc_preprocess_pc(pcacc_t h, const double *pc_dev, int64_t n, int cols, co
 
 /* partition_semantic_pc + gen_gridmap_count_map (+ gen_sem_probmap / gen_intensity_map),
  * bev_generator/bev_generator.py:373-453: a point is "selected" when column sem_col equals one of
- * sems[0..n_sems) (n_sems < 0: every point).  np.histogram2d's binning over [0,P]x[0,P] of the
- * grid coordinates in columns 1, 0, flipped along the first axis.  Any of the three (P,P) float64
+ * sems[0..n_sems) (n_sems < 0: every point; at most PCACC_MAX_SEMS = 32 classes).
+ * np.histogram2d's binning over [0,P]x[0,P] of the grid coordinates in columns 1, 0, flipped along
+ * the first axis.  Any of the three (P,P) float64
  * outputs may be NULL: count_sel_dev / count_rest_dev = number of selected / other points per cell,
  * wsum_sel_dev = sum over the selected points of column weight_col (or of weights_dev[point] when
  * weight_col < 0; order-dependent rounding, ~1e-16 relative).  finish: 0 = raw maps; 1 = the
  * Dirichlet expectation with a uniform prior of the two counts, in place (gen_sem_probmap);
  * 2 = wsum / (count_sel + 1) in place (gen_intensity_map). */
+#define PCACC_MAX_SEMS 32
 int pcacc_cell_stats(pcacc_t h, const double *pc_dev, int64_t n, int cols, int P, int sem_col,
                      const int32_t *sems, int n_sems, int weight_col, const double *weights_dev,
                      int finish, double *count_sel_dev, double *count_rest_dev, double *wsum_sel_dev,

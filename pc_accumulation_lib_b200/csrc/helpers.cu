@@ -11,7 +11,17 @@ namespace {
 
 struct Mat34 { double m[12]; };
 struct Mat33 { double m[9]; };
-struct SemSel { int n; double v[PCACC_MAX_FILTERS]; };
+#define HELPER_MAX_SEMS 32   /* classes one selection may list (PCACC_MAX_SEMS in pcacc.h) */
+struct SemSel { int n; double v[HELPER_MAX_SEMS]; };
+
+// statically indexed and predicated (a loop to sel.n would index the by-value kernel parameter at run
+// time and send it to local memory)
+__device__ __forceinline__ bool sel_hit(const SemSel &sel, double s) {
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < HELPER_MAX_SEMS; k++) hit |= (k < sel.n) && (s == sel.v[k]);
+    return hit;
+}
 
 struct LookBackH {
     unsigned long long *state;
@@ -106,8 +116,7 @@ k_cell_stats(const double *__restrict__ pc, int64_t n, int cols, int P, int sem_
     const double *r = pc + t * cols;
     bool hit = sel.n < 0;
     if (!hit) {
-        const double s = r[sem_col];
-        for (int k = 0; k < sel.n; k++) hit |= (s == sel.v[k]);
+        hit = sel_hit(sel, r[sem_col]);
     }
     int bi, bj;
     // first histogram axis = column 1 (j), second = column 0 (i); then np.flip(axis=0)
@@ -184,8 +193,7 @@ k_partition_sem(const double *__restrict__ pc, int64_t n, int cols, int sem_col,
     const int64_t t = (int64_t)tile * HB + threadIdx.x;
     bool hit = false;
     if (t < n) {
-        const double s = pc[t * cols + sem_col];
-        for (int k = 0; k < sel.n; k++) hit |= (s == sel.v[k]);
+        hit = sel_hit(sel, pc[t * cols + sem_col]);
     }
     uint32_t tile_end;
     const uint32_t rank = compact_rank<HB>(hit, lb.state, lb.epoch, tile, s_warp, &tile_end);
@@ -256,7 +264,7 @@ extern "C" int pcacc_cell_stats(pcacc_t h, const double *pc_dev, int64_t n, int 
                                 int finish, double *count_sel_dev, double *count_rest_dev,
                                 double *wsum_sel_dev, void *stream) {
     if (!h) return PCACC_ERR_ARG;
-    if (n < 0 || cols < 2 || P <= 0 || n_sems > PCACC_MAX_FILTERS || (n_sems > 0 && !sems) ||
+    if (n < 0 || cols < 2 || P <= 0 || n_sems > HELPER_MAX_SEMS || (n_sems > 0 && !sems) ||
         (n_sems >= 0 && (sem_col < 0 || sem_col >= cols)) || weight_col >= cols || (n > 0 && !pc_dev) ||
         (wsum_sel_dev && weight_col < 0 && !weights_dev) || finish < 0 || finish > 2 ||
         (finish == 1 && (!count_sel_dev || !count_rest_dev)) ||
@@ -319,7 +327,7 @@ extern "C" int pcacc_partition_semantic_pc(pcacc_t h, const double *pc_dev, int6
                                            const int32_t *sems, int n_sems, double *out_sel_dev,
                                            double *out_rest_dev, int64_t *n_sel_dev, void *stream) {
     if (!h) return PCACC_ERR_ARG;
-    if (n < 0 || cols < 1 || sem_col < 0 || sem_col >= cols || n_sems < 0 || n_sems > PCACC_MAX_FILTERS ||
+    if (n < 0 || cols < 1 || sem_col < 0 || sem_col >= cols || n_sems < 0 || n_sems > HELPER_MAX_SEMS ||
         (n_sems > 0 && !sems) || !n_sel_dev || (n > 0 && (!pc_dev || !out_sel_dev || !out_rest_dev)))
         return pcacc_fail(h, PCACC_ERR_ARG, "bad partition_semantic_pc arguments");
     cudaStream_t st = (cudaStream_t)stream;

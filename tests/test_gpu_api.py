@@ -397,3 +397,61 @@ def test_per_step_methods_match_reference_golden():
     m = gen.gen_sem_probmap(t, ['road'])
     assert isinstance(m, torch.Tensor) and m.is_cuda
     eq(m.cpu().numpy(), g['sem_probmap_road'])
+
+
+def test_per_step_operators_edge_cases():
+    """Empty clouds, every step switched off, rows of odd width, all-selected / none-selected partitions and
+    the oracle on random inputs of other sizes for the stand-alone operators (pcacc_preprocess_pc,
+    pcacc_cell_stats, pcacc_partition_semantic_pc, pcacc_dirichlet_expectation, pcacc_road_marking,
+    pcacc_elevation_map, pcacc_velo2frame)."""
+    import torch
+    from pc_accumulation_lib_b200.device import DeviceCloud
+    ops = DeviceCloud(1024, 8)
+    rng = np.random.default_rng(3)
+    eq = np.testing.assert_array_equal
+    # empty inputs
+    assert ops.preprocess_pc(np.zeros((0, 10)), np.eye(3), 0., 0., 10., 1., 10., 16).shape == (0, 10)
+    m = ops.cell_stats(np.zeros((0, 10)), 8, [1], 7, weight_col=3)
+    assert all(float(v.abs().sum()) == 0. for v in m.values())
+    m = ops.cell_stats(np.zeros((0, 10)), 8, [1], 7, finish=1, want=('sel', 'rest'))
+    eq(m['sel'].cpu().numpy(), np.full((8, 8), 0.5))                   # uniform prior alone
+    a, b = ops.partition_semantic_pc(np.zeros((0, 10)), [1], 7)
+    assert a.shape == (0, 10) and b.shape == (0, 10)
+    assert ops.velo2frame(np.zeros((0, 3), dtype=np.float32), np.eye(3, 4)).shape == (0, 3)
+    assert ops.road_marking(np.zeros((0,))).shape == (0,)
+    elev, obs = ops.elevation_map(np.zeros((0, 3)), 8)
+    assert not obs.any() and float(elev.abs().sum()) == 0.
+    # every step off: the identity, rows of width 3 and 13
+    for cols in (3, 13):
+        pc = rng.normal(0., 5., (1000, cols))
+        eq(ops.preprocess_pc(pc).cpu().numpy(), pc)
+    # several sizes against the oracle (tile boundaries of the look-back compaction: 255, 256, 257, 70001)
+    for n in (1, 255, 256, 257, 70001):
+        pc = np.zeros((n, 10))
+        pc[:, :2] = rng.uniform(-30., 30., (n, 2))
+        pc[:, 2] = rng.normal(0., 1.5, n)
+        pc[:, 3] = rng.uniform(0., 1., n)
+        pc[:, 7] = rng.integers(0, 19, n)
+        R = orc.rotation_matrix_3d(1.1)
+        want = orc.preprocess_pc(pc, R, 0.7, -1.3, 44., 64, 1.0) if n > 1 else None
+        got = ops.preprocess_pc(pc, R, 0.7, -1.3, 44., 1.0, 44., 64).cpu().numpy()
+        if want is not None:           # (a single point takes another BLAS path in the reference: SURVEY 8c)
+            eq(got, want)
+        grid = orc.preprocess_pc(pc, np.eye(3), 0., 0., 60., 64, None) if n > 1 else pc * 0
+        sel, rest = ops.partition_semantic_pc(grid, [0, 5, 7], 7)
+        ws, wr = orc.partition_semantic_pc(grid, [0, 5, 7], 7)
+        eq(sel.cpu().numpy(), ws)
+        eq(rest.cpu().numpy(), wr)
+        alls, none = ops.partition_semantic_pc(grid, list(range(19)), 7)
+        assert alls.shape[0] == grid.shape[0] and none.shape[0] == 0
+        m = ops.cell_stats(grid, 64, [0], 7, weight_col=3, finish=2, want=('sel', 'wsum'))
+        np.testing.assert_allclose(m['wsum'].cpu().numpy(), orc.intensity_map(grid, 64, 0), rtol=0, atol=1e-13)
+        m = ops.cell_stats(grid, 64, [13, 14, 15, 17], 7, finish=1, want=('sel', 'rest'))
+        eq(m['sel'].cpu().numpy(), orc.sem_probmap(grid, 64, [13, 14, 15, 17]))
+    maps = rng.integers(0, 5, (4, 9, 7)).astype(np.float64)
+    eq(ops.dirichlet_expectation(maps, 3.).cpu().numpy(), np.stack(orc.dirichlet_expectation(list(maps), 3.)))
+    t = torch.from_numpy(maps).cuda()
+    ops.dirichlet_expectation(t, 3.)
+    eq(t.cpu().numpy(), maps)                                           # the caller's tensor is not modified
+    assert ops.sync() == 0
+    ops.close()

@@ -26,13 +26,14 @@ def wrap(obj, name, label=None):
     setattr(obj, name, g)
 
 
-for name in ('integrate', 'obs2sem_vec_space', 'get_split_dyn_obj_trajs', 'generate_bev', '_boxes_to_world'):
+for name in ('integrate', 'obs2sem_vec_space', 'get_split_dyn_obj_trajs', 'generate_bev', '_boxes_to_world', 'get_dyn_obj_trajs'):
     wrap(Acc, name)
 for name in ('_window_inputs', '_generate', '_sync'):
     wrap(sem_pc_accum.SemanticPointCloudAccumulator, name)
-for name in ('generate_batch', '_rasterise_windows_begin', '_rasterise_device', 'preprocess_trajs_batch', 'rand_aug_params'):
+for name in ('generate_batch', '_rasterise_windows_begin', '_rasterise_device', 'preprocess_trajs_batch', 'rand_aug_params',
+             'draw_warp', 'warp_trajs', '_assemble', 'get_random_warp_params'):
     wrap(bg.BEVGenerator, name)
-for name in ('rasterise', 'planes_to_host_begin', 'planes_to_host_finish', 'integrate_records_host', 'mark_dynamic', 'flush_marks'):
+for name in ('rasterise', 'planes_to_host_begin', 'planes_to_host_finish', 'integrate_records_host', 'mark_dynamic', 'flush_marks', 'warp_planes'):
     wrap(device.DeviceCloud, name)
 wrap(device, 'make_bev_params_batch')
 bg.make_bev_params_batch = device.make_bev_params_batch
