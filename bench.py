@@ -678,14 +678,18 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
         bev = acc.generate_bev(present_idx, 1, True)[0]
         t2 = time.perf_counter()
         assert bev['rgb_full'].shape == (3, P, P)
+        # the first call of a fresh accumulator allocates the rasteriser's workspace; a sequence calls
+        # generate_bev once per present index, so the steady rate is the second call's
+        acc.generate_bev(present_idx, 1, True)
+        t3 = time.perf_counter()
         n_res = acc.cloud.resident_points()
         acc.cloud.close()
-        return t1 - t0, t2 - t1, n_res
+        return t1 - t0, t2 - t1, n_res, t3 - t2
 
     run_gpu()
-    ti, tb, n_res = min((run_gpu() for _ in range(3)), key=lambda r: r[0] + r[1])
+    ti, tb, n_res, tb2 = min((run_gpu() for _ in range(3)), key=lambda r: r[0] + r[1])
     run_gpu(frames_pin)
-    ti_pin, tb_pin, _ = min((run_gpu(frames_pin) for _ in range(3)), key=lambda r: r[0] + r[1])
+    ti_pin, tb_pin, _, tb2_pin = min((run_gpu(frames_pin) for _ in range(3)), key=lambda r: r[0] + r[1])
     from oracle import oracle as orc          # CPU port, the baseline of this row only
     bp = synth.kitti_bev_params(pixel_size=P)
     gp = dict(sem_idxs=synth.SEM_IDXS, view_size=bp['view_size'], pixel_size=P,
@@ -700,9 +704,9 @@ def kitti_seq_extra(torch, F=20, present_idx=10):
     c2 = time.perf_counter()
     return {'frames': F, 'points': n_pts, 'resident_points': n_res,
             'integrate_ms_per_frame': ti / F * 1e3, 'integrate_points_per_s': n_pts / ti,
-            'bev_ms': tb * 1e3,
+            'bev_ms': tb * 1e3, 'bev_ms_second_call': tb2 * 1e3,
             'pinned_inputs': {'integrate_ms_per_frame': ti_pin / F * 1e3, 'integrate_points_per_s': n_pts / ti_pin,
-                              'bev_ms': tb_pin * 1e3,
+                              'bev_ms': tb_pin * 1e3, 'bev_ms_second_call': tb2_pin * 1e3,
                               'note': 'arrays in page-locked memory: no staging copy (camera maps read in place)'},
             'cpu_port_integrate_ms_per_frame': (c1 - c0) / F * 1e3, 'cpu_port_bev_ms': (c2 - c1) * 1e3,
             'cpu_port_cores': 1,
