@@ -156,8 +156,15 @@ class SemanticPointCloudAccumulator:
 
     # -- pose / cloud updates (sem_pc_accum.py:156-209) ------------------
     def update_poses(self, T_new_prev):
-        self.poses = [list(np.matmul(T_new_prev, np.array([p + [1]]).T)[:, 0][:-1])
-                      for p in self.poses]
+        """sem_pc_accum.py:156-165: every stored pose <- T_new_prev @ [pose 1].  One numpy call for all
+        poses: a stacked (F,4,1) operand runs the reference's (4,4) @ (4,1) product once per pose, so
+        the bits are the reference's (tests/test_cabi_cpu.py), without F interpreter round trips per
+        integrated frame."""
+        if not self.poses:
+            return
+        col = np.ones((len(self.poses), 4, 1))
+        col[:, :3, 0] = self.poses
+        self.poses = np.matmul(np.asarray(T_new_prev, dtype=np.float64), col)[:, :3, 0].tolist()
 
     def update_sem_pcs(self, T_new_prev):
         """Every stored point <- T_new_prev @ point.  On the device this is

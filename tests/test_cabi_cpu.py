@@ -235,3 +235,26 @@ def test_dataset_mirror_transforms_match_oracle():
         nu.homo_transform(np.eye(3), np.zeros((2, 3)))
     with pytest.raises(AssertionError):
         nu.homo_transform(np.eye(4), np.zeros((2, 4)))
+
+
+def test_update_poses_keeps_the_reference_bits():
+    """sem_pc_accum.py:156-165 evaluates (4,4) @ (4,1) once per stored pose; the mirror's single stacked
+    call must give the same float64 bits (the poses decide eviction and the BEV origin)."""
+    from pc_accumulation_lib_b200.sem_pc_accum import SemanticPointCloudAccumulator as Acc
+    rng = np.random.default_rng(11)
+    acc = Acc.__new__(Acc)
+    for _ in range(50):
+        a, b = rng.normal(0, 0.5), rng.normal(0, 0.02)
+        T = np.eye(4)
+        T[:3, :3] = (np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+                     @ np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]]))
+        T[:3, 3] = rng.normal(0, 3, 3)
+        poses = [list(rng.normal(0, 50, 3)) for _ in range(int(rng.integers(1, 40)))]
+        want = [list(np.matmul(T, np.array([p + [1]]).T)[:, 0][:-1]) for p in poses]
+        acc.poses = [list(p) for p in poses]
+        acc.update_poses(T)
+        assert acc.poses == want
+        assert all(type(p) is list and len(p) == 3 for p in acc.poses)
+    acc.poses = []
+    acc.update_poses(np.eye(4))
+    assert acc.poses == []
