@@ -7,6 +7,11 @@
   an independent per-cell count (torch.bincount over the debug cell indices) against the
   road / vehicle probability planes, window consistency (full = present when the split is
   moved to the end), and equivariance under an exact 90 degree rotation.
+* configs[3] (batched dataset generation: 128 scenes x 32 variants = 4096 BEVs on four handles /
+  streams) through determinism across handles, a checksum of checksums, and equality of the
+  batched launch with 32 single-variant launches.
+* configs[0] and configs[4] (20 x 120,000-point frustum frames; 1024 x 1024 grid) against the
+  oracle directly.
 """
 import numpy as np
 import pytest
@@ -270,3 +275,101 @@ def test_full_size_highres_1024_matches_oracle(dev):
         np.testing.assert_array_equal(window_cells(cloud, cells, fids[:split], P), dbg['cells_present'])
         np.testing.assert_array_equal(window_cells(cloud, cells, fids[split:], P), dbg['cells_future'])
     cloud.close()
+
+
+def test_full_size_batched_dataset_properties(dev):
+    """configs[3] at full size: 128 scenes x 32 (present index, augmentation) variants = 4096 BEVs through
+    the batched device path as bench.py drives it (one integrate launch and one rasterise call per scene,
+    four handles on four CUDA streams, the ring reset between scenes).  The oracle needs ~3 s per scene, so
+    the 128 scenes are checked through properties: (i) scenes with the same inputs give bit-identical planes
+    whichever handle, stream and turn processed them (3 distinct scenes, 128 passes); (ii) the checksum of
+    checksums over all 4096 BEVs equals the multiplicity-weighted sum of the distinct scenes'; (iii) the kept
+    counts are those of a fresh pass; (iv) the 32 variants of scene 0 rasterised ONE AT A TIME (the single-variant kernels,
+    which tests/test_gpu_core.py and the scene test above hold against the oracle) equal the batched ones;
+    (v) moving the window split to the end makes `full` of the batched launch the `present` of that call."""
+    P, S, V, n_sw, D = 256, 128, 32, 40, 3
+    gp = gen_params(synth.nusc_bev_params(pixel_size=P))
+    rng = np.random.default_rng(404)
+    scenes, params_rel, n_in = [], [], 0
+    for k in range(D):
+        sc = synth.nusc_scene(synth.seed_for(4, 100 + k), n_sw)
+        T_gw = np.linalg.inv(sc[0]['ego_at_lidar_ts'])
+        sweeps, poses = [], []
+        for o in sc:
+            T = T_gw @ o['ego_at_lidar_ts']
+            poses.append(T[:3, 3] + [0., 0., 1.])
+            sweeps.append(dict(pc=torch.from_numpy(o['pc']).cuda(), cam=torch.from_numpy(o['pc_cam_idx']).cuda(),
+                               rgb=[torch.from_numpy(np.ascontiguousarray(i)).cuda() for i in o['images']],
+                               sem=[torch.from_numpy(c.astype(np.uint8)).cuda() for c in o['_semseg']], T=T))
+        n_in = max(n_in, sum(o['pc'].shape[0] for o in sc))
+        ps = []
+        for p in (6, 10, 14, 18, 22, 26, 30, 34):
+            for _ in range(4):
+                ps.append((p, poses[p], rng.uniform(0, 2 * np.pi), rng.normal(0, 1.5), rng.normal(0, 1.5),
+                           1. + float(np.clip(rng.normal(0, .1), -.2, .2))))
+        scenes.append(sweeps)
+        params_rel.append(ps)
+
+    def params_for(k, first, split_at_end=False):
+        return [bev_params_from(dev, gp, first, first + (n_sw if split_at_end else p), first + n_sw, origin,
+                                rot, dx, dy, zoom) for p, origin, rot, dx, dy, zoom in params_rel[k]]
+
+    n_str = 4
+    clouds = [dev.DeviceCloud(n_in + 8 * n_sw + 4096, n_sw + 8) for _ in range(n_str)]
+    streams = [torch.cuda.Stream() for _ in range(n_str)]
+    outs = [torch.empty((V, 3, 7, P, P), dtype=torch.float16, device='cuda') for _ in range(n_str)]
+    w = (torch.arange(V * 21 * P * P, device='cuda', dtype=torch.int64) % 8191 + 1)
+    first_planes, sums, tail = {}, [], []
+    order = rng.integers(0, D, S)
+    order[:D] = np.arange(D)
+    main = torch.cuda.current_stream()
+    for st in streams:
+        st.wait_stream(main)
+    for s, k in enumerate(order):                  # nothing in this loop waits for the device
+        c, st, out = clouds[s % n_str], streams[s % n_str], outs[s % n_str]
+        with torch.cuda.stream(st):
+            c.reset()
+            first = c.integrate_records_batch(scenes[k], synth.NUSC_FILTERS, 255.)
+            c.rasterise(params_for(k, first), P, out=out)
+            sums.append(((out.view(torch.int16).to(torch.int64).reshape(-1) * w).sum(), int(k)))
+            if k not in first_planes:
+                first_planes[k] = out.clone()
+            elif s >= S - 8:                       # the last passes: kept whole, not just as a checksum
+                tail.append((out.clone(), int(k), s))
+    torch.cuda.synchronize()
+    for c in clouds:
+        assert c.sync() & ~2 == 0
+    for planes, k, s in tail:
+        assert torch.equal(planes.view(torch.int16), first_planes[k].view(torch.int16)), (s, k)
+    per_scene = {}
+    for v, k in sums:
+        per_scene.setdefault(k, set()).add(int(v))
+    assert all(len(v) == 1 for v in per_scene.values()), per_scene          # (i)
+    total = sum(int(v) for v, _ in sums)
+    mult = np.bincount(order, minlength=D)
+    assert total == sum(int(mult[k]) * next(iter(per_scene[k])) for k in range(D))   # (ii)
+    assert len({next(iter(v)) for v in per_scene.values()}) == D            # the scenes do differ
+    # (iii) the ring of each handle holds what a fresh pass over its last scene keeps
+    fresh = dev.DeviceCloud(n_in + 8 * n_sw + 4096, n_sw + 8)
+    for ci, c in enumerate(clouds):
+        k = int(order[S - n_str + ci])
+        fresh.reset()
+        fresh.integrate_records_batch(scenes[k], synth.NUSC_FILTERS, 255.)
+        assert fresh.sync() & ~2 == 0
+        assert c.resident_points() == fresh.resident_points() > 50000
+    fresh.close()
+
+    c = clouds[0]
+    c.reset()
+    first = c.integrate_records_batch(scenes[0], synth.NUSC_FILTERS, 255.)
+    bps = params_for(0, first)
+    for v in range(V):                                                       # (iv)
+        one, _, _ = c.rasterise([bps[v]], P)
+        assert torch.equal(one[0].view(torch.int16), first_planes[0][v].view(torch.int16)), v
+    full_as_present, _, _ = c.rasterise(params_for(0, first, split_at_end=True), P)   # (v)
+    assert torch.equal(full_as_present[:, 0].view(torch.int16), first_planes[0][:, 2].view(torch.int16))
+    assert c.sync() & ~2 == 0
+    n_nonempty = int((first_planes[0][:, 2, 0] != first_planes[0][0, 2, 0, 0, 0]).sum())
+    assert n_nonempty > 32 * 5000                   # every variant bins thousands of cells
+    for c in clouds:
+        c.close()
