@@ -82,6 +82,13 @@ int pcacc_project(const float *pts_dev, int64_t n, int pts_stride, const double 
                   int img_h, int img_w, double max_depth,
                   int32_t *u_dev, int32_t *v_dev, uint8_t *mask_dev, void *stream);
 
+/* velo2img as the reference returns it, sem_pc_accum.py:367-402: out_dev (n_kept, pts_stride + 2)
+ * float64 = the rows [pc_velo, u, v] of the points inside the image (and 0 < depth < max_depth), in
+ * input order; *n_kept_dev = their number (out_dev must hold n rows). */
+int pcacc_velo2img(pcacc_t h, const float *pts_dev, int64_t n, int pts_stride, const double *P,
+                   int img_h, int img_w, double max_depth, double *out_dev, int64_t *n_kept_dev,
+                   void *stream);
+
 /* gen_semantic_pc, sem_pc_accum.py:323-345: projection, order-preserving
  * compaction of in-image points and the K-channel gather map[v,u,:].
  * out_dev: (n, 4+K) float64 (only the first *n_kept rows are written),

@@ -57,6 +57,7 @@ SIGNATURES = {
     'pcacc_reset': (_i32, [_vp, _vp]),
     'pcacc_project': (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _dbl, _vp, _vp,
                              _vp, _vp]),
+    'pcacc_velo2img': (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _dbl, _vp, _vp, _vp]),
     'pcacc_gen_semantic_pc': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _i32,
                                      _i32, _i32, _vp, _vp, _vp]),
     'pcacc_integrate_frustum': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32,

@@ -226,6 +226,37 @@ k_gen_semantic_pc(const float4 *__restrict__ pts, int64_t n, PMat P, const void 
 }
 
 // ---------------------------------------------------------------------------
+// velo2img as the reference returns it (sem_pc_accum.py:367-402): the rows [pc_velo, u, v] of the
+// points that fall into the image, float64, in input order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBLOCK)
+k_velo2img(const float *__restrict__ pts, int64_t n, int stride, PMat P, int img_h, int img_w,
+           double max_depth, double *__restrict__ out, int64_t *__restrict__ n_kept, LookBack lb) {
+    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
+    bool keep = false;
+    Proj r;
+    r.u = r.v = 0;
+    if (i < n) {
+        const float *p = pts + i * stride;
+        r = project_point(P.m, p[0], p[1], p[2], img_h, img_w, max_depth);
+        keep = r.in_img;
+    }
+    uint32_t tile_end;
+    const uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
+    if (keep) {
+        const float *p = pts + i * stride;
+        double *o = out + (int64_t)rank * (stride + 2);
+        for (int c = 0; c < stride; c++) o[c] = (double)p[c];
+        o[stride] = r.u;       // integral doubles inside the image: what astype(int) -> float64 gives
+        o[stride + 1] = r.v;
+    }
+    if (tile == lb.n_tiles - 1 && threadIdx.x == 0) *n_kept = (int64_t)tile_end;
+}
+
+// ---------------------------------------------------------------------------
 // KITTI-360 frustum integrate (K1-K4 fused)
 // ---------------------------------------------------------------------------
 template <int DT>
@@ -821,6 +852,31 @@ extern "C" int pcacc_gen_semantic_pc(pcacc_t h, const float *pts_dev, int64_t n,
     }
 #undef LAUNCH_GSP
     pcacc_prof_end(h, PCACC_K_INTEGRATE, pe, st);
+    PCACC_CUDA(h, cudaGetLastError());
+    return PCACC_OK;
+}
+
+extern "C" int pcacc_velo2img(pcacc_t h, const float *pts_dev, int64_t n, int pts_stride, const double *P,
+                              int img_h, int img_w, double max_depth, double *out_dev, int64_t *n_kept_dev,
+                              void *stream) {
+    if (!h) return PCACC_ERR_ARG;
+    if (n < 0 || !P || pts_stride < 3 || img_h <= 0 || img_w <= 0 || !n_kept_dev || (n > 0 && (!pts_dev || !out_dev)))
+        return pcacc_fail(h, PCACC_ERR_ARG, "bad velo2img arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCACC_CUDA(h, cudaSetDevice(h->device));
+    if (n == 0) {
+        PCACC_CUDA(h, cudaMemsetAsync(n_kept_dev, 0, sizeof(int64_t), st));
+        return PCACC_OK;
+    }
+    PMat pm;
+    memcpy(pm.m, P, sizeof(pm.m));
+    const int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    LookBack lb;
+    int rc = make_lookback(h, tiles, &lb);
+    if (rc) return rc;
+    h->launches[PCACC_K_INTEGRATE]++;
+    k_velo2img<<<(unsigned)tiles, IBLOCK, 0, st>>>(pts_dev, n, pts_stride, pm, img_h, img_w, max_depth, out_dev,
+                                                   n_kept_dev, lb);
     PCACC_CUDA(h, cudaGetLastError());
     return PCACC_OK;
 }

@@ -576,6 +576,21 @@ class DeviceCloud:
         self.stage.fence()
         return u, v, m
 
+    def velo2img(self, pc, P, img_h, img_w, max_depth=np.inf):
+        """sem_pc_accum.py:367-402 -> (M, cols + 2) float64 CUDA tensor [pc_velo, u, v] of the points
+        inside the image, input order (one kernel: projection + order-preserving compaction)."""
+        pts = self.stage.put('pc', self._f32_cloud(pc)).contiguous()
+        assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.shape[1] >= 3
+        n, stride = int(pts.shape[0]), int(pts.shape[1])
+        out = torch.empty((n, stride + 2), dtype=torch.float64, device=self.device)
+        nk = torch.zeros(1, dtype=torch.int64, device=self.device)
+        Pm = _hostd(P, 12)
+        self._check(self.lib.pcacc_velo2img(self.h, _ptr(pts), n, stride, Pm.ctypes.data_as(C.c_void_p),
+                                            int(img_h), int(img_w), float(max_depth), _ptr(out), _ptr(nk),
+                                            _stream()))
+        self.stage.fence()
+        return out[:int(nk.item())]
+
     def gen_semantic_pc(self, pc, semantic_map, P):
         """(M,4+K) float64 device tensor, rows in input order."""
         pts = self.stage.put('pc', self._f32_cloud(pc))

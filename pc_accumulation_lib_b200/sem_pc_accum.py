@@ -240,22 +240,18 @@ class SemanticPointCloudAccumulator:
 
     # -- stand-alone operators (sem_pc_accum.py:317-402), device-backed ------
     def filter_semseg_pc(self, pc):
-        t = torch.from_numpy(np.ascontiguousarray(pc)).to(self.cloud.device)
-        keep = torch.ones(t.shape[0], dtype=torch.bool, device=t.device)
-        for f in self.semseg_filters:
-            keep &= t[:, -1] != f
-        return t[keep].cpu().numpy()
+        """sem_pc_accum.py:317-321: rows whose last column is none of the filtered classes, input
+        order (`pcacc_partition_semantic_pc`: the rows that are NOT selected)."""
+        pc = np.ascontiguousarray(pc, dtype=np.float64)
+        _, rest = self.cloud.partition_semantic_pc(pc, self.semseg_filters, pc.shape[1] - 1)
+        return rest.cpu().numpy()
 
     def gen_semantic_pc(self, pc_velo, semantic_map, P_velo_frame):
         return self.cloud.gen_semantic_pc(pc_velo, semantic_map, P_velo_frame).cpu().numpy()
 
     def velo2img(self, pc_velo, P_velo_frame, img_h, img_w, max_depth=np.inf):
-        pc = np.ascontiguousarray(self.cloud._f32_cloud(pc_velo))
-        u, v, m = self.cloud.project(pc, P_velo_frame, img_h, img_w, max_depth)
-        m = m.bool()
-        pts = torch.from_numpy(np.asarray(pc_velo)).to(self.cloud.device).double()
-        out = torch.cat([pts, u.double()[:, None], v.double()[:, None]], dim=1)
-        return out[m].cpu().numpy()
+        """sem_pc_accum.py:367-402 (`pcacc_velo2img`)."""
+        return self.cloud.velo2img(pc_velo, P_velo_frame, img_h, img_w, max_depth).cpu().numpy()
 
     @staticmethod
     def velo2frame(pc_velo, P_velo_frame):

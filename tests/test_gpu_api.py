@@ -99,6 +99,14 @@ def test_kitti_helpers_match_reference():
     kept = acc.filter_semseg_pc(np.concatenate([sem, sem[:, -1:]], axis=1))
     assert not np.isin(kept[:, -1], synth.KITTI_FILTERS).any()
     assert kept.shape[0] == (~np.isin(sem[:, -1], synth.KITTI_FILTERS)).sum()
+    # whole rows and their order against the oracle's restatements (sem_pc_accum.py:317-321, 367-402)
+    np.testing.assert_array_equal(img, orc.velo2img(pc5, inp['P'], synth.KITTI_IMG_H, synth.KITTI_IMG_W))
+    near = acc.velo2img(inp['pc'], inp['P'], synth.KITTI_IMG_H, synth.KITTI_IMG_W, max_depth=12.)
+    np.testing.assert_array_equal(near, orc.velo2img(inp['pc'], inp['P'], synth.KITTI_IMG_H, synth.KITTI_IMG_W, 12.))
+    assert 0 < near.shape[0] < img.shape[0] and near.dtype == np.float64 and near.shape[1] == 6
+    sem8 = np.concatenate([sem, sem[:, -1:]], axis=1)
+    np.testing.assert_array_equal(kept, orc.filter_semseg_pc(sem8, synth.KITTI_FILTERS))
+    assert acc.velo2img(inp['pc'][:0], inp['P'], 10, 10).shape == (0, 6)
 
 
 def test_nuscenes_oracle_accumulator_matches_reference():
