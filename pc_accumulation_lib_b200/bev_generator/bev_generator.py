@@ -53,10 +53,12 @@ _OPS = {}
 
 
 def _ops_cloud() -> DeviceCloud:
-    """One small DeviceCloud per (process, device) whose handle serves the stand-alone operators
-    (static methods of the reference have no generator instance to hang it on)."""
+    """One small DeviceCloud per (process, thread, device) whose handle serves the stand-alone
+    operators (static methods of the reference have no generator instance to hang it on; a handle's
+    scan state must not be shared by two threads)."""
+    import threading
     import torch
-    key = (os.getpid(), torch.cuda.current_device())
+    key = (os.getpid(), threading.get_ident(), torch.cuda.current_device())
     c = _OPS.get(key)
     if c is None:
         c = _OPS[key] = DeviceCloud(1024, max_frames=8)
