@@ -607,6 +607,13 @@ def c3_extra(torch, DeviceCloud, pk, F=200, P=P, elevation_max=False):
         return e0.elapsed_time(e1) / n
 
     ms_int = timed(integrate_all, 3)
+    # the per-frame loop above is bound by its two host calls per frame (re-base + integrate, ~20 us):
+    # the kernels' own time, from CUDA events around every launch
+    cloud.profile(('integrate', 'rebase'))
+    cloud.profile_read()
+    integrate_all()
+    kprof = cloud.profile_read()
+    cloud.profile(False)
     cloud.sync()
     first, n_live = cloud.live_frames()
     p = F // 2
@@ -631,6 +638,9 @@ def c3_extra(torch, DeviceCloud, pk, F=200, P=P, elevation_max=False):
         'exact_chain_replays': st['replays'],
         'integrate_ms_per_frame': ms_int / F, 'integrate_points_per_s': F * N / (ms_int * 1e-3),
         'integrate_alg_GBps': b_int * F / (ms_int * 1e-3) / 1e9,
+        'integrate_kernel_us_per_frame': round(kprof['integrate'][0] / max(kprof['integrate'][1], 1) * 1e3, 2),
+        'integrate_kernel_alg_GBps': b_int / (kprof['integrate'][0] / max(kprof['integrate'][1], 1) * 1e-3) / 1e9,
+        'rebase_kernel_us_per_frame': round(kprof['rebase'][0] / max(kprof['rebase'][1], 1) * 1e3, 2),
         'rasterise_ms_per_bev': ms_ras, 'bevs_per_s': 1e3 / ms_ras,
         'rasterise_alg_GBps': b_ras / (ms_ras * 1e-3) / 1e9,
         'rasterise_frac_of_hbm_peak': b_ras / (ms_ras * 1e-3) / 1e9 / pk['hbm_gbs'],

@@ -259,53 +259,73 @@ k_velo2img(const float *__restrict__ pts, int64_t n, int stride, PMat P, int img
 // ---------------------------------------------------------------------------
 // KITTI-360 frustum integrate (K1-K4 fused)
 // ---------------------------------------------------------------------------
+// KI_ITEMS points per thread (element k of thread t = point k * IBLOCK + t of the tile): a 120 000-point
+// frame is 235 tiles instead of 938 — a shorter look-back chain — and every thread has its KI_ITEMS
+// independent point loads and map gathers in flight at once.
+#define KI_ITEMS 4
 template <int DT>
 __global__ void __launch_bounds__(IBLOCK)
 k_integrate_frustum(const float4 *__restrict__ pts, int64_t n, PMat P,
                     const uint8_t *__restrict__ rgb, const void *__restrict__ sem, int K, int img_h,
                     int img_w, double max_depth, Filters filt, RingDev ring, FrameSlots fs,
                     LookBack lb, uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[KI_ITEMS * IBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
-    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
     const int64_t base = frame_base(fs);
-    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
-    bool keep = false;
-    float4 p = make_float4(0, 0, 0, 0);
-    uint32_t packed = 0;
-    if (i < n) {
-        p = pts[i];
-        Proj r = project_point(P.m, p.x, p.y, p.z, img_h, img_w, max_depth);
-        if (r.in_img) {
-            int64_t pix = (int64_t)r.v * img_w + (int64_t)r.u;
-            int cls = load_class<DT>(sem, pix, K);
-            keep = !class_filtered(filt, cls);
-            if (keep) {
-                if (cls < 0 || cls > 255) {
-                    atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-                    cls &= 255;
+    const int64_t i0 = (int64_t)tile * (IBLOCK * KI_ITEMS) + threadIdx.x;
+    bool keep[KI_ITEMS];
+    float4 p[KI_ITEMS];
+    uint32_t packed[KI_ITEMS];
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        const int64_t i = i0 + k * IBLOCK;
+        p[k] = i < n ? pts[i] : make_float4(0, 0, 0, 0);
+        keep[k] = false;
+        packed[k] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        if (i0 + k * IBLOCK < n) {
+            const Proj r = project_point(P.m, p[k].x, p[k].y, p[k].z, img_h, img_w, max_depth);
+            if (r.in_img) {
+                const int64_t pix = (int64_t)r.v * img_w + (int64_t)r.u;
+                int cls = load_class<DT>(sem, pix, K);
+                keep[k] = !class_filtered(filt, cls);
+                if (keep[k]) {
+                    if (cls < 0 || cls > 255) {
+                        atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
+                        cls &= 255;
+                    }
+                    const uint8_t *c = rgb + pix * 3;
+                    packed[k] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
+                                ((uint32_t)cls << 24);
                 }
-                const uint8_t *c = rgb + pix * 3;
-                packed = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
-                         ((uint32_t)cls << 24);
             }
         }
     }
-    uint32_t tile_end;
-    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
-    if (keep) {
-        int64_t o = base + rank;
-        if (o < fs.capacity) {
-            ring.x[o] = (double)p.x;
-            ring.y[o] = (double)p.y;
-            ring.z[o] = (double)p.z;
-            ring.inten[o] = p.w;
-            ring.rgbs[o] = packed;
-            ring.inst[o] = 0;
-            ring.dyn[o] = 0;
+    uint32_t rank[KI_ITEMS], tile_end;
+    compact_rank_multi<IBLOCK, KI_ITEMS>(keep, lb.state, lb.epoch, tile, s_cnt, rank, &tile_end);
+    double bb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        if (keep[k]) {
+            const double x = (double)p[k].x, y = (double)p[k].y, z = (double)p[k].z;
+            bb[0] = fmin(bb[0], x); bb[1] = fmin(bb[1], y); bb[2] = fmin(bb[2], z);
+            bb[3] = fmax(bb[3], x); bb[4] = fmax(bb[4], y); bb[5] = fmax(bb[5], z);
+            const int64_t o = base + rank[k];
+            if (o < fs.capacity) {
+                ring.x[o] = x;
+                ring.y[o] = y;
+                ring.z[o] = z;
+                ring.inten[o] = p[k].w;
+                ring.rgbs[o] = packed[k];
+                ring.inst[o] = 0;
+                ring.dyn[o] = 0;
+            }
         }
     }
-    aabb_update<IBLOCK>(fs.aabb, keep, (double)p.x, (double)p.y, (double)p.z);
+    aabb_update_v<IBLOCK>(fs.aabb, bb);
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
@@ -313,38 +333,51 @@ k_integrate_frustum(const float4 *__restrict__ pts, int64_t n, PMat P,
 __global__ void __launch_bounds__(IBLOCK)
 k_integrate_gt(const float4 *__restrict__ pts, int64_t n, const int16_t *__restrict__ sem_gt,
                Filters filt, RingDev ring, FrameSlots fs, LookBack lb, uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_warp[IBLOCK / 32 + 1];
+    __shared__ uint32_t s_cnt[KI_ITEMS * IBLOCK / 32 + 1];
     __shared__ uint32_t s_tile;
-    uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
+    const uint32_t tile = lb_take_ticket(lb.ticket, lb.n_tiles, &s_tile);
     const int64_t base = frame_base(fs);
-    int64_t i = (int64_t)tile * IBLOCK + threadIdx.x;
-    bool keep = false;
-    float4 p = make_float4(0, 0, 0, 0);
-    int cls = 0;
-    if (i < n) {
-        p = pts[i];
-        cls = (int)sem_gt[i];
-        keep = !class_filtered(filt, cls);
-        if (keep && (cls < 0 || cls > 255)) {
+    const int64_t i0 = (int64_t)tile * (IBLOCK * KI_ITEMS) + threadIdx.x;
+    bool keep[KI_ITEMS];
+    float4 p[KI_ITEMS];
+    int cls[KI_ITEMS];
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        const int64_t i = i0 + k * IBLOCK;
+        const bool in = i < n;
+        p[k] = in ? pts[i] : make_float4(0, 0, 0, 0);
+        cls[k] = in ? (int)sem_gt[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        keep[k] = (i0 + k * IBLOCK < n) && !class_filtered(filt, cls[k]);
+        if (keep[k] && (cls[k] < 0 || cls[k] > 255)) {
             atomicOr(flags, PCACC_FLAG_ATTR_RANGE);
-            cls &= 255;
+            cls[k] &= 255;
         }
     }
-    uint32_t tile_end;
-    uint32_t rank = compact_rank<IBLOCK>(keep, lb.state, lb.epoch, tile, s_warp, &tile_end);
-    if (keep) {
-        int64_t o = base + rank;
-        if (o < fs.capacity) {
-            ring.x[o] = (double)p.x;
-            ring.y[o] = (double)p.y;
-            ring.z[o] = (double)p.z;
-            ring.inten[o] = p.w;
-            ring.rgbs[o] = (uint32_t)cls << 24;
-            ring.inst[o] = 0;
-            ring.dyn[o] = 0;
+    uint32_t rank[KI_ITEMS], tile_end;
+    compact_rank_multi<IBLOCK, KI_ITEMS>(keep, lb.state, lb.epoch, tile, s_cnt, rank, &tile_end);
+    double bb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int k = 0; k < KI_ITEMS; k++) {
+        if (keep[k]) {
+            const double x = (double)p[k].x, y = (double)p[k].y, z = (double)p[k].z;
+            bb[0] = fmin(bb[0], x); bb[1] = fmin(bb[1], y); bb[2] = fmin(bb[2], z);
+            bb[3] = fmax(bb[3], x); bb[4] = fmax(bb[4], y); bb[5] = fmax(bb[5], z);
+            const int64_t o = base + rank[k];
+            if (o < fs.capacity) {
+                ring.x[o] = x;
+                ring.y[o] = y;
+                ring.z[o] = z;
+                ring.inten[o] = p[k].w;
+                ring.rgbs[o] = (uint32_t)cls[k] << 24;
+                ring.inst[o] = 0;
+                ring.dyn[o] = 0;
+            }
         }
     }
-    aabb_update<IBLOCK>(fs.aabb, keep, (double)p.x, (double)p.y, (double)p.z);
+    aabb_update_v<IBLOCK>(fs.aabb, bb);
     if (tile == lb.n_tiles - 1 && threadIdx.x == 0) finish_frame(fs, base, tile_end);
 }
 
@@ -898,7 +931,7 @@ extern "C" int pcacc_integrate_frustum(pcacc_t h, const float *pts_dev, int64_t 
     if (rc) return rc;
     rc = set_inten_div(h, 1.0);
     if (rc) return rc;
-    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    int64_t tiles = (n + IBLOCK * KI_ITEMS - 1) / (IBLOCK * KI_ITEMS);
     if (tiles == 0) tiles = 1;
     LookBack lb;
     rc = make_lookback(h, tiles, &lb);
@@ -939,7 +972,7 @@ extern "C" int pcacc_integrate_gt(pcacc_t h, const float *pts_dev, int64_t n,
     if (rc) return rc;
     rc = set_inten_div(h, 1.0);
     if (rc) return rc;
-    int64_t tiles = (n + IBLOCK - 1) / IBLOCK;
+    int64_t tiles = (n + IBLOCK * KI_ITEMS - 1) / (IBLOCK * KI_ITEMS);
     if (tiles == 0) tiles = 1;
     LookBack lb;
     rc = make_lookback(h, tiles, &lb);
