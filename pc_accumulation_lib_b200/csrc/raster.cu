@@ -193,16 +193,28 @@ __global__ void k_bev_cull(BinArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_frames * a.n_var) return;
     const int f = t / a.n_var, v = t - f * a.n_var;
-    if (f == 0) bev_write_consts(a.params[v], a.P, (BevConsts *)a.consts + v);
     const int64_t fid = a.frame_lo + f;
     const int slot = (int)(fid % a.max_frames);
-    const pcacc_bev_params &bp = a.params[v];
-    if (!(fid >= bp.frame_begin && fid < bp.frame_end)) return;
+    // Everything this thread may read is addressed by (f, v) alone: all of it is requested here, before
+    // the first decision, so the loads travel together.  Taken where they are used — behind the window
+    // test, the empty-frame test and the box test — they were a chain of four dependent DRAM round trips,
+    // most of this small kernel's 8 us on every rasterise call's critical path.
+    const pcacc_bev_params bp = a.params[v];
     const int64_t cnt = a.frame_cnt[slot];
+    double Mp[12], M[12];
+    unsigned long long bbw[6];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        Mp[k] = a.comp[(int64_t)slot * 12 + k];   // identity unless lazily re-based
+        M[k] = a.cull[(int64_t)slot * 12 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) bbw[k] = a.aabb[(int64_t)slot * 6 + k];
+    if (f == 0) bev_write_consts(bp, a.P, (BevConsts *)a.consts + v);
+    if (!(fid >= bp.frame_begin && fid < bp.frame_end)) return;
     const uint32_t tiles = (uint32_t)((cnt + BIN_TILE - 1) / BIN_TILE);
     if (tiles == 0) return;
     {
-        const double *Mp = a.comp + (int64_t)slot * 12;  // identity unless lazily re-based
         FrameVar fv;
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -219,16 +231,14 @@ __global__ void k_bev_cull(BinArgs a) {
         }
         a.fvar[(int64_t)f * a.n_var + v] = fv;
     }
-    const unsigned long long *bb = a.aabb + (int64_t)slot * 6;
     double lo[3], hi[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        lo[k] = ord_decode(bb[k]);
-        hi[k] = ord_decode(bb[3 + k]);
+        lo[k] = ord_decode(bbw[k]);
+        hi[k] = ord_decode(bbw[3 + k]);
     }
     bool touch = true;
     if (lo[0] <= hi[0]) {  // a tracked, non-empty box (otherwise let the points decide)
-        const double *M = a.cull + (int64_t)slot * 12;
         double q0lo = INFINITY, q0hi = -INFINITY, q1lo = INFINITY, q1hi = -INFINITY, amax = 0.0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
