@@ -36,6 +36,11 @@ for name in ('generate_batch', '_rasterise_windows_begin', '_rasterise_device', 
 for name in ('rasterise', 'planes_to_host_begin', 'planes_to_host_finish', 'integrate_records_host', 'mark_dynamic', 'flush_marks', 'warp_planes'):
     wrap(device.DeviceCloud, name)
 wrap(device, 'make_bev_params_batch')
+from pc_accumulation_lib_b200.bev_generator import sem_bev
+wrap(sem_bev.SemBEVGenerator, '_assemble')
+wrap(sem_pc_accum._LazyTrajs, '_materialise')
+wrap(device.DeviceCloud, 'sync')
+wrap(device.DeviceCloud, 'refresh')
 bg.make_bev_params_batch = device.make_bev_params_batch
 
 scene = [pin_observation(o) for o in bench.make_scenes(0, 1)[0]]
