@@ -463,3 +463,33 @@ def test_per_step_operators_edge_cases():
     eq(t.cpu().numpy(), maps)                                           # the caller's tensor is not modified
     assert ops.sync() == 0
     ops.close()
+
+
+def test_per_step_operators_reject_bad_arguments():
+    """The stand-alone entry points fail loudly (PcaccError with the library's message) instead of reading
+    out of bounds: too many classes, a class column outside the row, a weight column outside the row, a
+    non-positive grid."""
+    from pc_accumulation_lib_b200.device import DeviceCloud
+    from pc_accumulation_lib_b200._lib import PcaccError
+    ops = DeviceCloud(1024, 8)
+    pc = np.zeros((10, 10))
+    with pytest.raises(PcaccError, match='cell_stats'):
+        ops.cell_stats(pc, 8, list(range(40)), 7)
+    with pytest.raises(PcaccError, match='cell_stats'):
+        ops.cell_stats(pc, 8, [1], 12)
+    with pytest.raises(PcaccError, match='cell_stats'):
+        ops.cell_stats(pc, 8, [1], 7, weight_col=10)
+    with pytest.raises(PcaccError, match='cell_stats'):
+        ops.cell_stats(pc, 0, [1], 7)
+    with pytest.raises(PcaccError, match='partition_semantic_pc'):
+        ops.partition_semantic_pc(pc, [1], 10)
+    with pytest.raises(PcaccError, match='preprocess_pc'):
+        ops.preprocess_pc(pc, np.eye(3), 0., 0., 10., None, 10., 0)        # pos2grid needs P > 0
+    with pytest.raises(AssertionError):
+        ops.preprocess_pc(np.zeros((4, 2)))                                  # rows need x, y, z
+    with pytest.raises(AssertionError):
+        ops.cell_stats(pc, 8, weights=np.zeros(3))                           # one weight per point
+    # the handle stays usable after an error return
+    m = ops.cell_stats(pc, 8, want=('sel',))
+    assert float(m['sel'].sum()) == 10.
+    ops.close()
