@@ -290,7 +290,7 @@ extern "C" int pcacc_create(int device, int64_t capacity_pts, int max_frames, pc
         h->reduce_strips = e && e[0] == '1';
         const char *c = getenv("PCACC_CLS_MULT"), *b = getenv("PCACC_BIN_MULT");
         h->cls_mult = c && atoi(c) > 0 ? atoi(c) : 4;
-        h->bin_mult = b && atoi(b) > 0 ? atoi(b) : 8;   // (4 = one wave: 23.0 vs 25 us on the bench workload, but 123 vs 103 us on the long-horizon window)
+        h->bin_mult = b && atoi(b) > 0 ? atoi(b) : 0;   // 0 = by launch shape (raster.cu): 6 blocks per SM for batches of variants, 9 otherwise
         const char *cs = getenv("PCACC_CLASSIFY_SINGLE");
         h->classify_single = cs && cs[0] == '1';
     }
